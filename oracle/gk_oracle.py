@@ -1,0 +1,552 @@
+"""CPU oracle for the WL-subtree / Shortest-Path Gram hot path.
+
+TEST INFRASTRUCTURE ONLY.  This module is a CPU restatement of the reference's
+(ysig/GraKeL v0.1.11) algorithm for the path named in BASELINE.json.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import it, and only as the checker or the timed
+CPU baseline -- the product (``grakel_b200``) never imports anything from
+``oracle/`` and fails loudly when its CUDA library is missing.
+
+Parity pinning: every function here is checked against the *real* reference
+(imported from /root/reference in the build container) by
+``tests/golden/make_golden.py``; the resulting vectors are committed under
+``tests/golden/`` and re-checked by ``tests/test_oracle_golden.py``.
+
+The port deliberately keeps the reference's *cost structure* (per-vertex Python
+string/tuple keys, per-level sparse feature matrices, one N x N matrix per WL
+level summed at the end) so that timing it is a fair stand-in for timing the
+reference itself ("kind": "port" in bench.py).
+
+Citations are file:line in /root/reference/grakel/.
+"""
+from __future__ import annotations
+
+import numbers
+from collections import Counter
+from collections.abc import Iterable
+
+import numpy as np
+from scipy.sparse import csr_matrix, issparse
+
+INF = float("inf")
+
+
+# --------------------------------------------------------------------------
+# input normalisation  (graph.py:147-230, 912-1053, 1542-1709)
+# --------------------------------------------------------------------------
+def _looks_like_adjacency(g):
+    """graph.py:1542-1585 -- 2-D ndarray, scipy sparse, or list of number lists."""
+    if isinstance(g, np.ndarray) and g.ndim == 2:
+        return True
+    if issparse(g):
+        return True
+    if type(g) is list and all(
+        isinstance(r, list) and all(isinstance(x, numbers.Number) for x in r) for r in g
+    ):
+        return True
+    return False
+
+
+def _edge_dict_from_any(g):
+    """Return (vertex set, {u: {v: w}}) or None.  graph.py:1588-1709.
+
+    Five spellings: {(u,v): w}, {u: [v..]}, {u: {v: w}}, iterable of (u,v),
+    iterable of (u,v,w).  Vertices that only ever appear as targets get an
+    empty out-list (graph.py:1627-1630 and siblings).
+    """
+    ed = {}
+
+    def put(u, v, w):
+        ed.setdefault(u, {})[v] = w
+
+    if type(g) is dict:
+        items = list(g.items())
+        if all(type(k) is tuple and len(k) == 2 and isinstance(w, numbers.Number) for k, w in items):
+            heads, tails = set(), set()
+            for (u, v), w in items:
+                heads.add(u)
+                tails.add(v)
+                put(u, v, w)
+            for v in tails - heads:
+                ed[v] = {}
+            return heads | tails, ed
+        if all(isinstance(d, list) for d in g.values()):
+            heads, tails = set(), set()
+            for u, lst in items:
+                heads.add(u)
+                tails |= set(lst)
+                for v in lst:
+                    put(u, v, 1.0)
+            for v in tails - heads:
+                ed[v] = {}
+            return heads | tails, ed
+        if all(
+            isinstance(d, dict) and all(isinstance(w, numbers.Number) for w in d.values())
+            for d in g.values()
+        ):
+            ed = {u: dict(d) for u, d in items}
+            heads = set(ed.keys())
+            tails = {v for d in ed.values() for v in d}
+            for v in tails - heads:
+                ed[v] = {}
+            return heads | tails, ed
+    if isinstance(g, Iterable) and not isinstance(g, (str, bytes, dict)):
+        seq = list(g)
+        if all(type(t) is tuple and len(t) == 2 for t in seq):
+            heads, tails = set(), set()
+            for u, v in seq:
+                heads.add(u)
+                tails.add(v)
+                put(u, v, 1.0)
+            for v in tails - heads:
+                ed[v] = {}
+            return heads | tails, ed
+        if all(type(t) is tuple and len(t) == 3 for t in seq):
+            heads, tails = set(), set()
+            for u, v, w in seq:
+                heads.add(u)
+                tails.add(v)
+                put(u, v, w)
+            for v in tails - heads:
+                ed[v] = {}
+            return heads | tails, ed
+    return None
+
+
+class OGraph:
+    """Canonical form used by the oracle.
+
+    kind        'adjacency' | 'dictionary'   (what the user passed; decides
+                 the "auto" APSP algorithm, graph.py:652-656)
+    A           dense float ndarray (adjacency input only)
+    verts       sorted vertex symbols (dictionary input: graph.py:902-905;
+                 adjacency input: range(n))
+    ed          {u: {v: w}} out-neighbour dictionary
+    labels      {vertex symbol (dictionary) or index (adjacency): label}
+    """
+
+    def __init__(self, g, labels):
+        self.labels = labels
+        if _looks_like_adjacency(g):
+            A = np.asarray(g.todense()) if issparse(g) else np.asarray(g)
+            if A.shape[0] != A.shape[1]:
+                raise ValueError("input matrix must be squared")
+            self.kind = "adjacency"
+            self.A = A
+            n = A.shape[0]
+            self.verts = list(range(n))
+            # graph.py:963-965 / 1198-1201: an edge is an entry > 0
+            ed = {i: {} for i in range(n)}
+            ii, jj = np.where(A > 0)
+            for i, j in zip(ii.tolist(), jj.tolist()):
+                ed[i][j] = A[i, j]
+            self.ed = ed
+        else:
+            r = _edge_dict_from_any(g)
+            if r is None:
+                raise ValueError("Unsupported input type.")
+            verts, ed = r
+            self.kind = "dictionary"
+            self.A = None
+            self.verts = sorted(verts)
+            self.ed = ed
+
+    # -- labels aligned with the APSP matrix index (graph.py:375-399, 689-772)
+    def index_labels(self):
+        if not self.labels:
+            raise ValueError("Graph does not have any labels for vertices.")
+        if self.kind == "adjacency":
+            return {i: self.labels[i] for i in range(len(self.verts))}
+        return {i: self.labels[v] for i, v in enumerate(self.verts)}
+
+    # -- APSP ------------------------------------------------------------
+    def floyd_warshall(self):
+        """graph.py:1767-1794 (classic k-ordered relaxation, float64)."""
+        if self.kind == "adjacency":
+            A = self.A
+        else:  # graph.py:1026-1038: adjacency built from the edge dictionary
+            n = len(self.verts)
+            pos = {v: i for i, v in enumerate(self.verts)}
+            A = np.zeros((n, n))
+            for u, d in self.ed.items():
+                for v, w in d.items():
+                    A[pos[u], pos[v]] = w
+        n = A.shape[0]
+        dist = np.array(A, dtype=float, copy=True)
+        dist[dist == 0] = INF
+        np.fill_diagonal(dist, 0)
+        for k in range(n):
+            # row form of the reference's i-loop (graph.py:1790-1792): row k and
+            # column k are fixed points of step k, so the whole-matrix update is
+            # the same arithmetic, one fp64 add + min per entry.
+            dist = np.minimum(dist, dist[:, k : k + 1] + dist[k : k + 1, :])
+        return dist
+
+    def dijkstra_all(self):
+        """graph.py:658-671 + 1712-1764: SSSP from every vertex of the edge dict."""
+        import heapq
+
+        n = len(self.verts)
+        pos = {v: i for i, v in enumerate(self.verts)}
+        S = np.full((n, n), INF)
+        for src in self.verts:
+            done = {}
+            heap = [(0, 0, src)]
+            tie = 1
+            best = {src: 0}
+            while heap:
+                d, _, u = heapq.heappop(heap)
+                if u in done:
+                    continue
+                done[u] = d
+                for v, w in self.ed[u].items():
+                    nd = d + w
+                    if v in done:
+                        continue
+                    if v not in best or nd < best[v]:
+                        best[v] = nd
+                        heapq.heappush(heap, (nd, tie, v))
+                        tie += 1
+            for v, d in done.items():
+                S[pos[src], pos[v]] = d
+        return S
+
+    def shortest_paths(self, algorithm_type="auto"):
+        if algorithm_type == "auto":
+            algorithm_type = "floyd_warshall" if self.kind == "adjacency" else "dijkstra"
+        if algorithm_type == "floyd_warshall":
+            return self.floyd_warshall()
+        if algorithm_type == "dijkstra":
+            return self.dijkstra_all()
+        raise ValueError('Unsupported "algorithm_type"')
+
+
+def _parse(X, min_len=2):
+    """Element handling shared by the kernels (weisfeiler_lehman.py:143-194,
+    shortest_path.py:432-466): empty elements are skipped, the rest become
+    OGraph objects."""
+    if not isinstance(X, Iterable):
+        raise TypeError("input must be an iterable\n")
+    out = []
+    for x in X:
+        x = list(x)
+        if len(x) == 0:
+            continue
+        lab = x[1] if len(x) > 1 else {}
+        out.append(OGraph(x[0], lab))
+    if not out:
+        raise ValueError("parsed input is empty")
+    return out
+
+
+# --------------------------------------------------------------------------
+# Vertex histogram  (vertex_histogram.py:57-219)
+# --------------------------------------------------------------------------
+class _VH:
+    """One fitted base kernel of a WL level: column dictionary + sparse counts."""
+
+    def fit(self, label_dicts):
+        self.cols = {}
+        self.X = self._features(label_dicts, self.cols)
+        return self
+
+    @staticmethod
+    def _features(label_dicts, cols):
+        r, c, d = [], [], []
+        for gi, L in enumerate(label_dicts):
+            for lab, cnt in Counter(L.values()).items():
+                j = cols.get(lab)
+                if j is None:
+                    j = len(cols)
+                    cols[lab] = j
+                r.append(gi)
+                c.append(j)
+                d.append(cnt)
+        return csr_matrix((d, (r, c)), shape=(len(label_dicts), len(cols)), dtype="float64")
+
+    def gram(self):
+        return self.X.dot(self.X.T).toarray()  # vertex_histogram.py:177,181-182
+
+    def transform(self, label_dicts):
+        cols = dict(self.cols)  # vertex_histogram.py:84 (unseen labels get columns >= D_fit)
+        self.Y = self._features(label_dicts, cols)
+        return self.Y[:, : self.X.shape[1]].dot(self.X.T).toarray()  # :179
+
+    def xdiag(self):
+        return np.asarray(self.X.multiply(self.X).sum(axis=1)).ravel()
+
+    def ydiag(self):
+        return np.asarray(self.Y.multiply(self.Y).sum(axis=1)).ravel()
+
+
+# --------------------------------------------------------------------------
+# Weisfeiler-Lehman subtree  (weisfeiler_lehman.py:117-555)
+# --------------------------------------------------------------------------
+class WLOracle:
+    def __init__(self, n_iter=5, normalize=False):
+        if type(n_iter) is not int or n_iter <= 0:
+            raise TypeError("'n_iter' must be a positive integer")
+        self.h = n_iter
+        self.normalize = normalize
+
+    @staticmethod
+    def _signature(own, nbr_labels):
+        # weisfeiler_lehman.py:235-239 -- own label, then the sorted multiset of
+        # out-neighbour labels.  A tuple keeps exactly the information of the
+        # reference's string credential.
+        return (own, tuple(sorted(nbr_labels)))
+
+    def fit_transform(self, X, return_levels=False):
+        Gs = _parse(X)
+        self._fit_graphs = Gs
+        L = [dict(g.labels) for g in Gs]
+        # level 0: weisfeiler_lehman.py:199-206
+        alphabet = sorted({v for l in L for v in l.values()})
+        inv0 = {lab: i for i, lab in enumerate(alphabet)}
+        self.inv = {0: inv0}
+        count = len(inv0)
+        L = [{v: inv0[lab] for v, lab in l.items()} for l in L]
+        self.levels = [_VH().fit(L)]
+        level_labels = [[dict(l) for l in L]]
+        Ks = [self.levels[0].gram()]
+        for it in range(1, self.h + 1):  # weisfeiler_lehman.py:223-258
+            sigs = []
+            seen = set()
+            for g, l in zip(Gs, L):
+                s = {}
+                for v in l.keys():  # every labelled vertex, sinks included (:230-234)
+                    s[v] = self._signature(l[v], [l[n] for n in g.ed.get(v, {}).keys()])
+                    seen.add(s[v])
+                sigs.append(s)
+            inv = {}
+            for sig in sorted(seen):
+                inv[sig] = count
+                count += 1
+            self.inv[it] = inv
+            L = [{v: inv[s] for v, s in sg.items()} for sg in sigs]
+            level_labels.append([dict(l) for l in L])
+            vh = _VH().fit(L)
+            self.levels.append(vh)
+            Ks.append(vh.gram())
+        K = np.sum(Ks, axis=0)  # weisfeiler_lehman.py:270
+        self.level_labels = level_labels
+        self.xdiag = np.diagonal(K).copy()
+        if self.normalize:  # :324-327
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = np.nan_to_num(K / np.sqrt(np.outer(self.xdiag, self.xdiag)))
+        if return_levels:
+            return K, level_labels
+        return K
+
+    def transform(self, Y):
+        Gs = _parse(Y)
+        L = [dict(g.labels) for g in Gs]
+        inv0 = self.inv[0]
+        nl = len(inv0)
+        fresh = sorted({v for l in L for v in l.values() if v not in inv0})
+        new0 = {lab: i for i, lab in enumerate(fresh, nl)}  # weisfeiler_lehman.py:417-418
+        L = [{v: (inv0[lab] if lab in inv0 else new0[lab]) for v, lab in l.items()} for l in L]
+        Ks = [self.levels[0].transform(L)]
+        for it in range(1, self.h + 1):  # :435-476
+            nl += len(self.inv[it])
+            inv = self.inv[it]
+            sigs, unseen = [], set()
+            for g, l in zip(Gs, L):
+                s = {}
+                for v in l.keys():
+                    s[v] = self._signature(l[v], [l[n] for n in g.ed.get(v, {}).keys()])
+                    if s[v] not in inv:
+                        unseen.add(s[v])
+                sigs.append(s)
+            new = {sig: i for i, sig in enumerate(sorted(unseen), nl)}
+            L = [{v: (inv[s] if s in inv else new[s]) for v, s in sg.items()} for sg in sigs]
+            Ks.append(self.levels[it].transform(L))
+        K = np.sum(Ks, axis=0)
+        self.ydiag = np.sum([lv.ydiag() for lv in self.levels], axis=0)
+        if self.normalize:  # :494-498
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = np.nan_to_num(K / np.sqrt(np.outer(self.ydiag, self.xdiag)))
+        return K
+
+
+def wl_partitions(level_labels):
+    """Canonical (first-occurrence) renumbering of each level's labels, vertices
+    taken graph by graph in sorted-vertex order.  Two implementations agree on
+    the WL partition iff these arrays are equal (SURVEY.md 8c parity rule)."""
+    out = []
+    for per_graph in level_labels:
+        ren, flat = {}, []
+        for l in per_graph:
+            for v in sorted(l.keys()):
+                flat.append(ren.setdefault(l[v], len(ren)))
+        out.append(np.asarray(flat, dtype=np.int64))
+    return out
+
+
+# --------------------------------------------------------------------------
+# Shortest path (labelled / unlabelled)  (shortest_path.py:167-515)
+# --------------------------------------------------------------------------
+class SPOracle:
+    def __init__(self, with_labels=True, algorithm_type="auto", normalize=False):
+        if algorithm_type not in ("auto", "floyd_warshall", "dijkstra"):
+            raise ValueError('Unsupported "algorithm_type"')
+        self.with_labels = with_labels
+        self.algorithm_type = algorithm_type
+        self.normalize = normalize
+
+    def _counts(self, X, enum, frozen=None):
+        """shortest_path.py:468-490: ordered pairs u != v with finite distance,
+        key (l(u), l(v), d) or d; first-seen column numbering."""
+        rows = []
+        for g in _parse(X, min_len=1):
+            S = g.shortest_paths(self.algorithm_type)
+            lab = g.index_labels() if self.with_labels else None
+            cnt = {}
+            n = S.shape[0]
+            for u in range(n):
+                for v in range(n):
+                    if u == v or S[u, v] == INF:
+                        continue
+                    key = (lab[u], lab[v], S[u, v]) if self.with_labels else S[u, v]
+                    if frozen is not None and key in frozen:
+                        j = frozen[key]
+                    else:
+                        j = enum.get(key)
+                        if j is None:
+                            j = len(enum) + (len(frozen) if frozen is not None else 0)
+                            enum[key] = j
+                    cnt[j] = cnt.get(j, 0) + 1
+            rows.append(cnt)
+        return rows
+
+    @staticmethod
+    def _dense(rows, D):
+        phi = np.zeros((len(rows), D))
+        for i, r in enumerate(rows):
+            for j, c in r.items():
+                phi[i, j] = c
+        return phi
+
+    def fit_transform(self, X):
+        self.enum = {}
+        rows = self._counts(X, self.enum)
+        self.phi_x = self._dense(rows, len(self.enum))
+        K = np.dot(self.phi_x, self.phi_x.T)  # shortest_path.py:404
+        self.xdiag = np.diagonal(K).copy()
+        if self.normalize:  # :407-408 (no nan_to_num here)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = K / np.sqrt(np.outer(self.xdiag, self.xdiag))
+        return K
+
+    def transform(self, Y):
+        yenum = {}
+        rows = self._counts(Y, yenum, frozen=self.enum)
+        phi_y = self._dense(rows, len(self.enum) + len(yenum))
+        K = np.dot(phi_y[:, : len(self.enum)], self.phi_x.T)  # :312
+        self.ydiag = np.sum(np.square(phi_y), axis=1)  # :365 (all Y columns)
+        if self.normalize:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = K / np.sqrt(np.outer(self.ydiag, self.xdiag))
+        return K
+
+
+# --------------------------------------------------------------------------
+# Shortest path on node attributes  (shortest_path.py:16-164)
+# --------------------------------------------------------------------------
+class SPAttrOracle:
+    """k(x,y) = sum_{i!=j} sum_{k!=m} [Sx[i,j] == Sy[k,m] < inf] <a_i,a_k><a_j,a_m>
+    (shortest_path.py:151-162, metric = np.dot).  Evaluated per pair with the
+    distance-grouped form  sum_d <F_x[d], F_y[d]>,  F[d] = sum_{(i,j):S=d} a_i (x) a_j,
+    which is the same bilinear sum re-associated (fp64; SURVEY.md 8a row a20
+    measured 1e-15 relative against the 4-deep loop)."""
+
+    def __init__(self, algorithm_type="auto", normalize=False):
+        self.algorithm_type = algorithm_type
+        self.normalize = normalize
+
+    def _maps(self, X):
+        out = []
+        for g in _parse(X):
+            S = g.shortest_paths(self.algorithm_type)
+            lab = g.index_labels()
+            n = S.shape[0]
+            A = np.asarray([np.asarray(lab[i], dtype=float) for i in range(n)])
+            F = {}
+            off = ~np.eye(n, dtype=bool)
+            for d in np.unique(S[off & np.isfinite(S)]):
+                M = ((S == d) & off).astype(float)
+                F[float(d)] = A.T @ M @ A
+            out.append(F)
+        return out
+
+    @staticmethod
+    def _pair(Fx, Fy):
+        return float(sum(np.vdot(Fx[d], Fy[d]) for d in Fx.keys() & Fy.keys()))
+
+    def pair_bruteforce(self, gx, gy):
+        """The reference's literal quadruple loop, for tiny cross-checks."""
+        (Sx, ax), (Sy, ay) = gx, gy
+        k = 0.0
+        for i in range(Sx.shape[0]):
+            for j in range(Sx.shape[0]):
+                if i == j:
+                    continue
+                for p in range(Sy.shape[0]):
+                    for q in range(Sy.shape[0]):
+                        if p == q:
+                            continue
+                        if Sx[i, j] == Sy[p, q] and Sx[i, j] != INF:
+                            k += np.dot(ax[i], ay[p]) * np.dot(ax[j], ay[q])
+        return k
+
+    def fit_transform(self, X):
+        self.Fx = self._maps(X)
+        n = len(self.Fx)
+        K = np.zeros((n, n))
+        for i in range(n):
+            for j in range(i, n):
+                K[i, j] = K[j, i] = self._pair(self.Fx[i], self.Fx[j])
+        self.xdiag = np.diagonal(K).copy()
+        if self.normalize:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = K / np.sqrt(np.outer(self.xdiag, self.xdiag))
+        return K
+
+    def transform(self, Y):
+        Fy = self._maps(Y)
+        K = np.array([[self._pair(fy, fx) for fx in self.Fx] for fy in Fy])
+        self.ydiag = np.array([self._pair(f, f) for f in Fy])
+        if self.normalize:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = K / np.sqrt(np.outer(self.ydiag, self.xdiag))
+        return K
+
+
+# --------------------------------------------------------------------------
+# Seeded synthetic generator (used by every golden and by bench)
+# --------------------------------------------------------------------------
+def gen(N, nbar, seed, nl=7, attr=0, as_adj=False):
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(N):
+        n = int(rs.randint(nbar // 2, nbar + nbar // 2 + 1))
+        p = 4.0 / (n - 1)
+        iu = np.triu_indices(n, 1)
+        m = rs.rand(len(iu[0])) < p
+        a, b = iu[0][m], iu[1][m]
+        if attr:
+            L = {i: rs.rand(attr) for i in range(n)}
+        else:
+            L = {i: int(rs.randint(nl)) for i in range(n)}
+        if as_adj:
+            A = np.zeros((n, n))
+            A[a, b] = 1.0
+            A = A + A.T
+            out.append([A, L])
+        else:
+            g = {}
+            for x, y in zip(a.tolist(), b.tolist()):
+                g[(x, y)] = 1
+                g[(y, x)] = 1
+            out.append([g, L])
+    return out
