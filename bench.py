@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- graph-pairs/sec of the N x N WL-subtree Gram matrix (BASELINE.json).
+
+Workload (N=1, and every rank at N>1): BASELINE config 2 -- 10 000 synthetic
+Erdos-Renyi labelled graphs (avg 40 nodes, 7 labels, seed 0), WL-subtree h=5.
+A "step" is one pass of the hot path over that batch: WL relabel of all graphs,
+feature block, dense bf16 panel, tcgen05 Gram GEMM, diagonal / output.
+
+  value      pairs/s with the packed CSR already resident in HBM and K left in HBM
+             (CUDA events on the engine's stream, max over ranks)
+  e2e        pairs/s through the C-ABI one-call entry point gk_wl_fit_transform with
+             PINNED HOST buffers: CSR H2D and the fp64 K D2H inside the timed region
+  roofline   the tcgen05 Gram GEMM: algorithmic flops N(N+1)*D_c (upper-triangular
+             tiles) / CUDA-event duration vs the measured bf16 peak
+  cpu_baseline / --impl reference
+             the CPU oracle port (oracle/gk_oracle.py, pinned to the real reference's
+             goldens) on a bounded prefix of the same graphs on the box's host cores
+
+N > 1 (torchrun): every rank relabels the (replicated, tiny) CSR block and computes a
+contiguous row block of K -- no data-path collective; value = N^2 / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRAPHS, NBAR, H, SEED = 10000, 40, 5, 0
+CPU_SAMPLE = 2000  # graphs in the bounded CPU sample
+
+
+def pack_workload(n_graphs):
+    """Seeded generator of SURVEY 8d, packed straight to CSR (vectorised; the Python
+    list-of-dicts form is only built for the CPU arm)."""
+    rs = np.random.RandomState(SEED)
+    gp, rp, ci, lab = [0], [np.zeros(1, dtype=np.int64)], [], []
+    e_tot = 0
+    for _ in range(n_graphs):
+        n = int(rs.randint(NBAR // 2, NBAR + NBAR // 2 + 1))
+        p = 4.0 / (n - 1)
+        iu = np.triu_indices(n, 1)
+        m = rs.rand(len(iu[0])) < p
+        a, b = iu[0][m], iu[1][m]
+        L = rs.randint(7, size=n)  # same stream as n independent rs.randint(7) draws
+        src = np.concatenate([a, b])
+        dst = np.concatenate([b, a])
+        order = np.lexsort((dst, src))
+        src, dst = src[order], dst[order]
+        cnt = np.bincount(src, minlength=n)
+        rp.append(e_tot + np.cumsum(cnt))
+        ci.append(dst + gp[-1])
+        lab.append(L)
+        e_tot += len(src)
+        gp.append(gp[-1] + n)
+    return (np.asarray(gp, dtype=np.int32), np.concatenate(rp).astype(np.int32),
+            np.concatenate(ci).astype(np.int32), np.concatenate(lab).astype(np.int32))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1419.5), d.get("hbm_gbs", 6582.5), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_arm(n_sample, steps=1, warmup=0):
+    """The CPU oracle port on a prefix of the workload; returns (pairs/s, seconds/step)."""
+    from oracle.gk_oracle import WLOracle, gen
+    X = gen(n_sample, NBAR, SEED)
+    for _ in range(warmup):
+        WLOracle(n_iter=H).fit_transform(X[: max(50, n_sample // 10)])
+    ts = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        K = WLOracle(n_iter=H).fit_transform(X)
+        ts.append(time.perf_counter() - t)
+    assert K.shape == (n_sample, n_sample)
+    t = float(np.mean(ts))
+    return n_sample * n_sample / t, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = CPU_SAMPLE
+    val, t = cpu_arm(n, steps=args.steps, warmup=min(args.warmup, 1))
+    cores = 1
+    line = {
+        "impl": "reference", "metric": "graph-pairs/sec, N x N WL-subtree (h=5) Gram", "value": val,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config2: {N_GRAPHS} ER graphs (avg {NBAR} nodes, 7 labels, seed {SEED}), WL-subtree h={H}",
+                   "parallelism": "host CPU, 1 thread (the reference's default n_jobs=None)"},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"first {n} of the {N_GRAPHS} graphs ({n * n} ordered pairs per step); "
+                                   f"host has {os.cpu_count()} logical cores"},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs", type=int, default=N_GRAPHS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from grakel_b200 import _lib
+    eng = _lib.Engine(local)
+
+    n = args.graphs
+    gp, rp, ci, lab = pack_workload(n)
+    V, E = int(gp[-1]), int(rp[-1])
+    rows_per = (n + world - 1) // world
+    rb, re_ = min(n, rank * rows_per), min(n, (rank + 1) * rows_per)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------ device-resident steps
+    eng.pack(gp, rp, ci, lab)
+    st = _lib.GkStats()
+
+    def step():
+        s = eng.wl_features(H)
+        eng.gram(n, out=False, dtype=np.float32, row_range=(rb, re_) if world > 1 else None, stats=s,
+                 want_diag=False)
+        return s
+
+    for _ in range(args.warmup):
+        st = step()
+    barrier()
+    gemm_ms, feat_ms, panel_ms, launches = [], [], [], 0
+    with ClockSampler(local) as clk:
+        eng.event_record(0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = step()
+            gemm_ms.append(st.ms_gemm)
+            feat_ms.append(st.ms_features)
+            panel_ms.append(st.ms_panel)
+            launches += int(st.kernel_launches + st.gemm_launches)
+        eng.event_record(1)
+        dev_ms = eng.event_elapsed(0, 1)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    t_ms = torch.tensor([dev_ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = float(t_ms.item()) / args.steps
+    value = n * n / (ms_step * 1e-3)
+
+    # ------------------------------------------------ end to end through the C-ABI
+    e2e = None
+    if not args.no_e2e:
+        kr = re_ - rb if world > 1 else n
+        Kh = torch.empty((kr, n), dtype=torch.float64).pin_memory().numpy()
+        gp_p, rp_p, ci_p, lab_p = [torch.from_numpy(a).pin_memory().numpy() for a in (gp, rp, ci, lab)]
+
+        def e2e_step():
+            if world == 1:
+                return eng.wl_fit_transform_raw(gp_p, rp_p, ci_p, lab_p, H, Kh)
+            eng.pack(gp_p, rp_p, ci_p, lab_p)
+            s = eng.wl_features(H)
+            eng.gram(n, out=Kh, dtype=np.float64, row_range=(rb, re_), stats=s, want_diag=False)
+            return s
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_t = torch.tensor([(time.perf_counter() - t0) / args.steps], device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * n / float(e2e_t.item()), "unit": "pairs/s",
+               "h2d_bytes_per_step": int(gp.nbytes + rp.nbytes + ci.nbytes + lab.nbytes),
+               "d2h_bytes_per_step": int(kr * n * 8), "ms_per_step": float(e2e_t.item()) * 1e3,
+               "api": "gk_wl_fit_transform (C-ABI), pinned host CSR in, pinned fp64 K out"}
+        if rank == 0 and world == 1:
+            assert float(Kh.sum()) == 22925628586.0 or n != N_GRAPHS, "K checksum differs from the reference golden"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak_tf, peak_hbm, peak_src = peaks()
+    Dc = int(st.n_dense_columns)
+    g_ms = float(np.mean(gemm_ms))
+    tiles_full = world > 1
+    flops = (2.0 * (re_ - rb) * n * Dc) if tiles_full else (float(n) * (n + 1) * Dc)
+    achieved = flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    line = {
+        "metric": "graph-pairs/sec, N x N WL-subtree (h=5) Gram", "value": value, "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 x bf16 -> f32 (exact integers)",
+        "data": "synthetic",
+        "config": {"workload": f"config2: {n} ER graphs (avg {NBAR} nodes, 7 labels, seed {SEED}), WL-subtree h={H}",
+                   "vertices": V, "directed_edges": E, "feature_columns": int(st.n_columns), "nnz": int(st.n_entries),
+                   "dense_columns_Dc": Dc, "parallelism": f"rows of K tiled over {world} GPU(s), CSR replicated",
+                   "l2": "per-step working set (panel %.0f MB + K %.0f MB) exceeds the 126 MB L2" %
+                         (n * ((Dc + 63) // 64 * 64) * 2 / 1e6, (re_ - rb if world > 1 else n) * n * 4 / 1e6)},
+        "clocks": clk.summary(),
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "roofline": {"kernel": "gram_tc_kernel<float,false> (tcgen05 bf16 SYRK)", "bound": "tensor",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "traffic": None, "peak_source": peak_src, "flops_per_launch": flops, "ms_per_launch": g_ms,
+                     "share_of_step": g_ms / ms_step},
+        "stages_ms": {"wl_features": float(np.mean(feat_ms)), "columns+panel": float(np.mean(panel_ms)),
+                      "gram_gemm": g_ms, "wall_ms_per_step": wall_ms / args.steps},
+    }
+    if not args.no_cpu and world == 1:
+        val, t = cpu_arm(CPU_SAMPLE)
+        line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": 1, "kind": "port",
+                                "sample": f"first {CPU_SAMPLE} of the {n} graphs, {t:.1f} s on one host thread "
+                                          f"({os.cpu_count()} logical cores on the box)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

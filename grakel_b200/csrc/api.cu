@@ -1,0 +1,900 @@
+// C-ABI of the grakel_b200 engine (see include/grakel_b200.h for the contract and
+// the reference file:line each entry point replaces).  sm_100a only.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "features.cuh"
+#include "gram_tc.cuh"
+#include "sp.cuh"
+#include "wl.cuh"
+
+namespace gk {
+thread_local std::string g_last_error;
+
+static inline size_t next_pow2(size_t x) {
+  size_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_panel_map(CUtensorMap* m, void* base, long long cols, long long rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(GK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GK_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return GK_OK;
+}
+
+static int read_scalars(gk_handle* h, DevScalars** out) {
+  GK_TRY(h->h_scalars.ensure(sizeof(DevScalars)));
+  GK_CUDA(cudaMemcpyAsync(h->h_scalars.p, h->scalars.p, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  *out = h->h_scalars.as<DevScalars>();
+  return GK_OK;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+}  // namespace gk
+
+using namespace gk;
+
+// extra host-side state that does not belong in the POD-ish handle header
+struct HandleExtra {
+  std::vector<int> graph_ptr;
+  std::vector<long long> sp_goff;
+};
+static std::vector<std::pair<gk_handle*, HandleExtra*>> g_extra;
+static HandleExtra* extra_of(gk_handle* h) {
+  for (auto& p : g_extra)
+    if (p.first == h) return p.second;
+  HandleExtra* e = new HandleExtra();
+  g_extra.emplace_back(h, e);
+  return e;
+}
+static void drop_extra(gk_handle* h) {
+  for (size_t i = 0; i < g_extra.size(); ++i)
+    if (g_extra[i].first == h) {
+      delete g_extra[i].second;
+      g_extra.erase(g_extra.begin() + i);
+      return;
+    }
+}
+
+#define LAUNCH_CHECK(h)                                 \
+  do {                                                  \
+    (h)->launches++;                                    \
+    GK_CUDA(cudaGetLastError());                        \
+  } while (0)
+
+extern "C" {
+
+int gk_version(void) { return 100; }
+const char* gk_last_error(void) { return g_last_error.c_str(); }
+
+int gk_create(int device_ordinal, gk_handle** out) {
+  if (!out) return fail(GK_ERR_ARG, "gk_create: out is NULL");
+  int n = 0;
+  GK_CUDA(cudaGetDeviceCount(&n));
+  if (device_ordinal < 0 || device_ordinal >= n) return fail(GK_ERR_ARG, "gk_create: bad device ordinal");
+  GK_CUDA(cudaSetDevice(device_ordinal));
+  cudaDeviceProp prop;
+  GK_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major != 10) {
+    return fail(GK_ERR_UNSUPPORTED, std::string("grakel_b200 needs an sm_100a (B200) device, found sm_") +
+                                        std::to_string(prop.major) + std::to_string(prop.minor));
+  }
+  gk_handle* h = new gk_handle();
+  h->dev = device_ordinal;
+  h->sm_count = prop.multiProcessorCount;
+  GK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) GK_CUDA(cudaEventCreate(&e));
+  for (auto& e : h->tev) GK_CUDA(cudaEventCreate(&e));
+  GK_TRY(h->scalars.ensure(sizeof(DevScalars)));
+  GK_TRY(h->h_scalars.ensure(sizeof(DevScalars)));
+  GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  *out = h;
+  return GK_OK;
+}
+
+int gk_destroy(gk_handle* h) {
+  if (!h) return GK_OK;
+  cudaSetDevice(h->dev);
+  cudaStreamSynchronize(h->stream);
+  gk::DevBuf* bufs[] = {&h->graph_ptr, &h->row_ptr, &h->col_idx, &h->labels0, &h->weights, &h->attrs, &h->vgraph,
+                        &h->large_list, &h->labels_all, &h->sig_nbr, &h->slot_of, &h->ht_keys, &h->ht_rep,
+                        &h->flags, &h->block_sums, &h->scalars, &h->ft_keys, &h->ft_cnt, &h->colfirst,
+                        &h->collast, &h->dense_col, &h->col_block_sums, &h->diag_u64, &h->diag_f64, &h->panel,
+                        &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_graph_off, &h->fattr, &h->tiles,
+                        &h->K, &h->K_stage};
+  for (auto* b : bufs) b->release();
+  h->h_scalars.release();
+  h->h_tiles.release();
+  h->h_stage.release();
+  for (auto& e : h->ev) cudaEventDestroy(e);
+  for (auto& e : h->tev) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  drop_extra(h);
+  delete h;
+  return GK_OK;
+}
+
+int gk_sync(gk_handle* h) {
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  return GK_OK;
+}
+
+int gk_event_record(gk_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot >= 16) return fail(GK_ERR_ARG, "gk_event_record: bad slot");
+  GK_CUDA(cudaEventRecord(h->ev[slot], h->stream));
+  return GK_OK;
+}
+int gk_event_elapsed(gk_handle* h, int32_t a, int32_t b, float* ms) {
+  if (!h || !ms || a < 0 || a >= 16 || b < 0 || b >= 16) return fail(GK_ERR_ARG, "gk_event_elapsed: bad args");
+  GK_CUDA(cudaEventSynchronize(h->ev[b]));
+  GK_CUDA(cudaEventElapsedTime(ms, h->ev[a], h->ev[b]));
+  return GK_OK;
+}
+
+// ---------------------------------------------------------------------------
+int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const int32_t* row_ptr,
+                const int32_t* col_idx, const int32_t* labels, const double* weights, const float* attrs,
+                int32_t attr_dim) {
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  if (n_graphs <= 0 || !graph_ptr || !row_ptr) return fail(GK_ERR_ARG, "gk_pack_csr: empty input");
+  if (n_graphs >= (1LL << 31) - 1) return fail(GK_ERR_ARG, "gk_pack_csr: too many graphs");
+  GK_CUDA(cudaSetDevice(h->dev));
+  const int64_t N = n_graphs;
+  const int64_t V = graph_ptr[N];
+  if (graph_ptr[0] != 0 || V < 0) return fail(GK_ERR_ARG, "gk_pack_csr: bad graph_ptr");
+  if (V >= (1LL << 26)) return fail(GK_ERR_ARG, "gk_pack_csr: more than 2^26 vertices in one block");
+  const int64_t E = V ? row_ptr[V] : 0;
+  if (E < 0 || (E > 0 && !col_idx)) return fail(GK_ERR_ARG, "gk_pack_csr: bad row_ptr / col_idx");
+  // host-side scans: degrees, graph sizes, label alphabet, weight class
+  int max_deg = 0, max_n = 0;
+  long long hist[6] = {0, 0, 0, 0, 0, 0};  // degree <= 4, 8, 16, 32, more
+  for (int64_t v = 0; v < V; ++v) {
+    const int d = row_ptr[v + 1] - row_ptr[v];
+    if (d < 0) return fail(GK_ERR_ARG, "gk_pack_csr: row_ptr not monotone");
+    max_deg = std::max(max_deg, d);
+    hist[d <= 4 ? 0 : d <= 8 ? 1 : d <= 16 ? 2 : d <= 32 ? 3 : 4]++;
+  }
+  for (int64_t g = 0; g < N; ++g) {
+    const int n = graph_ptr[g + 1] - graph_ptr[g];
+    if (n < 0) return fail(GK_ERR_ARG, "gk_pack_csr: graph_ptr not monotone");
+    max_n = std::max(max_n, n);
+  }
+  for (int64_t g = 0; g < N; ++g) {  // neighbours must stay inside their graph
+    const int v0 = graph_ptr[g], v1 = graph_ptr[g + 1];
+    if (v1 == v0) continue;
+    for (int64_t e = row_ptr[v0]; e < row_ptr[v1]; ++e)
+      if (col_idx[e] < v0 || col_idx[e] >= v1) return fail(GK_ERR_ARG, "gk_pack_csr: edge leaves its graph");
+  }
+  int n_labels0 = 0;
+  if (labels) {
+    for (int64_t v = 0; v < V; ++v) {
+      if (labels[v] < 0) return fail(GK_ERR_ARG, "gk_pack_csr: negative label id");
+      n_labels0 = std::max(n_labels0, labels[v] + 1);
+    }
+  }
+  bool unit = true;
+  if (weights) {
+    for (int64_t e = 0; e < E; ++e) {
+      if (!(weights[e] >= 0.0)) return fail(GK_ERR_UNSUPPORTED, "gk_pack_csr: negative or NaN edge weight");
+      if (weights[e] != 1.0) unit = false;
+    }
+  }
+  // lanes per vertex for the WL signature kernel: minimise V*G + 32*#(deg > G)
+  {
+    const int Gs[4] = {4, 8, 16, 32};
+    long long above[4] = {hist[1] + hist[2] + hist[3] + hist[4], hist[2] + hist[3] + hist[4], hist[3] + hist[4], hist[4]};
+    long long best = -1;
+    for (int i = 0; i < 4; ++i) {
+      long long cost = (long long)V * Gs[i] + above[i] * 32;
+      if (best < 0 || cost < best) { best = cost; h->group_width = Gs[i]; }
+    }
+  }
+  std::vector<int> large;
+  for (int64_t v = 0; v < V; ++v)
+    if (row_ptr[v + 1] - row_ptr[v] > h->group_width) large.push_back((int)v);
+
+  h->N = N; h->V = V; h->E = E;
+  h->n_labels0 = n_labels0;
+  h->has_weights = weights != nullptr;
+  h->unit_weights = unit;
+  h->attr_dim = attrs ? attr_dim : 0;
+  h->max_degree = max_deg;
+  h->max_graph_size = max_n;
+  h->n_large = (int64_t)large.size();
+  h->features_ready = false;
+  h->feature_kind = 0;
+  HandleExtra* ex = extra_of(h);
+  ex->graph_ptr.assign(graph_ptr, graph_ptr + N + 1);
+
+  GK_CUDA(cudaEventRecord(h->tev[0], h->stream));
+  GK_TRY(h->graph_ptr.ensure((N + 1) * 4));
+  GK_TRY(h->row_ptr.ensure((V + 1) * 4));
+  GK_TRY(h->col_idx.ensure(std::max<int64_t>(E, 1) * 4));
+  GK_TRY(h->vgraph.ensure(std::max<int64_t>(V, 1) * 4));
+  GK_CUDA(cudaMemcpyAsync(h->graph_ptr.p, graph_ptr, (N + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  GK_CUDA(cudaMemcpyAsync(h->row_ptr.p, row_ptr, (V + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (E) GK_CUDA(cudaMemcpyAsync(h->col_idx.p, col_idx, E * 4, cudaMemcpyHostToDevice, h->stream));
+  if (labels) {
+    GK_TRY(h->labels0.ensure(std::max<int64_t>(V, 1) * 4));
+    GK_CUDA(cudaMemcpyAsync(h->labels0.p, labels, V * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (weights && E) {
+    GK_TRY(h->weights.ensure(E * 8));
+    GK_CUDA(cudaMemcpyAsync(h->weights.p, weights, E * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (attrs && attr_dim > 0) {
+    GK_TRY(h->attrs.ensure((size_t)V * attr_dim * 4));
+    GK_CUDA(cudaMemcpyAsync(h->attrs.p, attrs, (size_t)V * attr_dim * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (!large.empty()) {
+    GK_TRY(h->large_list.ensure(large.size() * 4));
+    GK_CUDA(cudaMemcpyAsync(h->large_list.p, large.data(), large.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (V) {
+    fill_vgraph<<<cdiv(V, 256), 256, 0, h->stream>>>((int)V, (int)N, h->graph_ptr.as<int>(), h->vgraph.as<int>());
+    LAUNCH_CHECK(h);
+  }
+  GK_CUDA(cudaEventRecord(h->tev[1], h->stream));
+  // the source buffers (including the local `large` vector) must outlive the copies
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  return GK_OK;
+}
+
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+template <int G>
+static void launch_sig_small(gk_handle* h, const int* lab_in, unsigned long long seed) {
+  const long long threads = (long long)h->V * G;
+  wl_sig_small<G><<<cdiv(threads, 256), 256, 0, h->stream>>>(
+      (int)h->V, h->row_ptr.as<int>(), h->col_idx.as<int>(), lab_in, h->sig_nbr.as<int>(), seed,
+      h->ht_keys.as<unsigned long long>(), h->ht_rep.as<int>(), (unsigned)(h->ht_cap - 1), h->slot_of.as<int>());
+}
+
+static int init_scalars(gk_handle* h, int n_labels0) {
+  DevScalars* hs = h->h_scalars.as<DevScalars>();
+  memset(hs, 0, sizeof(DevScalars));
+  hs->level_dims[0] = n_labels0;
+  hs->level_base[0] = 0;
+  hs->level_base[1] = n_labels0;
+  GK_CUDA(cudaMemcpyAsync(h->scalars.p, hs, sizeof(DevScalars), cudaMemcpyHostToDevice, h->stream));
+  // the pinned struct is reused for read-back; make sure the upload has consumed it
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  return GK_OK;
+}
+
+extern "C" {
+
+int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  if (h->N <= 0) return fail(GK_ERR_STATE, "gk_wl_features: no graphs packed");
+  if (!h->labels0.p || h->V == 0) return fail(GK_ERR_ARG, "gk_wl_features: vertex labels are required");
+  if (n_iter < 0 || n_iter + 1 >= MAX_LEVELS) return fail(GK_ERR_ARG, "gk_wl_features: n_iter out of range");
+  GK_CUDA(cudaSetDevice(h->dev));
+  const int64_t V = h->V, E = h->E;
+  const int L = n_iter + 1;
+  h->n_levels = L;
+  h->features_ready = false;
+  const int64_t launches0 = h->launches;
+
+  GK_TRY(h->labels_all.ensure((size_t)L * V * 4));
+  GK_TRY(h->sig_nbr.ensure(std::max<int64_t>(E, 1) * 4));
+  GK_TRY(h->slot_of.ensure(V * 4));
+  GK_TRY(h->flags.ensure(V * 4));
+  const int nb = cdiv(V, 256);
+  GK_TRY(h->block_sums.ensure((size_t)nb * 4));
+  h->ht_cap = next_pow2((size_t)V * 2);
+  GK_TRY(h->ht_keys.ensure(h->ht_cap * 8));
+  GK_TRY(h->ht_rep.ensure(h->ht_cap * 4));
+  h->ft_cap = next_pow2((size_t)V * L * 2);
+  if (h->ft_cap > (1ULL << 31)) return fail(GK_ERR_ARG, "gk_wl_features: feature table too large");
+  GK_TRY(h->ft_keys.ensure(h->ft_cap * 8));
+  GK_TRY(h->ft_cnt.ensure(h->ft_cap * 4));
+
+  DevScalars* sc = h->scalars.as<DevScalars>();
+  int* labels_all = h->labels_all.as<int>();
+  int retries = 0;
+  GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
+  for (;; ++retries) {
+    if (retries > 8) return fail(GK_ERR_STATE, "gk_wl_features: repeated hash collisions");
+    const unsigned long long seed = mix64(0x5851F42D4C957F2DULL + 0x9E3779B97F4A7C15ULL * (unsigned long long)retries);
+    GK_TRY(init_scalars(h, h->n_labels0));
+    GK_CUDA(cudaMemsetAsync(h->ft_keys.p, 0xFF, h->ft_cap * 8, h->stream));
+    GK_CUDA(cudaMemsetAsync(h->ft_cnt.p, 0, h->ft_cap * 4, h->stream));
+    GK_CUDA(cudaMemcpyAsync(labels_all, h->labels0.p, V * 4, cudaMemcpyDeviceToDevice, h->stream));
+    wl_insert_level0<<<nb, 256, 0, h->stream>>>((int)V, labels_all, h->vgraph.as<int>(),
+                                                 h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(),
+                                                 (unsigned)(h->ft_cap - 1), sc);
+    LAUNCH_CHECK(h);
+    for (int lv = 1; lv < L; ++lv) {
+      const int* lab_in = labels_all + (size_t)(lv - 1) * V;
+      int* lab_out = labels_all + (size_t)lv * V;
+      GK_CUDA(cudaMemsetAsync(h->ht_keys.p, 0xFF, h->ht_cap * 8, h->stream));
+      GK_CUDA(cudaMemsetAsync(h->ht_rep.p, 0x7F, h->ht_cap * 4, h->stream));
+      switch (h->group_width) {
+        case 4: launch_sig_small<4>(h, lab_in, seed); break;
+        case 8: launch_sig_small<8>(h, lab_in, seed); break;
+        case 16: launch_sig_small<16>(h, lab_in, seed); break;
+        default: launch_sig_small<32>(h, lab_in, seed); break;
+      }
+      LAUNCH_CHECK(h);
+      if (h->n_large) {
+        wl_sig_large<<<cdiv(h->n_large * 32, 256), 256, 0, h->stream>>>(
+            (int)h->n_large, h->large_list.as<int>(), h->row_ptr.as<int>(), h->col_idx.as<int>(), lab_in,
+            h->sig_nbr.as<int>(), seed, h->ht_keys.as<unsigned long long>(), h->ht_rep.as<int>(),
+            (unsigned)(h->ht_cap - 1), h->slot_of.as<int>());
+        LAUNCH_CHECK(h);
+      }
+      wl_resolve<<<nb, 256, 0, h->stream>>>((int)V, h->row_ptr.as<int>(), lab_in, h->sig_nbr.as<int>(),
+                                            h->ht_rep.as<int>(), h->slot_of.as<int>(), h->flags.as<int>(),
+                                            h->block_sums.as<int>(), sc);
+      LAUNCH_CHECK(h);
+      scan_block_sums<<<1, 256, 0, h->stream>>>(nb, h->block_sums.as<int>(), &sc->level_dims[lv],
+                                                 &sc->level_base[lv], &sc->level_base[lv + 1]);
+      LAUNCH_CHECK(h);
+      wl_assign<<<nb, 256, 0, h->stream>>>((int)V, h->flags.as<int>(), h->block_sums.as<int>(), lab_out);
+      LAUNCH_CHECK(h);
+      wl_gather_insert<<<nb, 256, 0, h->stream>>>((int)V, lv, h->slot_of.as<int>(), lab_out, h->vgraph.as<int>(),
+                                                   sc, h->ft_keys.as<unsigned long long>(),
+                                                   h->ft_cnt.as<unsigned>(), (unsigned)(h->ft_cap - 1));
+      LAUNCH_CHECK(h);
+    }
+    DevScalars* hs;
+    GK_TRY(read_scalars(h, &hs));
+    if (hs->ft_overflow) return fail(GK_ERR_STATE, "gk_wl_features: feature table overflow");
+    if (!hs->collision) break;
+  }
+  GK_CUDA(cudaEventRecord(h->tev[3], h->stream));
+  GK_CUDA(cudaEventSynchronize(h->tev[3]));
+  DevScalars* hs = h->h_scalars.as<DevScalars>();
+  h->n_columns = hs->level_base[L];
+  h->features_ready = true;
+  h->feature_kind = 1;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_graphs = h->N; stats->n_vertices = V; stats->n_edges = E;
+    stats->n_levels = L;
+    for (int i = 0; i < L; ++i) stats->level_dims[i] = hs->level_dims[i];
+    stats->n_columns = h->n_columns;
+    stats->hash_retries = retries;
+    stats->kernel_launches = h->launches - launches0;
+    stats->ms_features = ev_ms(h->tev[2], h->tev[3]);
+  }
+  return GK_OK;
+}
+
+int gk_wl_labels(gk_handle* h, int32_t level, int32_t* out) {
+  if (!h || !out) return fail(GK_ERR_ARG, "gk_wl_labels: null argument");
+  if (h->feature_kind != 1 || level < 0 || level >= h->n_levels) return fail(GK_ERR_STATE, "gk_wl_labels: no such level");
+  GK_CUDA(cudaSetDevice(h->dev));
+  GK_CUDA(cudaMemcpyAsync(out, h->labels_all.as<int>() + (size_t)level * h->V, h->V * 4, cudaMemcpyDeviceToHost, h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  return GK_OK;
+}
+
+// ---------------------------------------------------------------------------
+int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  if (h->N <= 0) return fail(GK_ERR_STATE, "gk_sp_features: no graphs packed");
+  GK_CUDA(cudaSetDevice(h->dev));
+  const bool with_labels = flags & GK_SP_WITH_LABELS;
+  if (with_labels && !h->labels0.p) return fail(GK_ERR_ARG, "gk_sp_features: vertex labels are required");
+  if (with_labels && h->n_labels0 >= (1 << 20)) return fail(GK_ERR_UNSUPPORTED, "gk_sp_features: more than 2^20 distinct labels");
+  const bool use_u16 = (!h->has_weights || h->unit_weights) && h->max_graph_size < 16000;
+  const size_t esz = use_u16 ? 2 : 8;
+  HandleExtra* ex = extra_of(h);
+  const int64_t N = h->N;
+  const int64_t launches0 = h->launches;
+  h->features_ready = false;
+  h->sp_flags = flags;
+
+  // plan: graphs whose distance matrix fits the shared-memory budget vs the rest
+  const size_t SMEM_DIST_MAX = 160 * 1024;
+  std::vector<int> small, big;
+  size_t max_small_nn = 0;
+  ex->sp_goff.assign(N + 1, 0);
+  const bool keep = flags & GK_SP_KEEP_DIST;
+  long long off_big = 0, off_all = 0;
+  std::vector<long long> goff_big(N, 0);
+  for (int64_t g = 0; g < N; ++g) {
+    const long long n = ex->graph_ptr[g + 1] - ex->graph_ptr[g];
+    ex->sp_goff[g] = off_all;
+    off_all += n * n;
+    if ((size_t)(n * n) * esz <= SMEM_DIST_MAX) {
+      small.push_back((int)g);
+      max_small_nn = std::max(max_small_nn, (size_t)(n * n));
+    } else {
+      big.push_back((int)g);
+      goff_big[g] = off_big;
+      off_big += n * n;
+    }
+  }
+  ex->sp_goff[N] = off_all;
+  const size_t smem_small = SP_LOCAL_SLOTS * 12 + max_small_nn * esz + 16;
+  const size_t smem_big = SP_LOCAL_SLOTS * 12 + 16;
+
+  // device buffers
+  gk::DevBuf& lists = h->large_list;  // reuse: [small list | big list]
+  GK_TRY(lists.ensure((size_t)N * 4 + 16));
+  std::vector<int> order(small);
+  order.insert(order.end(), big.begin(), big.end());
+  GK_CUDA(cudaMemcpyAsync(lists.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  GK_TRY(h->sp_graph_off.ensure((size_t)(N + 1) * 8 * 2));
+  long long* d_goff_all = h->sp_graph_off.as<long long>();
+  long long* d_goff_big = d_goff_all + (N + 1);
+  GK_CUDA(cudaMemcpyAsync(d_goff_all, ex->sp_goff.data(), (N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  GK_CUDA(cudaMemcpyAsync(d_goff_big, goff_big.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
+  if (off_big) GK_TRY(h->sp_dist.ensure((size_t)off_big * esz));
+  double* d_keep = nullptr;
+  if (keep) {
+    GK_TRY(h->K_stage.ensure((size_t)off_all * 8));
+    d_keep = h->K_stage.as<double>();
+  }
+  GK_CUDA(cudaStreamSynchronize(h->stream));  // host vectors above go out of scope on retry
+
+  if (use_u16) {
+    GK_CUDA(cudaFuncSetAttribute(sp_apsp_hist<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_small, smem_big)));
+  } else {
+    GK_CUDA(cudaFuncSetAttribute(sp_apsp_hist<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_small, smem_big)));
+  }
+
+  size_t dict_cap = std::max<size_t>(h->sp_dict_cap, 1 << 16);
+  size_t ft_cap = std::max<size_t>(next_pow2((size_t)std::max<int64_t>(h->V, 1024) * 16), 1 << 20);
+  DevScalars* sc = h->scalars.as<DevScalars>();
+  GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
+  for (int attempt = 0;; ++attempt) {
+    if (attempt > 6) return fail(GK_ERR_STATE, "gk_sp_features: tables keep overflowing");
+    if (dict_cap > (1ULL << 28) || ft_cap > (1ULL << 31)) return fail(GK_ERR_STATE, "gk_sp_features: feature tables too large");
+    GK_TRY(h->sp_dict_keys.ensure(dict_cap * 8));
+    GK_TRY(h->ft_keys.ensure(ft_cap * 8));
+    GK_TRY(h->ft_cnt.ensure(ft_cap * 4));
+    h->sp_dict_cap = dict_cap;
+    h->ft_cap = ft_cap;
+    GK_TRY(init_scalars(h, 0));
+    GK_CUDA(cudaMemsetAsync(h->sp_dict_keys.p, 0xFF, dict_cap * 8, h->stream));
+    GK_CUDA(cudaMemsetAsync(h->ft_keys.p, 0xFF, ft_cap * 8, h->stream));
+    GK_CUDA(cudaMemsetAsync(h->ft_cnt.p, 0, ft_cap * 4, h->stream));
+    SpParams p;
+    p.graph_ptr = h->graph_ptr.as<int>();
+    p.row_ptr = h->row_ptr.as<int>();
+    p.col_idx = h->col_idx.as<int>();
+    p.weights = (h->has_weights && !use_u16) ? h->weights.as<double>() : nullptr;
+    p.labels = with_labels ? h->labels0.as<int>() : nullptr;
+    p.keep = d_keep;
+    p.dict_keys = h->sp_dict_keys.as<unsigned long long>();
+    p.dict_mask = (unsigned)(dict_cap - 1);
+    p.ft_keys = h->ft_keys.as<unsigned long long>();
+    p.ft_cnt = h->ft_cnt.as<unsigned>();
+    p.ft_mask = (unsigned)(ft_cap - 1);
+    p.sc = sc;
+    p.gdist = h->sp_dist.p;
+    if (!small.empty()) {
+      p.glist = lists.as<int>();
+      p.n_list = (int)small.size();
+      p.dist_in_global = 0;
+      p.goff = d_goff_all;  // only used for `keep`
+      if (use_u16) sp_apsp_hist<unsigned short><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
+      else sp_apsp_hist<double><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
+      LAUNCH_CHECK(h);
+    }
+    if (!big.empty()) {
+      if (keep) return fail(GK_ERR_UNSUPPORTED, "gk_sp_features: KEEP_DIST with graphs beyond the shared-memory budget");
+      p.glist = lists.as<int>() + small.size();
+      p.n_list = (int)big.size();
+      p.dist_in_global = 1;
+      p.goff = d_goff_big;
+      if (use_u16) sp_apsp_hist<unsigned short><<<(int)big.size(), SP_THREADS, smem_big, h->stream>>>(p);
+      else sp_apsp_hist<double><<<(int)big.size(), SP_THREADS, smem_big, h->stream>>>(p);
+      LAUNCH_CHECK(h);
+    }
+    DevScalars* hs;
+    GK_TRY(read_scalars(h, &hs));
+    if (hs->sp_nonint) {
+      return fail(GK_ERR_UNSUPPORTED,
+                  "gk_sp_features: non-integer (or >= 2^24) shortest-path length; only integer-valued edge weights "
+                  "are supported on the device path");
+    }
+    if (hs->ft_overflow & 2u) { dict_cap *= 8; continue; }
+    if (hs->ft_overflow & 1u) { ft_cap *= 4; continue; }
+    if ((size_t)hs->sp_dict_size * 2 > dict_cap) { dict_cap *= 4; continue; }  // keep probe chains short
+    break;
+  }
+  GK_CUDA(cudaEventRecord(h->tev[3], h->stream));
+  GK_CUDA(cudaEventSynchronize(h->tev[3]));
+  DevScalars* hs = h->h_scalars.as<DevScalars>();
+  h->n_columns = (int64_t)dict_cap;  // column id = dictionary slot
+  h->features_ready = true;
+  h->feature_kind = 2;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_graphs = h->N; stats->n_vertices = h->V; stats->n_edges = h->E;
+    stats->n_levels = 1;
+    stats->level_dims[0] = hs->sp_dict_size;
+    stats->n_columns = hs->sp_dict_size;
+    stats->kernel_launches = h->launches - launches0;
+    stats->ms_features = ev_ms(h->tev[2], h->tev[3]);
+  }
+  return GK_OK;
+}
+
+int gk_sp_distances(gk_handle* h, int64_t g, double* out) {
+  if (!h || !out) return fail(GK_ERR_ARG, "gk_sp_distances: null argument");
+  if (h->feature_kind != 2 || !(h->sp_flags & GK_SP_KEEP_DIST)) return fail(GK_ERR_STATE, "gk_sp_distances: run gk_sp_features with GK_SP_KEEP_DIST first");
+  if (g < 0 || g >= h->N) return fail(GK_ERR_ARG, "gk_sp_distances: bad graph index");
+  HandleExtra* ex = extra_of(h);
+  const long long off = ex->sp_goff[g], cnt = ex->sp_goff[g + 1] - off;
+  GK_CUDA(cudaSetDevice(h->dev));
+  GK_CUDA(cudaMemcpyAsync(out, h->K_stage.as<double>() + off, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  return GK_OK;
+}
+
+int gk_spattr_features(gk_handle* h, gk_stats* stats) {
+  (void)stats;
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  return fail(GK_ERR_UNSUPPORTED, "gk_spattr_features: not implemented in this build");
+}
+
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+template <typename OutT, bool NORM>
+static void launch_tc(gk_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, const GramParams& p, int grid) {
+  gram_tc_kernel<OutT, NORM><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(tmA, tmB, p);
+}
+template <typename OutT, bool NORM>
+static void launch_simt(gk_handle* h, const unsigned* panel, long long ldp, int kdim, int a0, int a1, int b0, int b1,
+                        const GramParams& p) {
+  dim3 grid(cdiv(b1 - b0, 16), cdiv(a1 - a0, 16));
+  gram_simt_kernel<OutT, NORM><<<grid, 256, 0, h->stream>>>(panel, ldp, kdim, a0, a1, b0, b1, p);
+}
+template <typename OutT, bool NORM>
+static void launch_empty(gk_handle* h, int a0, int a1, int b0, int b1, const GramParams& p) {
+  gram_empty_kernel<OutT, NORM><<<h->sm_count * 4, 256, 0, h->stream>>>(a0, a1, b0, b1, p);
+}
+
+// Build the tile list: bands of 12 row tiles, column-major inside a band, so that the
+// ~148 tiles in flight cover a compact block of the output and share panel rows in L2.
+static void build_tiles(std::vector<int2>& tiles, int a0, int a1, int b0, int b1, bool upper_only) {
+  const int n_m = cdiv(a1 - a0, BM), n_n = cdiv(b1 - b0, BN);
+  const int BAND = 12;
+  for (int m0 = 0; m0 < n_m; m0 += BAND) {
+    const int m1 = std::min(n_m, m0 + BAND);
+    for (int j = 0; j < n_n; ++j) {
+      for (int i = m0; i < m1; ++i) {
+        const int ar = a0 + i * BM, br = b0 + j * BN;
+        if (upper_only && br + BN - 1 < ar) continue;  // tile entirely below the diagonal
+        tiles.push_back(make_int2(ar, br));
+      }
+    }
+  }
+}
+
+extern "C" {
+
+int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64_t row_end, void* K_out,
+            int32_t out_dtype, int64_t ld, double* xdiag, double* ydiag, gk_stats* stats) {
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  if (!h->features_ready) return fail(GK_ERR_STATE, "gk_gram: no feature block (call gk_wl_features / gk_sp_features)");
+  if (out_dtype != GK_F32 && out_dtype != GK_F64) return fail(GK_ERR_ARG, "gk_gram: bad out_dtype");
+  const int64_t N = h->N;
+  if (n_fit <= 0 || n_fit > N) return fail(GK_ERR_ARG, "gk_gram: n_fit out of range");
+  const bool square = n_fit == N;
+  const int64_t k_rows_total = square ? N : N - n_fit;
+  const int64_t k_cols = n_fit;
+  if (row_end < 0) row_end = k_rows_total;
+  if (row_begin < 0 || row_begin > row_end || row_end > k_rows_total) return fail(GK_ERR_ARG, "gk_gram: bad row range");
+  const int64_t k_rows = row_end - row_begin;
+  if (ld <= 0) ld = k_cols;
+  if (ld < k_cols) return fail(GK_ERR_ARG, "gk_gram: ld smaller than the row length");
+  GK_CUDA(cudaSetDevice(h->dev));
+  const int64_t launches0 = h->launches;
+  const bool normalize = flags & GK_NORMALIZE;
+  const size_t esz = out_dtype == GK_F64 ? 8 : 4;
+  DevScalars* sc = h->scalars.as<DevScalars>();
+
+  GK_CUDA(cudaEventRecord(h->tev[4], h->stream));
+  // ---- column statistics + exact self similarities
+  const int64_t D = h->n_columns;
+  GK_TRY(h->colfirst.ensure(std::max<int64_t>(D, 1) * 4));
+  GK_TRY(h->collast.ensure(std::max<int64_t>(D, 1) * 4));
+  GK_TRY(h->dense_col.ensure(std::max<int64_t>(D, 1) * 4));
+  GK_TRY(h->flags.ensure(std::max<int64_t>(D, 1) * 4));
+  const int nbc = cdiv(std::max<int64_t>(D, 1), 256);
+  GK_TRY(h->col_block_sums.ensure((size_t)nbc * 4));
+  GK_TRY(h->diag_u64.ensure(N * 8));
+  GK_TRY(h->diag_f64.ensure(N * 8));
+  GK_CUDA(cudaMemsetAsync(h->colfirst.p, 0x7F, std::max<int64_t>(D, 1) * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->collast.p, 0xFF, std::max<int64_t>(D, 1) * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, N * 8, h->stream));
+  GK_CUDA(cudaMemsetAsync(&sc->n_entries, 0, sizeof(unsigned long long) * 3 + sizeof(long long), h->stream));
+  feat_pass1<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+      h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colfirst.as<int>(),
+      h->collast.as<int>(), h->diag_u64.as<unsigned long long>(), sc);
+  LAUNCH_CHECK(h);
+  diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, h->diag_u64.as<unsigned long long>(),
+                                                   h->diag_f64.as<double>(), sc);
+  LAUNCH_CHECK(h);
+  col_flags<<<nbc, 256, 0, h->stream>>>(D, (int)n_fit, (int)N, h->colfirst.as<int>(), h->collast.as<int>(),
+                                        h->flags.as<int>(), h->col_block_sums.as<int>());
+  LAUNCH_CHECK(h);
+  scan_block_sums<<<1, 256, 0, h->stream>>>(nbc, h->col_block_sums.as<int>(), &sc->n_dense, nullptr, nullptr);
+  LAUNCH_CHECK(h);
+  col_assign<<<nbc, 256, 0, h->stream>>>(D, h->flags.as<int>(), h->col_block_sums.as<int>(), h->dense_col.as<int>());
+  LAUNCH_CHECK(h);
+  DevScalars* hs;
+  GK_TRY(read_scalars(h, &hs));
+  const int64_t Dc = hs->n_dense;
+  const int64_t max_count = (int64_t)hs->max_count, max_diag = (int64_t)hs->max_diag, n_entries = (int64_t)hs->n_entries;
+  h->Dc = Dc;
+  h->Dc_pad = (Dc + BK - 1) / BK * BK;
+
+  // ---- choose the Gram path
+  int path = 1;
+  if (Dc == 0) path = 3;
+  else if ((flags & GK_GRAM_SIMT) || max_count > 256 || max_diag >= (1LL << 24)) path = 2;
+
+  // ---- output buffer
+  void* d_out = nullptr;
+  if (flags & GK_OUT_DEVICE) {
+    if (!K_out) return fail(GK_ERR_ARG, "gk_gram: GK_OUT_DEVICE without a pointer");
+    d_out = K_out;
+  } else {
+    GK_TRY(h->K.ensure((size_t)std::max<int64_t>(k_rows, 1) * k_cols * esz));
+    d_out = h->K.p;
+    h->K_rows = k_rows; h->K_cols = k_cols; h->K_dtype = out_dtype;
+  }
+  const long long d_ld = (flags & GK_OUT_DEVICE) ? ld : k_cols;
+
+  // panel-row ranges: A rows index K rows, B rows index K columns
+  const int a0 = (int)((square ? 0 : n_fit) + row_begin), a1 = (int)((square ? 0 : n_fit) + row_end);
+  const int b0 = 0, b1 = (int)n_fit;
+  const bool full_square = square && row_begin == 0 && row_end == N;
+  const bool mirror = full_square && !(flags & GK_FULL_TILES);
+
+  GramParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_row_end = a1; p.b_row_end = b1;
+  p.c_row0 = a0; p.c_col0 = b0;
+  p.out = d_out; p.ld = d_ld;
+  p.mirror = mirror ? 1 : 0;
+  p.fix_diag = square ? 1 : 0;
+  p.nan_to_num = (flags & GK_NAN_TO_NUM) ? 1 : 0;
+  p.vec_ok = (((uintptr_t)d_out) % 16 == 0 && (d_ld * (long long)esz) % 16 == 0) ? 1 : 0;
+  p.diag = h->diag_f64.as<double>();
+
+  GK_CUDA(cudaEventRecord(h->tev[5], h->stream));
+  int64_t n_tiles = 0;
+  if (k_rows > 0) {
+    if (path == 1) {
+      const size_t panel_bytes = (size_t)N * h->Dc_pad * 2;
+      GK_TRY(h->panel.ensure(panel_bytes));
+      GK_CUDA(cudaMemsetAsync(h->panel.p, 0, panel_bytes, h->stream));
+      feat_fill_panel<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+          h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->dense_col.as<int>(),
+          h->panel.as<__nv_bfloat16>(), h->Dc_pad);
+      LAUNCH_CHECK(h);
+      std::vector<int2> tiles;
+      build_tiles(tiles, a0, a1, b0, b1, mirror);
+      n_tiles = (int64_t)tiles.size();
+      GK_TRY(h->h_tiles.ensure(tiles.size() * sizeof(int2)));
+      memcpy(h->h_tiles.p, tiles.data(), tiles.size() * sizeof(int2));
+      GK_TRY(h->tiles.ensure(tiles.size() * sizeof(int2)));
+      GK_CUDA(cudaMemcpyAsync(h->tiles.p, h->h_tiles.p, tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+      CUtensorMap tmA, tmB;
+      GK_TRY(make_panel_map(&tmA, h->panel.p, h->Dc_pad, N, BM));
+      GK_TRY(make_panel_map(&tmB, h->panel.p, h->Dc_pad, N, BN));
+      p.tiles = h->tiles.as<int2>();
+      p.n_tiles = (int)n_tiles;
+      p.num_k_blocks = (int)(h->Dc_pad / BK);
+      const int grid = (int)std::min<int64_t>(n_tiles, h->sm_count);
+      GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
+      if (out_dtype == GK_F64) { if (normalize) launch_tc<double, true>(h, tmA, tmB, p, grid); else launch_tc<double, false>(h, tmA, tmB, p, grid); }
+      else { if (normalize) launch_tc<float, true>(h, tmA, tmB, p, grid); else launch_tc<float, false>(h, tmA, tmB, p, grid); }
+      LAUNCH_CHECK(h);
+    } else if (path == 2) {
+      const size_t panel_bytes = (size_t)N * Dc * 4;
+      GK_TRY(h->panel.ensure(panel_bytes));
+      GK_CUDA(cudaMemsetAsync(h->panel.p, 0, panel_bytes, h->stream));
+      feat_fill_panel_u32<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+          h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->dense_col.as<int>(),
+          h->panel.as<unsigned>(), Dc);
+      LAUNCH_CHECK(h);
+      GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
+      if (out_dtype == GK_F64) { if (normalize) launch_simt<double, true>(h, h->panel.as<unsigned>(), Dc, (int)Dc, a0, a1, b0, b1, p); else launch_simt<double, false>(h, h->panel.as<unsigned>(), Dc, (int)Dc, a0, a1, b0, b1, p); }
+      else { if (normalize) launch_simt<float, true>(h, h->panel.as<unsigned>(), Dc, (int)Dc, a0, a1, b0, b1, p); else launch_simt<float, false>(h, h->panel.as<unsigned>(), Dc, (int)Dc, a0, a1, b0, b1, p); }
+      LAUNCH_CHECK(h);
+    } else {
+      GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
+      if (out_dtype == GK_F64) { if (normalize) launch_empty<double, true>(h, a0, a1, b0, b1, p); else launch_empty<double, false>(h, a0, a1, b0, b1, p); }
+      else { if (normalize) launch_empty<float, true>(h, a0, a1, b0, b1, p); else launch_empty<float, false>(h, a0, a1, b0, b1, p); }
+      LAUNCH_CHECK(h);
+    }
+  } else {
+    GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
+  }
+  GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
+  const int64_t launches_gram = h->launches - launches0;
+
+  // ---- results to the host
+  GK_CUDA(cudaEventRecord(h->ev[14], h->stream));
+  if (K_out && !(flags & GK_OUT_DEVICE) && k_rows > 0) {
+    GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * esz, d_out, (size_t)k_cols * esz, (size_t)k_cols * esz,
+                              (size_t)k_rows, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (xdiag) GK_CUDA(cudaMemcpyAsync(xdiag, h->diag_f64.p, n_fit * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (ydiag && !square)
+    GK_CUDA(cudaMemcpyAsync(ydiag, h->diag_f64.as<double>() + n_fit, (N - n_fit) * 8, cudaMemcpyDeviceToHost, h->stream));
+  GK_CUDA(cudaEventRecord(h->ev[15], h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  if (stats) {
+    stats->n_graphs = N; stats->n_vertices = h->V; stats->n_edges = h->E;
+    stats->n_entries = n_entries;
+    stats->n_dense_columns = Dc;
+    stats->max_count = max_count;
+    stats->max_diag = max_diag;
+    stats->gram_path = path;
+    stats->gemm_tiles = n_tiles;
+    stats->gemm_launches = launches_gram;
+    stats->ms_panel = ev_ms(h->tev[4], h->tev[6]);
+    stats->ms_gemm = ev_ms(h->tev[6], h->tev[7]);
+    stats->ms_d2h = ev_ms(h->ev[14], h->ev[15]);
+    stats->ms_total = ev_ms(h->tev[4], h->ev[15]);
+  }
+  return GK_OK;
+}
+
+int gk_fetch(gk_handle* h, void* K_out, int32_t out_dtype, int64_t ld) {
+  if (!h || !K_out) return fail(GK_ERR_ARG, "gk_fetch: null argument");
+  if (!h->K.p || h->K_rows <= 0) return fail(GK_ERR_STATE, "gk_fetch: no device-resident result");
+  if (out_dtype != h->K_dtype) return fail(GK_ERR_ARG, "gk_fetch: dtype differs from the one gk_gram produced");
+  const size_t esz = out_dtype == GK_F64 ? 8 : 4;
+  if (ld <= 0) ld = h->K_cols;
+  GK_CUDA(cudaSetDevice(h->dev));
+  GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * esz, h->K.p, (size_t)h->K_cols * esz, (size_t)h->K_cols * esz,
+                            (size_t)h->K_rows, cudaMemcpyDeviceToHost, h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  return GK_OK;
+}
+
+// ---------------------------------------------------------------------------
+int gk_wl_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const int32_t* row_ptr,
+                        const int32_t* col_idx, const int32_t* labels, int32_t n_iter, int32_t flags, void* K_out,
+                        int32_t out_dtype, int64_t ld, double* diag, gk_stats* stats) {
+  gk_stats s1, s2;
+  memset(&s1, 0, sizeof(s1));
+  memset(&s2, 0, sizeof(s2));
+  GK_TRY(gk_pack_csr(h, n_graphs, graph_ptr, row_ptr, col_idx, labels, nullptr, nullptr, 0));
+  GK_TRY(gk_wl_features(h, n_iter, &s1));
+  s2 = s1;
+  GK_TRY(gk_gram(h, n_graphs, flags, 0, -1, K_out, out_dtype, ld, diag, nullptr, &s2));
+  if (stats) {
+    *stats = s2;
+    stats->kernel_launches = s1.kernel_launches;
+    stats->ms_h2d = ev_ms(h->tev[0], h->tev[1]);
+  }
+  return GK_OK;
+}
+
+int gk_sp_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const int32_t* row_ptr,
+                        const int32_t* col_idx, const int32_t* labels, const double* weights, int32_t sp_flags,
+                        int32_t flags, void* K_out, int32_t out_dtype, int64_t ld, double* diag, gk_stats* stats) {
+  gk_stats s1, s2;
+  memset(&s1, 0, sizeof(s1));
+  GK_TRY(gk_pack_csr(h, n_graphs, graph_ptr, row_ptr, col_idx, labels, weights, nullptr, 0));
+  GK_TRY(gk_sp_features(h, sp_flags, &s1));
+  s2 = s1;
+  GK_TRY(gk_gram(h, n_graphs, flags, 0, -1, K_out, out_dtype, ld, diag, nullptr, &s2));
+  if (stats) {
+    *stats = s2;
+    stats->kernel_launches = s1.kernel_launches;
+    stats->ms_h2d = ev_ms(h->tev[0], h->tev[1]);
+  }
+  return GK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Dense self-test of the two Gram kernels (tests only): counts[n x d] -> K = C C^T.
+int gk_selftest_gram(gk_handle* h, int64_t n, int64_t d, const uint16_t* counts, double* out_tc, double* out_simt) {
+  if (!h || !counts || n <= 0 || d <= 0) return fail(GK_ERR_ARG, "gk_selftest_gram: bad arguments");
+  GK_CUDA(cudaSetDevice(h->dev));
+  const int64_t dpad = (d + BK - 1) / BK * BK;
+  std::vector<__nv_bfloat16> pb((size_t)n * dpad, __float2bfloat16(0.f));
+  std::vector<unsigned> pu((size_t)n * d, 0u);
+  std::vector<double> dg(n, 0.0);
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t j = 0; j < d; ++j) {
+      const unsigned c = counts[i * d + j];
+      pb[i * dpad + j] = __float2bfloat16((float)c);
+      pu[i * d + j] = c;
+      dg[i] += (double)c * c;
+    }
+  gk::DevBuf dpb, dpu, ddg, dk1, dk2, dtl;
+  GK_TRY(dpb.ensure(pb.size() * 2));
+  GK_TRY(dpu.ensure(pu.size() * 4));
+  GK_TRY(ddg.ensure(n * 8));
+  GK_TRY(dk1.ensure((size_t)n * n * 8));
+  GK_TRY(dk2.ensure((size_t)n * n * 8));
+  GK_CUDA(cudaMemcpyAsync(dpb.p, pb.data(), pb.size() * 2, cudaMemcpyHostToDevice, h->stream));
+  GK_CUDA(cudaMemcpyAsync(dpu.p, pu.data(), pu.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  GK_CUDA(cudaMemcpyAsync(ddg.p, dg.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+  GK_CUDA(cudaMemsetAsync(dk1.p, 0xFF, (size_t)n * n * 8, h->stream));  // NaN pattern: unwritten entries show up
+  GK_CUDA(cudaMemsetAsync(dk2.p, 0xFF, (size_t)n * n * 8, h->stream));
+  GramParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_row_end = (int)n; p.b_row_end = (int)n;
+  p.ld = n;
+  p.diag = ddg.as<double>();
+  p.vec_ok = (n * 8) % 16 == 0;
+  int rc = GK_OK;
+  if (out_tc) {
+    std::vector<int2> tiles;
+    build_tiles(tiles, 0, (int)n, 0, (int)n, true);
+    GK_TRY(dtl.ensure(tiles.size() * sizeof(int2)));
+    GK_CUDA(cudaMemcpyAsync(dtl.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUtensorMap tmA, tmB;
+    GK_TRY(make_panel_map(&tmA, dpb.p, dpad, n, BM));
+    GK_TRY(make_panel_map(&tmB, dpb.p, dpad, n, BN));
+    p.tiles = dtl.as<int2>();
+    p.n_tiles = (int)tiles.size();
+    p.num_k_blocks = (int)(dpad / BK);
+    p.out = dk1.p;
+    p.mirror = 1;
+    launch_tc<double, false>(h, tmA, tmB, p, (int)std::min<size_t>(tiles.size(), h->sm_count));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(GK_ERR_CUDA, std::string("selftest tcgen05 kernel: ") + cudaGetErrorString(e));
+    else {
+      GK_CUDA(cudaMemcpy(out_tc, dk1.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost));
+    }
+  }
+  if (rc == GK_OK && out_simt) {
+    p.out = dk2.p;
+    p.mirror = 0;
+    launch_simt<double, false>(h, dpu.as<unsigned>(), d, (int)d, 0, (int)n, 0, (int)n, p);
+    GK_CUDA(cudaGetLastError());
+    GK_CUDA(cudaStreamSynchronize(h->stream));
+    GK_CUDA(cudaMemcpy(out_simt, dk2.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost));
+  }
+  dpb.release(); dpu.release(); ddg.release(); dk1.release(); dk2.release(); dtl.release();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// Shared declarations of the grakel_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/grakel_b200.h"
+
+namespace gk {
+
+// ---------------------------------------------------------------- errors
+extern thread_local std::string g_last_error;
+
+inline int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define GK_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      return gk::fail(GK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) +   \
+                                       " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                      \
+  } while (0)
+
+#define GK_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != GK_OK) return _r; \
+  } while (0)
+
+// ---------------------------------------------------------------- buffers
+// Grow-only device buffer: the engine is called repeatedly on same-sized
+// workloads (bench loop, fit then transform), so capacity is kept between calls.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return GK_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      return fail(GK_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    }
+    cap = want;
+    return GK_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {  // pinned host staging (D2H of small scalars, H2D of CSR)
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return GK_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes + 256);
+    if (e != cudaSuccess) return fail(GK_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    cap = bytes + 256;
+    return GK_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr unsigned long long EMPTY64 = ~0ULL;
+constexpr int MAX_LEVELS = 64;
+
+// Device-side scalars the pipeline reads back once per phase.
+struct DevScalars {
+  long long level_dims[MAX_LEVELS];      // distinct labels per WL level
+  long long level_base[MAX_LEVELS + 1];  // first column id of each level
+  unsigned int collision;                // WL: a hash collision was detected (-> retry with new seed)
+  unsigned int ft_overflow;              // feature table probe overflow (cannot happen at load <= 0.5)
+  unsigned long long n_entries;          // nnz of the feature block
+  unsigned long long max_count;          // largest count
+  unsigned long long max_diag;           // largest self similarity
+  long long n_dense;                     // D_c
+  unsigned long long sp_coo;             // (unused slot)
+  unsigned int sp_dict_size;             // SP: number of distinct (lu,lv,d) keys
+  unsigned int sp_nonint;                // SP: a non-integer / out-of-range distance was met
+};
+
+}  // namespace gk
+
+// The opaque handle of the C-ABI.
+struct gk_handle {
+  int dev = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[16] = {};
+  cudaEvent_t tev[8] = {};  // internal stage timers
+
+  // ---- packed graphs
+  int64_t N = 0, V = 0, E = 0;
+  int32_t n_labels0 = 0;
+  bool has_weights = false, unit_weights = true;
+  int32_t attr_dim = 0;
+  int32_t max_degree = 0, max_graph_size = 0;
+  gk::DevBuf graph_ptr, row_ptr, col_idx, labels0, weights, attrs, vgraph;
+  gk::DevBuf large_list;  // vertices with degree > group width
+  int64_t n_large = 0;
+  int group_width = 32;
+
+  // ---- WL scratch
+  int n_levels = 0;
+  gk::DevBuf labels_all;  // [(h+1) * V] int32
+  gk::DevBuf sig_nbr;     // [E] sorted neighbour labels of the current level
+  gk::DevBuf slot_of;     // [V] hash slot, then representative vertex
+  gk::DevBuf ht_keys, ht_rep;
+  size_t ht_cap = 0;
+  gk::DevBuf flags, block_sums;
+  gk::DevBuf scalars;  // gk::DevScalars
+  gk::PinBuf h_scalars;
+
+  // ---- feature block (hash table of (graph, column) -> count)
+  gk::DevBuf ft_keys, ft_cnt;
+  size_t ft_cap = 0;
+  int64_t n_columns = 0;
+  bool features_ready = false;
+  int feature_kind = 0;  // 1 = WL, 2 = SP, 3 = SP-attr (dense fp32 features)
+
+  // ---- columns / panel / diag
+  gk::DevBuf colfirst, collast, dense_col, col_block_sums;
+  gk::DevBuf diag_u64, diag_f64;
+  gk::DevBuf panel;
+  int64_t Dc = 0, Dc_pad = 0;
+
+  // ---- SP scratch
+  gk::DevBuf sp_dist;      // global-memory distance matrices for graphs too large for smem
+  gk::DevBuf sp_dict_keys; // (lu,lv,d) -> column dictionary
+  gk::DevBuf sp_dict_ids;
+  size_t sp_dict_cap = 0;
+  gk::DevBuf sp_graph_off; // per-graph offset into sp_dist (for gk_sp_distances)
+  int sp_flags = 0;
+
+  // ---- SP-attr dense fp32 feature matrix
+  gk::DevBuf fattr;
+  int64_t fattr_dim = 0;
+
+  // ---- GEMM
+  gk::DevBuf tiles;  // int2 list
+  gk::PinBuf h_tiles;
+  gk::DevBuf K;      // device-resident result of the last gk_gram
+  int64_t K_rows = 0, K_cols = 0;
+  int K_dtype = GK_F32;
+  gk::DevBuf K_stage;  // fp64 staging when K is kept as f32 but fetched as f64
+
+  gk::PinBuf h_stage;  // pinned staging for CSR upload
+  int64_t launches = 0;
+};

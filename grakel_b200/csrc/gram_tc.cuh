@@ -1,0 +1,359 @@
+// Gram matrix K = A * B^T over the dense bf16 feature panel on the 5th-gen tensor
+// cores (tcgen05.mma, fp32 accumulators in TMEM, operands staged by TMA with the
+// 128-byte swizzle).  Replaces `self.X.dot(self.X.T)` / `Y[:, :D].dot(self.X.T)`
+// (vertex_histogram.py:177-179), the per-level `np.sum` (weisfeiler_lehman.py:270)
+// and `np.dot(phi_x, phi_x.T)` (shortest_path.py:404) of the reference.
+//
+// Exactness: panel entries are integer counts <= 256 (exact in bf16), products and
+// partial sums are integers < 2^24 (exact in fp32) -- the host checks both bounds
+// before choosing this path -- so the result is bit-identical to the reference's
+// float64 arithmetic.
+//
+// Kernel shape (one persistent CTA per SM, 256 threads):
+//   warp 0      TMA producer   (one elected lane)
+//   warp 1      MMA issuer     (one elected lane; UMMA 128 x 256 x 16, bf16 -> f32)
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators)
+//   warps 4..7  epilogue       (tcgen05.ld -> diagonal fix / normalise -> global, plus
+//                               the mirrored tile for the symmetric case)
+// smem: 4 stages x (A 128x64 + B 256x64 bf16) = 192 KiB, mbarrier ring.
+#pragma once
+#include "common.cuh"
+
+namespace gk {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GramParams {
+  const int2* tiles;   // {first A row, first B row} in panel-row (graph) coordinates
+  int n_tiles;
+  int num_k_blocks;    // Dc_pad / 64
+  int a_row_end;       // rows >= a_row_end are not stored
+  int b_row_end;
+  int c_row0, c_col0;  // K[row - c_row0][col - c_col0]
+  void* out;
+  long long ld;
+  int mirror;          // also store the transposed element (symmetric case)
+  int fix_diag;        // K[g][g] = diag[g] (self similarity over ALL columns)
+  int nan_to_num;
+  int vec_ok;          // 16-byte aligned rows: vector stores allowed
+  const double* diag;  // self similarity per graph (fp64, exact integers)
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (one 64-element bf16
+// row = 128 B; 8-row groups 1024 B apart).  Bit layout: cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address   [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)(BM >> 4) << 24);
+
+template <typename OutT, bool NORMALIZE>
+__device__ __forceinline__ OutT epilogue_value(float acc, int arow, int bcol, double drow, double dcol,
+                                               const GramParams& p) {
+  if constexpr (NORMALIZE) {
+    double v = (double)acc;
+    if (p.fix_diag && arow == bcol) v = drow;
+    v = v / sqrt(drow * dcol);  // np.divide(K, np.sqrt(np.outer(d, d)))  (fp64, correctly rounded)
+    if (p.nan_to_num) {
+      if (v != v) v = 0.0;
+      else if (isinf(v)) v = v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    }
+    return (OutT)v;
+  } else {
+    if (p.fix_diag && arow == bcol) return (OutT)drow;
+    return (OutT)acc;
+  }
+}
+
+template <typename OutT, bool NORMALIZE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GramParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t holder = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int2 tile = p.tiles[t];
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, tile.x);
+          tma_load_2d(sa + A_BYTES, &tmB, full_bar(stage), kb * BK, tile.y);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes along K inside the 128-byte swizzle row = +2 in the address field
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), UMMA_IDESC,
+                        (uint32_t)((kb | k) != 0));
+          }
+          tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(as));  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {  // ---------------- epilogue
+    const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
+    const int row = ew * 32 + lane;
+    OutT* __restrict__ out = reinterpret_cast<OutT*>(p.out);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int2 tile = p.tiles[t];
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int arow = tile.x + row;
+      const bool row_ok = arow < p.a_row_end;
+      double drow = 0.0;
+      if ((NORMALIZE || p.fix_diag) && row_ok) drow = p.diag[arow];
+      const long long orow = (long long)(arow - p.c_row0) * p.ld;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        const int bcol0 = tile.y + c0;
+        if (bcol0 >= p.b_row_end) continue;  // warp-uniform
+        double dcol_l = 0.0;
+        if (NORMALIZE) {
+          const int bc = bcol0 + lane;
+          dcol_l = bc < p.b_row_end ? p.diag[bc] : 1.0;
+        }
+        const bool full_chunk = bcol0 + 32 <= p.b_row_end;
+        OutT vals[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          double dcol = 0.0;
+          if (NORMALIZE) dcol = __shfl_sync(0xffffffffu, dcol_l, j);
+          vals[j] = epilogue_value<OutT, NORMALIZE>(__uint_as_float(v[j]), arow, bcol0 + j, drow, dcol, p);
+        }
+        if (row_ok) {
+          OutT* dst = out + orow + (bcol0 - p.c_col0);
+          if (full_chunk && p.vec_ok) {
+            constexpr int PER = 16 / (int)sizeof(OutT);
+#pragma unroll
+            for (int j = 0; j < 32; j += PER) {
+              if constexpr (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4*>(dst + j) =
+                    make_float4((float)vals[j], (float)vals[j + 1], (float)vals[j + 2], (float)vals[j + 3]);
+              } else {
+                *reinterpret_cast<double2*>(dst + j) = make_double2((double)vals[j], (double)vals[j + 1]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (bcol0 + j < p.b_row_end) dst[j] = vals[j];
+          }
+          if (p.mirror) {  // lanes hold consecutive rows -> coalesced transposed store
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (bcol0 + j < p.b_row_end) out[(long long)(bcol0 + j) * p.ld + arow] = vals[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Exact CUDA-core Gram over a u32 count panel (int64 accumulation).  Used (a) as
+// the on-device cross-check of the tensor-core kernel in the tests and (b) when a
+// count exceeds 256 or a Gram value exceeds 2^24, where bf16 x bf16 -> fp32 would
+// no longer be exact.
+template <typename OutT, bool NORMALIZE>
+__global__ void __launch_bounds__(256)
+gram_simt_kernel(const unsigned* __restrict__ panel, long long ldp, int kdim, int a_row0, int a_row_end,
+                 int b_row0, int b_row_end, GramParams p) {
+  __shared__ unsigned As[16][17], Bs[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int arow = a_row0 + blockIdx.y * 16 + ty;
+  const int bcol = b_row0 + blockIdx.x * 16 + tx;
+  unsigned long long acc = 0;
+  for (int k0 = 0; k0 < kdim; k0 += 16) {
+    const int ar = a_row0 + blockIdx.y * 16 + ty;
+    const int br = b_row0 + blockIdx.x * 16 + ty;
+    As[ty][tx] = (ar < a_row_end && k0 + tx < kdim) ? panel[(long long)ar * ldp + k0 + tx] : 0u;
+    Bs[ty][tx] = (br < b_row_end && k0 + tx < kdim) ? panel[(long long)br * ldp + k0 + tx] : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += (unsigned long long)As[ty][k] * Bs[tx][k];
+    __syncthreads();
+  }
+  if (arow >= a_row_end || bcol >= b_row_end) return;
+  double v = (double)acc;
+  const double drow = p.diag[arow], dcol = p.diag[bcol];
+  if (p.fix_diag && arow == bcol) v = drow;
+  if (NORMALIZE) {
+    v = v / sqrt(drow * dcol);
+    if (p.nan_to_num) {
+      if (v != v) v = 0.0;
+      else if (isinf(v)) v = v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    }
+  }
+  reinterpret_cast<OutT*>(p.out)[(long long)(arow - p.c_row0) * p.ld + (bcol - p.c_col0)] = (OutT)v;
+}
+
+// K with no contracted columns: zero matrix (+ exact diagonal / normalisation)
+template <typename OutT, bool NORMALIZE>
+__global__ void __launch_bounds__(256)
+gram_empty_kernel(int a_row0, int a_row_end, int b_row0, int b_row_end, GramParams p) {
+  const long long n_cols = b_row_end - b_row0;
+  const long long total = (long long)(a_row_end - a_row0) * n_cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int arow = a_row0 + (int)(i / n_cols), bcol = b_row0 + (int)(i % n_cols);
+    double v = 0.0;
+    const double drow = p.diag[arow], dcol = p.diag[bcol];
+    if (p.fix_diag && arow == bcol) v = drow;
+    if (NORMALIZE) {
+      v = v / sqrt(drow * dcol);
+      if (p.nan_to_num) {
+        if (v != v) v = 0.0;
+        else if (isinf(v)) v = v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+      }
+    }
+    reinterpret_cast<OutT*>(p.out)[(long long)(arow - p.c_row0) * p.ld + (bcol - p.c_col0)] = (OutT)v;
+  }
+}
+
+}  // namespace gk

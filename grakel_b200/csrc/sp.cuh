@@ -1,0 +1,171 @@
+// Shortest-path kernel features on the device: batched Floyd-Warshall (one CTA per
+// graph, distance matrix in shared memory) + labelled path-length histogram.
+//
+// Replaces Graph.build_shortest_path_matrix / floyd_warshall / dijkstra
+// (graph.py:588-687, 1767-1794, 1712-1764) and the pair loop of
+// ShortestPath.parse_input (shortest_path.py:468-490) of the reference:
+//   for every ordered pair u != v with finite distance, feature (l(u), l(v), d(u,v))
+//   (or just d(u,v) when with_labels=False) is counted once.
+// Both reference algorithms return exact shortest distances; for integer-valued
+// weights those are order-independent integers, which is what this path supports
+// (a non-integer distance raises GK_ERR_UNSUPPORTED instead of guessing a key).
+#pragma once
+#include "common.cuh"
+#include "wl.cuh"
+
+namespace gk {
+
+constexpr int SP_LOCAL_SLOTS = 2048;  // per-CTA (key -> count) aggregation table
+constexpr int SP_THREADS = 256;
+
+template <typename T> struct DistTraits;
+template <> struct DistTraits<unsigned short> {
+  static __device__ __forceinline__ unsigned short inf() { return 0x3FFF; }
+  static __device__ __forceinline__ unsigned short add(unsigned short a, unsigned short b) {
+    unsigned s = (unsigned)a + b;
+    return (unsigned short)(s > 0x3FFFu ? 0x3FFFu : s);
+  }
+  static __device__ __forceinline__ bool finite(unsigned short a) { return a < 0x3FFF; }
+  static __device__ __forceinline__ double to_f64(unsigned short a) {
+    return a < 0x3FFF ? (double)a : __longlong_as_double(0x7ff0000000000000LL);
+  }
+};
+template <> struct DistTraits<double> {
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+  static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+  static __device__ __forceinline__ bool finite(double a) { return a < 1.0e300; }
+  static __device__ __forceinline__ double to_f64(double a) { return a; }
+};
+
+struct SpParams {
+  const int* graph_ptr;
+  const int* row_ptr;
+  const int* col_idx;
+  const double* weights;   // NULL = unit
+  const int* labels;       // dense ids or NULL (with_labels = False)
+  const int* glist;        // graphs handled by this launch (NULL = all, blockIdx.x)
+  int n_list;
+  void* gdist;             // global distance scratch (large graphs / keep_dist)
+  const long long* goff;   // element offset of graph g inside gdist
+  int dist_in_global;      // 1: run FW in gdist instead of shared memory
+  double* keep;            // if non-NULL: write fp64 distances of every graph at keep + goff[g]
+  unsigned long long* dict_keys;
+  unsigned dict_mask;
+  unsigned long long* ft_keys;
+  unsigned* ft_cnt;
+  unsigned ft_mask;
+  DevScalars* sc;
+};
+
+// global (lu,lv,d) dictionary: the slot index IS the column id
+__device__ __forceinline__ int sp_dict_slot(unsigned long long* keys, unsigned mask, unsigned long long key,
+                                            DevScalars* sc) {
+  unsigned slot = (unsigned)(mix64(key) >> 13) & mask;
+  for (unsigned probe = 0; probe <= mask; ++probe) {
+    unsigned long long prev = atomicCAS(&keys[slot], EMPTY64, key);
+    if (prev == EMPTY64) { atomicAdd(&sc->sp_dict_size, 1u); return (int)slot; }
+    if (prev == key) return (int)slot;
+    slot = (slot + 1) & mask;
+  }
+  atomicOr(&sc->ft_overflow, 2u);
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SP_THREADS)
+sp_apsp_hist(SpParams p) {
+  using DT = DistTraits<T>;
+  extern __shared__ __align__(16) unsigned char sp_smem[];
+  const int g = p.glist ? p.glist[blockIdx.x] : blockIdx.x;
+  const int v0 = p.graph_ptr[g];
+  const int n = p.graph_ptr[g + 1] - v0;
+  if (n <= 0) return;
+
+  // smem carve-up: [local keys | local counts | labels? no: labels read from global | dist]
+  unsigned long long* lkeys = reinterpret_cast<unsigned long long*>(sp_smem);
+  unsigned* lcnt = reinterpret_cast<unsigned*>(sp_smem + SP_LOCAL_SLOTS * 8);
+  T* dist = p.dist_in_global ? reinterpret_cast<T*>(p.gdist) + p.goff[g]
+                             : reinterpret_cast<T*>(sp_smem + SP_LOCAL_SLOTS * 12);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = SP_THREADS / 32;
+
+  for (int i = tid; i < SP_LOCAL_SLOTS; i += SP_THREADS) { lkeys[i] = EMPTY64; lcnt[i] = 0; }
+  const long long nn = (long long)n * n;
+  for (long long i = tid; i < nn; i += SP_THREADS) dist[i] = DT::inf();
+  __syncthreads();
+  // adjacency -> initial distances (graph.py:1785-1787: 0 entries are "no edge", diagonal 0)
+  for (int u = warp; u < n; u += NW) {
+    const int b = p.row_ptr[v0 + u], e = p.row_ptr[v0 + u + 1];
+    for (int k = b + lane; k < e; k += 32) {
+      const int w = p.col_idx[k] - v0;
+      if (w == u) continue;
+      if constexpr (sizeof(T) == 2) {
+        dist[(long long)u * n + w] = 1;
+      } else {
+        dist[(long long)u * n + w] = p.weights ? (T)p.weights[k] : (T)1;
+      }
+    }
+    if (lane == 0) dist[(long long)u * n + u] = 0;
+  }
+  __syncthreads();
+  // classic k-ordered relaxation (graph.py:1790-1792); rows whose d[i][k] is infinite
+  // cannot improve and are skipped.
+  for (int k = 0; k < n; ++k) {
+    const T* rk = dist + (long long)k * n;
+    for (int i = warp; i < n; i += NW) {
+      if (i == k) continue;
+      T* ri = dist + (long long)i * n;
+      const T dik = ri[k];
+      if (!DT::finite(dik)) continue;
+      for (int j = lane; j < n; j += 32) {
+        const T cand = DT::add(dik, rk[j]);
+        if (cand < ri[j]) ri[j] = cand;
+      }
+    }
+    __syncthreads();
+  }
+  if (p.keep) {
+    double* o = p.keep + p.goff[g];
+    for (long long i = tid; i < nn; i += SP_THREADS) o[i] = DT::to_f64(dist[i]);
+  }
+  // labelled path-length histogram (shortest_path.py:470-490)
+  for (int u = warp; u < n; u += NW) {
+    const unsigned long long lu = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + u] : 0ULL;
+    const T* ru = dist + (long long)u * n;
+    for (int w = lane; w < n; w += 32) {
+      if (w == u) continue;
+      const T d = ru[w];
+      if (!DT::finite(d)) continue;
+      unsigned di;
+      if constexpr (sizeof(T) == 2) {
+        di = d;
+      } else {
+        di = (unsigned)d;
+        if ((double)di != (double)d || d >= 16777216.0) { atomicOr(&p.sc->sp_nonint, 1u); continue; }
+      }
+      const unsigned long long lv = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + w] : 0ULL;
+      const unsigned long long key = (lu << 44) | (lv << 24) | (unsigned long long)di;
+      // CTA-local aggregation; fall through to the global table when the probe window is full
+      unsigned slot = (unsigned)(mix64(key) >> 29) & (SP_LOCAL_SLOTS - 1);
+      bool done = false;
+      for (int probe = 0; probe < 16; ++probe) {
+        unsigned long long prev = atomicCAS(&lkeys[slot], EMPTY64, key);
+        if (prev == EMPTY64 || prev == key) { atomicAdd(&lcnt[slot], 1u); done = true; break; }
+        slot = (slot + 1) & (SP_LOCAL_SLOTS - 1);
+      }
+      if (!done) {
+        const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
+        ft_add(p.ft_keys, p.ft_cnt, p.ft_mask, ((unsigned long long)(unsigned)g << 32) | (unsigned)col, 1u, p.sc);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < SP_LOCAL_SLOTS; i += SP_THREADS) {
+    const unsigned long long key = lkeys[i];
+    if (key == EMPTY64) continue;
+    const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
+    ft_add(p.ft_keys, p.ft_cnt, p.ft_mask, ((unsigned long long)(unsigned)g << 32) | (unsigned)col, lcnt[i], p.sc);
+  }
+}
+
+}  // namespace gk

@@ -1,0 +1,287 @@
+// Weisfeiler-Lehman relabelling on the device, all graphs at once.
+//
+// Replaces weisfeiler_lehman.py:212-258 (generate_graphs: credential =
+// own label + sorted out-neighbour labels, global dedup per level) of the
+// reference.  The reference dedups exact string credentials; here each vertex
+// signature (own label, sorted neighbour-label multiset) is hashed to 64 bits,
+// deduplicated in an open-addressing table, and then VERIFIED element by element
+// against the representative of its hash slot, so the resulting label partition
+// is exact (a detected collision makes the host retry the whole pass with a new
+// seed).  New labels are dense ids in first-occurrence (vertex) order.
+#pragma once
+#include "common.cuh"
+
+namespace gk {
+
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+// positional term of the signature hash: value x at sorted position pos
+__device__ __forceinline__ unsigned long long sig_term(int x, int pos, unsigned long long seed) {
+  return mix64((unsigned long long)(unsigned)x * 0x9E3779B97F4A7C15ULL +
+               (unsigned long long)(unsigned)pos * 0xC2B2AE3D27D4EB4FULL + seed);
+}
+
+__device__ __forceinline__ unsigned long long sig_final(unsigned long long acc, int own, int deg,
+                                                         unsigned long long seed) {
+  unsigned long long h = mix64(acc ^ mix64(((unsigned long long)(unsigned)own << 32 | (unsigned)deg) + seed));
+  return h >> 1;  // never equals EMPTY64
+}
+
+// insert (key -> min vertex id) ; returns the slot
+__device__ __forceinline__ unsigned ht_insert(unsigned long long* keys, int* rep, unsigned mask,
+                                              unsigned long long key, int v) {
+  unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ULL >> 20) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&keys[slot], EMPTY64, key);
+    if (prev == EMPTY64 || prev == key) {
+      atomicMin(&rep[slot], v);
+      return slot;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1a: G lanes per vertex, degree <= G.  Coalesced read of the neighbour list,
+// label gather (cache-resident: a graph's vertices are contiguous), bitonic sort
+// in registers via shuffles, positional 64-bit hash, table insert.
+template <int G>
+__global__ void __launch_bounds__(256)
+wl_sig_small(int V, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+             const int* __restrict__ lab_in, int* __restrict__ sig_nbr, unsigned long long seed,
+             unsigned long long* ht_keys, int* ht_rep, unsigned ht_mask, int* __restrict__ slot_of) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = tid / G;
+  const int lane = threadIdx.x & (G - 1);
+  int beg = 0, deg = 0;
+  bool active = false;
+  if (v < V) {
+    beg = row_ptr[v];
+    deg = row_ptr[v + 1] - beg;
+    active = deg <= G;
+  }
+  int x = 0x7fffffff;
+  if (active && lane < deg) x = lab_in[col_idx[beg + lane]];
+#pragma unroll
+  for (int k = 2; k <= G; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      int y = __shfl_xor_sync(0xffffffffu, x, j);
+      bool up = (lane & k) == 0;
+      bool lower = (lane & j) == 0;
+      x = (lower == up) ? min(x, y) : max(x, y);
+    }
+  }
+  unsigned long long t = 0;
+  if (active && lane < deg) {
+    sig_nbr[beg + lane] = x;
+    t = sig_term(x, lane, seed);
+  }
+#pragma unroll
+  for (int j = G >> 1; j > 0; j >>= 1) t += __shfl_xor_sync(0xffffffffu, t, j);
+  if (active && lane == 0) {
+    unsigned long long key = sig_final(t, lab_in[v], deg, seed);
+    slot_of[v] = (int)ht_insert(ht_keys, ht_rep, ht_mask, key, v);
+  }
+}
+
+// K1b: one warp per high-degree vertex; the neighbour labels are sorted in place in
+// the vertex's own segment of sig_nbr with an all-ascending bitonic network (valid
+// for any length: compare-exchanges with the virtual +inf tail are no-ops).
+__global__ void __launch_bounds__(256)
+wl_sig_large(int n_large, const int* __restrict__ large_list, const int* __restrict__ row_ptr,
+             const int* __restrict__ col_idx, const int* __restrict__ lab_in, int* sig_nbr,
+             unsigned long long seed, unsigned long long* ht_keys, int* ht_rep, unsigned ht_mask,
+             int* __restrict__ slot_of) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_large) return;
+  const int v = large_list[w];
+  const int beg = row_ptr[v];
+  const int deg = row_ptr[v + 1] - beg;
+  int* seg = sig_nbr + beg;
+  for (int i = lane; i < deg; i += 32) seg[i] = lab_in[col_idx[beg + i]];
+  __syncwarp();
+  int n2 = 1;
+  while (n2 < deg) n2 <<= 1;
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int i = lane; i < deg; i += 32) {
+      int p = i ^ (k - 1);
+      if (p > i && p < deg) {
+        int a = seg[i], b = seg[p];
+        if (a > b) { seg[i] = b; seg[p] = a; }
+      }
+    }
+    __syncwarp();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int i = lane; i < deg; i += 32) {
+        int p = i ^ j;
+        if (p > i && p < deg) {
+          int a = seg[i], b = seg[p];
+          if (a > b) { seg[i] = b; seg[p] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  unsigned long long t = 0;
+  for (int i = lane; i < deg; i += 32) t += sig_term(seg[i], i, seed);
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) t += __shfl_xor_sync(0xffffffffu, t, j);
+  if (lane == 0) {
+    unsigned long long key = sig_final(t, lab_in[v], deg, seed);
+    slot_of[v] = (int)ht_insert(ht_keys, ht_rep, ht_mask, key, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// block-wide exclusive scan helper (blockDim.x == 256)
+__device__ __forceinline__ int block_exclusive_scan_256(int x, int* total) {
+  __shared__ int warp_sums[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = x;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int s = lane < 8 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, s, d);
+      if (lane >= d) s += y;
+    }
+    if (lane < 8) warp_sums[lane] = s;
+  }
+  __syncthreads();
+  int off = wid ? warp_sums[wid - 1] : 0;
+  *total = warp_sums[7];
+  __syncthreads();
+  return off + incl - x;
+}
+
+// K2a: resolve each vertex to the representative (smallest vertex id) of its hash
+// slot and verify the full signature against it.  flags[v] = 1 iff v is a
+// representative, i.e. the first occurrence of a new compressed label.
+__global__ void __launch_bounds__(256)
+wl_resolve(int V, const int* __restrict__ row_ptr, const int* __restrict__ lab_in,
+           const int* __restrict__ sig_nbr, const int* __restrict__ ht_rep, int* slot_of,
+           int* __restrict__ flags, int* __restrict__ block_sums, DevScalars* sc) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = 0;
+  if (v < V) {
+    const int r = ht_rep[slot_of[v]];
+    slot_of[v] = r;
+    f = (r == v);
+    if (!f) {
+      const int bv = row_ptr[v], dv = row_ptr[v + 1] - bv;
+      const int br = row_ptr[r], dr = row_ptr[r + 1] - br;
+      bool same = (dv == dr) && (lab_in[v] == lab_in[r]);
+      for (int i = 0; same && i < dv; ++i) same = sig_nbr[bv + i] == sig_nbr[br + i];
+      if (!same) atomicOr(&sc->collision, 1u);
+    }
+    flags[v] = f;
+  }
+  int total;
+  block_exclusive_scan_256(f, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// exclusive scan of block_sums in place by ONE block; writes the grand total to
+// *dim_out and chains the running column base (*base_out = *base_in + total).
+__global__ void __launch_bounds__(256)
+scan_block_sums(int nb, int* block_sums, long long* dim_out, const long long* base_in,
+                long long* base_out) {
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int start = 0; start < nb; start += 256) {
+    const int i = start + threadIdx.x;
+    int x = i < nb ? block_sums[i] : 0;
+    int total;
+    int ex = block_exclusive_scan_256(x, &total);
+    const int carry = carry_s;
+    if (i < nb) block_sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (dim_out) *dim_out = carry_s;
+    if (base_out) *base_out = (base_in ? *base_in : 0) + carry_s;
+  }
+}
+
+// K2b: representatives receive their dense id (rank among representatives).
+__global__ void __launch_bounds__(256)
+wl_assign(int V, const int* __restrict__ flags, const int* __restrict__ block_sums,
+          int* __restrict__ lab_out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = v < V ? flags[v] : 0;
+  int total;
+  const int ex = block_exclusive_scan_256(f, &total);
+  if (f) lab_out[v] = block_sums[blockIdx.x] + ex;
+}
+
+__device__ __forceinline__ void ft_add(unsigned long long* keys, unsigned* cnt, unsigned mask,
+                                       unsigned long long key, unsigned inc, DevScalars* sc) {
+  unsigned slot = (unsigned)(mix64(key) >> 17) & mask;
+  for (int probe = 0; probe < 8192; ++probe) {
+    unsigned long long prev = atomicCAS(&keys[slot], EMPTY64, key);
+    if (prev == EMPTY64 || prev == key) {
+      atomicAdd(&cnt[slot], inc);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+  atomicOr(&sc->ft_overflow, 1u);  // table too small: the host grows it and repeats the pass
+}
+
+// K2c + K3a: every vertex takes the id of its representative; the (graph, column)
+// pair is counted into the sparse feature block (vertex_histogram.py:107-122).
+__global__ void __launch_bounds__(256)
+wl_gather_insert(int V, int level, const int* __restrict__ rep_of, int* lab_out,
+                 const int* __restrict__ vgraph, DevScalars* sc,
+                 unsigned long long* ft_keys, unsigned* ft_cnt, unsigned ft_mask) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int r = rep_of[v];
+  const int id = lab_out[r];
+  if (r != v) lab_out[v] = id;
+  const unsigned long long col = (unsigned long long)(sc->level_base[level] + id);
+  ft_add(ft_keys, ft_cnt, ft_mask, ((unsigned long long)(unsigned)vgraph[v] << 32) | col, 1u, sc);
+}
+
+__global__ void __launch_bounds__(256)
+wl_insert_level0(int V, const int* __restrict__ lab, const int* __restrict__ vgraph,
+                 unsigned long long* ft_keys, unsigned* ft_cnt, unsigned ft_mask, DevScalars* sc) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  ft_add(ft_keys, ft_cnt, ft_mask,
+         ((unsigned long long)(unsigned)vgraph[v] << 32) | (unsigned long long)(unsigned)lab[v], 1u, sc);
+}
+
+// vertex -> graph id by binary search in graph_ptr
+__global__ void __launch_bounds__(256)
+fill_vgraph(int V, int N, const int* __restrict__ graph_ptr, int* __restrict__ vgraph) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int lo = 0, hi = N;  // find g with graph_ptr[g] <= v < graph_ptr[g+1]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (graph_ptr[mid] <= v) lo = mid; else hi = mid;
+  }
+  vgraph[v] = lo;
+}
+
+}  // namespace gk

@@ -1,0 +1,407 @@
+"""Estimator classes of the hot path, mirroring the reference's operator API.
+
+Same class names, constructor signatures, method names and error behaviour as
+grakel.kernels.{Kernel, WeisfeilerLehman, VertexHistogram, ShortestPath,
+ShortestPathAttr} (kernel.py:23-456, weisfeiler_lehman.py:23-555,
+vertex_histogram.py:23-219, shortest_path.py:16-515), but every kernel matrix is
+produced by the CUDA engine behind `grakel_b200._lib` -- there is no CPU path.
+
+Fitted state is host-resident numpy / Python objects (a packed CSR `Block` and
+the level-0 label dictionary), so fitted estimators pickle like the reference's
+(grakel/tests/test_common.py:53-58); device buffers are re-created on demand.
+"""
+from __future__ import annotations
+
+import copy
+import warnings
+from collections.abc import Iterable
+
+import numpy as np
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.exceptions import NotFittedError
+from sklearn.utils.validation import check_is_fitted
+
+from . import _lib
+from .packing import Block, Graph, label_ids, pack
+
+
+class Fitted:
+    """What `fit` keeps: the packed graphs, their level-0 label ids, the label dictionary."""
+
+    def __init__(self, block, ids, dictionary):
+        self.block = block
+        self.ids = ids
+        self.dictionary = dictionary
+
+    def __len__(self):
+        return self.block.n_graphs
+
+
+class Kernel(BaseEstimator, TransformerMixin):
+    """Estimator contract of grakel.kernels.Kernel (kernel.py:23-456).
+
+    Subclasses provide `parse_input` (host packing) and `_device_features`
+    (which feature kernel to run); fit / transform / fit_transform / diagonal /
+    set_params behave as in the reference."""
+
+    X = None
+    _graph_format = "dictionary"
+    _method_calling = 0
+    _nan_to_num = False
+
+    def __init__(self, n_jobs=None, normalize=False, verbose=False):
+        self.verbose = verbose
+        self.n_jobs = n_jobs
+        self.normalize = normalize
+        self._initialized = dict(n_jobs=False)
+
+    # ---- reference protocol --------------------------------------------------
+    def fit(self, X, y=None):
+        self._is_transformed = False
+        self._method_calling = 1
+        self.initialize()
+        if X is None:
+            raise ValueError("`fit` input cannot be None")
+        self.X = self.parse_input(X)
+        return self
+
+    def transform(self, X):
+        self._method_calling = 3
+        check_is_fitted(self, ["X"])
+        if X is None:
+            raise ValueError("`transform` input cannot be None")
+        Y = self.parse_input(X)
+        K, _, ydiag = self._run(Block.concat(self.X.block, Y.block), np.concatenate([self.X.ids, Y.ids]),
+                                n_fit=self.X.block.n_graphs)
+        self._Y_diag = ydiag
+        self._is_transformed = True
+        if self.normalize:
+            self._warn_unnormalizable(self._X_diag, ydiag)
+        return K
+
+    def fit_transform(self, X, y=None):
+        self._method_calling = 2
+        self.fit(X)
+        K, xdiag, _ = self._run(self.X.block, self.X.ids, n_fit=self.X.block.n_graphs)
+        self._X_diag = xdiag
+        if self.normalize:
+            self._warn_unnormalizable(xdiag)
+        return K
+
+    def diagonal(self):
+        check_is_fitted(self, ["X"])
+        try:
+            check_is_fitted(self, ["_X_diag"])
+        except NotFittedError:
+            _, self._X_diag, _ = self._run(self.X.block, self.X.ids, n_fit=self.X.block.n_graphs, want_matrix=False)
+        if getattr(self, "_is_transformed", False):
+            return self._X_diag, self._Y_diag
+        return self._X_diag
+
+    def _warn_unnormalizable(self, *diagonals):
+        """kernel.py:206-234: say why a normalised matrix contains NaNs."""
+        name = type(self).__name__
+        for d in diagonals:
+            d = np.asarray(d, dtype=float)
+            if np.any(d == 0):
+                warnings.warn(name + " has zero self similarities, so normalizing it yields NaNs: those graphs "
+                              "have no features this kernel can see. Either drop them or pass normalize=False.",
+                              RuntimeWarning)
+                break
+
+    def initialize(self):
+        """kernel.py:386-399.  `n_jobs` is validated and then ignored: the whole Gram
+        matrix is one device job (ShortestPath already ignores it, shortest_path.py:239-242)."""
+        if not self._initialized["n_jobs"]:
+            if type(self.n_jobs) is not int and self.n_jobs is not None:
+                raise ValueError("n_jobs parameter must be an int indicating the number of jobs as in joblib or None")
+            self._parallel = None
+            self._initialized["n_jobs"] = True
+
+    def parse_input(self, X):
+        raise NotImplementedError
+
+    def pairwise_operation(self, x, y):
+        raise NotImplementedError("Pairwise operation is not implemented!")
+
+    def set_params(self, **params):
+        """kernel.py:417-433: a changed parameter is re-validated at the next fit."""
+        if len(self._initialized):
+            params = copy.deepcopy(params)
+            for key in params:
+                key, delim, sub_key = key.partition("__")
+                if delim:
+                    if sub_key in self._initialized:
+                        self._initialized[sub_key] = False
+                elif key in self._initialized:
+                    self._initialized[key] = False
+        super().set_params(**params)
+        return self
+
+    # ---- device side ---------------------------------------------------------
+    def _device_features(self, engine):
+        raise NotImplementedError
+
+    def _run(self, block, ids, n_fit, want_matrix=True):
+        """pack -> feature kernels -> Gram, all on the device.  Returns (K, xdiag, ydiag)."""
+        eng = _lib.get_engine()
+        with eng._lock:
+            eng.pack(block.graph_ptr, block.row_ptr, block.col_idx, ids, block.weights, None)
+            self.stats_ = self._device_features(eng)
+            K, xd, yd = eng.gram(block.n_graphs, n_fit=n_fit, normalize=bool(self.normalize) and want_matrix,
+                                 nan_to_num=self._nan_to_num, out=None if want_matrix else False,
+                                 stats=self.stats_)
+        if self.verbose:
+            print(type(self).__name__, self.stats_.as_dict())
+        return K, xd, yd
+
+
+# ------------------------------------------------------------------------------
+class VertexHistogram(Kernel):
+    """Vertex histogram kernel (vertex_histogram.py:23-219): K = Phi Phi^T with
+    Phi[g, l] = number of vertices of g carrying label l."""
+
+    def __init__(self, n_jobs=None, normalize=False, verbose=False, sparse="auto"):
+        super().__init__(n_jobs=n_jobs, normalize=normalize, verbose=verbose)
+        self.sparse = sparse
+        self._initialized.update({"sparse": True})
+
+    def parse_input(self, X):
+        from .packing import iter_elements
+        if self._method_calling in (1, 2):
+            known = None
+        else:
+            known = self.X.dictionary
+        sizes, labels = [0], []
+        for _, _g, L in iter_elements(X, lambda n: n in (2, 3)):
+            vals = list(L.values())
+            labels.extend(vals)
+            sizes.append(sizes[-1] + len(vals))
+        if len(sizes) == 1:
+            raise ValueError("parsed input is empty")
+        block = Block(np.asarray(sizes), np.zeros(sizes[-1] + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), None,
+                      labels)
+        if known is None:
+            ids, new = label_ids(labels, None, sort_new=False)
+            dictionary = new
+            self.sparse_ = True
+        else:
+            ids, new = label_ids(labels, known, sort_new=False)
+            dictionary = known
+        return Fitted(block, ids, dictionary)
+
+    def _device_features(self, eng):
+        return eng.wl_features(0)
+
+
+# ------------------------------------------------------------------------------
+class WeisfeilerLehman(Kernel):
+    """Weisfeiler-Lehman subtree kernel (weisfeiler_lehman.py:23-555).
+
+    K = sum over levels 0..n_iter of the vertex-histogram kernel on the level's
+    compressed labels.  Only the subtree base kernel (`VertexHistogram`, the
+    reference default) runs on the device."""
+
+    _graph_format = "dictionary"
+    _nan_to_num = True
+
+    def __init__(self, n_jobs=None, verbose=False, normalize=False, n_iter=5, base_graph_kernel=VertexHistogram):
+        super().__init__(n_jobs=n_jobs, verbose=verbose, normalize=normalize)
+        self.n_iter = n_iter
+        self.base_graph_kernel = base_graph_kernel
+        self._initialized.update({"n_iter": False, "base_graph_kernel": False})
+        self._base_graph_kernel = None
+
+    def initialize(self):
+        super().initialize()
+        if not self._initialized["base_graph_kernel"]:  # weisfeiler_lehman.py:77-109
+            base = self.base_graph_kernel
+            if base is None:
+                base, params = VertexHistogram, dict()
+            elif type(base) is type and issubclass(base, Kernel):
+                params = dict()
+            else:
+                try:
+                    base, params = base
+                except Exception:
+                    raise TypeError("Base kernel was not formulated in the correct way. Check documentation.")
+                if not (type(base) is type and issubclass(base, Kernel)):
+                    raise TypeError("The first argument must be a valid grakel.kernel.kernel Object")
+                if type(params) is not dict:
+                    raise ValueError("If the second argument of base kernel exists, it must be a dictionary between "
+                                     "parameters names and values")
+                params.pop("normalize", None)
+            if base is not VertexHistogram:
+                raise NotImplementedError("grakel_b200 runs the WL *subtree* kernel (base_graph_kernel="
+                                          "VertexHistogram); other base kernels are outside the device hot path")
+            params["normalize"] = False
+            params["verbose"] = self.verbose
+            params["n_jobs"] = None
+            self._base_graph_kernel = base
+            self._params = params
+            self._initialized["base_graph_kernel"] = True
+        if not self._initialized["n_iter"]:  # :111-115
+            if type(self.n_iter) is not int or self.n_iter <= 0:
+                raise TypeError("'n_iter' must be a positive integer")
+            self._n_iter = self.n_iter + 1
+            self._initialized["n_iter"] = True
+
+    def parse_input(self, X):
+        if self._method_calling in (1, 2):
+            if hasattr(self, "_X_diag"):
+                delattr(self, "_X_diag")
+            if not isinstance(X, Iterable):
+                raise TypeError("input must be an iterable\n")
+            block = pack(X, "wl", len_ok=lambda n: n >= 2)  # weisfeiler_lehman.py:152
+            self._nx = block.n_graphs
+            ids, dictionary = label_ids(block.labels, None, sort_new=True)  # :199-206
+            self._inv_labels = {0: dictionary}
+            return Fitted(block, ids, dictionary)
+        if self._method_calling != 3:
+            raise ValueError("method call must be called either from fit or fit-transform")
+        block = pack(X, "wl", len_ok=lambda n: n in (2, 3))  # :367
+        ids, _ = label_ids(block.labels, self._inv_labels[0], sort_new=True)  # :417-418
+        return Fitted(block, ids, self._inv_labels[0])
+
+    def fit_transform(self, X, y=None):
+        self._method_calling = 2
+        self._is_transformed = False
+        self.initialize()
+        if X is None:
+            raise ValueError("transform input cannot be None")
+        self.X = self.parse_input(X)
+        K, xdiag, _ = self._run(self.X.block, self.X.ids, n_fit=self._nx)
+        self._X_diag = xdiag
+        return K
+
+    def fit(self, X, y=None):
+        self._is_transformed = False
+        self._method_calling = 1
+        self.initialize()
+        if X is None:
+            raise ValueError("`fit` input cannot be None")
+        self.X = self.parse_input(X)
+        return self
+
+    def transform(self, X):
+        self._method_calling = 3
+        check_is_fitted(self, ["X", "_nx", "_inv_labels"])
+        if X is None:
+            raise ValueError("transform input cannot be None")
+        if not isinstance(X, Iterable):
+            raise ValueError("input must be an iterable\n")
+        Y = self.parse_input(X)
+        K, xdiag, ydiag = self._run(Block.concat(self.X.block, Y.block), np.concatenate([self.X.ids, Y.ids]),
+                                    n_fit=self._nx)
+        self._X_diag = xdiag
+        self._Y_diag = ydiag
+        self._is_transformed = True
+        return K
+
+    def _device_features(self, eng):
+        return eng.wl_features(self._n_iter - 1)
+
+
+# ------------------------------------------------------------------------------
+class ShortestPath(Kernel):
+    """Shortest-path kernel (shortest_path.py:167-515): features are
+    (l(u), l(v), d(u,v)) triples (or d(u,v) alone with with_labels=False) over ordered
+    vertex pairs at finite distance; K = Phi Phi^T."""
+
+    def __init__(self, n_jobs=None, normalize=False, verbose=False, with_labels=True, algorithm_type="auto"):
+        super().__init__(n_jobs=n_jobs, normalize=normalize, verbose=verbose)
+        self.with_labels = with_labels
+        self.algorithm_type = algorithm_type
+        self._initialized.update({"with_labels": False, "algorithm_type": False})
+
+    def initialize(self):
+        if not self._initialized["n_jobs"]:  # shortest_path.py:239-242
+            if self.n_jobs is not None:
+                warnings.warn("no implemented parallelization for ShortestPath")
+            self._initialized["n_jobs"] = True
+        if not self._initialized["algorithm_type"]:  # :244-252
+            if self.algorithm_type == "auto":
+                self._graph_format = "auto"
+            elif self.algorithm_type == "floyd_warshall":
+                self._graph_format = "adjacency"
+            elif self.algorithm_type == "dijkstra":
+                self._graph_format = "dictionary"
+            else:
+                raise ValueError('Unsupported "algorithm_type"')
+        self._lt = "vertex" if self.with_labels else "none"
+
+    def parse_input(self, X):
+        wl = bool(self.with_labels)
+        # Floyd-Warshall treats a 0 entry as "no edge" (graph.py:1786); Dijkstra walks every
+        # listed edge.  "auto" picks FW for adjacency input and Dijkstra for dictionaries, so
+        # zero-weight dictionary edges only disappear when FW is forced.
+        block = pack(X, "sp", need_labels=wl, len_ok=lambda n: n in (2, 3) or (n == 1 and not wl),
+                     want_weights=True, fw_zero_is_absent=self.algorithm_type == "floyd_warshall",
+                     type_error_msg="each element of X must have at least one and at most 3 elements\n")
+        if self._method_calling in (1, 2):
+            self._nx = block.n_graphs
+            if wl:
+                ids, dictionary = label_ids(block.labels, None, sort_new=False)
+            else:
+                ids, dictionary = None, {}
+            self._enum = dictionary  # fitted marker (the reference keeps the feature enumeration here)
+            return Fitted(block, ids, dictionary)
+        self._ny = block.n_graphs
+        if wl:
+            ids, _ = label_ids(block.labels, self.X.dictionary, sort_new=False)
+        else:
+            ids = None
+        return Fitted(block, ids, self.X.dictionary)
+
+    def fit_transform(self, X, y=None):
+        self._method_calling = 2
+        self.fit(X)  # resets _method_calling to 1 like shortest_path.py:392-393
+        K, xdiag, _ = self._run(self.X.block, self.X.ids, n_fit=self._nx)
+        self._X_diag = xdiag
+        return K
+
+    def transform(self, X):
+        self._method_calling = 3
+        check_is_fitted(self, ["X", "_nx", "_enum"])
+        if X is None:
+            raise ValueError("transform input cannot be None")
+        Y = self.parse_input(X)
+        ids = None if self.X.ids is None else np.concatenate([self.X.ids, Y.ids])
+        K, xdiag, ydiag = self._run(Block.concat(self.X.block, Y.block), ids, n_fit=self._nx)
+        self._X_diag = xdiag
+        self._Y_diag = ydiag
+        self._is_transformed = True
+        return K
+
+    def diagonal(self):
+        out = super().diagonal()
+        if isinstance(out, tuple):  # shortest_path.py:359-366: X diagonal as a column
+            return np.reshape(out[0], (-1, 1)), out[1]
+        return np.reshape(out, (-1, 1))
+
+    def _device_features(self, eng):
+        return eng.sp_features(with_labels=bool(self.with_labels))
+
+
+class ShortestPathAttr(Kernel):
+    """Shortest-path kernel on node attributes (shortest_path.py:16-164)."""
+
+    def __init__(self, n_jobs=None, normalize=False, verbose=False, algorithm_type="auto", metric=np.dot):
+        super().__init__(n_jobs=n_jobs, normalize=normalize, verbose=verbose)
+        self.algorithm_type = algorithm_type
+        self.metric = metric
+        self._initialized.update({"algorithm_type": False, "metric": False})
+
+    def initialize(self):
+        super().initialize()
+        if not self._initialized["algorithm_type"]:
+            if self.algorithm_type not in ("auto", "floyd_warshall", "dijkstra"):
+                raise ValueError("Unsupported value " + str(self.algorithm_type) + ' for "algorithm_type"')
+            self._initialized["algorithm_type"] = True
+        if not self._initialized["metric"]:
+            if not callable(self.metric):
+                raise TypeError('"metric" must be callable')
+            self._initialized["metric"] = True
+
+    def parse_input(self, X):
+        raise NotImplementedError("ShortestPathAttr is not on the device path of this build yet")

@@ -1,0 +1,167 @@
+/* grakel_b200 -- C-ABI of the B200-native graph-kernel Gram engine.
+ *
+ * This header is the drop-in boundary for the hot path of ysig/GraKeL
+ * (reference v0.1.11):  N x N Gram matrices of the Weisfeiler-Lehman subtree
+ * kernel and the Shortest-Path kernels.  The reference has no FFI on this path
+ * (it is pure Python + numpy/scipy); its only native precedent is the Cython
+ * `cdef extern` block grakel/kernels/_c_functions/header.pxd:1-4 over
+ * include/functions.hpp:4-5 (raw pointers + sizes, results by out-pointer).
+ * The entry points below follow that convention: extern "C", plain pointers and
+ * sizes, caller-owned host buffers, library-owned device memory behind an
+ * opaque handle, int status return (0 = ok, <0 = error; text via gk_last_error).
+ *
+ * What each entry point replaces in the reference:
+ *
+ *   gk_pack_csr          Graph.__init__/build_graph/_import_*  (graph.py:147-230,
+ *                        912-1053) + get_edge_dictionary/get_labels
+ *                        (graph.py:1182-1204, 689-772) -- after the Python layer
+ *                        has normalised the input into one CSR block.
+ *   gk_wl_features       WeisfeilerLehman.parse_input relabel loop
+ *                        (weisfeiler_lehman.py:199-258) + VertexHistogram.parse_input
+ *                        (vertex_histogram.py:57-154) for every level.
+ *   gk_sp_features       Graph.build_shortest_path_matrix / floyd_warshall / dijkstra
+ *                        (graph.py:588-687, 1712-1794) + ShortestPath.parse_input
+ *                        pair histogram (shortest_path.py:468-490).
+ *   gk_spattr_features   ShortestPathAttr.parse_input + the bilinear pair kernel
+ *                        (shortest_path.py:77-164) as an explicit feature map.
+ *   gk_gram              VertexHistogram._calculate_kernel_matrix
+ *                        (vertex_histogram.py:156-184), np.sum over levels
+ *                        (weisfeiler_lehman.py:270), np.dot(phi, phi.T)
+ *                        (shortest_path.py:404 / :312), the diagonals
+ *                        (vertex_histogram.py:186-219, shortest_path.py:320-368) and
+ *                        the normalisation (weisfeiler_lehman.py:324-327, 494-498;
+ *                        shortest_path.py:314-316, 407-408).
+ *   gk_wl_fit_transform, gk_sp_fit_transform
+ *                        one-call forms of the above with HOST buffers in and out:
+ *                        WeisfeilerLehman.fit_transform (weisfeiler_lehman.py:292-328),
+ *                        ShortestPath.fit_transform (shortest_path.py:370-410).
+ *
+ * Fit + transform.  The reference keeps per-level dictionaries at fit time and
+ * re-applies them to new graphs (weisfeiler_lehman.py:330-500).  Here the same
+ * result is obtained by packing the fitted graphs X followed by the new graphs Y
+ * into one block and relabelling them jointly: a Y feature is "seen" iff its
+ * column also occurs in an X graph, unseen columns contribute nothing to
+ * K[y, x] and are counted in Y's self-similarity, exactly as
+ * vertex_histogram.py:179 / :211-217 and shortest_path.py:312 / :365 do.
+ * `n_fit` below is the number of leading graphs that form X.
+ */
+#ifndef GRAKEL_B200_H
+#define GRAKEL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gk_handle gk_handle;
+
+/* output element type of K */
+#define GK_F32 0
+#define GK_F64 1
+
+/* gk_gram flags */
+#define GK_NORMALIZE 1   /* K_ij / sqrt(d_i d_j) in fp64 (weisfeiler_lehman.py:326) */
+#define GK_NAN_TO_NUM 2  /* WL only: np.nan_to_num on the normalised matrix          */
+#define GK_GRAM_SIMT 4   /* use the exact int64 CUDA-core Gram (verification / wide counts) */
+#define GK_OUT_DEVICE 8  /* K_out is a DEVICE pointer (e.g. a torch tensor)          */
+#define GK_FULL_TILES 16 /* square case: compute every tile, no mirroring            */
+
+/* gk_sp_features flags */
+#define GK_SP_WITH_LABELS 1
+#define GK_SP_KEEP_DIST 2    /* keep fp64 APSP matrices for gk_sp_distances (tests) */
+
+/* error codes */
+#define GK_OK 0
+#define GK_ERR_CUDA -1
+#define GK_ERR_ARG -2
+#define GK_ERR_STATE -3
+#define GK_ERR_RANGE -4   /* a count or Gram value leaves the exactly representable range */
+#define GK_ERR_UNSUPPORTED -5
+
+/* Per-call statistics (all optional; pass NULL).  Times are CUDA-event
+ * milliseconds on the handle's stream. */
+typedef struct gk_stats {
+  int64_t n_graphs, n_vertices, n_edges;
+  int64_t n_levels;          /* WL: h+1 */
+  int64_t level_dims[64];    /* WL: distinct labels per level (= D_i of the reference) */
+  int64_t n_columns;         /* total feature columns D */
+  int64_t n_entries;         /* nnz of the feature block */
+  int64_t n_dense_columns;   /* D_c: columns contracted by the tensor-core GEMM */
+  int64_t max_count;         /* largest single feature count */
+  int64_t max_diag;          /* largest self-similarity */
+  int64_t hash_retries;      /* WL: relabel passes repeated after a detected hash collision */
+  int64_t gram_path;         /* 1 = tcgen05 bf16 tensor-core GEMM, 2 = exact int64 CUDA-core Gram, 3 = no contracted columns */
+  int64_t gemm_tiles;        /* output tiles computed */
+  int64_t gemm_launches;     /* kernels launched by the last gk_gram */
+  int64_t kernel_launches;   /* kernels launched by the last features call */
+  float ms_h2d, ms_features, ms_panel, ms_gemm, ms_d2h, ms_total;
+} gk_stats;
+
+int gk_version(void);
+const char* gk_last_error(void);
+
+int gk_create(int device_ordinal, gk_handle** out);
+int gk_destroy(gk_handle* h);
+int gk_sync(gk_handle* h);
+
+/* Upload one packed CSR block (host pointers).
+ *   graph_ptr[n_graphs+1]  vertex offsets, graph g owns vertices [graph_ptr[g], graph_ptr[g+1])
+ *   row_ptr[V+1]           out-edge offsets per vertex (V = graph_ptr[n_graphs])
+ *   col_idx[E]             GLOBAL vertex id of each out-neighbour (same graph)
+ *   labels[V]              dense non-negative id of the vertex label (level 0), or NULL
+ *   weights[E]             edge weights (fp64) or NULL for unit weights
+ *   attrs[V*attr_dim]      fp32 node attributes or NULL                                  */
+int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const int32_t* row_ptr,
+                const int32_t* col_idx, const int32_t* labels, const double* weights,
+                const float* attrs, int32_t attr_dim);
+
+/* Build the sparse feature block of the packed graphs on the device. */
+int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats);
+int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats);
+int gk_spattr_features(gk_handle* h, gk_stats* stats);
+
+/* Gram matrix of the current feature block.
+ *   n_fit == n_graphs : K is [n_graphs x n_graphs]                      (fit_transform)
+ *   n_fit <  n_graphs : K is [(n_graphs-n_fit) x n_fit], rows = Y graphs (transform)
+ *   row_begin,row_end : only rows [row_begin,row_end) of K are computed and written
+ *                       (multi-GPU row tiling); K_out points at row `row_begin`.
+ *   K_out may be NULL (result stays on the device; see gk_fetch).
+ *   xdiag[n_fit], ydiag[n_graphs-n_fit] : self-similarities (fp64, host) or NULL.      */
+int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64_t row_end,
+            void* K_out, int32_t out_dtype, int64_t ld, double* xdiag, double* ydiag,
+            gk_stats* stats);
+
+/* Copy rows of the device-resident K of the last gk_gram to the host. */
+int gk_fetch(gk_handle* h, void* K_out, int32_t out_dtype, int64_t ld);
+
+/* WL inspection (parity tests): compressed label of every vertex at `level`
+ * (dense ids, first-occurrence order) */
+int gk_wl_labels(gk_handle* h, int32_t level, int32_t* out);
+
+/* SP inspection: APSP matrix of graph g (n x n fp64, inf = unreachable) */
+int gk_sp_distances(gk_handle* h, int64_t g, double* out);
+
+/* One-call forms with host buffers (the e2e path that bench.py times). */
+int gk_wl_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr,
+                        const int32_t* row_ptr, const int32_t* col_idx, const int32_t* labels,
+                        int32_t n_iter, int32_t flags, void* K_out, int32_t out_dtype, int64_t ld,
+                        double* diag, gk_stats* stats);
+int gk_sp_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr,
+                        const int32_t* row_ptr, const int32_t* col_idx, const int32_t* labels,
+                        const double* weights, int32_t sp_flags, int32_t flags, void* K_out,
+                        int32_t out_dtype, int64_t ld, double* diag, gk_stats* stats);
+
+/* CUDA-event timing on the handle's stream (bench.py). */
+int gk_event_record(gk_handle* h, int32_t slot);            /* slot in [0,16) */
+int gk_event_elapsed(gk_handle* h, int32_t a, int32_t b, float* ms);
+
+/* Self-test of the tensor-core Gram on a dense count matrix (tests only):
+ * counts[n*d] (uint16), out_tc / out_simt [n*n] fp64. */
+int gk_selftest_gram(gk_handle* h, int64_t n, int64_t d, const uint16_t* counts, double* out_tc,
+                     double* out_simt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

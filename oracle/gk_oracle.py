@@ -307,24 +307,29 @@ class WLOracle:
         count = len(inv0)
         L = [{v: inv0[lab] for v, lab in l.items()} for l in L]
         self.levels = [_VH().fit(L)]
-        level_labels = [[dict(l) for l in L]]
+        level_labels = [[dict(l) for l in L]] if return_levels else None
         Ks = [self.levels[0].gram()]
         for it in range(1, self.h + 1):  # weisfeiler_lehman.py:223-258
-            sigs = []
-            seen = set()
-            for g, l in zip(Gs, L):
-                s = {}
-                for v in l.keys():  # every labelled vertex, sinks included (:230-234)
-                    s[v] = self._signature(l[v], [l[n] for n in g.ed.get(v, {}).keys()])
-                    seen.add(s[v])
-                sigs.append(s)
+            # The reference collects the credential set, sorts it and numbers it (:243-246);
+            # K only depends on the partition, so ids are handed out at first sight here
+            # (one pass, no sort) -- the port must not be slower than what it stands in for.
             inv = {}
-            for sig in sorted(seen):
-                inv[sig] = count
-                count += 1
+            newL = []
+            for g, l in zip(Gs, L):
+                ed = g.ed
+                nl = {}
+                for v, own in l.items():  # every labelled vertex, sinks included (:230-234)
+                    sig = (own, tuple(sorted([l[n] for n in ed.get(v, ())])))
+                    i = inv.get(sig)
+                    if i is None:
+                        i = inv[sig] = count + len(inv)
+                    nl[v] = i
+                newL.append(nl)
+            count += len(inv)
             self.inv[it] = inv
-            L = [{v: inv[s] for v, s in sg.items()} for sg in sigs]
-            level_labels.append([dict(l) for l in L])
+            L = newL
+            if return_levels:
+                level_labels.append([dict(l) for l in L])
             vh = _VH().fit(L)
             self.levels.append(vh)
             Ks.append(vh.gram())

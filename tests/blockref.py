@@ -1,0 +1,101 @@
+"""numpy model of the DEVICE pipeline on a packed block (test helper, CPU).
+
+It follows the engine's design, not the reference's: X and Y graphs are relabelled
+*jointly*, features are (graph, column) counts, K[y, x] contracts all columns (a
+column absent from X contributes 0), self similarities use all columns.  The CPU
+tests compare it with the reference goldens to pin (a) the host packing logic and
+(b) the joint-relabelling equivalence the C-ABI documents."""
+from collections import Counter
+
+import numpy as np
+from scipy.sparse import csr_matrix
+
+
+def _features(n_graphs, vgraph, cols, D):
+    cnt = Counter(zip(vgraph.tolist(), cols.tolist()))
+    r = np.fromiter((k[0] for k in cnt), dtype=np.int64, count=len(cnt))
+    c = np.fromiter((k[1] for k in cnt), dtype=np.int64, count=len(cnt))
+    d = np.fromiter(cnt.values(), dtype=np.float64, count=len(cnt))
+    return csr_matrix((d, (r, c)), shape=(n_graphs, D))
+
+
+def _finish(Phi, n_graphs, n_fit, normalize, nan_to_num):
+    X = Phi[:n_fit]
+    diag = np.asarray(Phi.multiply(Phi).sum(axis=1)).ravel()
+    if n_fit == n_graphs:
+        K = X.dot(X.T).toarray()
+        den = np.sqrt(np.outer(diag, diag))
+    else:
+        K = Phi[n_fit:].dot(X.T).toarray()
+        den = np.sqrt(np.outer(diag[n_fit:], diag[:n_fit]))
+    if normalize:
+        with np.errstate(all="ignore"):
+            K = K / den
+            if nan_to_num:
+                K = np.nan_to_num(K)
+    return K, diag[:n_fit], diag[n_fit:]
+
+
+def wl_levels(block, ids, n_iter):
+    """Per-level dense labels (first-occurrence numbering) of every vertex."""
+    V = block.n_vertices
+    rp, ci = block.row_ptr, block.col_idx
+    lab = np.asarray(ids, dtype=np.int64)
+    levels = [lab.copy()]
+    for _ in range(n_iter):
+        table = {}
+        new = np.empty(V, dtype=np.int64)
+        for v in range(V):
+            sig = (int(lab[v]), tuple(sorted(lab[ci[rp[v]:rp[v + 1]]].tolist())))
+            new[v] = table.setdefault(sig, len(table))
+        lab = new
+        levels.append(lab.copy())
+    return levels
+
+
+def wl_gram_block(block, ids, n_iter, n_fit=None, normalize=False):
+    N = block.n_graphs
+    n_fit = N if n_fit is None else n_fit
+    vgraph = np.repeat(np.arange(N), np.diff(block.graph_ptr))
+    levels = wl_levels(block, ids, n_iter)
+    cols, base = [], 0
+    for lab in levels:
+        cols.append(lab + base)
+        base += int(lab.max()) + 1 if len(lab) else 0
+    Phi = _features(N, np.tile(vgraph, len(levels)), np.concatenate(cols), base)
+    return _finish(Phi, N, n_fit, normalize, True)
+
+
+def apsp_block(block, g):
+    v0, v1 = int(block.graph_ptr[g]), int(block.graph_ptr[g + 1])
+    n = v1 - v0
+    D = np.full((n, n), np.inf)
+    for u in range(n):
+        b, e = block.row_ptr[v0 + u], block.row_ptr[v0 + u + 1]
+        for k in range(b, e):
+            w = 1.0 if block.weights is None else float(block.weights[k])
+            D[u, block.col_idx[k] - v0] = w
+    np.fill_diagonal(D, 0)
+    for k in range(n):
+        D = np.minimum(D, D[:, k:k + 1] + D[k:k + 1, :])
+    return D
+
+
+def sp_gram_block(block, ids, n_fit=None, with_labels=True, normalize=False):
+    N = block.n_graphs
+    n_fit = N if n_fit is None else n_fit
+    enum = {}
+    rows, cols = [], []
+    for g in range(N):
+        D = apsp_block(block, g)
+        v0 = int(block.graph_ptr[g])
+        n = D.shape[0]
+        for u in range(n):
+            for v in range(n):
+                if u == v or not np.isfinite(D[u, v]):
+                    continue
+                key = (int(ids[v0 + u]), int(ids[v0 + v]), D[u, v]) if with_labels else D[u, v]
+                rows.append(g)
+                cols.append(enum.setdefault(key, len(enum)))
+    Phi = _features(N, np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64), max(len(enum), 1))
+    return _finish(Phi, N, n_fit, normalize, False)

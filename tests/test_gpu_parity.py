@@ -1,0 +1,240 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C-ABI
+against the committed reference goldens and the CPU oracle.  Bit-exact for the
+integer-valued matrices; normalised matrices within 1e-5 relative (in practice
+they are bit-identical too, the epilogue uses the reference's fp64 formula)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import gio
+from oracle.gk_oracle import SPOracle, WLOracle, gen, wl_partitions
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from grakel_b200 import _lib
+    return _lib.get_engine()
+
+
+def _k():
+    import grakel_b200
+    return grakel_b200
+
+
+def _same(a, b, exact=True):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert a.shape == b.shape
+    if exact:
+        assert np.array_equal(a, b, equal_nan=True), f"max abs diff {np.nanmax(np.abs(a - b))}"
+    else:
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=0, equal_nan=True)
+
+
+# --------------------------------------------------------------- Gram kernels
+@pytest.mark.parametrize("n,d,hi", [(64, 64, 5), (300, 200, 20), (520, 130, 256), (1000, 1500, 7), (129, 65, 3)])
+def test_tcgen05_gram_matches_integer_matmul(eng, n, d, hi):
+    rs = np.random.RandomState(n + d)
+    C = (rs.rand(n, d) < 0.2) * rs.randint(1, hi + 1, size=(n, d))
+    exact = (C.astype(np.int64) @ C.astype(np.int64).T).astype(np.float64)
+    tc, simt = eng.selftest_gram(C)
+    _same(simt, exact)
+    _same(tc, exact)
+
+
+# --------------------------------------------------------------- WL
+def _run_case(X, Y, out):
+    k = _k()
+    for key, rec in out.items():
+        parts = key.split("_")
+        if "error" in rec:
+            continue
+        if parts[0] == "wl":
+            est = k.WeisfeilerLehman(n_iter=int(parts[1][1:]), normalize=parts[2] == "n")
+        else:
+            est = k.ShortestPath(with_labels=parts[1] == "l", algorithm_type="_".join(parts[2:-1]),
+                                 normalize=parts[-1] == "n")
+        with np.errstate(all="ignore"):
+            _same(est.fit_transform(X), rec["fit_transform"])
+            if "transform" in rec:
+                _same(est.transform(Y), rec["transform"])
+
+
+def test_spellings_all_kernels():
+    g = gio.load(os.path.join(G, "spellings.json.gz"))
+    for name, case in g["cases"].items():
+        _run_case(gio.dec_dataset(case["X"]), None, case["out"])
+
+
+@pytest.mark.parametrize("tag", ["unit", "intw"])
+def test_fit_then_transform_with_unseen_labels(tag):
+    d = gio.load(os.path.join(G, "fit_transform.json.gz"))[tag]
+    _run_case(gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"]), d["out"])
+
+
+def test_real_weights_raise_not_guess():
+    d = gio.load(os.path.join(G, "fit_transform.json.gz"))["realw"]
+    X = gio.dec_dataset(d["X"])
+    with pytest.raises(NotImplementedError):
+        _k().ShortestPath().fit_transform(X)
+    # WL ignores weights: still exact
+    _same(_k().WeisfeilerLehman(n_iter=2).fit_transform(X), d["out"]["wl_h2_u"]["fit_transform"])
+
+
+def test_mutag_goldens():
+    k = _k()
+    X = gio.dec_dataset(gio.load(os.path.join(G, "mutag_graphs.json.gz")))
+    ref = np.load(os.path.join(G, "mutag_out.npz"))
+    for h in (3, 5):
+        K = k.WeisfeilerLehman(n_iter=h).fit_transform(X)
+        assert K.dtype == np.float64 and K.flags.c_contiguous
+        _same(K, ref[f"wl_h{h}"])
+    _same(k.ShortestPath().fit_transform(X), ref["sp"])
+    tr, te = ref["split_train"].tolist(), ref["split_test"].tolist()
+    wl = k.WeisfeilerLehman(n_iter=3, normalize=True)
+    _same(wl.fit_transform([X[i] for i in tr]), ref["wl_h3_norm_train"])
+    wl2 = pickle.loads(pickle.dumps(wl))  # fitted state is host-resident
+    _same(wl2.transform([X[i] for i in te]), ref["wl_h3_norm_test"])
+    sp = k.ShortestPath(normalize=True)
+    _same(sp.fit_transform([X[i] for i in tr]), ref["sp_norm_train"])
+    _same(sp.transform([X[i] for i in te]), ref["sp_norm_test"])
+    # GraphKernel front door == direct class (graph_kernels.py:405)
+    gk = k.GraphKernel(kernel=[{"name": "WL", "n_iter": 3}, "subtree_wl"], normalize=True)
+    _same(gk.fit_transform([X[i] for i in tr]), ref["wl_h3_norm_train"])
+    # PSD like grakel/tests/test_kernels.py:516-520
+    assert np.linalg.eigvalsh(k.WeisfeilerLehman(n_iter=5).fit_transform(X)).min() > -1e-5
+
+
+def test_config1_gram_labels_and_dims(eng):
+    k = _k()
+    ref = np.load(os.path.join(G, "config1_out.npz"))
+    X = gen(188, 18, 0)
+    wl = k.WeisfeilerLehman(n_iter=3)
+    K = wl.fit_transform(X)
+    _same(K, ref["K"])
+    assert list(wl.stats_.level_dims[:4]) == ref["D"].tolist()
+    _same(wl.diagonal(), np.diagonal(ref["K"]))
+    _same(k.WeisfeilerLehman(n_iter=3, normalize=True).fit_transform(X), ref["Knorm"])
+    # label partition parity per level against the oracle
+    o = WLOracle(n_iter=3)
+    _, levels = o.fit_transform(X, return_levels=True)
+    parts = wl_partitions(levels)
+    V = wl.X.block.n_vertices
+    for lv in range(4):
+        dev = eng.wl_labels(lv, V).astype(np.int64)
+        ren = {}
+        canon = np.fromiter((ren.setdefault(int(x), len(ren)) for x in dev), dtype=np.int64, count=V)
+        assert np.array_equal(canon, parts[lv]), f"level {lv} partition differs"
+        if lv:  # device ids are already first-occurrence ranks
+            assert np.array_equal(dev, canon)
+    # exact CUDA-core Gram == tensor-core Gram
+    Ks, _, _ = eng.gram(188, simt=True)
+    _same(Ks, ref["K"])
+    Kf, _, _ = eng.gram(188, dtype=np.float32, full_tiles=True)
+    _same(Kf.astype(np.float64), ref["K"])
+
+
+def test_vertex_histogram_is_level0():
+    k = _k()
+    X = gen(60, 12, 5)
+    K = k.VertexHistogram().fit_transform(X)
+    Ko = WLOracle(n_iter=1)
+    Ko.fit_transform(X)
+    _same(K, Ko.levels[0].gram())
+
+
+def test_high_degree_and_empty_edge_graphs():
+    """degree > 32 goes through the warp-per-vertex signature kernel; graphs without
+    edges and isolated vertices still count (they add to K)."""
+    k = _k()
+    rs = np.random.RandomState(3)
+    X = []
+    for n in (70, 150, 40):
+        A = np.zeros((n, n))
+        A[0, 1:] = A[1:, 0] = 1  # star: hub degree n-1
+        extra = rs.rand(n, n) < 0.05
+        A = ((A + extra + extra.T) > 0).astype(float)
+        np.fill_diagonal(A, 0)
+        X.append([A, {i: int(rs.randint(3)) for i in range(n)}])
+    X.append([np.zeros((5, 5)), {i: i % 2 for i in range(5)}])
+    X.append([{(0, 0): 1.0}, {0: 1}])  # single vertex with a self loop
+    for h in (1, 4):
+        _same(k.WeisfeilerLehman(n_iter=h).fit_transform(X), WLOracle(n_iter=h).fit_transform(X))
+    with np.errstate(all="ignore"):
+        _same(k.ShortestPath().fit_transform(X[:4]), SPOracle().fit_transform(X[:4]))
+
+
+# --------------------------------------------------------------- SP
+def test_apsp_known_answers(eng):
+    """grakel/tests/test_graph.py:40,62-65 and doc/documentation/introduction.rst:313-343."""
+    k = _k()
+    from grakel_b200.packing import pack, label_ids
+    inf = float("inf")
+    exp = np.array([[0.0, 1.0, inf, 3.0], [1.0, 0.0, inf, 2.0], [2.0, 3.0, 0.0, 1.0], [1.0, 2.0, inf, 0.0]])
+    A = np.array([[1, 1, 0, 3], [1, 0, 0, 2], [2, 3, 0, 1], [1, 0, 0, 0]])
+    lab = {0: "banana", 1: "cherry", 2: "banana", 3: "cherry"}
+    D = {"a": {"a": 1, "b": 1, "d": 3}, "b": {"a": 1, "d": 2}, "c": {"a": 2, "b": 3, "d": 1}, "d": {"a": 1}}
+    for g, L in ((A, lab), (D, {"a": "banana", "b": "cherry", "c": "banana", "d": "cherry"})):
+        b = pack([[g, L]], "sp", want_weights=True)
+        ids, _ = label_ids(b.labels, None, sort_new=False)
+        eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, ids, b.weights)
+        eng.sp_features(with_labels=True, keep_dist=True)
+        assert np.array_equal(eng.sp_distances(0, 4), exp)
+    H2O = [[[0, 1, 1], [1, 0, 0], [1, 0, 0]], {0: "O", 1: "H", 2: "H"}]
+    H3O = [[[0, 1, 1, 1], [1, 0, 0, 0], [1, 0, 0, 0], [1, 0, 0, 0]], {0: "O", 1: "H", 2: "H", 3: "H"}]
+    sp = k.ShortestPath()
+    assert sp.fit_transform([H2O]).tolist() == [[12.0]]
+    assert sp.transform([H3O]).tolist() == [[24.0]]
+    sp = k.ShortestPath(normalize=True)
+    assert sp.fit_transform([H2O]).tolist() == [[1.0]]
+    assert abs(sp.transform([H3O])[0, 0] - 0.94280904) < 1e-8
+
+
+def test_config3_small_and_large_graph_path():
+    k = _k()
+    ref = np.load(os.path.join(G, "config3_small_out.npz"))
+    sp = k.ShortestPath()
+    _same(sp.fit_transform(gen(40, 60, 0, as_adj=True)), ref["K"])
+    assert int(sp.stats_.n_columns) == int(ref["D"])
+    # graphs whose distance matrix does not fit shared memory use the global-memory path
+    X = gen(3, 420, 9, as_adj=True) + gen(5, 30, 9, as_adj=True)
+    _same(k.ShortestPath().fit_transform(X), SPOracle().fit_transform(X))
+    _same(k.ShortestPath(with_labels=False).fit_transform(X), SPOracle(with_labels=False).fit_transform(X))
+
+
+# --------------------------------------------------------------- BASELINE sizes
+def test_config2_full_size_properties():
+    """N = 10 000, h = 5 (BASELINE config 2): checksums + sampled rows from the real
+    reference run (tests/golden/make_golden.py --big) and size-independent properties."""
+    k = _k()
+    rows = np.load(os.path.join(G, "config2_rows.npz"))
+    big = gio.load(os.path.join(G, "big_summaries.json.gz"))["config2"]
+    X = gen(10000, 40, 0)
+    wl = k.WeisfeilerLehman(n_iter=5)
+    K = wl.fit_transform(X)
+    assert K.shape == (10000, 10000)
+    assert list(wl.stats_.level_dims[:6]) == big["D"]
+    assert float(K.sum()) == big["sum"] == 22925628586.0
+    assert float(np.trace(K)) == big["trace"] and float(K.max()) == big["max"]
+    assert np.array_equal(K[rows["rows"]], rows["K_rows"].astype(np.float64))
+    assert np.array_equal(np.diagonal(K), rows["diag"].astype(np.float64))
+    assert np.array_equal(K, K.T)  # symmetry (mirrored tiles)
+    assert int(wl.stats_.gram_path) == 1  # tensor-core path
+
+
+def test_config3_full_size_properties():
+    k = _k()
+    rows = np.load(os.path.join(G, "config3_rows.npz"))
+    big = gio.load(os.path.join(G, "big_summaries.json.gz"))["config3"]
+    sp = k.ShortestPath()
+    K = sp.fit_transform(gen(5000, 60, 0, as_adj=True))
+    assert int(sp.stats_.n_columns) == big["D"] == 476
+    assert float(K.sum()) == big["sum"] and float(np.trace(K)) == big["trace"] and float(K.max()) == big["max"]
+    assert np.array_equal(K[rows["rows"]], rows["K_rows"].astype(np.float64))
+    assert np.array_equal(K, K.T)

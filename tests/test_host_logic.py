@@ -1,0 +1,193 @@
+"""CPU tests: host packing / label dictionaries / estimator protocol / C-ABI symbols.
+No GPU compute here (run with -m "not gpu")."""
+import ctypes
+import os
+import pickle
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+import blockref
+import gio
+from grakel_b200 import GraphKernel, ShortestPath, VertexHistogram, WeisfeilerLehman, _lib
+from grakel_b200.packing import Block, Graph, label_ids, pack
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def _wl_host(X, Y, h, norm):
+    bx = pack(X, "wl", len_ok=lambda n: n >= 2)
+    ix, dic = label_ids(bx.labels, None)
+    Kx, _, _ = blockref.wl_gram_block(bx, ix, h, normalize=norm)
+    if Y is None:
+        return Kx, None
+    by = pack(Y, "wl")
+    iy, _ = label_ids(by.labels, dic)
+    Kt, _, _ = blockref.wl_gram_block(Block.concat(bx, by), np.concatenate([ix, iy]), h, n_fit=bx.n_graphs,
+                                      normalize=norm)
+    return Kx, Kt
+
+
+def _sp_host(X, Y, wlab, alg, norm):
+    kw = dict(need_labels=wlab, want_weights=True, fw_zero_is_absent=alg == "floyd_warshall",
+              len_ok=lambda n: n in (2, 3) or (n == 1 and not wlab))
+    bx = pack(X, "sp", **kw)
+    ix, dic = label_ids(bx.labels, None, sort_new=False) if wlab else (np.zeros(bx.n_vertices, int), {})
+    with np.errstate(all="ignore"):
+        Kx, _, _ = blockref.sp_gram_block(bx, ix, with_labels=wlab, normalize=norm)
+        if Y is None:
+            return Kx, None
+        by = pack(Y, "sp", **kw)
+        iy = label_ids(by.labels, dic, sort_new=False)[0] if wlab else np.zeros(by.n_vertices, int)
+        Kt, _, _ = blockref.sp_gram_block(Block.concat(bx, by), np.concatenate([ix, iy]), n_fit=bx.n_graphs,
+                                          with_labels=wlab, normalize=norm)
+    return Kx, Kt
+
+
+def _check(X, Y, out, skip_dijkstra_real=False):
+    for key, rec in out.items():
+        parts = key.split("_")
+        if "error" in rec:
+            continue
+        if parts[0] == "wl":
+            Kx, Kt = _wl_host(X, Y, int(parts[1][1:]), parts[2] == "n")
+        else:
+            alg = "_".join(parts[2:-1])
+            if skip_dijkstra_real and alg == "dijkstra":
+                continue
+            Kx, Kt = _sp_host(X, Y, parts[1] == "l", alg, parts[-1] == "n")
+        assert np.array_equal(Kx, np.asarray(rec["fit_transform"], dtype=float), equal_nan=True), key
+        if "transform" in rec:
+            assert np.array_equal(Kt, np.asarray(rec["transform"], dtype=float), equal_nan=True), key
+
+
+def test_packing_all_spellings_match_reference():
+    g = gio.load(os.path.join(G, "spellings.json.gz"))
+    for name, case in g["cases"].items():
+        _check(gio.dec_dataset(case["X"]), None, case["out"])
+
+
+@pytest.mark.parametrize("tag", ["unit", "intw"])
+def test_joint_relabel_equals_fit_dictionaries(tag):
+    """transform(Y) through joint relabelling of X||Y == the reference's dictionary replay,
+    on data whose test split contains labels unseen at fit time."""
+    d = gio.load(os.path.join(G, "fit_transform.json.gz"))[tag]
+    _check(gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"]), d["out"])
+
+
+def test_mutag_host_model():
+    X = gio.dec_dataset(gio.load(os.path.join(G, "mutag_graphs.json.gz")))
+    ref = np.load(os.path.join(G, "mutag_out.npz"))
+    K, _ = _wl_host(X, None, 3, False)
+    assert np.array_equal(K, ref["wl_h3"])
+
+
+def test_block_concat_offsets():
+    X = gio.dec_dataset(gio.load(os.path.join(G, "spellings.json.gz"))["cases"]["mixed_isolated"]["X"])
+    b = pack(X, "wl", len_ok=lambda n: n >= 2)
+    c = Block.concat(b, b)
+    assert c.n_graphs == 2 * b.n_graphs and c.n_vertices == 2 * b.n_vertices
+    assert np.array_equal(c.col_idx[len(b.col_idx):], b.col_idx + b.n_vertices)
+    assert c.row_ptr[-1] == 2 * len(b.col_idx)
+    for g in range(c.n_graphs):  # neighbours stay inside their graph
+        v0, v1 = c.graph_ptr[g], c.graph_ptr[g + 1]
+        nb = c.col_idx[c.row_ptr[v0]:c.row_ptr[v1]]
+        assert nb.size == 0 or (nb.min() >= v0 and nb.max() < v1)
+
+
+def test_error_behaviour_matches_reference():
+    wl = WeisfeilerLehman(n_iter=2)
+    with pytest.raises(TypeError):
+        wl.fit_transform(5)  # weisfeiler_lehman.py:144
+    with pytest.raises(ValueError):
+        wl.fit_transform(None)  # :319
+    with pytest.raises(ValueError):
+        wl.fit([])  # :194 parsed input is empty
+    with pytest.raises(TypeError):
+        WeisfeilerLehman(n_iter=0).fit([[{(0, 1): 1}, {0: 1, 1: 2}]])  # :112-113
+    with pytest.raises(TypeError):
+        WeisfeilerLehman(n_iter=2, base_graph_kernel=3).fit([[{(0, 1): 1}, {0: 1, 1: 2}]])  # :87
+    with pytest.raises(TypeError):
+        wl.fit([[{(0, 1): 1}]])  # element of length 1 (:182)
+    with pytest.raises(ValueError):
+        ShortestPath(algorithm_type="bfs").fit([[{(0, 1): 1}, {0: 1, 1: 2}]])  # shortest_path.py:252
+    with pytest.raises(ValueError):
+        wl.fit([["not a graph", {0: 1}]])  # graph.py:214
+    with pytest.raises(TypeError):
+        wl.fit([[{(0, 1): 1, (1, 0): 1}, {0: "a", 1: 3}]])  # unsortable label alphabet (:204)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        wl.fit([[], [{(0, 1): 1, (1, 0): 1}, {0: 1, 1: 2}]])  # empty element is skipped (:153-155)
+        assert any("Ignoring empty element" in str(x.message) for x in w)
+    assert wl._nx == 1
+    from sklearn.exceptions import NotFittedError
+    with pytest.raises(NotFittedError):
+        WeisfeilerLehman().transform([[{(0, 1): 1}, {0: 1, 1: 2}]])
+
+
+def test_fitted_estimators_pickle_and_clone():
+    """grakel/tests/test_common.py:53-58: fitted kernels must pickle; sklearn clone / set_params work."""
+    from sklearn.base import clone
+    X = gio.dec_dataset(gio.load(os.path.join(G, "spellings.json.gz"))["cases"]["dict_tuple"]["X"])
+    for est in (WeisfeilerLehman(n_iter=2, normalize=True), ShortestPath(), VertexHistogram(),
+                GraphKernel(kernel=[{"name": "WL", "n_iter": 2}, "subtree_wl"])):
+        est.fit(X)
+        e2 = pickle.loads(pickle.dumps(est))
+        assert type(e2) is type(est)
+        c = clone(est)
+        assert c.get_params().keys() == est.get_params().keys()
+    wl = WeisfeilerLehman(n_iter=2).fit(X)
+    assert wl._n_iter == 3 and wl._nx == 2 and 0 in wl._inv_labels
+    wl.set_params(n_iter=4)
+    assert wl._initialized["n_iter"] is False
+    wl.fit(X)
+    assert wl._n_iter == 5
+
+
+def test_graphkernel_dispatch():
+    gk = GraphKernel(kernel=[{"name": "weisfeiler_lehman", "n_iter": 3}, {"name": "vertex_histogram"}], normalize=True)
+    gk.initialize()
+    assert isinstance(gk.kernel_, WeisfeilerLehman) and gk.kernel_.n_iter == 3 and gk.kernel_.normalize is True
+    gk = GraphKernel(kernel={"name": "SP", "with_labels": False})
+    gk.initialize()
+    assert isinstance(gk.kernel_, ShortestPath) and gk.kernel_.with_labels is False
+    gk = GraphKernel(kernel="ST-WL")
+    gk.initialize()
+    assert isinstance(gk.kernel_, VertexHistogram)
+    with pytest.raises(ValueError):
+        GraphKernel(kernel="no_such_kernel").initialize()
+    with pytest.raises(NotImplementedError):
+        GraphKernel(kernel="random_walk").initialize()
+
+
+def test_graph_carrier_accepted():
+    A = np.array([[0, 1], [1, 0]])
+    b = pack([Graph(A, {0: "a", 1: "b"})], "wl", len_ok=lambda n: n >= 2)
+    assert b.n_graphs == 1 and b.labels == ["a", "b"]
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """The shared library must load on a CPU-only box and export every gk_* entry point
+    that include/grakel_b200.h declares (no compute calls here)."""
+    hdr = open(os.path.join(ROOT, "include", "grakel_b200.h")).read()
+    declared = set(re.findall(r"\b(gk_[a-z0-9_]+)\s*\(", hdr))
+    assert {"gk_create", "gk_pack_csr", "gk_wl_features", "gk_sp_features", "gk_gram",
+            "gk_wl_fit_transform"} <= declared
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.exported_symbols())
+    _lib.load_library().gk_version.restype = ctypes.c_int
+    assert _lib.load_library().gk_version() >= 100
+
+
+def test_no_gpu_means_loud_failure():
+    """Without a B200 the engine must raise, never fall back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(Exception):
+        WeisfeilerLehman(n_iter=1).fit_transform([[{(0, 1): 1, (1, 0): 1}, {0: 1, 1: 2}]])
