@@ -200,7 +200,7 @@ def main():
     for _ in range(args.warmup):
         st = step()
     barrier()
-    gemm_ms, feat_ms, panel_ms, launches = [], [], [], 0
+    gemm_ms, feat_ms, panel_ms, tail_ms, launches = [], [], [], [], 0
     with ClockSampler(local) as clk:
         eng.event_record(0)
         t0 = time.perf_counter()
@@ -209,6 +209,7 @@ def main():
             gemm_ms.append(st.ms_gemm)
             feat_ms.append(st.ms_features)
             panel_ms.append(st.ms_panel)
+            tail_ms.append(st.ms_tail)
             launches += int(st.kernel_launches + st.gemm_launches)
         eng.event_record(1)
         dev_ms = eng.event_elapsed(0, 1)
@@ -257,6 +258,19 @@ def main():
             dist.destroy_process_group()
         return
 
+    # the tensor-bound configuration of the same GEMM kernel (every shared column dense), for the
+    # "GEMM % of tensor-core peak" half of the BASELINE metric
+    dense = None
+    if world == 1:
+        ds = _lib.GkStats()
+        dms = []
+        for i in range(3 + 5):
+            eng.gram(n, out=False, dtype=np.float32, stats=ds, want_diag=False, dense_all=True)
+            if i >= 3:
+                dms.append(ds.ms_gemm)
+        dflops = float(n) * (n + 1) * int(ds.n_dense_columns)
+        dense = {"dense_columns": int(ds.n_dense_columns), "ms_per_launch": float(np.mean(dms)),
+                 "flops_per_launch": dflops, "achieved_tflops": dflops / (np.mean(dms) * 1e-3) / 1e12}
     peak_tf, peak_hbm, peak_src = peaks()
     Dc = int(st.n_dense_columns)
     g_ms = float(np.mean(gemm_ms))
@@ -281,7 +295,10 @@ def main():
                      "traffic": None, "peak_source": peak_src, "flops_per_launch": flops, "ms_per_launch": g_ms,
                      "share_of_step": g_ms / ms_step},
         "stages_ms": {"wl_features": float(np.mean(feat_ms)), "columns+panel": float(np.mean(panel_ms)),
-                      "gram_gemm": g_ms, "wall_ms_per_step": wall_ms / args.steps},
+                      "gram_gemm": g_ms, "tail_pairs": float(np.mean(tail_ms)), "wall_ms_per_step": wall_ms / args.steps},
+        "head_tail": {"threshold_T": int(st.threshold), "head_columns": Dc, "tail_columns": int(st.n_tail_columns),
+                      "tail_pair_updates": int(st.tail_updates)},
+        "dense_gemm_mode": dense,
     }
     if not args.no_cpu and world == 1:
         val, t = cpu_arm(CPU_SAMPLE)

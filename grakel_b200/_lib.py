@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgrakel_b200.so")
 
 GK_F32, GK_F64 = 0, 1
-GK_NORMALIZE, GK_NAN_TO_NUM, GK_GRAM_SIMT, GK_OUT_DEVICE, GK_FULL_TILES = 1, 2, 4, 8, 16
+GK_NORMALIZE, GK_NAN_TO_NUM, GK_GRAM_SIMT, GK_OUT_DEVICE, GK_FULL_TILES, GK_DENSE_ALL = 1, 2, 4, 8, 16, 32
 GK_SP_WITH_LABELS, GK_SP_KEEP_DIST = 1, 2
 GK_ERR_RANGE, GK_ERR_UNSUPPORTED = -4, -5
 
@@ -26,11 +26,12 @@ class GkStats(C.Structure):
         ("n_graphs", C.c_int64), ("n_vertices", C.c_int64), ("n_edges", C.c_int64),
         ("n_levels", C.c_int64), ("level_dims", C.c_int64 * 64),
         ("n_columns", C.c_int64), ("n_entries", C.c_int64), ("n_dense_columns", C.c_int64),
+        ("n_tail_columns", C.c_int64), ("tail_updates", C.c_int64), ("threshold", C.c_int64),
         ("max_count", C.c_int64), ("max_diag", C.c_int64), ("hash_retries", C.c_int64),
         ("gram_path", C.c_int64), ("gemm_tiles", C.c_int64), ("gemm_launches", C.c_int64),
         ("kernel_launches", C.c_int64),
         ("ms_h2d", C.c_float), ("ms_features", C.c_float), ("ms_panel", C.c_float),
-        ("ms_gemm", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+        ("ms_gemm", C.c_float), ("ms_tail", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
     ]
 
     def as_dict(self):
@@ -165,7 +166,8 @@ class Engine:
         return st
 
     def gram(self, n_graphs, n_fit=None, normalize=False, nan_to_num=False, out=None, dtype=np.float64,
-             row_range=None, simt=False, full_tiles=False, stats=None, want_diag=True, device_ptr=None, ld=0):
+             row_range=None, simt=False, full_tiles=False, stats=None, want_diag=True, device_ptr=None, ld=0,
+             dense_all=False):
         """Returns (K, xdiag, ydiag).  K is a fresh C-order numpy array unless
         `out` (host array) or `device_ptr` (raw device pointer) is given."""
         n_fit = n_graphs if n_fit is None else int(n_fit)
@@ -175,7 +177,7 @@ class Engine:
         dt = np.dtype(dtype)
         code = GK_F64 if dt == np.float64 else GK_F32
         flags = (GK_NORMALIZE if normalize else 0) | (GK_NAN_TO_NUM if nan_to_num else 0)
-        flags |= (GK_GRAM_SIMT if simt else 0) | (GK_FULL_TILES if full_tiles else 0)
+        flags |= (GK_GRAM_SIMT if simt else 0) | (GK_FULL_TILES if full_tiles else 0) | (GK_DENSE_ALL if dense_all else 0)
         K = None
         kptr = None
         if device_ptr is not None:

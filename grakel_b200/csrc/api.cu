@@ -2,6 +2,7 @@
 // the reference file:line each entry point replaces).  sm_100a only.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "features.cuh"
@@ -134,12 +135,14 @@ int gk_destroy(gk_handle* h) {
   cudaStreamSynchronize(h->stream);
   gk::DevBuf* bufs[] = {&h->graph_ptr, &h->row_ptr, &h->col_idx, &h->labels0, &h->weights, &h->attrs, &h->vgraph,
                         &h->large_list, &h->labels_all, &h->sig_nbr, &h->slot_of, &h->ht_keys, &h->ht_rep,
-                        &h->flags, &h->block_sums, &h->scalars, &h->ft_keys, &h->ft_cnt, &h->colfirst,
-                        &h->collast, &h->dense_col, &h->col_block_sums, &h->diag_u64, &h->diag_f64, &h->panel,
+                        &h->flags, &h->block_sums, &h->scalars, &h->ft_keys, &h->ft_cnt, &h->colcnt_x,
+                        &h->colcnt_y, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
+                        &h->tail_ent, &h->tail_cur, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_graph_off, &h->fattr, &h->tiles,
                         &h->K, &h->K_stage};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
+  h->h_colstats.release();
   h->h_tiles.release();
   h->h_stage.release();
   for (auto& e : h->ev) cudaEventDestroy(e);
@@ -366,10 +369,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
                                             h->ht_rep.as<int>(), h->slot_of.as<int>(), h->flags.as<int>(),
                                             h->block_sums.as<int>(), sc);
       LAUNCH_CHECK(h);
-      scan_block_sums<<<1, 256, 0, h->stream>>>(nb, h->block_sums.as<int>(), &sc->level_dims[lv],
-                                                 &sc->level_base[lv], &sc->level_base[lv + 1]);
-      LAUNCH_CHECK(h);
-      wl_assign<<<nb, 256, 0, h->stream>>>((int)V, h->flags.as<int>(), h->block_sums.as<int>(), lab_out);
+      wl_assign<<<nb, 256, 0, h->stream>>>((int)V, lv, h->flags.as<int>(), h->block_sums.as<int>(), lab_out, sc);
       LAUNCH_CHECK(h);
       wl_gather_insert<<<nb, 256, 0, h->stream>>>((int)V, lv, h->slot_of.as<int>(), lab_out, h->vgraph.as<int>(),
                                                    sc, h->ft_keys.as<unsigned long long>(),
@@ -632,44 +632,76 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
 
   GK_CUDA(cudaEventRecord(h->tev[4], h->stream));
   // ---- column statistics + exact self similarities
-  const int64_t D = h->n_columns;
-  GK_TRY(h->colfirst.ensure(std::max<int64_t>(D, 1) * 4));
-  GK_TRY(h->collast.ensure(std::max<int64_t>(D, 1) * 4));
-  GK_TRY(h->dense_col.ensure(std::max<int64_t>(D, 1) * 4));
-  GK_TRY(h->flags.ensure(std::max<int64_t>(D, 1) * 4));
-  const int nbc = cdiv(std::max<int64_t>(D, 1), 256);
-  GK_TRY(h->col_block_sums.ensure((size_t)nbc * 4));
+  const int64_t D = std::max<int64_t>(h->n_columns, 1);
+  const int nbc = cdiv(D, 256);
+  GK_TRY(h->colcnt_x.ensure(D * 4));
+  GK_TRY(h->colcnt_y.ensure(D * 4));
+  GK_TRY(h->colslot.ensure(D * 4));
+  GK_TRY(h->tail_cur.ensure(D * 4));
+  GK_TRY(h->col_flags3.ensure(D * sizeof(int3)));
+  GK_TRY(h->col_block_sums.ensure((size_t)nbc * sizeof(int3)));
+  GK_TRY(h->colstats.ensure(sizeof(ColStats)));
+  GK_TRY(h->h_colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->diag_u64.ensure(N * 8));
   GK_TRY(h->diag_f64.ensure(N * 8));
-  GK_CUDA(cudaMemsetAsync(h->colfirst.p, 0x7F, std::max<int64_t>(D, 1) * 4, h->stream));
-  GK_CUDA(cudaMemsetAsync(h->collast.p, 0xFF, std::max<int64_t>(D, 1) * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->colcnt_x.p, 0, D * 4, h->stream));
+  if (!square) GK_CUDA(cudaMemsetAsync(h->colcnt_y.p, 0, D * 4, h->stream));
   GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, N * 8, h->stream));
   GK_CUDA(cudaMemsetAsync(&sc->n_entries, 0, sizeof(unsigned long long) * 3 + sizeof(long long), h->stream));
   feat_pass1<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
-      h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colfirst.as<int>(),
-      h->collast.as<int>(), h->diag_u64.as<unsigned long long>(), sc);
+      h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), (int)n_fit,
+      h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), h->diag_u64.as<unsigned long long>(), sc);
   LAUNCH_CHECK(h);
   diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, h->diag_u64.as<unsigned long long>(),
                                                    h->diag_f64.as<double>(), sc);
   LAUNCH_CHECK(h);
-  col_flags<<<nbc, 256, 0, h->stream>>>(D, (int)n_fit, (int)N, h->colfirst.as<int>(), h->collast.as<int>(),
-                                        h->flags.as<int>(), h->col_block_sums.as<int>());
-  LAUNCH_CHECK(h);
-  scan_block_sums<<<1, 256, 0, h->stream>>>(nbc, h->col_block_sums.as<int>(), &sc->n_dense, nullptr, nullptr);
-  LAUNCH_CHECK(h);
-  col_assign<<<nbc, 256, 0, h->stream>>>(D, h->flags.as<int>(), h->col_block_sums.as<int>(), h->dense_col.as<int>());
-  LAUNCH_CHECK(h);
-  DevScalars* hs;
-  GK_TRY(read_scalars(h, &hs));
-  const int64_t Dc = hs->n_dense;
-  const int64_t max_count = (int64_t)hs->max_count, max_diag = (int64_t)hs->max_diag, n_entries = (int64_t)hs->n_entries;
+
+  // ---- head / tail split.  force_T: 1 = every contributing column dense.
+  const double flops_per_col = square ? (double)k_rows * (double)(N + 1) : 2.0 * (double)k_rows * (double)k_cols;
+  const double store_seconds = (double)k_rows * (double)k_cols * (double)esz * (square && k_rows == N ? 1.0 : 1.0) / 5.0e12;
+  int force_T = (flags & (GK_GRAM_SIMT | GK_DENSE_ALL)) ? 1 : -1;
+  if (force_T < 0) {  // testing knob: GRAKEL_B200_FORCE_T=<threshold>
+    const char* e = getenv("GRAKEL_B200_FORCE_T");
+    if (e && *e) force_T = std::max(1, atoi(e));
+  }
+  ColStats* cs = h->colstats.as<ColStats>();
+  ColStats hc;
+  DevScalars* hs = nullptr;
+  int path = 1;
+  int64_t Dc = 0, max_count = 0, max_diag = 0, n_entries = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    GK_CUDA(cudaMemsetAsync(cs, 0, sizeof(ColStats), h->stream));
+    col_hist<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), cs);
+    LAUNCH_CHECK(h);
+    choose_threshold<<<1, 1, 0, h->stream>>>(cs, flops_per_col, store_seconds, force_T);
+    LAUNCH_CHECK(h);
+    col_flags<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), cs,
+                                          h->col_flags3.as<int3>(), h->col_block_sums.as<int3>());
+    LAUNCH_CHECK(h);
+    // tail descriptors: at most one per column
+    GK_TRY(h->tail_desc.ensure((size_t)D * sizeof(int2)));
+    col_assign<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->col_flags3.as<int3>(), h->col_block_sums.as<int3>(),
+                                           h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(),
+                                           h->colslot.as<int>(), h->tail_desc.as<int2>(), cs);
+    LAUNCH_CHECK(h);
+    GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, cs, sizeof(ColStats), cudaMemcpyDeviceToHost, h->stream));
+    GK_TRY(read_scalars(h, &hs));  // synchronises the stream
+    hc = *h->h_colstats.as<ColStats>();
+    Dc = hc.n_dense;
+    max_count = (int64_t)hs->max_count; max_diag = (int64_t)hs->max_diag; n_entries = (int64_t)hs->n_entries;
+    // ---- choose the Gram path
+    path = 1;
+    if ((flags & GK_GRAM_SIMT) || max_count > 256 || max_diag >= (1LL << 24)) path = 2;
+    if (path == 2 && force_T != 1) { force_T = 1; continue; }  // exact path contracts every column densely
+    break;
+  }
+  if (path == 1 && Dc == 0) path = 3;
   h->Dc = Dc;
   h->Dc_pad = (Dc + BK - 1) / BK * BK;
-
-  // ---- choose the Gram path
-  int path = 1;
-  if (Dc == 0) path = 3;
-  else if ((flags & GK_GRAM_SIMT) || max_count > 256 || max_diag >= (1LL << 24)) path = 2;
+  const int64_t n_tail_cols = hc.n_tail_cols, n_tail_ent = hc.n_tail_entries;
+  unsigned long long tail_work = 0;
+  for (int b = 0; b < HIST_BUCKETS; ++b)
+    if ((1 << b) <= hc.T) tail_work += hc.hist_work[b];
 
   // ---- output buffer
   void* d_out = nullptr;
@@ -688,6 +720,8 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   const int b0 = 0, b1 = (int)n_fit;
   const bool full_square = square && row_begin == 0 && row_end == N;
   const bool mirror = full_square && !(flags & GK_FULL_TILES);
+  const bool has_tail = path != 2 && n_tail_cols > 0;
+  const bool norm_in_epilogue = normalize && !has_tail;
 
   GramParams p;
   memset(&p, 0, sizeof(p));
@@ -703,14 +737,22 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   GK_CUDA(cudaEventRecord(h->tev[5], h->stream));
   int64_t n_tiles = 0;
   if (k_rows > 0) {
-    if (path == 1) {
-      const size_t panel_bytes = (size_t)N * h->Dc_pad * 2;
+    if (has_tail) {
+      GK_TRY(h->tail_ent.ensure((size_t)n_tail_ent * sizeof(int2)));
+      GK_CUDA(cudaMemsetAsync(h->tail_cur.p, 0, D * 4, h->stream));
+    }
+    if (path == 1 || path == 3) {
+      const size_t panel_bytes = (size_t)N * std::max<int64_t>(h->Dc_pad, BK) * 2;
       GK_TRY(h->panel.ensure(panel_bytes));
-      GK_CUDA(cudaMemsetAsync(h->panel.p, 0, panel_bytes, h->stream));
-      feat_fill_panel<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
-          h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->dense_col.as<int>(),
-          h->panel.as<__nv_bfloat16>(), h->Dc_pad);
-      LAUNCH_CHECK(h);
+      if (Dc) GK_CUDA(cudaMemsetAsync(h->panel.p, 0, panel_bytes, h->stream));
+      if (Dc || has_tail) {
+        feat_scatter<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+            h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(),
+            h->panel.as<__nv_bfloat16>(), h->Dc_pad, h->tail_cur.as<unsigned>(), h->tail_ent.as<int2>());
+        LAUNCH_CHECK(h);
+      }
+    }
+    if (path == 1) {
       std::vector<int2> tiles;
       build_tiles(tiles, a0, a1, b0, b1, mirror);
       n_tiles = (int64_t)tiles.size();
@@ -726,31 +768,54 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       p.num_k_blocks = (int)(h->Dc_pad / BK);
       const int grid = (int)std::min<int64_t>(n_tiles, h->sm_count);
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
-      if (out_dtype == GK_F64) { if (normalize) launch_tc<double, true>(h, tmA, tmB, p, grid); else launch_tc<double, false>(h, tmA, tmB, p, grid); }
-      else { if (normalize) launch_tc<float, true>(h, tmA, tmB, p, grid); else launch_tc<float, false>(h, tmA, tmB, p, grid); }
+      if (out_dtype == GK_F64) { if (norm_in_epilogue) launch_tc<double, true>(h, tmA, tmB, p, grid); else launch_tc<double, false>(h, tmA, tmB, p, grid); }
+      else { if (norm_in_epilogue) launch_tc<float, true>(h, tmA, tmB, p, grid); else launch_tc<float, false>(h, tmA, tmB, p, grid); }
       LAUNCH_CHECK(h);
     } else if (path == 2) {
-      const size_t panel_bytes = (size_t)N * Dc * 4;
+      const size_t panel_bytes = (size_t)N * std::max<int64_t>(Dc, 1) * 4;
       GK_TRY(h->panel.ensure(panel_bytes));
       GK_CUDA(cudaMemsetAsync(h->panel.p, 0, panel_bytes, h->stream));
       feat_fill_panel_u32<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
-          h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->dense_col.as<int>(),
-          h->panel.as<unsigned>(), Dc);
+          h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(),
+          h->panel.as<unsigned>(), std::max<int64_t>(Dc, 1));
       LAUNCH_CHECK(h);
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
-      if (out_dtype == GK_F64) { if (normalize) launch_simt<double, true>(h, h->panel.as<unsigned>(), Dc, (int)Dc, a0, a1, b0, b1, p); else launch_simt<double, false>(h, h->panel.as<unsigned>(), Dc, (int)Dc, a0, a1, b0, b1, p); }
-      else { if (normalize) launch_simt<float, true>(h, h->panel.as<unsigned>(), Dc, (int)Dc, a0, a1, b0, b1, p); else launch_simt<float, false>(h, h->panel.as<unsigned>(), Dc, (int)Dc, a0, a1, b0, b1, p); }
+      if (out_dtype == GK_F64) { if (normalize) launch_simt<double, true>(h, h->panel.as<unsigned>(), std::max<int64_t>(Dc, 1), (int)Dc, a0, a1, b0, b1, p); else launch_simt<double, false>(h, h->panel.as<unsigned>(), std::max<int64_t>(Dc, 1), (int)Dc, a0, a1, b0, b1, p); }
+      else { if (normalize) launch_simt<float, true>(h, h->panel.as<unsigned>(), std::max<int64_t>(Dc, 1), (int)Dc, a0, a1, b0, b1, p); else launch_simt<float, false>(h, h->panel.as<unsigned>(), std::max<int64_t>(Dc, 1), (int)Dc, a0, a1, b0, b1, p); }
       LAUNCH_CHECK(h);
     } else {
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
-      if (out_dtype == GK_F64) { if (normalize) launch_empty<double, true>(h, a0, a1, b0, b1, p); else launch_empty<double, false>(h, a0, a1, b0, b1, p); }
-      else { if (normalize) launch_empty<float, true>(h, a0, a1, b0, b1, p); else launch_empty<float, false>(h, a0, a1, b0, b1, p); }
+      if (out_dtype == GK_F64) { if (norm_in_epilogue) launch_empty<double, true>(h, a0, a1, b0, b1, p); else launch_empty<double, false>(h, a0, a1, b0, b1, p); }
+      else { if (norm_in_epilogue) launch_empty<float, true>(h, a0, a1, b0, b1, p); else launch_empty<float, false>(h, a0, a1, b0, b1, p); }
       LAUNCH_CHECK(h);
+    }
+    GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
+    if (has_tail) {
+      const int grid = cdiv(n_tail_cols * 32, 256);
+      if (out_dtype == GK_F64)
+        tail_pairs<double><<<grid, 256, 0, h->stream>>>(n_tail_cols, h->tail_desc.as<int2>(), h->tail_ent.as<int2>(),
+                                                        (int)n_fit, square ? 1 : 0, (int)row_begin, (int)row_end,
+                                                        (double*)d_out, d_ld);
+      else
+        tail_pairs<float><<<grid, 256, 0, h->stream>>>(n_tail_cols, h->tail_desc.as<int2>(), h->tail_ent.as<int2>(),
+                                                       (int)n_fit, square ? 1 : 0, (int)row_begin, (int)row_end,
+                                                       (float*)d_out, d_ld);
+      LAUNCH_CHECK(h);
+      if (normalize) {
+        const double* drow = h->diag_f64.as<double>() + a0;
+        const double* dcol = h->diag_f64.as<double>() + b0;
+        if (out_dtype == GK_F64)
+          normalize_rows<double><<<h->sm_count * 8, 256, 0, h->stream>>>(k_rows, k_cols, (double*)d_out, d_ld, drow, dcol, p.nan_to_num);
+        else
+          normalize_rows<float><<<h->sm_count * 8, 256, 0, h->stream>>>(k_rows, k_cols, (float*)d_out, d_ld, drow, dcol, p.nan_to_num);
+        LAUNCH_CHECK(h);
+      }
     }
   } else {
     GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
+    GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
   }
-  GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
+  GK_CUDA(cudaEventRecord(h->ev[13], h->stream));
   const int64_t launches_gram = h->launches - launches0;
 
   // ---- results to the host
@@ -768,6 +833,9 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     stats->n_graphs = N; stats->n_vertices = h->V; stats->n_edges = h->E;
     stats->n_entries = n_entries;
     stats->n_dense_columns = Dc;
+    stats->n_tail_columns = n_tail_cols;
+    stats->tail_updates = (int64_t)tail_work;
+    stats->threshold = hc.T;
     stats->max_count = max_count;
     stats->max_diag = max_diag;
     stats->gram_path = path;
@@ -775,6 +843,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     stats->gemm_launches = launches_gram;
     stats->ms_panel = ev_ms(h->tev[4], h->tev[6]);
     stats->ms_gemm = ev_ms(h->tev[6], h->tev[7]);
+    stats->ms_tail = ev_ms(h->tev[7], h->ev[13]);
     stats->ms_d2h = ev_ms(h->ev[14], h->ev[15]);
     stats->ms_total = ev_ms(h->tev[4], h->ev[15]);
   }

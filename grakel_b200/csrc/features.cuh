@@ -1,28 +1,46 @@
-// Sparse feature block -> column statistics -> dense bf16 panel.
+// Sparse feature block -> column statistics -> (dense bf16 head panel, sparse tail).
 //
 // The feature block is the (graph, column) -> count hash table filled by the WL /
 // SP feature kernels: it is the reference's per-level `csr_matrix` Phi_i
 // (vertex_histogram.py:125-150) for all levels side by side, or the dense
 // `phi_x` of ShortestPath (shortest_path.py:396-400).
 //
-// Only columns that can contribute to an off-diagonal entry are contracted on the
-// tensor cores:
-//    square case  (fit_transform): columns present in >= 2 graphs;
-//    rectangular  (transform)    : columns present in an X graph AND a Y graph
-// (this is exactly the `Y[:, :X.shape[1]]` slice of vertex_histogram.py:179 --
-// unseen columns are dropped).  Self similarities use ALL columns
-// (vertex_histogram.py:186-219) and are computed here as exact integers.
+// K = Phi Phi^T is split by column frequency m_c (number of graphs holding column c):
+//   m_c = 1 (square) / column missing from X or from Y (rectangular):
+//       contributes to self similarities only -- never contracted;
+//       the rectangular rule is exactly the `Y[:, :X.shape[1]]` slice of
+//       vertex_histogram.py:179 (unseen columns are dropped);
+//   m_c >  T : "head" -- scattered into a dense bf16 panel, contracted on the tensor cores;
+//   m_c <= T : "tail" -- m_c^2 exact atomic updates of K (config 2: 94 % of the shared
+//       columns are in <= 64 of the 10 000 graphs; contracting them densely would be
+//       18x the tensor work for 4.5 M updates).
+// T is chosen on the device from a log2 histogram of m_c with a two-term cost model.
+// Self similarities use ALL columns (vertex_histogram.py:186-219) and are exact integers.
 #pragma once
 #include "common.cuh"
 #include "wl.cuh"
 
 namespace gk {
 
-// pass 1 over the table: per-column first/last graph, per-graph sum of squares,
-// global nnz / max count.
+constexpr unsigned COL_CAP = 1u << 13;  // column counters saturate here ("certainly head")
+constexpr int HIST_BUCKETS = 16;        // bucket b: 2^(b-1) < m <= 2^b ; last = saturated
+
+struct ColStats {           // device-side, zeroed per gk_gram
+  unsigned long long hist_cols[HIST_BUCKETS];
+  unsigned long long hist_work[HIST_BUCKETS];
+  long long n_dense;        // D_c (head columns)
+  long long n_tail_cols;
+  long long n_tail_entries;
+  long long tail_work;      // pair updates the tail kernel performs
+  int T;                    // chosen threshold
+  int pad;
+};
+
+// pass 1 over the table: capped per-column graph counts (X side / Y side), per-graph
+// sum of squares, global nnz / max count.
 __global__ void __launch_bounds__(256)
 feat_pass1(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
-           int* colfirst, int* collast, unsigned long long* diag, DevScalars* sc) {
+           int n_fit, unsigned* colcnt_x, unsigned* colcnt_y, unsigned long long* diag, DevScalars* sc) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned my = 0;
   unsigned has = 0;
@@ -33,12 +51,11 @@ feat_pass1(size_t cap, const unsigned long long* __restrict__ keys, const unsign
       const unsigned c = (unsigned)k;
       my = cnt[i];
       has = 1;
-      atomicMin(&colfirst[c], g);
-      atomicMax(&collast[c], g);
+      unsigned* cc = g < n_fit ? colcnt_x : colcnt_y;
+      if (__ldcg(&cc[c]) < COL_CAP) atomicAdd(&cc[c], 1u);  // popular columns stop counting
       atomicAdd(&diag[g], (unsigned long long)my * my);
     }
   }
-  // block-level reductions before the global atomics
   unsigned mx = my, n = has;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -68,56 +85,220 @@ diag_finish(int N, const unsigned long long* __restrict__ diag, double* __restri
   if ((threadIdx.x & 31) == 0 && d) atomicMax(&sc->max_diag, d);
 }
 
-// dense-column selection flags + per-block sums (first half of the column scan)
+// does column (x, y) contribute to an off-diagonal / cross entry, and how much pair work
+__device__ __forceinline__ bool col_contributes(unsigned x, unsigned y, bool square, unsigned long long* work) {
+  if (square) {
+    *work = (unsigned long long)x * (x - 1);
+    return x >= 2;
+  }
+  *work = (unsigned long long)x * y;
+  return x >= 1 && y >= 1;
+}
+
+__device__ __forceinline__ int size_bucket(unsigned m) {
+  if (m >= COL_CAP) return HIST_BUCKETS - 1;
+  int b = 0;
+  while ((1u << b) < m) ++b;
+  return b < HIST_BUCKETS - 1 ? b : HIST_BUCKETS - 2;
+}
+
+// log2 histogram of contributing columns: count and pair work per size bucket
 __global__ void __launch_bounds__(256)
-col_flags(long long D, int n_fit, int N, const int* __restrict__ colfirst,
-          const int* __restrict__ collast, int* __restrict__ flags, int* __restrict__ block_sums) {
+col_hist(long long D, int square, const unsigned* __restrict__ colcnt_x, const unsigned* __restrict__ colcnt_y,
+         ColStats* cs) {
+  __shared__ unsigned long long hc[HIST_BUCKETS], hw[HIST_BUCKETS];
+  if (threadIdx.x < HIST_BUCKETS) { hc[threadIdx.x] = 0; hw[threadIdx.x] = 0; }
+  __syncthreads();
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int f = 0;
   if (c < D) {
-    const int a = colfirst[c], b = collast[c];
-    if (b >= 0) f = (n_fit >= N) ? (a != b) : (a < n_fit && b >= n_fit);
+    const unsigned x = colcnt_x[c], y = square ? 0u : colcnt_y[c];
+    unsigned long long work;
+    if (col_contributes(x, y, square, &work)) {
+      const int b = size_bucket(x + y);
+      atomicAdd(&hc[b], 1ULL);
+      atomicAdd(&hw[b], work);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < HIST_BUCKETS && hc[threadIdx.x]) {
+    atomicAdd(&cs->hist_cols[threadIdx.x], hc[threadIdx.x]);
+    atomicAdd(&cs->hist_work[threadIdx.x], hw[threadIdx.x]);
+  }
+}
+
+// One thread: pick T = 2^k minimising  max(t_store, head_cols * flops_per_col / rate) + tail_work * t_atomic.
+__global__ void choose_threshold(ColStats* cs, double flops_per_col, double store_seconds, int force_T) {
+  if (force_T >= 0) { cs->T = force_T; return; }
+  const double rate = 1.2e15;      // sustained dense bf16 rate of gram_tc_kernel (flop/s)
+  const double t_atomic = 1.2e-8;  // per scattered pair update of K (beyond-L2 RMW), measured order
+  double best = -1.0;
+  int best_T = 1;
+  for (int k = 0; k <= HIST_BUCKETS - 2; ++k) {
+    double head_cols = 0, tail_work = 0;
+    for (int b = 0; b < HIST_BUCKETS; ++b) {
+      if (b > k) head_cols += (double)cs->hist_cols[b];
+      else tail_work += (double)cs->hist_work[b];
+    }
+    double t_dense = head_cols * flops_per_col / rate;
+    if (head_cols > 0 && t_dense < store_seconds) t_dense = store_seconds;
+    const double t = t_dense + tail_work * t_atomic + (head_cols > 0 ? 0.0 : 0.0);
+    if (best < 0 || t < best) { best = t; best_T = 1 << k; }
+  }
+  cs->T = best_T;
+}
+
+// classification + first half of three scans (head column index, tail column index,
+// tail entry offset).  colslot: >= 0 head index, -1 unused, <= -2 tail (offset = -(v+2)).
+__global__ void __launch_bounds__(256)
+col_flags(long long D, int square, const unsigned* __restrict__ colcnt_x, const unsigned* __restrict__ colcnt_y,
+          const ColStats* __restrict__ cs, int3* __restrict__ flags, int3* __restrict__ block_sums) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int3 f = make_int3(0, 0, 0);
+  if (c < D) {
+    const unsigned x = colcnt_x[c], y = square ? 0u : colcnt_y[c];
+    unsigned long long work;
+    if (col_contributes(x, y, square, &work)) {
+      const unsigned m = x + y;
+      if (m > (unsigned)cs->T || m >= COL_CAP) f.x = 1;
+      else { f.y = 1; f.z = (int)m; }
+    }
     flags[c] = f;
   }
-  int total;
-  block_exclusive_scan_256(f, &total);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+  int t0, t1, t2;
+  block_exclusive_scan_256(f.x, &t0);
+  block_exclusive_scan_256(f.y, &t1);
+  block_exclusive_scan_256(f.z, &t2);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = make_int3(t0, t1, t2);
 }
 
 __global__ void __launch_bounds__(256)
-col_assign(long long D, const int* __restrict__ flags, const int* __restrict__ block_sums,
-           int* __restrict__ dense_col) {
+col_assign(long long D, int square, const int3* __restrict__ flags, const int3* __restrict__ block_sums,
+           const unsigned* __restrict__ colcnt_x, const unsigned* __restrict__ colcnt_y,
+           int* __restrict__ colslot, int2* __restrict__ tail_desc, ColStats* cs) {
+  __shared__ long long red[3][8];
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int f = c < D ? flags[c] : 0;
-  int total;
-  const int ex = block_exclusive_scan_256(f, &total);
-  if (c < D) dense_col[c] = f ? block_sums[blockIdx.x] + ex : -1;
+  const int3 f = c < D ? flags[c] : make_int3(0, 0, 0);
+  int t0, t1, t2;
+  const int e0 = block_exclusive_scan_256(f.x, &t0);
+  const int e1 = block_exclusive_scan_256(f.y, &t1);
+  const int e2 = block_exclusive_scan_256(f.z, &t2);
+  long long s0 = 0, s1 = 0, s2 = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += blockDim.x) {
+    const int3 b = block_sums[i];
+    s0 += b.x; s1 += b.y; s2 += b.z;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; red[2][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  long long b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { b0 += red[0][i]; b1 += red[1][i]; b2 += red[2][i]; }
+  if (c < D) {
+    int slot = -1;
+    if (f.x) slot = (int)(b0 + e0);
+    else if (f.y) {
+      const int off = (int)(b2 + e2);
+      slot = -(off + 2);
+      // x = number of X-side entries is needed by the rectangular pair loop
+      tail_desc[b1 + e1] = make_int2(off, f.z);
+    }
+    colslot[c] = slot;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    cs->n_dense = b0 + t0;
+    cs->n_tail_cols = b1 + t1;
+    cs->n_tail_entries = b2 + t2;
+  }
 }
 
-// pass 2 over the table: scatter the selected columns into the zeroed bf16 panel
+// pass 2 over the table: head entries -> zeroed bf16 panel, tail entries -> per-column lists
 __global__ void __launch_bounds__(256)
-feat_fill_panel(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
-                const int* __restrict__ dense_col, __nv_bfloat16* __restrict__ panel, long long ld) {
+feat_scatter(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
+             const int* __restrict__ colslot, __nv_bfloat16* __restrict__ panel, long long ld,
+             unsigned* __restrict__ tail_cur, int2* __restrict__ tail_ent) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   unsigned long long k = keys[i];
   if (k == EMPTY64) return;
-  const int dc = dense_col[(unsigned)k];
-  if (dc < 0) return;
-  panel[(long long)(k >> 32) * ld + dc] = __float2bfloat16_rn((float)cnt[i]);
+  const unsigned c = (unsigned)k;
+  const int slot = colslot[c];
+  if (slot == -1) return;
+  const int g = (int)(k >> 32);
+  if (slot >= 0) {
+    panel[(long long)g * ld + slot] = __float2bfloat16_rn((float)cnt[i]);
+  } else {
+    const int off = -(slot + 2);
+    const unsigned pos = atomicAdd(&tail_cur[c], 1u);
+    tail_ent[off + pos] = make_int2(g, (int)cnt[i]);
+  }
 }
 
-// same, into a u32 panel (exact CUDA-core Gram)
+// same, into a u32 panel (exact CUDA-core Gram; no tail in that mode)
 __global__ void __launch_bounds__(256)
 feat_fill_panel_u32(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
-                    const int* __restrict__ dense_col, unsigned* __restrict__ panel, long long ld) {
+                    const int* __restrict__ colslot, unsigned* __restrict__ panel, long long ld) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   unsigned long long k = keys[i];
   if (k == EMPTY64) return;
-  const int dc = dense_col[(unsigned)k];
+  const int dc = colslot[(unsigned)k];
   if (dc < 0) return;
   panel[(long long)(k >> 32) * ld + dc] = cnt[i];
+}
+
+// Tail contraction: one warp per tail column, all ordered pairs of its entries.
+//   square      : K[ga][gb] += ca*cb for a != b (the diagonal is written exactly elsewhere)
+//   rectangular : rows are Y graphs (g >= n_fit), columns X graphs (g < n_fit)
+// Values are integers < 2^24 (checked by the host), so float atomics are exact and
+// order independent.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+tail_pairs(long long n_tail_cols, const int2* __restrict__ tail_desc, const int2* __restrict__ tail_ent,
+           int n_fit, int square, int row0, int row1, OutT* __restrict__ out, long long ld) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_tail_cols) return;
+  const int2 d = tail_desc[w];
+  const int2* ent = tail_ent + d.x;
+  const int m = d.y;
+  const int mm = m * m;
+  for (int p = lane; p < mm; p += 32) {
+    const int a = p / m, b = p - a * m;
+    if (a == b) continue;
+    const int2 ea = ent[a], eb = ent[b];
+    int r, c;
+    if (square) { r = ea.x; c = eb.x; }
+    else {
+      if (ea.x < n_fit || eb.x >= n_fit) continue;
+      r = ea.x - n_fit; c = eb.x;
+    }
+    if (r < row0 || r >= row1) continue;
+    atomicAdd(&out[(long long)(r - row0) * ld + c], (OutT)((float)ea.y * (float)eb.y));
+  }
+}
+
+// normalisation pass when a tail exists: K_ij / sqrt(d_i d_j)  (+ nan_to_num)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+normalize_rows(long long rows, long long cols, OutT* __restrict__ out, long long ld,
+               const double* __restrict__ diag_rows, const double* __restrict__ diag_cols, int nan_to_num) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    double v = (double)out[r * ld + c];
+    v = v / sqrt(diag_rows[r] * diag_cols[c]);
+    if (nan_to_num) {
+      if (v != v) v = 0.0;
+      else if (isinf(v)) v = v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    }
+    out[r * ld + c] = (OutT)v;
+  }
 }
 
 }  // namespace gk

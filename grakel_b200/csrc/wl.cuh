@@ -34,14 +34,17 @@ __device__ __forceinline__ unsigned long long sig_final(unsigned long long acc, 
   return h >> 1;  // never equals EMPTY64
 }
 
-// insert (key -> min vertex id) ; returns the slot
+// insert (key -> min vertex id) ; returns the slot.  Popular signatures are hit by
+// thousands of vertices: an L2 read (ld.cg) filters out the CAS / atomicMin once the
+// key is present / the representative is already smaller, so hot slots do not serialise.
 __device__ __forceinline__ unsigned ht_insert(unsigned long long* keys, int* rep, unsigned mask,
                                               unsigned long long key, int v) {
   unsigned slot = (unsigned)(key * 0x9E3779B97F4A7C15ULL >> 20) & mask;
   while (true) {
-    unsigned long long prev = atomicCAS(&keys[slot], EMPTY64, key);
+    unsigned long long prev = __ldcg(&keys[slot]);
+    if (prev == EMPTY64) prev = atomicCAS(&keys[slot], EMPTY64, key);
     if (prev == EMPTY64 || prev == key) {
-      atomicMin(&rep[slot], v);
+      if (__ldcg(&rep[slot]) > v) atomicMin(&rep[slot], v);
       return slot;
     }
     slot = (slot + 1) & mask;
@@ -107,32 +110,50 @@ wl_sig_large(int n_large, const int* __restrict__ large_list, const int* __restr
   const int beg = row_ptr[v];
   const int deg = row_ptr[v + 1] - beg;
   int* seg = sig_nbr + beg;
-  for (int i = lane; i < deg; i += 32) seg[i] = lab_in[col_idx[beg + i]];
-  __syncwarp();
-  int n2 = 1;
-  while (n2 < deg) n2 <<= 1;
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int i = lane; i < deg; i += 32) {
-      int p = i ^ (k - 1);
-      if (p > i && p < deg) {
-        int a = seg[i], b = seg[p];
-        if (a > b) { seg[i] = b; seg[p] = a; }
+  unsigned long long t = 0;
+  if (deg <= 32) {  // one element per lane: bitonic sort in registers
+    int x = lane < deg ? lab_in[col_idx[beg + lane]] : 0x7fffffff;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        int y = __shfl_xor_sync(0xffffffffu, x, j);
+        bool up = (lane & k) == 0;
+        bool lower = (lane & j) == 0;
+        x = (lower == up) ? min(x, y) : max(x, y);
       }
     }
+    if (lane < deg) {
+      seg[lane] = x;
+      t = sig_term(x, lane, seed);
+    }
+  } else {
+    for (int i = lane; i < deg; i += 32) seg[i] = lab_in[col_idx[beg + i]];
     __syncwarp();
-    for (int j = k >> 2; j > 0; j >>= 1) {
+    int n2 = 1;
+    while (n2 < deg) n2 <<= 1;
+    for (int k = 2; k <= n2; k <<= 1) {
       for (int i = lane; i < deg; i += 32) {
-        int p = i ^ j;
+        int p = i ^ (k - 1);
         if (p > i && p < deg) {
           int a = seg[i], b = seg[p];
           if (a > b) { seg[i] = b; seg[p] = a; }
         }
       }
       __syncwarp();
+      for (int j = k >> 2; j > 0; j >>= 1) {
+        for (int i = lane; i < deg; i += 32) {
+          int p = i ^ j;
+          if (p > i && p < deg) {
+            int a = seg[i], b = seg[p];
+            if (a > b) { seg[i] = b; seg[p] = a; }
+          }
+        }
+        __syncwarp();
+      }
     }
+    for (int i = lane; i < deg; i += 32) t += sig_term(seg[i], i, seed);
   }
-  unsigned long long t = 0;
-  for (int i = lane; i < deg; i += 32) t += sig_term(seg[i], i, seed);
 #pragma unroll
   for (int j = 16; j > 0; j >>= 1) t += __shfl_xor_sync(0xffffffffu, t, j);
   if (lane == 0) {
@@ -222,15 +243,38 @@ scan_block_sums(int nb, int* block_sums, long long* dim_out, const long long* ba
   }
 }
 
-// K2b: representatives receive their dense id (rank among representatives).
+// sum of block_sums[0 .. blockIdx.x) computed by the block itself (replaces a separate
+// single-block scan launch; the array has V/256 entries and lives in L2)
+__device__ __forceinline__ long long block_prefix_of_sums(const int* __restrict__ block_sums) {
+  __shared__ long long red[8];
+  long long s = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += blockDim.x) s += block_sums[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  long long tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  __syncthreads();
+  return tot;
+}
+
+// K2b: representatives receive their dense id (rank among representatives).  The last
+// block also publishes the level's label count and the next level's first column.
 __global__ void __launch_bounds__(256)
-wl_assign(int V, const int* __restrict__ flags, const int* __restrict__ block_sums,
-          int* __restrict__ lab_out) {
+wl_assign(int V, int level, const int* __restrict__ flags, const int* __restrict__ block_sums,
+          int* __restrict__ lab_out, DevScalars* sc) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = v < V ? flags[v] : 0;
   int total;
   const int ex = block_exclusive_scan_256(f, &total);
-  if (f) lab_out[v] = block_sums[blockIdx.x] + ex;
+  const long long base = block_prefix_of_sums(block_sums);
+  if (f) lab_out[v] = (int)base + ex;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    sc->level_dims[level] = base + total;
+    sc->level_base[level + 1] = sc->level_base[level] + base + total;
+  }
 }
 
 __device__ __forceinline__ void ft_add(unsigned long long* keys, unsigned* cnt, unsigned mask,

@@ -66,6 +66,7 @@ typedef struct gk_handle gk_handle;
 #define GK_GRAM_SIMT 4   /* use the exact int64 CUDA-core Gram (verification / wide counts) */
 #define GK_OUT_DEVICE 8  /* K_out is a DEVICE pointer (e.g. a torch tensor)          */
 #define GK_FULL_TILES 16 /* square case: compute every tile, no mirroring            */
+#define GK_DENSE_ALL 32  /* contract every shared column on the tensor cores (no sparse tail) */
 
 /* gk_sp_features flags */
 #define GK_SP_WITH_LABELS 1
@@ -87,7 +88,10 @@ typedef struct gk_stats {
   int64_t level_dims[64];    /* WL: distinct labels per level (= D_i of the reference) */
   int64_t n_columns;         /* total feature columns D */
   int64_t n_entries;         /* nnz of the feature block */
-  int64_t n_dense_columns;   /* D_c: columns contracted by the tensor-core GEMM */
+  int64_t n_dense_columns;   /* D_c: "head" columns contracted by the tensor-core GEMM */
+  int64_t n_tail_columns;    /* low-frequency columns contracted by exact atomic pair updates */
+  int64_t tail_updates;      /* number of those pair updates */
+  int64_t threshold;         /* T: columns in more than T graphs are head columns */
   int64_t max_count;         /* largest single feature count */
   int64_t max_diag;          /* largest self-similarity */
   int64_t hash_retries;      /* WL: relabel passes repeated after a detected hash collision */
@@ -95,7 +99,7 @@ typedef struct gk_stats {
   int64_t gemm_tiles;        /* output tiles computed */
   int64_t gemm_launches;     /* kernels launched by the last gk_gram */
   int64_t kernel_launches;   /* kernels launched by the last features call */
-  float ms_h2d, ms_features, ms_panel, ms_gemm, ms_d2h, ms_total;
+  float ms_h2d, ms_features, ms_panel, ms_gemm, ms_tail, ms_d2h, ms_total;
 } gk_stats;
 
 int gk_version(void);

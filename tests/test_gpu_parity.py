@@ -140,6 +140,34 @@ def test_config1_gram_labels_and_dims(eng):
     _same(Kf.astype(np.float64), ref["K"])
 
 
+@pytest.mark.parametrize("T", ["1", "2", "8", "64", "4096"])
+def test_head_tail_split_is_exact_for_every_threshold(T, monkeypatch, eng):
+    """K must not depend on where the column-frequency threshold falls: all-dense (T=1),
+    mixed, and all-tail (T=4096: every shared column goes through atomic pair updates)."""
+    monkeypatch.setenv("GRAKEL_B200_FORCE_T", T)
+    k = _k()
+    ref = np.load(os.path.join(G, "config1_out.npz"))
+    X = gen(188, 18, 0)
+    wl = k.WeisfeilerLehman(n_iter=3)
+    _same(wl.fit_transform(X), ref["K"])
+    if T == "4096":
+        assert int(wl.stats_.n_dense_columns) == 0 and int(wl.stats_.n_tail_columns) > 0
+    _same(k.WeisfeilerLehman(n_iter=3, normalize=True).fit_transform(X), ref["Knorm"])
+    Kf, _, _ = eng.gram(188, dtype=np.float32)
+    _same(Kf.astype(np.float64), ref["K"])
+    d = gio.load(os.path.join(G, "fit_transform.json.gz"))["unit"]
+    Xd, Yd = gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"])
+    for key in ("wl_h4_u", "wl_h4_n"):
+        est = k.WeisfeilerLehman(n_iter=4, normalize=key.endswith("n"))
+        _same(est.fit_transform(Xd), d["out"][key]["fit_transform"])
+        _same(est.transform(Yd), d["out"][key]["transform"])
+    with np.errstate(all="ignore"):
+        for key in ("sp_l_auto_u", "sp_l_auto_n"):
+            est = k.ShortestPath(normalize=key.endswith("n"))
+            _same(est.fit_transform(Xd), d["out"][key]["fit_transform"])
+            _same(est.transform(Yd), d["out"][key]["transform"])
+
+
 def test_vertex_histogram_is_level0():
     k = _k()
     X = gen(60, 12, 5)
@@ -225,7 +253,11 @@ def test_config2_full_size_properties():
     assert np.array_equal(K[rows["rows"]], rows["K_rows"].astype(np.float64))
     assert np.array_equal(np.diagonal(K), rows["diag"].astype(np.float64))
     assert np.array_equal(K, K.T)  # symmetry (mirrored tiles)
-    assert int(wl.stats_.gram_path) == 1  # tensor-core path
+    assert int(wl.stats_.gram_path) == 1  # tensor-core path for the head columns
+    # all shared columns on the tensor cores gives the same matrix
+    from grakel_b200 import _lib
+    Kd, _, _ = _lib.get_engine().gram(10000, dtype=np.float32, dense_all=True)
+    assert np.array_equal(Kd, K.astype(np.float32))
 
 
 def test_config3_full_size_properties():
