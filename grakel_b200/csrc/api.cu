@@ -667,41 +667,58 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   ColStats* cs = h->colstats.as<ColStats>();
   ColStats hc;
   DevScalars* hs = nullptr;
+  GK_CUDA(cudaMemsetAsync(cs, 0, sizeof(ColStats), h->stream));
+  col_hist<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), cs);
+  LAUNCH_CHECK(h);
+  GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, cs, sizeof(ColStats), cudaMemcpyDeviceToHost, h->stream));
+  GK_TRY(read_scalars(h, &hs));  // the one host synchronisation of gk_gram
+  hc = *h->h_colstats.as<ColStats>();
+  const int64_t max_count = (int64_t)hs->max_count, max_diag = (int64_t)hs->max_diag, n_entries = (int64_t)hs->n_entries;
+  // ---- choose the Gram path and the head/tail threshold (host side, from the histogram)
   int path = 1;
-  int64_t Dc = 0, max_count = 0, max_diag = 0, n_entries = 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    GK_CUDA(cudaMemsetAsync(cs, 0, sizeof(ColStats), h->stream));
-    col_hist<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), cs);
-    LAUNCH_CHECK(h);
-    choose_threshold<<<1, 1, 0, h->stream>>>(cs, flops_per_col, store_seconds, force_T);
-    LAUNCH_CHECK(h);
-    col_flags<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), cs,
-                                          h->col_flags3.as<int3>(), h->col_block_sums.as<int3>());
-    LAUNCH_CHECK(h);
-    // tail descriptors: at most one per column
-    GK_TRY(h->tail_desc.ensure((size_t)D * sizeof(int2)));
-    col_assign<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->col_flags3.as<int3>(), h->col_block_sums.as<int3>(),
-                                           h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(),
-                                           h->colslot.as<int>(), h->tail_desc.as<int2>(), cs);
-    LAUNCH_CHECK(h);
-    GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, cs, sizeof(ColStats), cudaMemcpyDeviceToHost, h->stream));
-    GK_TRY(read_scalars(h, &hs));  // synchronises the stream
-    hc = *h->h_colstats.as<ColStats>();
-    Dc = hc.n_dense;
-    max_count = (int64_t)hs->max_count; max_diag = (int64_t)hs->max_diag; n_entries = (int64_t)hs->n_entries;
-    // ---- choose the Gram path
-    path = 1;
-    if ((flags & GK_GRAM_SIMT) || max_count > 256 || max_diag >= (1LL << 24)) path = 2;
-    if (path == 2 && force_T != 1) { force_T = 1; continue; }  // exact path contracts every column densely
-    break;
+  if ((flags & GK_GRAM_SIMT) || max_count > 256 || max_diag >= (1LL << 24)) { path = 2; force_T = 1; }
+  int T = 1;
+  {
+    // T = 2^k minimising  max(t_store, head_cols * flops_per_col / rate) + tail_updates * t_atomic
+    const double rate = 1.2e15;      // dense bf16 rate gram_tc_kernel sustains (flop/s)
+    const double t_atomic = 1.2e-8;  // one scattered pair update of K (RMW beyond L2)
+    double best = -1.0;
+    for (int k = 0; k <= HIST_BUCKETS - 2; ++k) {
+      double head_cols = 0, tail_upd = 0;
+      for (int b = 0; b < HIST_BUCKETS; ++b) {
+        if (b > k) head_cols += (double)hc.hist_cols[b];
+        else tail_upd += (double)hc.hist_work[b];
+      }
+      double t_dense = head_cols * flops_per_col / rate;
+      if (head_cols > 0 && t_dense < store_seconds) t_dense = store_seconds;
+      const double t = t_dense + tail_upd * t_atomic;
+      if (best < 0 || t < best) { best = t; T = 1 << k; }
+    }
+    if (force_T >= 1) T = force_T;
   }
+  int64_t Dc = 0, n_tail_cols = 0, n_tail_ent = 0;
+  unsigned long long tail_work = 0;
+  for (int b = 0; b < HIST_BUCKETS; ++b) {
+    if (b < HIST_BUCKETS - 1 && (1LL << b) <= T) {
+      n_tail_cols += (int64_t)hc.hist_cols[b];
+      n_tail_ent += (int64_t)hc.hist_entries[b];
+      tail_work += hc.hist_work[b];
+    } else {
+      Dc += (int64_t)hc.hist_cols[b];
+    }
+  }
+  hc.T = T;
+  col_flags<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), T,
+                                        h->col_flags3.as<int3>(), h->col_block_sums.as<int3>());
+  LAUNCH_CHECK(h);
+  GK_TRY(h->tail_desc.ensure((size_t)std::max<int64_t>(n_tail_cols, 1) * sizeof(int2)));
+  col_assign<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->col_flags3.as<int3>(), h->col_block_sums.as<int3>(),
+                                         h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(),
+                                         h->colslot.as<int>(), h->tail_desc.as<int2>(), cs);
+  LAUNCH_CHECK(h);
   if (path == 1 && Dc == 0) path = 3;
   h->Dc = Dc;
   h->Dc_pad = (Dc + BK - 1) / BK * BK;
-  const int64_t n_tail_cols = hc.n_tail_cols, n_tail_ent = hc.n_tail_entries;
-  unsigned long long tail_work = 0;
-  for (int b = 0; b < HIST_BUCKETS; ++b)
-    if ((1 << b) <= hc.T) tail_work += hc.hist_work[b];
 
   // ---- output buffer
   void* d_out = nullptr;

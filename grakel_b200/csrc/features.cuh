@@ -28,6 +28,7 @@ constexpr int HIST_BUCKETS = 16;        // bucket b: 2^(b-1) < m <= 2^b ; last =
 struct ColStats {           // device-side, zeroed per gk_gram
   unsigned long long hist_cols[HIST_BUCKETS];
   unsigned long long hist_work[HIST_BUCKETS];
+  unsigned long long hist_entries[HIST_BUCKETS];  // sum of m over the bucket's columns
   long long n_dense;        // D_c (head columns)
   long long n_tail_cols;
   long long n_tail_entries;
@@ -106,8 +107,8 @@ __device__ __forceinline__ int size_bucket(unsigned m) {
 __global__ void __launch_bounds__(256)
 col_hist(long long D, int square, const unsigned* __restrict__ colcnt_x, const unsigned* __restrict__ colcnt_y,
          ColStats* cs) {
-  __shared__ unsigned long long hc[HIST_BUCKETS], hw[HIST_BUCKETS];
-  if (threadIdx.x < HIST_BUCKETS) { hc[threadIdx.x] = 0; hw[threadIdx.x] = 0; }
+  __shared__ unsigned long long hc[HIST_BUCKETS], hw[HIST_BUCKETS], he[HIST_BUCKETS];
+  if (threadIdx.x < HIST_BUCKETS) { hc[threadIdx.x] = 0; hw[threadIdx.x] = 0; he[threadIdx.x] = 0; }
   __syncthreads();
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c < D) {
@@ -117,41 +118,22 @@ col_hist(long long D, int square, const unsigned* __restrict__ colcnt_x, const u
       const int b = size_bucket(x + y);
       atomicAdd(&hc[b], 1ULL);
       atomicAdd(&hw[b], work);
+      atomicAdd(&he[b], (unsigned long long)(x + y));
     }
   }
   __syncthreads();
   if (threadIdx.x < HIST_BUCKETS && hc[threadIdx.x]) {
     atomicAdd(&cs->hist_cols[threadIdx.x], hc[threadIdx.x]);
     atomicAdd(&cs->hist_work[threadIdx.x], hw[threadIdx.x]);
+    atomicAdd(&cs->hist_entries[threadIdx.x], he[threadIdx.x]);
   }
-}
-
-// One thread: pick T = 2^k minimising  max(t_store, head_cols * flops_per_col / rate) + tail_work * t_atomic.
-__global__ void choose_threshold(ColStats* cs, double flops_per_col, double store_seconds, int force_T) {
-  if (force_T >= 0) { cs->T = force_T; return; }
-  const double rate = 1.2e15;      // sustained dense bf16 rate of gram_tc_kernel (flop/s)
-  const double t_atomic = 1.2e-8;  // per scattered pair update of K (beyond-L2 RMW), measured order
-  double best = -1.0;
-  int best_T = 1;
-  for (int k = 0; k <= HIST_BUCKETS - 2; ++k) {
-    double head_cols = 0, tail_work = 0;
-    for (int b = 0; b < HIST_BUCKETS; ++b) {
-      if (b > k) head_cols += (double)cs->hist_cols[b];
-      else tail_work += (double)cs->hist_work[b];
-    }
-    double t_dense = head_cols * flops_per_col / rate;
-    if (head_cols > 0 && t_dense < store_seconds) t_dense = store_seconds;
-    const double t = t_dense + tail_work * t_atomic + (head_cols > 0 ? 0.0 : 0.0);
-    if (best < 0 || t < best) { best = t; best_T = 1 << k; }
-  }
-  cs->T = best_T;
 }
 
 // classification + first half of three scans (head column index, tail column index,
 // tail entry offset).  colslot: >= 0 head index, -1 unused, <= -2 tail (offset = -(v+2)).
 __global__ void __launch_bounds__(256)
 col_flags(long long D, int square, const unsigned* __restrict__ colcnt_x, const unsigned* __restrict__ colcnt_y,
-          const ColStats* __restrict__ cs, int3* __restrict__ flags, int3* __restrict__ block_sums) {
+          int T, int3* __restrict__ flags, int3* __restrict__ block_sums) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int3 f = make_int3(0, 0, 0);
   if (c < D) {
@@ -159,7 +141,7 @@ col_flags(long long D, int square, const unsigned* __restrict__ colcnt_x, const 
     unsigned long long work;
     if (col_contributes(x, y, square, &work)) {
       const unsigned m = x + y;
-      if (m > (unsigned)cs->T || m >= COL_CAP) f.x = 1;
+      if (m > (unsigned)T || m >= COL_CAP) f.x = 1;
       else { f.y = 1; f.z = (int)m; }
     }
     flags[c] = f;
