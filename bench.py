@@ -241,7 +241,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e2e_step()
+            es = e2e_step()
         barrier()
         e2e_t = torch.tensor([(time.perf_counter() - t0) / args.steps], device="cuda")
         if world > 1:
@@ -249,7 +249,9 @@ def main():
         e2e = {"value": n * n / float(e2e_t.item()), "unit": "pairs/s",
                "h2d_bytes_per_step": int(gp.nbytes + rp.nbytes + ci.nbytes + lab.nbytes),
                "d2h_bytes_per_step": int(kr * n * 8), "ms_per_step": float(e2e_t.item()) * 1e3,
-               "api": "gk_wl_fit_transform (C-ABI), pinned host CSR in, pinned fp64 K out"}
+               "api": "gk_wl_fit_transform (C-ABI), pinned host CSR in, pinned fp64 K out",
+               "last_step_ms": {"h2d+pack": es.ms_h2d, "features": es.ms_features, "columns+panel": es.ms_panel,
+                                "gemm": es.ms_gemm, "tail": es.ms_tail, "d2h": es.ms_d2h}}
         if rank == 0 and world == 1:
             assert float(Kh.sum()) == 22925628586.0 or n != N_GRAPHS, "K checksum differs from the reference golden"
 

@@ -185,25 +185,30 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
   if (V >= (1LL << 26)) return fail(GK_ERR_ARG, "gk_pack_csr: more than 2^26 vertices in one block");
   const int64_t E = V ? row_ptr[V] : 0;
   if (E < 0 || (E > 0 && !col_idx)) return fail(GK_ERR_ARG, "gk_pack_csr: bad row_ptr / col_idx");
-  // host-side scans: degrees, graph sizes, label alphabet, weight class
+  // host-side scans (one pass, branch-light so the compiler vectorises the inner loops):
+  // degrees, graph sizes, neighbours stay inside their graph
   int max_deg = 0, max_n = 0;
   long long hist[6] = {0, 0, 0, 0, 0, 0};  // degree <= 4, 8, 16, 32, more
-  for (int64_t v = 0; v < V; ++v) {
-    const int d = row_ptr[v + 1] - row_ptr[v];
-    if (d < 0) return fail(GK_ERR_ARG, "gk_pack_csr: row_ptr not monotone");
-    max_deg = std::max(max_deg, d);
-    hist[d <= 4 ? 0 : d <= 8 ? 1 : d <= 16 ? 2 : d <= 32 ? 3 : 4]++;
-  }
   for (int64_t g = 0; g < N; ++g) {
-    const int n = graph_ptr[g + 1] - graph_ptr[g];
-    if (n < 0) return fail(GK_ERR_ARG, "gk_pack_csr: graph_ptr not monotone");
-    max_n = std::max(max_n, n);
-  }
-  for (int64_t g = 0; g < N; ++g) {  // neighbours must stay inside their graph
     const int v0 = graph_ptr[g], v1 = graph_ptr[g + 1];
-    if (v1 == v0) continue;
-    for (int64_t e = row_ptr[v0]; e < row_ptr[v1]; ++e)
-      if (col_idx[e] < v0 || col_idx[e] >= v1) return fail(GK_ERR_ARG, "gk_pack_csr: edge leaves its graph");
+    if (v1 < v0 || v1 > V) return fail(GK_ERR_ARG, "gk_pack_csr: graph_ptr not monotone");
+    max_n = std::max(max_n, v1 - v0);
+    int bad = 0;
+    for (int v = v0; v < v1; ++v) {
+      const int d = row_ptr[v + 1] - row_ptr[v];
+      bad |= d < 0;
+      max_deg = std::max(max_deg, d);
+      hist[d <= 4 ? 0 : d <= 8 ? 1 : d <= 16 ? 2 : d <= 32 ? 3 : 4]++;
+    }
+    if (bad) return fail(GK_ERR_ARG, "gk_pack_csr: row_ptr not monotone");
+    if (v1 > v0) {
+      int lo = v0, hi = v0;
+      for (int64_t e = row_ptr[v0]; e < row_ptr[v1]; ++e) {
+        lo = std::min(lo, col_idx[e]);
+        hi = std::max(hi, col_idx[e]);
+      }
+      if (lo < v0 || hi >= v1) return fail(GK_ERR_ARG, "gk_pack_csr: edge leaves its graph");
+    }
   }
   int n_labels0 = 0;
   if (labels) {
@@ -219,15 +224,16 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
       if (weights[e] != 1.0) unit = false;
     }
   }
-  // lanes per vertex for the WL signature kernel: minimise V*G + 32*#(deg > G)
+  // WL signature kernel choice: one thread per vertex for degree <= 8 (cost ~1 lane), else
+  // 16 or 32 lanes per vertex; vertices above the width take the warp-per-vertex kernel.
   {
-    const int Gs[4] = {4, 8, 16, 32};
-    long long above[4] = {hist[1] + hist[2] + hist[3] + hist[4], hist[2] + hist[3] + hist[4], hist[3] + hist[4], hist[4]};
-    long long best = -1;
-    for (int i = 0; i < 4; ++i) {
-      long long cost = (long long)V * Gs[i] + above[i] * 32;
-      if (best < 0 || cost < best) { best = cost; h->group_width = Gs[i]; }
-    }
+    const long long above8 = hist[2] + hist[3] + hist[4], above16 = hist[3] + hist[4], above32 = hist[4];
+    const long long c8 = (long long)V * 1 + above8 * 32, c16 = (long long)V * 16 + above16 * 32,
+                    c32 = (long long)V * 32 + above32 * 32;
+    h->group_width = 8;
+    long long best = c8;
+    if (c16 < best) { best = c16; h->group_width = 16; }
+    if (c32 < best) { best = c32; h->group_width = 32; }
   }
   std::vector<int> large;
   for (int64_t v = 0; v < V; ++v)
@@ -326,7 +332,8 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   h->ht_cap = next_pow2((size_t)V * 2);
   GK_TRY(h->ht_keys.ensure(h->ht_cap * 8));
   GK_TRY(h->ht_rep.ensure(h->ht_cap * 4));
-  h->ft_cap = next_pow2((size_t)V * L * 2);
+  const size_t ft_level_cap = next_pow2((size_t)V * 2);  // one L2-sized sub-table per level
+  h->ft_cap = ft_level_cap * (size_t)L;
   if (h->ft_cap > (1ULL << 31)) return fail(GK_ERR_ARG, "gk_wl_features: feature table too large");
   GK_TRY(h->ft_keys.ensure(h->ft_cap * 8));
   GK_TRY(h->ft_cnt.ensure(h->ft_cap * 4));
@@ -344,18 +351,21 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     GK_CUDA(cudaMemcpyAsync(labels_all, h->labels0.p, V * 4, cudaMemcpyDeviceToDevice, h->stream));
     wl_insert_level0<<<nb, 256, 0, h->stream>>>((int)V, labels_all, h->vgraph.as<int>(),
                                                  h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(),
-                                                 (unsigned)(h->ft_cap - 1), sc);
+                                                 (unsigned)(ft_level_cap - 1), sc);
     LAUNCH_CHECK(h);
     for (int lv = 1; lv < L; ++lv) {
       const int* lab_in = labels_all + (size_t)(lv - 1) * V;
       int* lab_out = labels_all + (size_t)lv * V;
       GK_CUDA(cudaMemsetAsync(h->ht_keys.p, 0xFF, h->ht_cap * 8, h->stream));
       GK_CUDA(cudaMemsetAsync(h->ht_rep.p, 0x7F, h->ht_cap * 4, h->stream));
-      switch (h->group_width) {
-        case 4: launch_sig_small<4>(h, lab_in, seed); break;
-        case 8: launch_sig_small<8>(h, lab_in, seed); break;
-        case 16: launch_sig_small<16>(h, lab_in, seed); break;
-        default: launch_sig_small<32>(h, lab_in, seed); break;
+      if (h->group_width <= 8) {
+        wl_sig_thread8<<<nb, 256, 0, h->stream>>>((int)V, h->row_ptr.as<int>(), h->col_idx.as<int>(), lab_in,
+                                                  h->sig_nbr.as<int>(), seed, h->ht_keys.as<unsigned long long>(),
+                                                  h->ht_rep.as<int>(), (unsigned)(h->ht_cap - 1), h->slot_of.as<int>());
+      } else if (h->group_width == 16) {
+        launch_sig_small<16>(h, lab_in, seed);
+      } else {
+        launch_sig_small<32>(h, lab_in, seed);
       }
       LAUNCH_CHECK(h);
       if (h->n_large) {
@@ -373,7 +383,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       LAUNCH_CHECK(h);
       wl_gather_insert<<<nb, 256, 0, h->stream>>>((int)V, lv, h->slot_of.as<int>(), lab_out, h->vgraph.as<int>(),
                                                    sc, h->ft_keys.as<unsigned long long>(),
-                                                   h->ft_cnt.as<unsigned>(), (unsigned)(h->ft_cap - 1));
+                                                   h->ft_cnt.as<unsigned>(), (unsigned)(ft_level_cap - 1));
       LAUNCH_CHECK(h);
     }
     DevScalars* hs;
@@ -648,7 +658,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   if (!square) GK_CUDA(cudaMemsetAsync(h->colcnt_y.p, 0, D * 4, h->stream));
   GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, N * 8, h->stream));
   GK_CUDA(cudaMemsetAsync(&sc->n_entries, 0, sizeof(unsigned long long) * 3 + sizeof(long long), h->stream));
-  feat_pass1<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+  feat_pass1<<<h->sm_count * 16, 256, 0, h->stream>>>(
       h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), (int)n_fit,
       h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), h->diag_u64.as<unsigned long long>(), sc);
   LAUNCH_CHECK(h);
@@ -681,7 +691,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   {
     // T = 2^k minimising  max(t_store, head_cols * flops_per_col / rate) + tail_updates * t_atomic
     const double rate = 1.2e15;      // dense bf16 rate gram_tc_kernel sustains (flop/s)
-    const double t_atomic = 1.2e-8;  // one scattered pair update of K (RMW beyond L2)
+    const double t_atomic = 2.0e-11; // amortised cost of one scattered pair update of K (L2 RED throughput)
     double best = -1.0;
     for (int k = 0; k <= HIST_BUCKETS - 2; ++k) {
       double head_cols = 0, tail_upd = 0;
@@ -708,6 +718,12 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     }
   }
   hc.T = T;
+  if (getenv("GRAKEL_B200_DEBUG")) {
+    fprintf(stderr, "[gk_gram] flops_per_col %.3g store_s %.3g T %d Dc %lld tail_cols %lld tail_ent %lld\n", flops_per_col,
+            store_seconds, T, (long long)Dc, (long long)n_tail_cols, (long long)n_tail_ent);
+    for (int b = 0; b < HIST_BUCKETS; ++b)
+      fprintf(stderr, "  bucket %2d: cols %llu work %llu entries %llu\n", b, hc.hist_cols[b], hc.hist_work[b], hc.hist_entries[b]);
+  }
   col_flags<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), T,
                                         h->col_flags3.as<int3>(), h->col_block_sums.as<int3>());
   LAUNCH_CHECK(h);

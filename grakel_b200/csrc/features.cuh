@@ -37,35 +37,39 @@ struct ColStats {           // device-side, zeroed per gk_gram
   int pad;
 };
 
-// pass 1 over the table: capped per-column graph counts (X side / Y side), per-graph
-// sum of squares, global nnz / max count.
+// pass 1 over the table (grid-stride, one global atomic pair per BLOCK for the scalars):
+// capped per-column graph counts (X side / Y side), per-graph sum of squares, global
+// nnz / max count.
 __global__ void __launch_bounds__(256)
 feat_pass1(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
            int n_fit, unsigned* colcnt_x, unsigned* colcnt_y, unsigned long long* diag, DevScalars* sc) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned my = 0;
-  unsigned has = 0;
-  if (i < cap) {
-    unsigned long long k = keys[i];
-    if (k != EMPTY64) {
-      const int g = (int)(k >> 32);
-      const unsigned c = (unsigned)k;
-      my = cnt[i];
-      has = 1;
-      unsigned* cc = g < n_fit ? colcnt_x : colcnt_y;
-      if (__ldcg(&cc[c]) < COL_CAP) atomicAdd(&cc[c], 1u);  // popular columns stop counting
-      atomicAdd(&diag[g], (unsigned long long)my * my);
-    }
+  __shared__ unsigned s_mx[8], s_n[8];
+  unsigned mx = 0, n = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    if (k == EMPTY64) continue;
+    const int g = (int)(k >> 32);
+    const unsigned c = (unsigned)k;
+    const unsigned my = cnt[i];
+    mx = max(mx, my);
+    ++n;
+    unsigned* cc = g < n_fit ? colcnt_x : colcnt_y;
+    if (__ldcg(&cc[c]) < COL_CAP) atomicAdd(&cc[c], 1u);  // popular columns stop counting
+    atomicAdd(&diag[g], (unsigned long long)my * my);
   }
-  unsigned mx = my, n = has;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     n += __shfl_xor_sync(0xffffffffu, n, d);
   }
-  if ((threadIdx.x & 31) == 0 && n) {
-    atomicMax(&sc->max_count, (unsigned long long)mx);
-    atomicAdd(&sc->n_entries, (unsigned long long)n);
+  if ((threadIdx.x & 31) == 0) { s_mx[threadIdx.x >> 5] = mx; s_n[threadIdx.x >> 5] = n; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mx = max(mx, s_mx[w]); n += s_n[w]; }
+    if (n) {
+      atomicMax(&sc->max_count, (unsigned long long)mx);
+      atomicAdd(&sc->n_entries, (unsigned long long)n);
+    }
   }
 }
 

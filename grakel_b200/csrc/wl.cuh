@@ -95,6 +95,55 @@ wl_sig_small(int V, const int* __restrict__ row_ptr, const int* __restrict__ col
   }
 }
 
+// K1a': ONE THREAD per vertex for degree <= 8 (the common case of sparse graph sets:
+// molecules, ER graphs with mean degree 4).  All neighbour ids and then all neighbour
+// labels are loaded as independent requests, sorted with a fixed 19-comparator network
+// held in registers, hashed, and inserted.  8x fewer warps than the 8-lane version and
+// one dependent memory round trip less.
+#define GK_CSWAP(a, b) { const int _lo = min(a, b); const int _hi = max(a, b); a = _lo; b = _hi; }
+__global__ void __launch_bounds__(256)
+wl_sig_thread8(int V, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+               const int* __restrict__ lab_in, int* __restrict__ sig_nbr, unsigned long long seed,
+               unsigned long long* ht_keys, int* ht_rep, unsigned ht_mask, int* __restrict__ slot_of) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int beg = row_ptr[v];
+  const int deg = row_ptr[v + 1] - beg;
+  if (deg > 8) return;  // handled by wl_sig_large
+  int nb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) nb[i] = i < deg ? col_idx[beg + i] : -1;
+  int x0, x1, x2, x3, x4, x5, x6, x7;
+  x0 = nb[0] >= 0 ? lab_in[nb[0]] : 0x7fffffff;
+  x1 = nb[1] >= 0 ? lab_in[nb[1]] : 0x7fffffff;
+  x2 = nb[2] >= 0 ? lab_in[nb[2]] : 0x7fffffff;
+  x3 = nb[3] >= 0 ? lab_in[nb[3]] : 0x7fffffff;
+  x4 = nb[4] >= 0 ? lab_in[nb[4]] : 0x7fffffff;
+  x5 = nb[5] >= 0 ? lab_in[nb[5]] : 0x7fffffff;
+  x6 = nb[6] >= 0 ? lab_in[nb[6]] : 0x7fffffff;
+  x7 = nb[7] >= 0 ? lab_in[nb[7]] : 0x7fffffff;
+  const int own = lab_in[v];
+  // optimal 8-input sorting network (19 compare-exchanges)
+  GK_CSWAP(x0, x1) GK_CSWAP(x2, x3) GK_CSWAP(x4, x5) GK_CSWAP(x6, x7)
+  GK_CSWAP(x0, x2) GK_CSWAP(x1, x3) GK_CSWAP(x4, x6) GK_CSWAP(x5, x7)
+  GK_CSWAP(x1, x2) GK_CSWAP(x5, x6) GK_CSWAP(x0, x4) GK_CSWAP(x3, x7)
+  GK_CSWAP(x1, x5) GK_CSWAP(x2, x6)
+  GK_CSWAP(x1, x4) GK_CSWAP(x3, x6)
+  GK_CSWAP(x2, x4) GK_CSWAP(x3, x5)
+  GK_CSWAP(x3, x4)
+  const int xs[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+  unsigned long long t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < deg) {
+      sig_nbr[beg + i] = xs[i];
+      t += sig_term(xs[i], i, seed);
+    }
+  }
+  const unsigned long long key = sig_final(t, own, deg, seed);
+  slot_of[v] = (int)ht_insert(ht_keys, ht_rep, ht_mask, key, v);
+}
+
 // K1b: one warp per high-degree vertex; the neighbour labels are sorted in place in
 // the vertex's own segment of sig_nbr with an all-ascending bitonic network (valid
 // for any length: compare-exchanges with the virtual +inf tail are no-ops).
@@ -277,13 +326,16 @@ wl_assign(int V, int level, const int* __restrict__ flags, const int* __restrict
   }
 }
 
+// (graph, column) -> count.  `base` selects a sub-table (one per WL level) so that the
+// table being hammered by a level's insert pass stays L2-resident.
 __device__ __forceinline__ void ft_add(unsigned long long* keys, unsigned* cnt, unsigned mask,
-                                       unsigned long long key, unsigned inc, DevScalars* sc) {
+                                       unsigned long long key, unsigned inc, DevScalars* sc, size_t base = 0) {
   unsigned slot = (unsigned)(mix64(key) >> 17) & mask;
   for (int probe = 0; probe < 8192; ++probe) {
-    unsigned long long prev = atomicCAS(&keys[slot], EMPTY64, key);
+    unsigned long long prev = __ldcg(&keys[base + slot]);
+    if (prev == EMPTY64) prev = atomicCAS(&keys[base + slot], EMPTY64, key);
     if (prev == EMPTY64 || prev == key) {
-      atomicAdd(&cnt[slot], inc);
+      atomicAdd(&cnt[base + slot], inc);
       return;
     }
     slot = (slot + 1) & mask;
@@ -303,7 +355,8 @@ wl_gather_insert(int V, int level, const int* __restrict__ rep_of, int* lab_out,
   const int id = lab_out[r];
   if (r != v) lab_out[v] = id;
   const unsigned long long col = (unsigned long long)(sc->level_base[level] + id);
-  ft_add(ft_keys, ft_cnt, ft_mask, ((unsigned long long)(unsigned)vgraph[v] << 32) | col, 1u, sc);
+  ft_add(ft_keys, ft_cnt, ft_mask, ((unsigned long long)(unsigned)vgraph[v] << 32) | col, 1u, sc,
+         (size_t)level * ((size_t)ft_mask + 1));
 }
 
 __global__ void __launch_bounds__(256)
