@@ -135,8 +135,8 @@ int gk_destroy(gk_handle* h) {
   cudaStreamSynchronize(h->stream);
   gk::DevBuf* bufs[] = {&h->graph_ptr, &h->row_ptr, &h->col_idx, &h->labels0, &h->weights, &h->attrs, &h->vgraph,
                         &h->large_list, &h->labels_all, &h->sig_nbr, &h->slot_of, &h->ht_keys, &h->ht_rep,
-                        &h->flags, &h->block_sums, &h->scalars, &h->ft_keys, &h->ft_cnt, &h->colcnt_x,
-                        &h->colcnt_y, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
+                        &h->flags, &h->block_sums, &h->scalars, &h->ft_keys, &h->ft_cnt, &h->colcnt,
+                        &h->colmin, &h->colmax, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
                         &h->tail_ent, &h->tail_cur, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_graph_off, &h->fattr, &h->tiles,
                         &h->K, &h->K_stage};
@@ -297,6 +297,26 @@ static void launch_sig_small(gk_handle* h, const int* lab_in, unsigned long long
       h->ht_keys.as<unsigned long long>(), h->ht_rep.as<int>(), (unsigned)(h->ht_cap - 1), h->slot_of.as<int>());
 }
 
+// (re)allocate and clear the statistics the feature kernels maintain at insert time
+static int reset_feature_stats(gk_handle* h, int64_t col_cap, FeatStats* st) {
+  col_cap = std::max<int64_t>(col_cap, 1);
+  GK_TRY(h->colcnt.ensure(col_cap * 4));
+  GK_TRY(h->colmin.ensure(col_cap * 4));
+  GK_TRY(h->colmax.ensure(col_cap * 4));
+  GK_TRY(h->diag_u64.ensure(h->N * 8));
+  h->col_cap = col_cap;
+  GK_CUDA(cudaMemsetAsync(h->colcnt.p, 0, col_cap * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->colmin.p, 0x7F, col_cap * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->colmax.p, 0xFF, col_cap * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, h->N * 8, h->stream));
+  st->colcnt = h->colcnt.as<unsigned>();
+  st->colmin = h->colmin.as<int>();
+  st->colmax = h->colmax.as<int>();
+  st->diag = h->diag_u64.as<unsigned long long>();
+  st->sc = h->scalars.as<DevScalars>();
+  return GK_OK;
+}
+
 static int init_scalars(gk_handle* h, int n_labels0) {
   DevScalars* hs = h->h_scalars.as<DevScalars>();
   memset(hs, 0, sizeof(DevScalars));
@@ -346,12 +366,14 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     if (retries > 8) return fail(GK_ERR_STATE, "gk_wl_features: repeated hash collisions");
     const unsigned long long seed = mix64(0x5851F42D4C957F2DULL + 0x9E3779B97F4A7C15ULL * (unsigned long long)retries);
     GK_TRY(init_scalars(h, h->n_labels0));
+    FeatStats fst;
+    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, &fst));
     GK_CUDA(cudaMemsetAsync(h->ft_keys.p, 0xFF, h->ft_cap * 8, h->stream));
     GK_CUDA(cudaMemsetAsync(h->ft_cnt.p, 0, h->ft_cap * 4, h->stream));
     GK_CUDA(cudaMemcpyAsync(labels_all, h->labels0.p, V * 4, cudaMemcpyDeviceToDevice, h->stream));
     wl_insert_level0<<<nb, 256, 0, h->stream>>>((int)V, labels_all, h->vgraph.as<int>(),
                                                  h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(),
-                                                 (unsigned)(ft_level_cap - 1), sc);
+                                                 (unsigned)(ft_level_cap - 1), fst);
     LAUNCH_CHECK(h);
     for (int lv = 1; lv < L; ++lv) {
       const int* lab_in = labels_all + (size_t)(lv - 1) * V;
@@ -382,7 +404,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       wl_assign<<<nb, 256, 0, h->stream>>>((int)V, lv, h->flags.as<int>(), h->block_sums.as<int>(), lab_out, sc);
       LAUNCH_CHECK(h);
       wl_gather_insert<<<nb, 256, 0, h->stream>>>((int)V, lv, h->slot_of.as<int>(), lab_out, h->vgraph.as<int>(),
-                                                   sc, h->ft_keys.as<unsigned long long>(),
+                                                   fst, h->ft_keys.as<unsigned long long>(),
                                                    h->ft_cnt.as<unsigned>(), (unsigned)(ft_level_cap - 1));
       LAUNCH_CHECK(h);
     }
@@ -498,6 +520,8 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     h->sp_dict_cap = dict_cap;
     h->ft_cap = ft_cap;
     GK_TRY(init_scalars(h, 0));
+    FeatStats fst;
+    GK_TRY(reset_feature_stats(h, (int64_t)dict_cap, &fst));
     GK_CUDA(cudaMemsetAsync(h->sp_dict_keys.p, 0xFF, dict_cap * 8, h->stream));
     GK_CUDA(cudaMemsetAsync(h->ft_keys.p, 0xFF, ft_cap * 8, h->stream));
     GK_CUDA(cudaMemsetAsync(h->ft_cnt.p, 0, ft_cap * 4, h->stream));
@@ -514,6 +538,7 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     p.ft_cnt = h->ft_cnt.as<unsigned>();
     p.ft_mask = (unsigned)(ft_cap - 1);
     p.sc = sc;
+    p.st = fst;
     p.gdist = h->sp_dist.p;
     if (!small.empty()) {
       p.glist = lists.as<int>();
@@ -641,27 +666,18 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   DevScalars* sc = h->scalars.as<DevScalars>();
 
   GK_CUDA(cudaEventRecord(h->tev[4], h->stream));
-  // ---- column statistics + exact self similarities
+  // ---- column statistics were maintained by the feature kernels; finish the self similarities
   const int64_t D = std::max<int64_t>(h->n_columns, 1);
+  if (D > h->col_cap) return fail(GK_ERR_STATE, "gk_gram: column statistics missing");
   const int nbc = cdiv(D, 256);
-  GK_TRY(h->colcnt_x.ensure(D * 4));
-  GK_TRY(h->colcnt_y.ensure(D * 4));
   GK_TRY(h->colslot.ensure(D * 4));
   GK_TRY(h->tail_cur.ensure(D * 4));
   GK_TRY(h->col_flags3.ensure(D * sizeof(int3)));
   GK_TRY(h->col_block_sums.ensure((size_t)nbc * sizeof(int3)));
   GK_TRY(h->colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->h_colstats.ensure(sizeof(ColStats)));
-  GK_TRY(h->diag_u64.ensure(N * 8));
   GK_TRY(h->diag_f64.ensure(N * 8));
-  GK_CUDA(cudaMemsetAsync(h->colcnt_x.p, 0, D * 4, h->stream));
-  if (!square) GK_CUDA(cudaMemsetAsync(h->colcnt_y.p, 0, D * 4, h->stream));
-  GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, N * 8, h->stream));
-  GK_CUDA(cudaMemsetAsync(&sc->n_entries, 0, sizeof(unsigned long long) * 3 + sizeof(long long), h->stream));
-  feat_pass1<<<h->sm_count * 16, 256, 0, h->stream>>>(
-      h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), (int)n_fit,
-      h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), h->diag_u64.as<unsigned long long>(), sc);
-  LAUNCH_CHECK(h);
+  GK_CUDA(cudaMemsetAsync(&sc->max_diag, 0, sizeof(unsigned long long) + sizeof(long long), h->stream));
   diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, h->diag_u64.as<unsigned long long>(),
                                                    h->diag_f64.as<double>(), sc);
   LAUNCH_CHECK(h);
@@ -678,7 +694,8 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   ColStats hc;
   DevScalars* hs = nullptr;
   GK_CUDA(cudaMemsetAsync(cs, 0, sizeof(ColStats), h->stream));
-  col_hist<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), cs);
+  col_hist<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, (int)n_fit, h->colcnt.as<unsigned>(), h->colmin.as<int>(),
+                                       h->colmax.as<int>(), cs);
   LAUNCH_CHECK(h);
   GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, cs, sizeof(ColStats), cudaMemcpyDeviceToHost, h->stream));
   GK_TRY(read_scalars(h, &hs));  // the one host synchronisation of gk_gram
@@ -724,13 +741,14 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     for (int b = 0; b < HIST_BUCKETS; ++b)
       fprintf(stderr, "  bucket %2d: cols %llu work %llu entries %llu\n", b, hc.hist_cols[b], hc.hist_work[b], hc.hist_entries[b]);
   }
-  col_flags<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(), T,
-                                        h->col_flags3.as<int3>(), h->col_block_sums.as<int3>());
+  col_flags<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, (int)n_fit, h->colcnt.as<unsigned>(), h->colmin.as<int>(),
+                                        h->colmax.as<int>(), T, h->col_flags3.as<int3>(), h->col_block_sums.as<int3>());
+  LAUNCH_CHECK(h);
+  scan_sums3<<<1, 1024, 0, h->stream>>>(nbc, h->col_block_sums.as<int3>());
   LAUNCH_CHECK(h);
   GK_TRY(h->tail_desc.ensure((size_t)std::max<int64_t>(n_tail_cols, 1) * sizeof(int2)));
-  col_assign<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, h->col_flags3.as<int3>(), h->col_block_sums.as<int3>(),
-                                         h->colcnt_x.as<unsigned>(), h->colcnt_y.as<unsigned>(),
-                                         h->colslot.as<int>(), h->tail_desc.as<int2>(), cs);
+  col_assign<<<nbc, 256, 0, h->stream>>>(D, h->col_flags3.as<int3>(), h->col_block_sums.as<int3>(),
+                                         h->colslot.as<int>(), h->tail_desc.as<int2>());
   LAUNCH_CHECK(h);
   if (path == 1 && Dc == 0) path = 3;
   h->Dc = Dc;

@@ -145,7 +145,8 @@ struct gk_handle {
   int feature_kind = 0;  // 1 = WL, 2 = SP, 3 = SP-attr (dense fp32 features)
 
   // ---- columns / panel / diag
-  gk::DevBuf colcnt_x, colcnt_y, colslot, col_flags3, col_block_sums, colstats;
+  gk::DevBuf colcnt, colmin, colmax, colslot, col_flags3, col_block_sums, colstats;
+  int64_t col_cap = 0;  // allocated length of the per-column arrays
   gk::DevBuf tail_desc, tail_ent, tail_cur;
   gk::PinBuf h_colstats;
   gk::DevBuf diag_u64, diag_f64;

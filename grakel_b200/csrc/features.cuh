@@ -22,7 +22,6 @@
 
 namespace gk {
 
-constexpr unsigned COL_CAP = 1u << 13;  // column counters saturate here ("certainly head")
 constexpr int HIST_BUCKETS = 16;        // bucket b: 2^(b-1) < m <= 2^b ; last = saturated
 
 struct ColStats {           // device-side, zeroed per gk_gram
@@ -36,42 +35,6 @@ struct ColStats {           // device-side, zeroed per gk_gram
   int T;                    // chosen threshold
   int pad;
 };
-
-// pass 1 over the table (grid-stride, one global atomic pair per BLOCK for the scalars):
-// capped per-column graph counts (X side / Y side), per-graph sum of squares, global
-// nnz / max count.
-__global__ void __launch_bounds__(256)
-feat_pass1(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
-           int n_fit, unsigned* colcnt_x, unsigned* colcnt_y, unsigned long long* diag, DevScalars* sc) {
-  __shared__ unsigned s_mx[8], s_n[8];
-  unsigned mx = 0, n = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
-    const unsigned long long k = keys[i];
-    if (k == EMPTY64) continue;
-    const int g = (int)(k >> 32);
-    const unsigned c = (unsigned)k;
-    const unsigned my = cnt[i];
-    mx = max(mx, my);
-    ++n;
-    unsigned* cc = g < n_fit ? colcnt_x : colcnt_y;
-    if (__ldcg(&cc[c]) < COL_CAP) atomicAdd(&cc[c], 1u);  // popular columns stop counting
-    atomicAdd(&diag[g], (unsigned long long)my * my);
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    n += __shfl_xor_sync(0xffffffffu, n, d);
-  }
-  if ((threadIdx.x & 31) == 0) { s_mx[threadIdx.x >> 5] = mx; s_n[threadIdx.x >> 5] = n; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) { mx = max(mx, s_mx[w]); n += s_n[w]; }
-    if (n) {
-      atomicMax(&sc->max_count, (unsigned long long)mx);
-      atomicAdd(&sc->n_entries, (unsigned long long)n);
-    }
-  }
-}
 
 __global__ void __launch_bounds__(256)
 diag_finish(int N, const unsigned long long* __restrict__ diag, double* __restrict__ diag_f64,
@@ -90,14 +53,13 @@ diag_finish(int N, const unsigned long long* __restrict__ diag, double* __restri
   if ((threadIdx.x & 31) == 0 && d) atomicMax(&sc->max_diag, d);
 }
 
-// does column (x, y) contribute to an off-diagonal / cross entry, and how much pair work
-__device__ __forceinline__ bool col_contributes(unsigned x, unsigned y, bool square, unsigned long long* work) {
-  if (square) {
-    *work = (unsigned long long)x * (x - 1);
-    return x >= 2;
-  }
-  *work = (unsigned long long)x * y;
-  return x >= 1 && y >= 1;
+// does a column contribute to an off-diagonal (square) / cross (rectangular) entry, and an
+// upper bound of the pair updates it would cost in the tail
+__device__ __forceinline__ bool col_contributes(unsigned m, int gmin, int gmax, int n_fit, bool square,
+                                                unsigned long long* work) {
+  *work = (unsigned long long)m * (m - 1);
+  if (square) return m >= 2;
+  return m >= 2 && gmin < n_fit && gmax >= n_fit;
 }
 
 __device__ __forceinline__ int size_bucket(unsigned m) {
@@ -109,20 +71,20 @@ __device__ __forceinline__ int size_bucket(unsigned m) {
 
 // log2 histogram of contributing columns: count and pair work per size bucket
 __global__ void __launch_bounds__(256)
-col_hist(long long D, int square, const unsigned* __restrict__ colcnt_x, const unsigned* __restrict__ colcnt_y,
-         ColStats* cs) {
+col_hist(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt, const int* __restrict__ colmin,
+         const int* __restrict__ colmax, ColStats* cs) {
   __shared__ unsigned long long hc[HIST_BUCKETS], hw[HIST_BUCKETS], he[HIST_BUCKETS];
   if (threadIdx.x < HIST_BUCKETS) { hc[threadIdx.x] = 0; hw[threadIdx.x] = 0; he[threadIdx.x] = 0; }
   __syncthreads();
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c < D) {
-    const unsigned x = colcnt_x[c], y = square ? 0u : colcnt_y[c];
+    const unsigned m = colcnt[c];
     unsigned long long work;
-    if (col_contributes(x, y, square, &work)) {
-      const int b = size_bucket(x + y);
+    if (m && col_contributes(m, colmin[c], colmax[c], n_fit, square, &work)) {
+      const int b = size_bucket(m);
       atomicAdd(&hc[b], 1ULL);
       atomicAdd(&hw[b], work);
-      atomicAdd(&he[b], (unsigned long long)(x + y));
+      atomicAdd(&he[b], (unsigned long long)m);
     }
   }
   __syncthreads();
@@ -136,15 +98,14 @@ col_hist(long long D, int square, const unsigned* __restrict__ colcnt_x, const u
 // classification + first half of three scans (head column index, tail column index,
 // tail entry offset).  colslot: >= 0 head index, -1 unused, <= -2 tail (offset = -(v+2)).
 __global__ void __launch_bounds__(256)
-col_flags(long long D, int square, const unsigned* __restrict__ colcnt_x, const unsigned* __restrict__ colcnt_y,
-          int T, int3* __restrict__ flags, int3* __restrict__ block_sums) {
+col_flags(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt, const int* __restrict__ colmin,
+          const int* __restrict__ colmax, int T, int3* __restrict__ flags, int3* __restrict__ block_sums) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int3 f = make_int3(0, 0, 0);
   if (c < D) {
-    const unsigned x = colcnt_x[c], y = square ? 0u : colcnt_y[c];
+    const unsigned m = colcnt[c];
     unsigned long long work;
-    if (col_contributes(x, y, square, &work)) {
-      const unsigned m = x + y;
+    if (m && col_contributes(m, colmin[c], colmax[c], n_fit, square, &work)) {
       if (m > (unsigned)T || m >= COL_CAP) f.x = 1;
       else { f.y = 1; f.z = (int)m; }
     }
@@ -157,48 +118,64 @@ col_flags(long long D, int square, const unsigned* __restrict__ colcnt_x, const 
   if (threadIdx.x == 0) block_sums[blockIdx.x] = make_int3(t0, t1, t2);
 }
 
+// exclusive scan of up to ~1M int3 block sums by ONE block of 1024 threads (serial chunk per
+// thread + shuffle scan of the 1024 partials)
+__global__ void __launch_bounds__(1024)
+scan_sums3(int nb, int3* __restrict__ sums) {
+  __shared__ int3 wsum[32];
+  const int chunk = (nb + 1023) / 1024;
+  const int beg = min(nb, (int)threadIdx.x * chunk), end = min(nb, beg + chunk);
+  int3 acc = make_int3(0, 0, 0);
+  for (int i = beg; i < end; ++i) { const int3 v = sums[i]; acc.x += v.x; acc.y += v.y; acc.z += v.z; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int3 incl = acc;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int x = __shfl_up_sync(0xffffffffu, incl.x, d), y = __shfl_up_sync(0xffffffffu, incl.y, d),
+              z = __shfl_up_sync(0xffffffffu, incl.z, d);
+    if (lane >= d) { incl.x += x; incl.y += y; incl.z += z; }
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int3 w = wsum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, w.x, d), y = __shfl_up_sync(0xffffffffu, w.y, d),
+                z = __shfl_up_sync(0xffffffffu, w.z, d);
+      if (lane >= d) { w.x += x; w.y += y; w.z += z; }
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  int3 run = make_int3(incl.x - acc.x, incl.y - acc.y, incl.z - acc.z);
+  if (wid) { run.x += wsum[wid - 1].x; run.y += wsum[wid - 1].y; run.z += wsum[wid - 1].z; }
+  for (int i = beg; i < end; ++i) {
+    const int3 v = sums[i];
+    sums[i] = run;
+    run.x += v.x; run.y += v.y; run.z += v.z;
+  }
+}
+
 __global__ void __launch_bounds__(256)
-col_assign(long long D, int square, const int3* __restrict__ flags, const int3* __restrict__ block_sums,
-           const unsigned* __restrict__ colcnt_x, const unsigned* __restrict__ colcnt_y,
-           int* __restrict__ colslot, int2* __restrict__ tail_desc, ColStats* cs) {
-  __shared__ long long red[3][8];
+col_assign(long long D, const int3* __restrict__ flags, const int3* __restrict__ block_sums,
+           int* __restrict__ colslot, int2* __restrict__ tail_desc) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int3 f = c < D ? flags[c] : make_int3(0, 0, 0);
   int t0, t1, t2;
   const int e0 = block_exclusive_scan_256(f.x, &t0);
   const int e1 = block_exclusive_scan_256(f.y, &t1);
   const int e2 = block_exclusive_scan_256(f.z, &t2);
-  long long s0 = 0, s1 = 0, s2 = 0;
-  for (int i = threadIdx.x; i < (int)blockIdx.x; i += blockDim.x) {
-    const int3 b = block_sums[i];
-    s0 += b.x; s1 += b.y; s2 += b.z;
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, d);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
-  }
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; red[2][threadIdx.x >> 5] = s2; }
-  __syncthreads();
-  long long b0 = 0, b1 = 0, b2 = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { b0 += red[0][i]; b1 += red[1][i]; b2 += red[2][i]; }
+  const int3 b = block_sums[blockIdx.x];  // already exclusive (scan_sums3)
   if (c < D) {
     int slot = -1;
-    if (f.x) slot = (int)(b0 + e0);
+    if (f.x) slot = b.x + e0;
     else if (f.y) {
-      const int off = (int)(b2 + e2);
+      const int off = b.z + e2;
       slot = -(off + 2);
-      // x = number of X-side entries is needed by the rectangular pair loop
-      tail_desc[b1 + e1] = make_int2(off, f.z);
+      tail_desc[b.y + e1] = make_int2(off, f.z);
     }
     colslot[c] = slot;
-  }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-    cs->n_dense = b0 + t0;
-    cs->n_tail_cols = b1 + t1;
-    cs->n_tail_entries = b2 + t2;
   }
 }
 

@@ -55,7 +55,18 @@ struct SpParams {
   unsigned* ft_cnt;
   unsigned ft_mask;
   DevScalars* sc;
+  FeatStats st;
 };
+
+// one ft_add of `inc` occurrences + its self-similarity / max-count bookkeeping
+__device__ __forceinline__ void sp_feature_add(const SpParams& p, int g, int col, unsigned inc) {
+  bool is_new;
+  const unsigned old = ft_add(p.ft_keys, p.ft_cnt, p.ft_mask, ((unsigned long long)(unsigned)g << 32) | (unsigned)col,
+                              inc, p.st, &is_new);
+  atomicAdd(&p.st.diag[g], (unsigned long long)inc * (2ULL * old + inc));  // (old+inc)^2 - old^2
+  if (old + inc > __ldcg(&p.sc->max_count)) atomicMax(&p.sc->max_count, (unsigned long long)(old + inc));
+  if (is_new) atomicAdd(&p.sc->n_entries, 1ULL);
+}
 
 // global (lu,lv,d) dictionary: the slot index IS the column id
 __device__ __forceinline__ int sp_dict_slot(unsigned long long* keys, unsigned mask, unsigned long long key,
@@ -155,7 +166,7 @@ sp_apsp_hist(SpParams p) {
       }
       if (!done) {
         const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
-        ft_add(p.ft_keys, p.ft_cnt, p.ft_mask, ((unsigned long long)(unsigned)g << 32) | (unsigned)col, 1u, p.sc);
+        sp_feature_add(p, g, col, 1u);
       }
     }
   }
@@ -164,7 +175,7 @@ sp_apsp_hist(SpParams p) {
     const unsigned long long key = lkeys[i];
     if (key == EMPTY64) continue;
     const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
-    ft_add(p.ft_keys, p.ft_cnt, p.ft_mask, ((unsigned long long)(unsigned)g << 32) | (unsigned)col, lcnt[i], p.sc);
+    sp_feature_add(p, g, col, lcnt[i]);
   }
 }
 

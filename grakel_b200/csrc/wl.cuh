@@ -326,46 +326,118 @@ wl_assign(int V, int level, const int* __restrict__ flags, const int* __restrict
   }
 }
 
+// Per-column / per-graph statistics maintained while the feature block is being filled,
+// so that no extra pass over the (4x over-provisioned) table is needed afterwards.
+struct FeatStats {
+  unsigned* colcnt;            // graphs holding the column (saturating at COL_CAP)
+  int* colmin;                 // smallest / largest graph id holding the column
+  int* colmax;
+  unsigned long long* diag;    // per graph: sum of squared counts (exact self similarity)
+  DevScalars* sc;
+};
+constexpr unsigned COL_CAP = 1u << 13;  // column counters saturate here ("certainly head")
+
 // (graph, column) -> count.  `base` selects a sub-table (one per WL level) so that the
-// table being hammered by a level's insert pass stays L2-resident.
-__device__ __forceinline__ void ft_add(unsigned long long* keys, unsigned* cnt, unsigned mask,
-                                       unsigned long long key, unsigned inc, DevScalars* sc, size_t base = 0) {
+// table being hammered by a level's insert pass stays L2-resident.  Returns the count
+// before this insertion; *is_new is set when the (graph, column) entry was created.
+__device__ __forceinline__ unsigned ft_add(unsigned long long* keys, unsigned* cnt, unsigned mask,
+                                           unsigned long long key, unsigned inc, const FeatStats& st,
+                                           bool* is_new, size_t base = 0) {
   unsigned slot = (unsigned)(mix64(key) >> 17) & mask;
   for (int probe = 0; probe < 8192; ++probe) {
     unsigned long long prev = __ldcg(&keys[base + slot]);
-    if (prev == EMPTY64) prev = atomicCAS(&keys[base + slot], EMPTY64, key);
-    if (prev == EMPTY64 || prev == key) {
-      atomicAdd(&cnt[base + slot], inc);
-      return;
+    bool created = false;
+    if (prev == EMPTY64) {
+      prev = atomicCAS(&keys[base + slot], EMPTY64, key);
+      created = prev == EMPTY64;
+    }
+    if (created || prev == key) {
+      const unsigned old = atomicAdd(&cnt[base + slot], inc);
+      if (created) {
+        const int g = (int)(key >> 32);
+        const unsigned c = (unsigned)key;
+        if (__ldcg(&st.colcnt[c]) < COL_CAP) atomicAdd(&st.colcnt[c], 1u);
+        if (__ldcg(&st.colmin[c]) > g) atomicMin(&st.colmin[c], g);
+        if (__ldcg(&st.colmax[c]) < g) atomicMax(&st.colmax[c], g);
+      }
+      *is_new = created;
+      return old;
     }
     slot = (slot + 1) & mask;
   }
-  atomicOr(&sc->ft_overflow, 1u);  // table too small: the host grows it and repeats the pass
+  atomicOr(&st.sc->ft_overflow, 1u);  // table too small: the host grows it and repeats the pass
+  *is_new = false;
+  return 0;
+}
+
+// Block-wide bookkeeping after every thread has done (at most) one ft_add with inc == 1:
+//   diag[g] += (old+1)^2 - old^2 = 2*old + 1, aggregated over runs of equal g inside a warp
+//   (vertices of a graph are contiguous); max count and entry count once per block.
+__device__ __forceinline__ void ft_account(bool did, int g, unsigned old, bool is_new, const FeatStats& st) {
+  __shared__ unsigned s_mx[8], s_n[8];
+  const int lane = threadIdx.x & 31;
+  unsigned long long val = did ? 2ULL * old + 1ULL : 0ULL;
+  const int gg = did ? g : -1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long y = __shfl_down_sync(0xffffffffu, val, d);
+    const int gy = __shfl_down_sync(0xffffffffu, gg, d);
+    if (lane + d < 32 && gy == gg) val += y;
+  }
+  const int gprev = __shfl_up_sync(0xffffffffu, gg, 1);
+  if (did && (lane == 0 || gprev != gg)) atomicAdd(&st.diag[g], val);
+  unsigned mx = did ? old + 1 : 0, n = is_new ? 1u : 0u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    n += __shfl_xor_sync(0xffffffffu, n, d);
+  }
+  if (lane == 0) { s_mx[threadIdx.x >> 5] = mx; s_n[threadIdx.x >> 5] = n; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mx = max(mx, s_mx[w]); n += s_n[w]; }
+    if (mx > __ldcg(&st.sc->max_count)) atomicMax(&st.sc->max_count, (unsigned long long)mx);
+    if (n) atomicAdd(&st.sc->n_entries, (unsigned long long)n);
+  }
 }
 
 // K2c + K3a: every vertex takes the id of its representative; the (graph, column)
 // pair is counted into the sparse feature block (vertex_histogram.py:107-122).
 __global__ void __launch_bounds__(256)
 wl_gather_insert(int V, int level, const int* __restrict__ rep_of, int* lab_out,
-                 const int* __restrict__ vgraph, DevScalars* sc,
+                 const int* __restrict__ vgraph, FeatStats st,
                  unsigned long long* ft_keys, unsigned* ft_cnt, unsigned ft_mask) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
-  const int r = rep_of[v];
-  const int id = lab_out[r];
-  if (r != v) lab_out[v] = id;
-  const unsigned long long col = (unsigned long long)(sc->level_base[level] + id);
-  ft_add(ft_keys, ft_cnt, ft_mask, ((unsigned long long)(unsigned)vgraph[v] << 32) | col, 1u, sc,
-         (size_t)level * ((size_t)ft_mask + 1));
+  bool did = false, is_new = false;
+  int g = 0;
+  unsigned old = 0;
+  if (v < V) {
+    const int r = rep_of[v];
+    const int id = lab_out[r];
+    if (r != v) lab_out[v] = id;
+    const unsigned long long col = (unsigned long long)(st.sc->level_base[level] + id);
+    g = vgraph[v];
+    old = ft_add(ft_keys, ft_cnt, ft_mask, ((unsigned long long)(unsigned)g << 32) | col, 1u, st, &is_new,
+                 (size_t)level * ((size_t)ft_mask + 1));
+    did = true;
+  }
+  ft_account(did, g, old, is_new, st);
 }
 
 __global__ void __launch_bounds__(256)
 wl_insert_level0(int V, const int* __restrict__ lab, const int* __restrict__ vgraph,
-                 unsigned long long* ft_keys, unsigned* ft_cnt, unsigned ft_mask, DevScalars* sc) {
+                 unsigned long long* ft_keys, unsigned* ft_cnt, unsigned ft_mask, FeatStats st) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
-  ft_add(ft_keys, ft_cnt, ft_mask,
-         ((unsigned long long)(unsigned)vgraph[v] << 32) | (unsigned long long)(unsigned)lab[v], 1u, sc);
+  bool did = false, is_new = false;
+  int g = 0;
+  unsigned old = 0;
+  if (v < V) {
+    g = vgraph[v];
+    old = ft_add(ft_keys, ft_cnt, ft_mask,
+                 ((unsigned long long)(unsigned)g << 32) | (unsigned long long)(unsigned)lab[v], 1u, st, &is_new);
+    did = true;
+  }
+  ft_account(did, g, old, is_new, st);
 }
 
 // vertex -> graph id by binary search in graph_ptr
