@@ -301,17 +301,11 @@ static void launch_sig_small(gk_handle* h, const int* lab_in, unsigned long long
 static int reset_feature_stats(gk_handle* h, int64_t col_cap, FeatStats* st) {
   col_cap = std::max<int64_t>(col_cap, 1);
   GK_TRY(h->colcnt.ensure(col_cap * 4));
-  GK_TRY(h->colmin.ensure(col_cap * 4));
-  GK_TRY(h->colmax.ensure(col_cap * 4));
   GK_TRY(h->diag_u64.ensure(h->N * 8));
   h->col_cap = col_cap;
   GK_CUDA(cudaMemsetAsync(h->colcnt.p, 0, col_cap * 4, h->stream));
-  GK_CUDA(cudaMemsetAsync(h->colmin.p, 0x7F, col_cap * 4, h->stream));
-  GK_CUDA(cudaMemsetAsync(h->colmax.p, 0xFF, col_cap * 4, h->stream));
   GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, h->N * 8, h->stream));
   st->colcnt = h->colcnt.as<unsigned>();
-  st->colmin = h->colmin.as<int>();
-  st->colmax = h->colmax.as<int>();
   st->diag = h->diag_u64.as<unsigned long long>();
   st->sc = h->scalars.as<DevScalars>();
   return GK_OK;
@@ -681,6 +675,15 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, h->diag_u64.as<unsigned long long>(),
                                                    h->diag_f64.as<double>(), sc);
   LAUNCH_CHECK(h);
+  if (!square) {  // which columns occur on both the X and the Y side
+    GK_TRY(h->colmin.ensure(D * 4));
+    GK_TRY(h->colmax.ensure(D * 4));
+    GK_CUDA(cudaMemsetAsync(h->colmin.p, 0x7F, D * 4, h->stream));
+    GK_CUDA(cudaMemsetAsync(h->colmax.p, 0xFF, D * 4, h->stream));
+    feat_minmax<<<h->sm_count * 16, 256, 0, h->stream>>>(h->ft_cap, h->ft_keys.as<unsigned long long>(),
+                                                         h->colmin.as<int>(), h->colmax.as<int>());
+    LAUNCH_CHECK(h);
+  }
 
   // ---- head / tail split.  force_T: 1 = every contributing column dense.
   const double flops_per_col = square ? (double)k_rows * (double)(N + 1) : 2.0 * (double)k_rows * (double)k_cols;

@@ -36,6 +36,21 @@ struct ColStats {           // device-side, zeroed per gk_gram
   int pad;
 };
 
+// rectangular (transform) case only: smallest / largest graph id per column.  In table
+// (hash) order the running extrema converge after O(log m) updates per column, so the
+// L2-read filter removes almost all atomics even for columns present in every graph.
+__global__ void __launch_bounds__(256)
+feat_minmax(size_t cap, const unsigned long long* __restrict__ keys, int* colmin, int* colmax) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    if (k == EMPTY64) continue;
+    const int g = (int)(k >> 32);
+    const unsigned c = (unsigned)k;
+    if (__ldcg(&colmin[c]) > g) atomicMin(&colmin[c], g);
+    if (__ldcg(&colmax[c]) < g) atomicMax(&colmax[c], g);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 diag_finish(int N, const unsigned long long* __restrict__ diag, double* __restrict__ diag_f64,
             DevScalars* sc) {
@@ -59,7 +74,7 @@ __device__ __forceinline__ bool col_contributes(unsigned m, int gmin, int gmax, 
                                                 unsigned long long* work) {
   *work = (unsigned long long)m * (m - 1);
   if (square) return m >= 2;
-  return m >= 2 && gmin < n_fit && gmax >= n_fit;
+  return m >= 2 && gmin < n_fit && gmax >= n_fit;  // present on both sides
 }
 
 __device__ __forceinline__ int size_bucket(unsigned m) {
@@ -80,7 +95,7 @@ col_hist(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt
   if (c < D) {
     const unsigned m = colcnt[c];
     unsigned long long work;
-    if (m && col_contributes(m, colmin[c], colmax[c], n_fit, square, &work)) {
+    if (m && col_contributes(m, square ? 0 : colmin[c], square ? 0 : colmax[c], n_fit, square, &work)) {
       const int b = size_bucket(m);
       atomicAdd(&hc[b], 1ULL);
       atomicAdd(&hw[b], work);
@@ -105,7 +120,7 @@ col_flags(long long D, int square, int n_fit, const unsigned* __restrict__ colcn
   if (c < D) {
     const unsigned m = colcnt[c];
     unsigned long long work;
-    if (m && col_contributes(m, colmin[c], colmax[c], n_fit, square, &work)) {
+    if (m && col_contributes(m, square ? 0 : colmin[c], square ? 0 : colmax[c], n_fit, square, &work)) {
       if (m > (unsigned)T || m >= COL_CAP) f.x = 1;
       else { f.y = 1; f.z = (int)m; }
     }

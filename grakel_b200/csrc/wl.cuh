@@ -330,8 +330,6 @@ wl_assign(int V, int level, const int* __restrict__ flags, const int* __restrict
 // so that no extra pass over the (4x over-provisioned) table is needed afterwards.
 struct FeatStats {
   unsigned* colcnt;            // graphs holding the column (saturating at COL_CAP)
-  int* colmin;                 // smallest / largest graph id holding the column
-  int* colmax;
   unsigned long long* diag;    // per graph: sum of squared counts (exact self similarity)
   DevScalars* sc;
 };
@@ -354,11 +352,8 @@ __device__ __forceinline__ unsigned ft_add(unsigned long long* keys, unsigned* c
     if (created || prev == key) {
       const unsigned old = atomicAdd(&cnt[base + slot], inc);
       if (created) {
-        const int g = (int)(key >> 32);
         const unsigned c = (unsigned)key;
         if (__ldcg(&st.colcnt[c]) < COL_CAP) atomicAdd(&st.colcnt[c], 1u);
-        if (__ldcg(&st.colmin[c]) > g) atomicMin(&st.colmin[c], g);
-        if (__ldcg(&st.colmax[c]) < g) atomicMax(&st.colmax[c], g);
       }
       *is_new = created;
       return old;
@@ -374,7 +369,6 @@ __device__ __forceinline__ unsigned ft_add(unsigned long long* keys, unsigned* c
 //   diag[g] += (old+1)^2 - old^2 = 2*old + 1, aggregated over runs of equal g inside a warp
 //   (vertices of a graph are contiguous); max count and entry count once per block.
 __device__ __forceinline__ void ft_account(bool did, int g, unsigned old, bool is_new, const FeatStats& st) {
-  __shared__ unsigned s_mx[8], s_n[8];
   const int lane = threadIdx.x & 31;
   unsigned long long val = did ? 2ULL * old + 1ULL : 0ULL;
   const int gg = did ? g : -1;
@@ -392,10 +386,7 @@ __device__ __forceinline__ void ft_account(bool did, int g, unsigned old, bool i
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     n += __shfl_xor_sync(0xffffffffu, n, d);
   }
-  if (lane == 0) { s_mx[threadIdx.x >> 5] = mx; s_n[threadIdx.x >> 5] = n; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) { mx = max(mx, s_mx[w]); n += s_n[w]; }
+  if (lane == 0) {
     if (mx > __ldcg(&st.sc->max_count)) atomicMax(&st.sc->max_count, (unsigned long long)mx);
     if (n) atomicAdd(&st.sc->n_entries, (unsigned long long)n);
   }
