@@ -137,7 +137,7 @@ int gk_destroy(gk_handle* h) {
                         &h->large_list, &h->labels_all, &h->sig_nbr, &h->slot_of, &h->ht_keys, &h->ht_rep,
                         &h->flags, &h->block_sums, &h->scalars, &h->ft_keys, &h->ft_cnt, &h->colcnt,
                         &h->colmin, &h->colmax, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
-                        &h->tail_ent, &h->tail_cur, &h->diag_u64, &h->diag_f64, &h->panel,
+                        &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_graph_off, &h->fattr, &h->tiles,
                         &h->K, &h->K_stage};
   for (auto* b : bufs) b->release();
@@ -298,8 +298,16 @@ static void launch_sig_small(gk_handle* h, const int* lab_in, unsigned long long
 }
 
 // (re)allocate and clear the statistics the feature kernels maintain at insert time
-static int reset_feature_stats(gk_handle* h, int64_t col_cap, FeatStats* st) {
+static int reset_feature_stats(gk_handle* h, int64_t col_cap, int64_t n_part, FeatStats* st) {
   col_cap = std::max<int64_t>(col_cap, 1);
+  n_part = std::max<int64_t>(n_part, 1);
+  GK_TRY(h->part_max.ensure(n_part * 4));
+  GK_TRY(h->part_new.ensure(n_part * 4));
+  h->n_part = n_part;
+  GK_CUDA(cudaMemsetAsync(h->part_max.p, 0, n_part * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->part_new.p, 0, n_part * 4, h->stream));
+  st->part_max = h->part_max.as<unsigned>();
+  st->part_new = h->part_new.as<unsigned>();
   GK_TRY(h->colcnt.ensure(col_cap * 4));
   GK_TRY(h->diag_u64.ensure(h->N * 8));
   h->col_cap = col_cap;
@@ -361,7 +369,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     const unsigned long long seed = mix64(0x5851F42D4C957F2DULL + 0x9E3779B97F4A7C15ULL * (unsigned long long)retries);
     GK_TRY(init_scalars(h, h->n_labels0));
     FeatStats fst;
-    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, &fst));
+    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)nb * L, &fst));
     GK_CUDA(cudaMemsetAsync(h->ft_keys.p, 0xFF, h->ft_cap * 8, h->stream));
     GK_CUDA(cudaMemsetAsync(h->ft_cnt.p, 0, h->ft_cap * 4, h->stream));
     GK_CUDA(cudaMemcpyAsync(labels_all, h->labels0.p, V * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -515,7 +523,7 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     h->ft_cap = ft_cap;
     GK_TRY(init_scalars(h, 0));
     FeatStats fst;
-    GK_TRY(reset_feature_stats(h, (int64_t)dict_cap, &fst));
+    GK_TRY(reset_feature_stats(h, (int64_t)dict_cap, N, &fst));
     GK_CUDA(cudaMemsetAsync(h->sp_dict_keys.p, 0xFF, dict_cap * 8, h->stream));
     GK_CUDA(cudaMemsetAsync(h->ft_keys.p, 0xFF, ft_cap * 8, h->stream));
     GK_CUDA(cudaMemsetAsync(h->ft_cnt.p, 0, ft_cap * 4, h->stream));
@@ -671,9 +679,10 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   GK_TRY(h->colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->h_colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->diag_f64.ensure(N * 8));
-  GK_CUDA(cudaMemsetAsync(&sc->max_diag, 0, sizeof(unsigned long long) + sizeof(long long), h->stream));
+  GK_CUDA(cudaMemsetAsync(&sc->n_entries, 0, sizeof(unsigned long long) * 3 + sizeof(long long), h->stream));
   diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, h->diag_u64.as<unsigned long long>(),
-                                                   h->diag_f64.as<double>(), sc);
+                                                   h->diag_f64.as<double>(), (int)h->n_part,
+                                                   h->part_max.as<unsigned>(), h->part_new.as<unsigned>(), sc);
   LAUNCH_CHECK(h);
   if (!square) {  // which columns occur on both the X and the Y side
     GK_TRY(h->colmin.ensure(D * 4));

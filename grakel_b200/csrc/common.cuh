@@ -147,6 +147,8 @@ struct gk_handle {
   // ---- columns / panel / diag
   gk::DevBuf colcnt, colmin, colmax, colslot, col_flags3, col_block_sums, colstats;
   int64_t col_cap = 0;  // allocated length of the per-column arrays
+  gk::DevBuf part_max, part_new;  // per-CTA partials of the feature kernels
+  int64_t n_part = 0;
   gk::DevBuf tail_desc, tail_ent, tail_cur;
   gk::PinBuf h_colstats;
   gk::DevBuf diag_u64, diag_f64;

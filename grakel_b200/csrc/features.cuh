@@ -53,6 +53,7 @@ feat_minmax(size_t cap, const unsigned long long* __restrict__ keys, int* colmin
 
 __global__ void __launch_bounds__(256)
 diag_finish(int N, const unsigned long long* __restrict__ diag, double* __restrict__ diag_f64,
+            int n_part, const unsigned* __restrict__ part_max, const unsigned* __restrict__ part_new,
             DevScalars* sc) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long d = 0;
@@ -60,12 +61,22 @@ diag_finish(int N, const unsigned long long* __restrict__ diag, double* __restri
     d = diag[g];
     diag_f64[g] = (double)d;
   }
+  // fold the per-CTA partials of the feature kernels (max count, created entries)
+  unsigned mx = 0;
+  unsigned long long nn = 0;
+  for (int i = g; i < n_part; i += gridDim.x * blockDim.x) { mx = max(mx, part_max[i]); nn += part_new[i]; }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     unsigned long long o = __shfl_xor_sync(0xffffffffu, d, s);
     d = d > o ? d : o;
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    nn += __shfl_xor_sync(0xffffffffu, nn, s);
   }
-  if ((threadIdx.x & 31) == 0 && d) atomicMax(&sc->max_diag, d);
+  if ((threadIdx.x & 31) == 0) {
+    if (d) atomicMax(&sc->max_diag, d);
+    if (mx) atomicMax(&sc->max_count, (unsigned long long)mx);
+    if (nn) atomicAdd(&sc->n_entries, nn);
+  }
 }
 
 // does a column contribute to an off-diagonal (square) / cross (rectangular) entry, and an

@@ -27,10 +27,7 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 256;
-constexpr int EPI_WARPS = 4;
-constexpr int EPI_TILE_ELEMS = 32 * 33;  // per-warp 32x32 transpose tile, padded rows
-// stages + alignment slack + barriers + per-warp epilogue transpose tiles (sized for fp64)
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EPI_WARPS * EPI_TILE_ELEMS * 8;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GramParams {
   const int2* tiles;   // {first A row, first B row} in panel-row (graph) coordinates
@@ -152,8 +149,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t holder = bar_base + 8u * (2 * STAGES + 4);
-  // generic pointer to the epilogue transpose area (after the 256-byte barrier block)
-  uint8_t* const epi_area = smem_raw + (bar_base + 256u - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -239,47 +234,70 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int arow = tile.x + row;
       const bool row_ok = arow < p.a_row_end;
-      double drow = 0.0;
-      if ((NORMALIZE || p.fix_diag) && row_ok) drow = p.diag[arow];
+      // Tile-level classification keeps per-element branches out of the common case: the
+      // epilogue is issue-bound (4 warps), so the interior path is pure tcgen05.ld + stores.
+      const bool interior = (tile.x + BM <= p.a_row_end) && (tile.y + BN <= p.b_row_end);
+      const bool diag_tile = p.fix_diag && (tile.x < tile.y + BN) && (tile.y < tile.x + BM);
+      if (!NORMALIZE && interior && !diag_tile && p.vec_ok) {
+        OutT* drow_ptr = out + (long long)(arow - p.c_row0) * p.ld + (tile.y - p.c_col0);
+        OutT* mptr = out + (long long)tile.y * p.ld + arow;  // mirror: K[col][row], one row of K per tile column
+        const long long ld = p.ld;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c0), v);
-        const int bcol0 = tile.y + c0;
-        if (bcol0 >= p.b_row_end) continue;  // warp-uniform
-        double dcol_l = 0.0;
-        if (NORMALIZE) {
-          const int bc = bcol0 + lane;
-          dcol_l = bc < p.b_row_end ? p.diag[bc] : 1.0;
-        }
-        OutT vals[32];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c0), v);
+          if constexpr (sizeof(OutT) == 4) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          double dcol = 0.0;
-          if (NORMALIZE) dcol = __shfl_sync(0xffffffffu, dcol_l, j);
-          vals[j] = epilogue_value<OutT, NORMALIZE>(__uint_as_float(v[j]), arow, bcol0 + j, drow, dcol, p);
-        }
-        if (p.mirror && row_ok) {  // lanes hold consecutive rows -> coalesced transposed store
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(drow_ptr + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.mirror) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (bcol0 + j < p.b_row_end) out[(long long)(bcol0 + j) * p.ld + arow] = vals[j];
-        }
-        // direct store: transpose the 32x32 chunk through shared memory so that every store
-        // instruction writes one contiguous 128-byte (fp32) / 256-byte (fp64) row segment
-        OutT* T = reinterpret_cast<OutT*>(epi_area) + ew * EPI_TILE_ELEMS;
+              for (int j = 0; j < 32; ++j) { *reinterpret_cast<uint32_t*>(mptr) = v[j]; mptr += ld; }
+            }
+          } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = vals[j];
-        __syncwarp();
-        const int bc = bcol0 + lane;
-        const bool col_ok = bc < p.b_row_end;
-        const int arow0 = tile.x + ew * 32;
-        OutT* dst0 = out + (long long)(arow0 - p.c_row0) * p.ld + (bc - p.c_col0);
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const OutT x = T[i * 33 + lane];
-          if (col_ok && arow0 + i < p.a_row_end) dst0[(long long)i * p.ld] = x;
+            for (int j = 0; j < 32; j += 2)
+              *reinterpret_cast<double2*>(drow_ptr + c0 + j) =
+                  make_double2((double)__uint_as_float(v[j]), (double)__uint_as_float(v[j + 1]));
+            if (p.mirror) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { *mptr = (OutT)__uint_as_float(v[j]); mptr += ld; }
+            }
+          }
         }
-        __syncwarp();
+      } else {
+        double drow = 0.0;
+        if ((NORMALIZE || p.fix_diag) && row_ok) drow = p.diag[arow];
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c0), v);
+          const int bcol0 = tile.y + c0;
+          if (bcol0 >= p.b_row_end) continue;  // warp-uniform
+          double dcol_l = 0.0;
+          if (NORMALIZE) {
+            const int bc = bcol0 + lane;
+            dcol_l = bc < p.b_row_end ? p.diag[bc] : 1.0;
+          }
+          OutT vals[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            double dcol = 0.0;
+            if (NORMALIZE) dcol = __shfl_sync(0xffffffffu, dcol_l, j);
+            vals[j] = epilogue_value<OutT, NORMALIZE>(__uint_as_float(v[j]), arow, bcol0 + j, drow, dcol, p);
+          }
+          if (row_ok) {
+            OutT* dst = out + (long long)(arow - p.c_row0) * p.ld + (bcol0 - p.c_col0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (bcol0 + j < p.b_row_end) dst[j] = vals[j];
+            if (p.mirror) {  // lanes hold consecutive rows -> coalesced transposed store
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (bcol0 + j < p.b_row_end) out[(long long)(bcol0 + j) * p.ld + arow] = vals[j];
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();

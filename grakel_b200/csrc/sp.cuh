@@ -64,8 +64,10 @@ __device__ __forceinline__ void sp_feature_add(const SpParams& p, int g, int col
   const unsigned old = ft_add(p.ft_keys, p.ft_cnt, p.ft_mask, ((unsigned long long)(unsigned)g << 32) | (unsigned)col,
                               inc, p.st, &is_new);
   atomicAdd(&p.st.diag[g], (unsigned long long)inc * (2ULL * old + inc));  // (old+inc)^2 - old^2
-  if (old + inc > __ldcg(&p.sc->max_count)) atomicMax(&p.sc->max_count, (unsigned long long)(old + inc));
-  if (is_new) atomicAdd(&p.sc->n_entries, 1ULL);
+  // graph g is owned by this CTA: its partial slots are private to the block (smem-free, L2 atomics
+  // on a per-CTA address do not contend across CTAs)
+  atomicMax(&p.st.part_max[blockIdx.x], old + inc);
+  if (is_new) atomicAdd(&p.st.part_new[blockIdx.x], 1u);
 }
 
 // global (lu,lv,d) dictionary: the slot index IS the column id

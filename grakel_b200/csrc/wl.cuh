@@ -331,6 +331,8 @@ wl_assign(int V, int level, const int* __restrict__ flags, const int* __restrict
 struct FeatStats {
   unsigned* colcnt;            // graphs holding the column (saturating at COL_CAP)
   unsigned long long* diag;    // per graph: sum of squared counts (exact self similarity)
+  unsigned* part_max;          // per-CTA partials (no same-address atomics in the hot path):
+  unsigned* part_new;          //   largest count seen / entries created by the CTA
   DevScalars* sc;
 };
 constexpr unsigned COL_CAP = 1u << 13;  // column counters saturate here ("certainly head")
@@ -367,8 +369,9 @@ __device__ __forceinline__ unsigned ft_add(unsigned long long* keys, unsigned* c
 
 // Block-wide bookkeeping after every thread has done (at most) one ft_add with inc == 1:
 //   diag[g] += (old+1)^2 - old^2 = 2*old + 1, aggregated over runs of equal g inside a warp
-//   (vertices of a graph are contiguous); max count and entry count once per block.
-__device__ __forceinline__ void ft_account(bool did, int g, unsigned old, bool is_new, const FeatStats& st) {
+//   (vertices of a graph are contiguous); max count and entry count go to per-CTA partials.
+__device__ __forceinline__ void ft_account(bool did, int g, unsigned old, bool is_new, const FeatStats& st,
+                                           size_t part_index) {
   const int lane = threadIdx.x & 31;
   unsigned long long val = did ? 2ULL * old + 1ULL : 0ULL;
   const int gg = did ? g : -1;
@@ -380,15 +383,19 @@ __device__ __forceinline__ void ft_account(bool did, int g, unsigned old, bool i
   }
   const int gprev = __shfl_up_sync(0xffffffffu, gg, 1);
   if (did && (lane == 0 || gprev != gg)) atomicAdd(&st.diag[g], val);
+  __shared__ unsigned s_mx[8], s_n[8];
   unsigned mx = did ? old + 1 : 0, n = is_new ? 1u : 0u;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     n += __shfl_xor_sync(0xffffffffu, n, d);
   }
-  if (lane == 0) {
-    if (mx > __ldcg(&st.sc->max_count)) atomicMax(&st.sc->max_count, (unsigned long long)mx);
-    if (n) atomicAdd(&st.sc->n_entries, (unsigned long long)n);
+  if (lane == 0) { s_mx[threadIdx.x >> 5] = mx; s_n[threadIdx.x >> 5] = n; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mx = max(mx, s_mx[w]); n += s_n[w]; }
+    st.part_max[part_index] = mx;
+    st.part_new[part_index] = n;
   }
 }
 
@@ -412,7 +419,7 @@ wl_gather_insert(int V, int level, const int* __restrict__ rep_of, int* lab_out,
                  (size_t)level * ((size_t)ft_mask + 1));
     did = true;
   }
-  ft_account(did, g, old, is_new, st);
+  ft_account(did, g, old, is_new, st, (size_t)level * gridDim.x + blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256)
@@ -428,7 +435,7 @@ wl_insert_level0(int V, const int* __restrict__ lab, const int* __restrict__ vgr
                  ((unsigned long long)(unsigned)g << 32) | (unsigned long long)(unsigned)lab[v], 1u, st, &is_new);
     did = true;
   }
-  ft_account(did, g, old, is_new, st);
+  ft_account(did, g, old, is_new, st, blockIdx.x);
 }
 
 // vertex -> graph id by binary search in graph_ptr
