@@ -794,7 +794,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   p.mirror = mirror ? 1 : 0;
   p.fix_diag = square ? 1 : 0;
   p.nan_to_num = (flags & GK_NAN_TO_NUM) ? 1 : 0;
-  p.vec_ok = (((uintptr_t)d_out) % 16 == 0 && (d_ld * (long long)esz) % 16 == 0) ? 1 : 0;
+  p.vec_ok = (((uintptr_t)d_out) % 32 == 0 && (d_ld * (long long)esz) % 32 == 0) ? 1 : 0;
   p.diag = h->diag_f64.as<double>();
 
   GK_CUDA(cudaEventRecord(h->tev[5], h->stream));
@@ -830,10 +830,25 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       p.n_tiles = (int)n_tiles;
       p.num_k_blocks = (int)(h->Dc_pad / BK);
       const int grid = (int)std::min<int64_t>(n_tiles, h->sm_count);
+      const bool prof = getenv("GRAKEL_B200_PROF") != nullptr;
+      if (prof) {
+        GK_TRY(h->K_stage.ensure((size_t)grid * 64));
+        GK_CUDA(cudaMemsetAsync(h->K_stage.p, 0, (size_t)grid * 64, h->stream));
+        p.prof = h->K_stage.as<long long>();
+      }
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
       if (out_dtype == GK_F64) { if (norm_in_epilogue) launch_tc<double, true>(h, tmA, tmB, p, grid); else launch_tc<double, false>(h, tmA, tmB, p, grid); }
       else { if (norm_in_epilogue) launch_tc<float, true>(h, tmA, tmB, p, grid); else launch_tc<float, false>(h, tmA, tmB, p, grid); }
       LAUNCH_CHECK(h);
+      if (prof) {
+        std::vector<long long> pr((size_t)grid * 8);
+        GK_CUDA(cudaMemcpyAsync(pr.data(), h->K_stage.p, pr.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        GK_CUDA(cudaStreamSynchronize(h->stream));
+        double a[8] = {0};
+        for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) a[i] += (double)pr[(size_t)b * 8 + i] / grid;
+        fprintf(stderr, "[gram_tc prof] tiles %lld kblocks %d grid %d | epi: wait_tfull %.0f work %.0f | mma: wait_tempty %.0f wait_full %.0f total %.0f | tma: wait_empty %.0f total %.0f (avg cycles per CTA)\n",
+                (long long)n_tiles, p.num_k_blocks, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+      }
     } else if (path == 2) {
       const size_t panel_bytes = (size_t)N * std::max<int64_t>(Dc, 1) * 4;
       GK_TRY(h->panel.ensure(panel_bytes));
@@ -994,7 +1009,7 @@ int gk_selftest_gram(gk_handle* h, int64_t n, int64_t d, const uint16_t* counts,
   p.a_row_end = (int)n; p.b_row_end = (int)n;
   p.ld = n;
   p.diag = ddg.as<double>();
-  p.vec_ok = (n * 8) % 16 == 0;
+  p.vec_ok = (n * 8) % 32 == 0;
   int rc = GK_OK;
   if (out_tc) {
     std::vector<int2> tiles;
