@@ -179,8 +179,8 @@ def main():
     n = args.graphs
     gp, rp, ci, lab = pack_workload(n)
     V, E = int(gp[-1]), int(rp[-1])
-    rows_per = (n + world - 1) // world
-    rb, re_ = min(n, rank * rows_per), min(n, (rank + 1) * rows_per)
+    from grakel_b200.dist import row_block
+    rb, re_ = row_block(n, rank, world)
 
     def barrier():
         if world > 1:

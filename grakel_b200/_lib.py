@@ -146,7 +146,7 @@ class Engine:
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         at, ad = None, 0
         if attrs is not None:
-            at = np.ascontiguousarray(attrs, dtype=np.float32)
+            at = np.ascontiguousarray(attrs, dtype=np.float64)
             ad = at.shape[1]
         with self._lock:
             self._check(self.lib.gk_pack_csr(self.h, len(gp) - 1, _ptr(gp), _ptr(rp), _ptr(ci), _ptr(lab), _ptr(w),
@@ -163,6 +163,12 @@ class Engine:
         flags = (GK_SP_WITH_LABELS if with_labels else 0) | (GK_SP_KEEP_DIST if keep_dist else 0)
         with self._lock:
             self._check(self.lib.gk_sp_features(self.h, flags, C.byref(st)))
+        return st
+
+    def spattr_features(self):
+        st = GkStats()
+        with self._lock:
+            self._check(self.lib.gk_spattr_features(self.h, C.byref(st)))
         return st
 
     def gram(self, n_graphs, n_fit=None, normalize=False, nan_to_num=False, out=None, dtype=np.float64,

@@ -8,6 +8,7 @@
 #include "features.cuh"
 #include "gram_tc.cuh"
 #include "sp.cuh"
+#include "spattr.cuh"
 #include "wl.cuh"
 
 namespace gk {
@@ -173,7 +174,7 @@ int gk_event_elapsed(gk_handle* h, int32_t a, int32_t b, float* ms) {
 
 // ---------------------------------------------------------------------------
 int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const int32_t* row_ptr,
-                const int32_t* col_idx, const int32_t* labels, const double* weights, const float* attrs,
+                const int32_t* col_idx, const int32_t* labels, const double* weights, const double* attrs,
                 int32_t attr_dim) {
   if (!h) return fail(GK_ERR_ARG, "null handle");
   if (n_graphs <= 0 || !graph_ptr || !row_ptr) return fail(GK_ERR_ARG, "gk_pack_csr: empty input");
@@ -269,8 +270,8 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
     GK_CUDA(cudaMemcpyAsync(h->weights.p, weights, E * 8, cudaMemcpyHostToDevice, h->stream));
   }
   if (attrs && attr_dim > 0) {
-    GK_TRY(h->attrs.ensure((size_t)V * attr_dim * 4));
-    GK_CUDA(cudaMemcpyAsync(h->attrs.p, attrs, (size_t)V * attr_dim * 4, cudaMemcpyHostToDevice, h->stream));
+    GK_TRY(h->attrs.ensure((size_t)V * attr_dim * 8));
+    GK_CUDA(cudaMemcpyAsync(h->attrs.p, attrs, (size_t)V * attr_dim * 8, cudaMemcpyHostToDevice, h->stream));
   }
   if (!large.empty()) {
     GK_TRY(h->large_list.ensure(large.size() * 4));
@@ -604,9 +605,186 @@ int gk_sp_distances(gk_handle* h, int64_t g, double* out) {
 }
 
 int gk_spattr_features(gk_handle* h, gk_stats* stats) {
-  (void)stats;
   if (!h) return fail(GK_ERR_ARG, "null handle");
-  return fail(GK_ERR_UNSUPPORTED, "gk_spattr_features: not implemented in this build");
+  if (h->N <= 0) return fail(GK_ERR_STATE, "gk_spattr_features: no graphs packed");
+  if (!h->attrs.p || h->attr_dim <= 0) return fail(GK_ERR_ARG, "gk_spattr_features: node attributes are required");
+  GK_CUDA(cudaSetDevice(h->dev));
+  const int64_t N = h->N;
+  const int da = h->attr_dim, dd = da * da;
+  if (dd > 1024) return fail(GK_ERR_UNSUPPORTED, "gk_spattr_features: attribute dimension above 32");
+  const bool use_u16 = (!h->has_weights || h->unit_weights) && h->max_graph_size < 16000;
+  const size_t esz = use_u16 ? 2 : 8;
+  HandleExtra* ex = extra_of(h);
+  const int64_t launches0 = h->launches;
+  h->features_ready = false;
+  if ((size_t)h->max_graph_size * h->max_graph_size * 2 + (size_t)h->max_graph_size * da * 8 + (size_t)dd * 8 > 200 * 1024)
+    return fail(GK_ERR_UNSUPPORTED, "gk_spattr_features: graph too large for the shared-memory feature kernel");
+
+  // per-graph offsets of the distance matrices (all kept in global memory for phase C)
+  std::vector<int> small, big;
+  size_t max_small_nn = 0;
+  ex->sp_goff.assign(N + 1, 0);
+  long long off_all = 0;
+  for (int64_t g = 0; g < N; ++g) {
+    const long long n = ex->graph_ptr[g + 1] - ex->graph_ptr[g];
+    ex->sp_goff[g] = off_all;
+    off_all += n * n;
+    if ((size_t)(n * n) * esz <= 160 * 1024) { small.push_back((int)g); max_small_nn = std::max(max_small_nn, (size_t)(n * n)); }
+    else big.push_back((int)g);
+  }
+  ex->sp_goff[N] = off_all;
+  std::vector<int> order(small);
+  order.insert(order.end(), big.begin(), big.end());
+  GK_TRY(h->large_list.ensure((size_t)N * 4 + 16));
+  GK_CUDA(cudaMemcpyAsync(h->large_list.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  GK_TRY(h->sp_graph_off.ensure((size_t)(N + 1) * 8));
+  GK_CUDA(cudaMemcpyAsync(h->sp_graph_off.p, ex->sp_goff.data(), (N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  GK_TRY(h->sp_dist.ensure((size_t)std::max<long long>(off_all, 1) * esz));
+  const size_t dict_cap = 1 << 16;
+  GK_TRY(h->sp_dict_keys.ensure(dict_cap * 8));
+  GK_TRY(h->sp_dict_ids.ensure(dict_cap * 4));
+  h->sp_dict_cap = dict_cap;
+  GK_TRY(init_scalars(h, 0));
+  GK_CUDA(cudaMemsetAsync(h->sp_dict_keys.p, 0xFF, dict_cap * 8, h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+
+  GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
+  SpParams p;
+  memset(&p, 0, sizeof(p));
+  p.graph_ptr = h->graph_ptr.as<int>();
+  p.row_ptr = h->row_ptr.as<int>();
+  p.col_idx = h->col_idx.as<int>();
+  p.weights = (h->has_weights && !use_u16) ? h->weights.as<double>() : nullptr;
+  p.gdist = h->sp_dist.p;
+  p.goff = h->sp_graph_off.as<long long>();
+  p.dict_keys = h->sp_dict_keys.as<unsigned long long>();
+  p.dict_mask = (unsigned)(dict_cap - 1);
+  p.sc = h->scalars.as<DevScalars>();
+  const size_t smem_small = max_small_nn * esz + 16;
+  if (use_u16) GK_CUDA(cudaFuncSetAttribute(spattr_apsp<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+  else GK_CUDA(cudaFuncSetAttribute(spattr_apsp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+  if (!small.empty()) {
+    p.glist = h->large_list.as<int>();
+    p.dist_in_global = 0;
+    if (use_u16) spattr_apsp<unsigned short><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
+    else spattr_apsp<double><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
+    LAUNCH_CHECK(h);
+  }
+  if (!big.empty()) {
+    p.glist = h->large_list.as<int>() + small.size();
+    p.dist_in_global = 1;
+    if (use_u16) spattr_apsp<unsigned short><<<(int)big.size(), SP_THREADS, 16, h->stream>>>(p);
+    else spattr_apsp<double><<<(int)big.size(), SP_THREADS, 16, h->stream>>>(p);
+    LAUNCH_CHECK(h);
+  }
+  // distinct distances -> block ids (ascending distance order, deterministic)
+  std::vector<unsigned long long> keys(dict_cap);
+  GK_CUDA(cudaMemcpyAsync(keys.data(), h->sp_dict_keys.p, dict_cap * 8, cudaMemcpyDeviceToHost, h->stream));
+  DevScalars* hs;
+  GK_TRY(read_scalars(h, &hs));
+  if (hs->ft_overflow) return fail(GK_ERR_UNSUPPORTED, "gk_spattr_features: more than 32768 distinct path lengths");
+  std::vector<std::pair<double, int>> found;
+  for (size_t i = 0; i < dict_cap; ++i)
+    if (keys[i] != EMPTY64) {
+      double d;
+      if (use_u16) d = (double)keys[i];
+      else { long long b = (long long)keys[i]; memcpy(&d, &b, 8); }
+      found.emplace_back(d, (int)i);
+    }
+  std::sort(found.begin(), found.end());
+  const int n_blocks = (int)found.size();
+  std::vector<int> slot_block(dict_cap, -1);
+  for (int b = 0; b < n_blocks; ++b) slot_block[found[b].second] = b;
+  GK_CUDA(cudaMemcpyAsync(h->sp_dict_ids.p, slot_block.data(), dict_cap * 4, cudaMemcpyHostToDevice, h->stream));
+  const int64_t Dfeat = (int64_t)std::max(n_blocks, 1) * dd;
+  if ((size_t)N * Dfeat * 8 > (size_t)64 << 30) return fail(GK_ERR_UNSUPPORTED, "gk_spattr_features: feature matrix above 64 GB");
+  GK_TRY(h->fattr.ensure((size_t)N * Dfeat * 8));
+  GK_CUDA(cudaMemsetAsync(h->fattr.p, 0, (size_t)N * Dfeat * 8, h->stream));
+  h->fattr_dim = Dfeat;
+  if (n_blocks > 0) {
+    const size_t fixed = (size_t)h->max_graph_size * da * 8 + (size_t)h->max_graph_size * h->max_graph_size * 2 + 64;
+    int chunk = (int)std::min<size_t>((size_t)n_blocks, (200 * 1024 - fixed) / ((size_t)dd * 8));
+    if (chunk < 1) return fail(GK_ERR_UNSUPPORTED, "gk_spattr_features: shared memory budget exceeded");
+    const size_t smem = (size_t)chunk * dd * 8 + fixed;
+    if (use_u16) {
+      GK_CUDA(cudaFuncSetAttribute(spattr_accumulate<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spattr_accumulate<unsigned short><<<(int)N, 256, smem, h->stream>>>(
+          h->graph_ptr.as<int>(), h->attrs.as<double>(), da, h->sp_dist.p, h->sp_graph_off.as<long long>(),
+          h->sp_dict_keys.as<unsigned long long>(), (unsigned)(dict_cap - 1), h->sp_dict_ids.as<int>(), n_blocks, chunk,
+          h->fattr.as<double>());
+    } else {
+      GK_CUDA(cudaFuncSetAttribute(spattr_accumulate<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spattr_accumulate<double><<<(int)N, 256, smem, h->stream>>>(
+          h->graph_ptr.as<int>(), h->attrs.as<double>(), da, h->sp_dist.p, h->sp_graph_off.as<long long>(),
+          h->sp_dict_keys.as<unsigned long long>(), (unsigned)(dict_cap - 1), h->sp_dict_ids.as<int>(), n_blocks, chunk,
+          h->fattr.as<double>());
+    }
+    LAUNCH_CHECK(h);
+  }
+  GK_TRY(h->diag_f64.ensure(N * 8));
+  rownorm_f64_kernel<<<(int)N, 256, 0, h->stream>>>(h->fattr.as<double>(), Dfeat, (int)N, h->diag_f64.as<double>());
+  LAUNCH_CHECK(h);
+  GK_CUDA(cudaEventRecord(h->tev[3], h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));  // host vectors above are sources of async copies
+  h->n_columns = Dfeat;
+  h->features_ready = true;
+  h->feature_kind = 3;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_graphs = N; stats->n_vertices = h->V; stats->n_edges = h->E;
+    stats->n_levels = 1;
+    stats->level_dims[0] = n_blocks;
+    stats->n_columns = Dfeat;
+    stats->n_dense_columns = Dfeat;
+    stats->kernel_launches = h->launches - launches0;
+    stats->ms_features = ev_ms(h->tev[2], h->tev[3]);
+  }
+  return GK_OK;
+}
+
+// Gram of the dense fp64 SP-attr feature matrix (feature_kind == 3)
+static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64_t row_end, void* K_out,
+                       int32_t out_dtype, int64_t ld, double* xdiag, double* ydiag, gk_stats* stats) {
+  if (out_dtype != GK_F64) return fail(GK_ERR_UNSUPPORTED, "ShortestPathAttr Gram is fp64 only");
+  if (flags & GK_OUT_DEVICE) return fail(GK_ERR_UNSUPPORTED, "ShortestPathAttr Gram: device output not supported");
+  const int64_t N = h->N;
+  const bool square = n_fit == N;
+  const int64_t k_rows_total = square ? N : N - n_fit, k_cols = n_fit;
+  if (row_end < 0) row_end = k_rows_total;
+  if (row_begin < 0 || row_begin > row_end || row_end > k_rows_total) return fail(GK_ERR_ARG, "gk_gram: bad row range");
+  const int64_t k_rows = row_end - row_begin;
+  if (ld <= 0) ld = k_cols;
+  const int64_t launches0 = h->launches;
+  GK_TRY(h->K.ensure((size_t)std::max<int64_t>(k_rows, 1) * k_cols * 8));
+  h->K_rows = k_rows; h->K_cols = k_cols; h->K_dtype = GK_F64;
+  const int a0 = (int)((square ? 0 : n_fit) + row_begin), a1 = (int)((square ? 0 : n_fit) + row_end);
+  GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
+  if (k_rows > 0) {
+    dim3 grid(cdiv(k_cols, 64), cdiv(k_rows, 64));
+    gram_f64_kernel<<<grid, 256, 0, h->stream>>>(h->fattr.as<double>(), h->fattr_dim, a0, a1, 0, (int)n_fit,
+                                                 h->K.as<double>(), k_cols);
+    LAUNCH_CHECK(h);
+    if (flags & GK_NORMALIZE) {
+      normalize_rows<double><<<h->sm_count * 8, 256, 0, h->stream>>>(k_rows, k_cols, h->K.as<double>(), k_cols,
+                                                                      h->diag_f64.as<double>() + a0,
+                                                                      h->diag_f64.as<double>(), (flags & GK_NAN_TO_NUM) ? 1 : 0);
+      LAUNCH_CHECK(h);
+    }
+  }
+  GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
+  if (K_out && k_rows > 0)
+    GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * 8, h->K.p, (size_t)k_cols * 8, (size_t)k_cols * 8, (size_t)k_rows,
+                              cudaMemcpyDeviceToHost, h->stream));
+  if (xdiag) GK_CUDA(cudaMemcpyAsync(xdiag, h->diag_f64.p, n_fit * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (ydiag && !square)
+    GK_CUDA(cudaMemcpyAsync(ydiag, h->diag_f64.as<double>() + n_fit, (N - n_fit) * 8, cudaMemcpyDeviceToHost, h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  if (stats) {
+    stats->gram_path = 4;
+    stats->gemm_launches = h->launches - launches0;
+    stats->ms_gemm = ev_ms(h->tev[6], h->tev[7]);
+  }
+  return GK_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -653,6 +831,10 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   if (out_dtype != GK_F32 && out_dtype != GK_F64) return fail(GK_ERR_ARG, "gk_gram: bad out_dtype");
   const int64_t N = h->N;
   if (n_fit <= 0 || n_fit > N) return fail(GK_ERR_ARG, "gk_gram: n_fit out of range");
+  if (h->feature_kind == 3) {
+    GK_CUDA(cudaSetDevice(h->dev));
+    return gram_spattr(h, n_fit, flags, row_begin, row_end, K_out, out_dtype, ld, xdiag, ydiag, stats);
+  }
   const bool square = n_fit == N;
   const int64_t k_rows_total = square ? N : N - n_fit;
   const int64_t k_cols = n_fit;

@@ -146,7 +146,7 @@ class Kernel(BaseEstimator, TransformerMixin):
         """pack -> feature kernels -> Gram, all on the device.  Returns (K, xdiag, ydiag)."""
         eng = _lib.get_engine()
         with eng._lock:
-            eng.pack(block.graph_ptr, block.row_ptr, block.col_idx, ids, block.weights, None)
+            eng.pack(block.graph_ptr, block.row_ptr, block.col_idx, ids, block.weights, block.attrs)
             self.stats_ = self._device_features(eng)
             K, xd, yd = eng.gram(block.n_graphs, n_fit=n_fit, normalize=bool(self.normalize) and want_matrix,
                                  nan_to_num=self._nan_to_num, out=None if want_matrix else False,
@@ -404,4 +404,37 @@ class ShortestPathAttr(Kernel):
             self._initialized["metric"] = True
 
     def parse_input(self, X):
-        raise NotImplementedError("ShortestPathAttr is not on the device path of this build yet")
+        if self.metric is not np.dot:
+            raise NotImplementedError("grakel_b200 evaluates ShortestPathAttr through its bilinear feature map, which "
+                                      "is only valid for the default metric=np.dot")
+        block = pack(X, "sp", need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=True,
+                     fw_zero_is_absent=self.algorithm_type == "floyd_warshall", attributes=True,
+                     type_error_msg="each element of X must be either a graph or an iterable with at least 2 and at "
+                                    "most 3 elements\n")
+        return Fitted(block, None, {})
+
+    def fit_transform(self, X, y=None):
+        self._method_calling = 2
+        self.fit(X)
+        K, xdiag, _ = self._run(self.X.block, None, n_fit=self.X.block.n_graphs)
+        self._X_diag = xdiag
+        if self.normalize:
+            self._warn_unnormalizable(xdiag)
+        return K
+
+    def transform(self, X):
+        self._method_calling = 3
+        check_is_fitted(self, ["X"])
+        if X is None:
+            raise ValueError("`transform` input cannot be None")
+        Y = self.parse_input(X)
+        K, xdiag, ydiag = self._run(Block.concat(self.X.block, Y.block), None, n_fit=self.X.block.n_graphs)
+        self._X_diag = xdiag
+        self._Y_diag = ydiag
+        self._is_transformed = True
+        if self.normalize:
+            self._warn_unnormalizable(xdiag, ydiag)
+        return K
+
+    def _device_features(self, eng):
+        return eng.spattr_features()

@@ -115,10 +115,10 @@ int gk_sync(gk_handle* h);
  *   col_idx[E]             GLOBAL vertex id of each out-neighbour (same graph)
  *   labels[V]              dense non-negative id of the vertex label (level 0), or NULL
  *   weights[E]             edge weights (fp64) or NULL for unit weights
- *   attrs[V*attr_dim]      fp32 node attributes or NULL                                  */
+ *   attrs[V*attr_dim]      fp64 node attributes or NULL                                  */
 int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const int32_t* row_ptr,
                 const int32_t* col_idx, const int32_t* labels, const double* weights,
-                const float* attrs, int32_t attr_dim);
+                const double* attrs, int32_t attr_dim);
 
 /* Build the sparse feature block of the packed graphs on the device. */
 int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats);

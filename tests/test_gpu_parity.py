@@ -236,6 +236,31 @@ def test_config3_small_and_large_graph_path():
     _same(k.ShortestPath(with_labels=False).fit_transform(X), SPOracle(with_labels=False).fit_transform(X))
 
 
+# --------------------------------------------------------------- SP-attr
+def test_shortest_path_attr_matches_reference_loop():
+    """Golden from the real reference's 4-deep loop (shortest_path.py:151-162) on tiny graphs,
+    then the oracle's feature-map form on a config-5 shaped subset (tolerance 1e-5 relative as
+    BASELINE.json states; the device path is fp64 end to end)."""
+    from oracle.gk_oracle import SPAttrOracle
+    k = _k()
+    d = gio.load(os.path.join(G, "spattr.json.gz"))
+    X, Y = gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"])
+    est = k.ShortestPathAttr()
+    np.testing.assert_allclose(est.fit_transform(X), np.asarray(d["K"]), rtol=1e-9)
+    np.testing.assert_allclose(est.transform(Y), np.asarray(d["Kt"]), rtol=1e-9)
+    est = k.ShortestPathAttr(normalize=True)
+    np.testing.assert_allclose(est.fit_transform(X), np.asarray(d["Kn"]), rtol=1e-9)
+    np.testing.assert_allclose(est.transform(Y), np.asarray(d["Ktn"]), rtol=1e-9)
+    Xc = gen(24, 40, 0, attr=16, as_adj=True)  # first graphs of BASELINE config 5
+    Ko = SPAttrOracle().fit_transform(Xc)
+    Kd = k.GraphKernel(kernel={"name": "shortest_path", "as_attributes": True}).fit_transform(Xc)
+    np.testing.assert_allclose(Kd, Ko, rtol=1e-5)
+    np.testing.assert_allclose(Kd[0, :5], [837683.171027, 2683836.635183, 1663520.495733, 1549141.171651, 2537314.325017],
+                               rtol=1e-9)  # SURVEY.md 8c: real-reference K[0,:5] of config 5
+    with pytest.raises(NotImplementedError):
+        k.ShortestPathAttr(metric=lambda a, b: float(np.dot(a, b))).fit_transform(Xc[:2])
+
+
 # --------------------------------------------------------------- BASELINE sizes
 def test_config2_full_size_properties():
     """N = 10 000, h = 5 (BASELINE config 2): checksums + sampled rows from the real
