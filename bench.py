@@ -16,8 +16,10 @@ feature block, dense bf16 panel, tcgen05 Gram GEMM, diagonal / output.
              the CPU oracle port (oracle/gk_oracle.py, pinned to the real reference's
              goldens) on a bounded prefix of the same graphs on the box's host cores
 
-N > 1 (torchrun): every rank relabels the (replicated, tiny) CSR block and computes a
-contiguous row block of K -- no data-path collective; value = N^2 / max-over-ranks time.
+N > 1 (torchrun): weak scaling -- the graph count grows as 10 000 * sqrt(N) so every rank owns
+the same number of K entries; every rank relabels the (replicated, tiny) CSR block and
+computes a contiguous row block of K -- no data-path collective;
+value = (graphs^2) / max-over-ranks time.
 """
 import argparse
 import json
@@ -138,7 +140,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "graph-pairs/sec, N x N WL-subtree (h=5) Gram", "value": val,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"config2: {N_GRAPHS} ER graphs (avg {NBAR} nodes, 7 labels, seed {SEED}), WL-subtree h={H}",
                    "parallelism": "host CPU, 1 thread (the reference's default n_jobs=None)"},
@@ -176,7 +178,9 @@ def main():
     from grakel_b200 import _lib
     eng = _lib.Engine(local)
 
-    n = args.graphs
+    # weak scaling: ordered pairs per GPU stay fixed (N = 10 000 * sqrt(world) graphs), every rank
+    # produces the same number of K entries; N = 1 is exactly BASELINE config 2
+    n = int(round(args.graphs * np.sqrt(world)))
     gp, rp, ci, lab = pack_workload(n)
     V, E = int(gp[-1]), int(rp[-1])
     from grakel_b200.dist import row_block
@@ -252,8 +256,8 @@ def main():
                "api": "gk_wl_fit_transform (C-ABI), pinned host CSR in, pinned fp64 K out",
                "last_step_ms": {"h2d+pack": es.ms_h2d, "features": es.ms_features, "columns+panel": es.ms_panel,
                                 "gemm": es.ms_gemm, "tail": es.ms_tail, "d2h": es.ms_d2h}}
-        if rank == 0 and world == 1:
-            assert float(Kh.sum()) == 22925628586.0 or n != N_GRAPHS, "K checksum differs from the reference golden"
+        if rank == 0 and world == 1 and n == N_GRAPHS:
+            assert float(Kh.sum()) == 22925628586.0, "K checksum differs from the reference golden"
 
     if rank != 0:
         if world > 1:
@@ -282,7 +286,7 @@ def main():
     line = {
         "metric": "graph-pairs/sec, N x N WL-subtree (h=5) Gram", "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 x bf16 -> f32 (exact integers)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 x bf16 -> f32 (exact integers)",
         "data": "synthetic",
         "config": {"workload": f"config2: {n} ER graphs (avg {NBAR} nodes, 7 labels, seed {SEED}), WL-subtree h={H}",
                    "vertices": V, "directed_edges": E, "feature_columns": int(st.n_columns), "nnz": int(st.n_entries),
