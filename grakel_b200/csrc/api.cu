@@ -463,6 +463,7 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   // plan: graphs whose distance matrix fits the shared-memory budget vs the rest
   const size_t SMEM_DIST_MAX = 160 * 1024;
   std::vector<int> small, big;
+  std::vector<int> bfs[4];  // unit weights: bitmask BFS with W = 1, 2, 4, 8 words (n <= 64 W)
   size_t max_small_nn = 0;
   ex->sp_goff.assign(N + 1, 0);
   const bool keep = flags & GK_SP_KEEP_DIST;
@@ -472,7 +473,9 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     const long long n = ex->graph_ptr[g + 1] - ex->graph_ptr[g];
     ex->sp_goff[g] = off_all;
     off_all += n * n;
-    if ((size_t)(n * n) * esz <= SMEM_DIST_MAX) {
+    if (use_u16 && n <= 512) {
+      bfs[n <= 64 ? 0 : n <= 128 ? 1 : n <= 256 ? 2 : 3].push_back((int)g);
+    } else if ((size_t)(n * n) * esz <= SMEM_DIST_MAX) {
       small.push_back((int)g);
       max_small_nn = std::max(max_small_nn, (size_t)(n * n));
     } else {
@@ -490,6 +493,8 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   GK_TRY(lists.ensure((size_t)N * 4 + 16));
   std::vector<int> order(small);
   order.insert(order.end(), big.begin(), big.end());
+  size_t bfs_off[4];
+  for (int i = 0; i < 4; ++i) { bfs_off[i] = order.size(); order.insert(order.end(), bfs[i].begin(), bfs[i].end()); }
   GK_CUDA(cudaMemcpyAsync(lists.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
   GK_TRY(h->sp_graph_off.ensure((size_t)(N + 1) * 8 * 2));
   long long* d_goff_all = h->sp_graph_off.as<long long>();
@@ -550,6 +555,31 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
       p.goff = d_goff_all;  // only used for `keep`
       if (use_u16) sp_apsp_hist<unsigned short><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
       else sp_apsp_hist<double><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
+      LAUNCH_CHECK(h);
+    }
+    for (int i = 0; i < 4; ++i) {
+      if (bfs[i].empty()) continue;
+      const int W = 1 << i;
+      int nmax = 0;
+      for (int g : bfs[i]) nmax = std::max(nmax, ex->graph_ptr[g + 1] - ex->graph_ptr[g]);
+      const size_t smem = SP_LOCAL_SLOTS * 12 + (size_t)nmax * W * 8 + (size_t)nmax * 4 + 16;
+      p.glist = lists.as<int>() + bfs_off[i];
+      p.n_list = (int)bfs[i].size();
+      p.dist_in_global = 0;
+      p.goff = d_goff_all;
+      const int threads = nmax <= 32 ? 32 : nmax <= 64 ? 64 : 128;
+      switch (W) {
+        case 1: GK_CUDA(cudaFuncSetAttribute(sp_bfs_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+        case 2: GK_CUDA(cudaFuncSetAttribute(sp_bfs_hist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+        case 4: GK_CUDA(cudaFuncSetAttribute(sp_bfs_hist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+        default: GK_CUDA(cudaFuncSetAttribute(sp_bfs_hist<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+      }
+      switch (W) {
+        case 1: sp_bfs_hist<1><<<(int)bfs[i].size(), threads, smem, h->stream>>>(p); break;
+        case 2: sp_bfs_hist<2><<<(int)bfs[i].size(), threads, smem, h->stream>>>(p); break;
+        case 4: sp_bfs_hist<4><<<(int)bfs[i].size(), threads, smem, h->stream>>>(p); break;
+        default: sp_bfs_hist<8><<<(int)bfs[i].size(), threads, smem, h->stream>>>(p); break;
+      }
       LAUNCH_CHECK(h);
     }
     if (!big.empty()) {

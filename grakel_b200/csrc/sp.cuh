@@ -75,13 +75,115 @@ __device__ __forceinline__ int sp_dict_slot(unsigned long long* keys, unsigned m
                                             DevScalars* sc) {
   unsigned slot = (unsigned)(mix64(key) >> 13) & mask;
   for (unsigned probe = 0; probe <= mask; ++probe) {
-    unsigned long long prev = atomicCAS(&keys[slot], EMPTY64, key);
-    if (prev == EMPTY64) { atomicAdd(&sc->sp_dict_size, 1u); return (int)slot; }
+    unsigned long long prev = __ldcg(&keys[slot]);
+    if (prev == EMPTY64) {
+      prev = atomicCAS(&keys[slot], EMPTY64, key);
+      if (prev == EMPTY64) { atomicAdd(&sc->sp_dict_size, 1u); return (int)slot; }
+    }
     if (prev == key) return (int)slot;
     slot = (slot + 1) & mask;
   }
   atomicOr(&sc->ft_overflow, 2u);
   return 0;
+}
+
+// CTA-local (key -> count) aggregation shared by the SP feature kernels; falls through to
+// the global tables when the probe window is full.
+__device__ __forceinline__ void sp_local_add(unsigned long long* lkeys, unsigned* lcnt, const SpParams& p, int g,
+                                             unsigned long long key) {
+  unsigned slot = (unsigned)(mix64(key) >> 29) & (SP_LOCAL_SLOTS - 1);
+  for (int probe = 0; probe < 16; ++probe) {
+    unsigned long long prev = lkeys[slot];
+    if (prev == EMPTY64) prev = atomicCAS(&lkeys[slot], EMPTY64, key);
+    if (prev == EMPTY64 || prev == key) { atomicAdd(&lcnt[slot], 1u); return; }
+    slot = (slot + 1) & (SP_LOCAL_SLOTS - 1);
+  }
+  const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
+  sp_feature_add(p, g, col, 1u);
+}
+
+// Unit-weight graphs: all-sources BFS on adjacency BITMASKS instead of Floyd-Warshall.
+// One CTA per graph, one thread per source vertex; visited / frontier sets are W 64-bit
+// words in registers (n <= 64*W).  Every newly reached vertex v at BFS level d is exactly
+// one ordered pair (s, v) with shortest distance d (graph.py:1712-1764 computes the same
+// distances), so the (l(s), l(v), d) feature is counted on the spot and no n x n distance
+// matrix is materialised: O(n (n + m)/64) word operations per graph instead of n^3
+// min-plus steps.
+template <int W>
+__global__ void __launch_bounds__(128)
+sp_bfs_hist(SpParams p) {
+  extern __shared__ __align__(16) unsigned char sp_smem[];
+  const int g = p.glist ? p.glist[blockIdx.x] : blockIdx.x;
+  const int v0 = p.graph_ptr[g];
+  const int n = p.graph_ptr[g + 1] - v0;
+  if (n <= 0) return;
+  unsigned long long* lkeys = reinterpret_cast<unsigned long long*>(sp_smem);
+  unsigned* lcnt = reinterpret_cast<unsigned*>(sp_smem + SP_LOCAL_SLOTS * 8);
+  unsigned long long* adj = reinterpret_cast<unsigned long long*>(sp_smem + SP_LOCAL_SLOTS * 12);  // [n][W]
+  int* lab = reinterpret_cast<int*>(adj + (size_t)n * W);                                          // [n]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < SP_LOCAL_SLOTS; i += blockDim.x) { lkeys[i] = EMPTY64; lcnt[i] = 0; }
+  for (int i = tid; i < n * W; i += blockDim.x) adj[i] = 0ULL;
+  for (int i = tid; i < n; i += blockDim.x) lab[i] = p.labels ? p.labels[v0 + i] : 0;
+  __syncthreads();
+  const int e0 = p.row_ptr[v0], e1 = p.row_ptr[v0 + n];
+  // edge list -> bitmask rows (vertex of edge k found by binary search in row_ptr)
+  for (int k = e0 + tid; k < e1; k += blockDim.x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.row_ptr[v0 + mid] <= k) lo = mid; else hi = mid;
+    }
+    const int w = p.col_idx[k] - v0;
+    if (w != lo) atomicOr(&adj[(size_t)lo * W + (w >> 6)], 1ULL << (w & 63));
+  }
+  __syncthreads();
+  double* keep = p.keep ? p.keep + p.goff[g] : nullptr;
+  for (int s = tid; s < n; s += blockDim.x) {
+    unsigned long long vis[W], fr[W], nx[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) { fr[w] = adj[(size_t)s * W + w]; vis[w] = fr[w]; }
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+      if (w == (s >> 6)) vis[w] |= 1ULL << (s & 63);
+    if (keep) {
+      for (int v = 0; v < n; ++v) keep[(size_t)s * n + v] = __longlong_as_double(0x7ff0000000000000LL);
+      keep[(size_t)s * n + s] = 0.0;
+    }
+    const unsigned long long ls = (unsigned long long)(unsigned)lab[s];
+    unsigned level = 1;
+    while (true) {
+      bool any = false;
+#pragma unroll
+      for (int w = 0; w < W; ++w) nx[w] = 0ULL;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        unsigned long long bits = fr[w];
+        any |= bits != 0ULL;
+        while (bits) {
+          const int b = __ffsll((long long)bits) - 1;
+          bits &= bits - 1;
+          const int v = (w << 6) + b;
+          const unsigned long long key = (ls << 44) | ((unsigned long long)(unsigned)lab[v] << 24) | level;
+          sp_local_add(lkeys, lcnt, p, g, key);
+          if (keep) keep[(size_t)s * n + v] = (double)level;
+#pragma unroll
+          for (int x = 0; x < W; ++x) nx[x] |= adj[(size_t)v * W + x];
+        }
+      }
+      if (!any) break;
+#pragma unroll
+      for (int w = 0; w < W; ++w) { nx[w] &= ~vis[w]; vis[w] |= nx[w]; fr[w] = nx[w]; }
+      ++level;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < SP_LOCAL_SLOTS; i += blockDim.x) {
+    const unsigned long long key = lkeys[i];
+    if (key == EMPTY64) continue;
+    const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
+    sp_feature_add(p, g, col, lcnt[i]);
+  }
 }
 
 template <typename T>
@@ -158,18 +260,7 @@ sp_apsp_hist(SpParams p) {
       }
       const unsigned long long lv = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + w] : 0ULL;
       const unsigned long long key = (lu << 44) | (lv << 24) | (unsigned long long)di;
-      // CTA-local aggregation; fall through to the global table when the probe window is full
-      unsigned slot = (unsigned)(mix64(key) >> 29) & (SP_LOCAL_SLOTS - 1);
-      bool done = false;
-      for (int probe = 0; probe < 16; ++probe) {
-        unsigned long long prev = atomicCAS(&lkeys[slot], EMPTY64, key);
-        if (prev == EMPTY64 || prev == key) { atomicAdd(&lcnt[slot], 1u); done = true; break; }
-        slot = (slot + 1) & (SP_LOCAL_SLOTS - 1);
-      }
-      if (!done) {
-        const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
-        sp_feature_add(p, g, col, 1u);
-      }
+      sp_local_add(lkeys, lcnt, p, g, key);
     }
   }
   __syncthreads();
