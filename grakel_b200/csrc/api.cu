@@ -51,6 +51,20 @@ static int make_panel_map(CUtensorMap* m, void* base, long long cols, long long 
   return GK_OK;
 }
 
+// fp32 K as a 2-D tensor for TMA stores of 32x32 blocks (128-byte swizzle)
+static int make_out_map(CUtensorMap* m, void* base, long long cols, long long rows, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(GK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GK_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: " + std::to_string((int)r));
+  return GK_OK;
+}
+
 static int read_scalars(gk_handle* h, DevScalars** out) {
   GK_TRY(h->h_scalars.ensure(sizeof(DevScalars)));
   GK_CUDA(cudaMemcpyAsync(h->h_scalars.p, h->scalars.p, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
@@ -821,8 +835,9 @@ static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_b
 }  // extern "C"
 
 template <typename OutT, bool NORM>
-static void launch_tc(gk_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, const GramParams& p, int grid) {
-  gram_tc_kernel<OutT, NORM><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(tmA, tmB, p);
+static void launch_tc(gk_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                      const GramParams& p, int grid) {
+  gram_tc_kernel<OutT, NORM><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(tmA, tmB, tmC, p);
 }
 template <typename OutT, bool NORM>
 static void launch_simt(gk_handle* h, const unsigned* panel, long long ldp, int kdim, int a0, int a1, int b0, int b1,
@@ -1035,9 +1050,16 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       memcpy(h->h_tiles.p, tiles.data(), tiles.size() * sizeof(int2));
       GK_TRY(h->tiles.ensure(tiles.size() * sizeof(int2)));
       GK_CUDA(cudaMemcpyAsync(h->tiles.p, h->h_tiles.p, tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-      CUtensorMap tmA, tmB;
+      CUtensorMap tmA, tmB, tmC;
       GK_TRY(make_panel_map(&tmA, h->panel.p, h->Dc_pad, N, BM));
       GK_TRY(make_panel_map(&tmB, h->panel.p, h->Dc_pad, N, BN));
+      memset(&tmC, 0, sizeof(tmC));
+      p.tma_store = 0;
+      if (out_dtype == GK_F32 && !norm_in_epilogue && ((uintptr_t)d_out) % 16 == 0 && (d_ld * 4) % 16 == 0 &&
+          !getenv("GRAKEL_B200_NO_TMA_STORE")) {
+        GK_TRY(make_out_map(&tmC, d_out, k_cols, k_rows, d_ld));
+        p.tma_store = 1;
+      }
       p.tiles = h->tiles.as<int2>();
       p.n_tiles = (int)n_tiles;
       p.num_k_blocks = (int)(h->Dc_pad / BK);
@@ -1049,8 +1071,8 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
         p.prof = h->K_stage.as<long long>();
       }
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
-      if (out_dtype == GK_F64) { if (norm_in_epilogue) launch_tc<double, true>(h, tmA, tmB, p, grid); else launch_tc<double, false>(h, tmA, tmB, p, grid); }
-      else { if (norm_in_epilogue) launch_tc<float, true>(h, tmA, tmB, p, grid); else launch_tc<float, false>(h, tmA, tmB, p, grid); }
+      if (out_dtype == GK_F64) { if (norm_in_epilogue) launch_tc<double, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<double, false>(h, tmA, tmB, tmC, p, grid); }
+      else { if (norm_in_epilogue) launch_tc<float, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<float, false>(h, tmA, tmB, tmC, p, grid); }
       LAUNCH_CHECK(h);
       if (prof) {
         std::vector<long long> pr((size_t)grid * 8);
@@ -1228,7 +1250,8 @@ int gk_selftest_gram(gk_handle* h, int64_t n, int64_t d, const uint16_t* counts,
     build_tiles(tiles, 0, (int)n, 0, (int)n, true);
     GK_TRY(dtl.ensure(tiles.size() * sizeof(int2)));
     GK_CUDA(cudaMemcpyAsync(dtl.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
+    memset(&tmC, 0, sizeof(tmC));
     GK_TRY(make_panel_map(&tmA, dpb.p, dpad, n, BM));
     GK_TRY(make_panel_map(&tmB, dpb.p, dpad, n, BN));
     p.tiles = dtl.as<int2>();
@@ -1236,7 +1259,7 @@ int gk_selftest_gram(gk_handle* h, int64_t n, int64_t d, const uint16_t* counts,
     p.num_k_blocks = (int)(dpad / BK);
     p.out = dk1.p;
     p.mirror = 1;
-    launch_tc<double, false>(h, tmA, tmB, p, (int)std::min<size_t>(tiles.size(), h->sm_count));
+    launch_tc<double, false>(h, tmA, tmB, tmC, p, (int)std::min<size_t>(tiles.size(), h->sm_count));
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) rc = fail(GK_ERR_CUDA, std::string("selftest tcgen05 kernel: ") + cudaGetErrorString(e));

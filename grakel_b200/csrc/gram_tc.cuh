@@ -27,7 +27,10 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// epilogue staging for TMA stores: per epilogue warp two 32x32 fp32 tiles (double buffer)
+constexpr int EPI_BUF_BYTES = 32 * 32 * 4;
+constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*align*/ + EPI_BYTES;
 
 struct GramParams {
   const int2* tiles;   // {first A row, first B row} in panel-row (graph) coordinates
@@ -44,6 +47,7 @@ struct GramParams {
   int vec_ok;          // 32-byte aligned rows: 256-bit vector stores allowed
   const double* diag;  // self similarity per graph (fp64, exact integers)
   long long* prof;     // optional [gridDim.x][8] cycle counters (GRAKEL_B200_PROF), else NULL
+  int tma_store;       // fp32 output through a TMA store of smem-staged 32x32 blocks (tmC valid)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -76,6 +80,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(x), "r"(y)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((unsigned long long)map), "r"(src), "r"(x), "r"(y)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -141,7 +150,8 @@ __device__ __forceinline__ OutT epilogue_value(float acc, int arow, int bcol, do
 
 template <typename OutT, bool NORMALIZE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GramParams p) {
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, GramParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -150,6 +160,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t holder = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t epi_base = (bar_base + 256u + 1023u) & ~1023u;  // 1024-byte aligned (128B swizzle atoms)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,6 +168,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmC) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -255,7 +267,64 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // epilogue is issue-bound (4 warps), so the interior path is pure tcgen05.ld + stores.
       const bool interior = (tile.x + BM <= p.a_row_end) && (tile.y + BN <= p.b_row_end);
       const bool diag_tile = p.fix_diag && (tile.x < tile.y + BN) && (tile.y < tile.x + BM);
-      if (!NORMALIZE && interior && !diag_tile && p.vec_ok) {
+      if (sizeof(OutT) == 4 && !NORMALIZE && p.tma_store) {
+        // Direct block: registers -> 128B-swizzled smem tile -> ONE TMA store per 32x32 block (the
+        // SM->L2 path is bound by write requests: 1 bulk request instead of 128).  TMA clips at the
+        // matrix edge, so partial tiles need no predicates.  Mirrored block: coalesced 128-byte
+        // stores straight from registers (lanes = consecutive rows of the tile).
+        const uint32_t my_buf = epi_base + (uint32_t)ew * (2u * EPI_BUF_BYTES);
+        const int arow0 = tile.x + ew * 32;
+        float dself = 0.f;
+        if (diag_tile && row_ok) dself = (float)p.diag[arow];
+        OutT* mptr = out + (long long)tile.y * p.ld + arow;
+        const long long ld = p.ld;
+        const bool rows_in = arow0 < p.a_row_end;  // warp-uniform: any row of this warp's block inside
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c0), v);
+          const int bcol0 = tile.y + c0;
+          if (bcol0 >= p.b_row_end || !rows_in) { mptr += 32 * ld; continue; }  // warp-uniform
+          if (diag_tile) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (arow == bcol0 + j) v[j] = __float_as_uint(dself);
+          }
+          const uint32_t buf = my_buf + (uint32_t)((c0 >> 5) & 1) * EPI_BUF_BYTES;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's previous store
+          __syncwarp();
+          const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t a = rowaddr + (uint32_t)((q ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * q]), "r"(v[4 * q + 1]),
+                         "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, bcol0 - p.c_col0, arow0 - p.c_row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (p.mirror && row_ok) {
+            if (bcol0 + 32 <= p.b_row_end) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { *reinterpret_cast<uint32_t*>(mptr) = v[j]; mptr += ld; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (bcol0 + j < p.b_row_end) *reinterpret_cast<uint32_t*>(mptr) = v[j];
+                mptr += ld;
+              }
+            }
+          } else {
+            mptr += 32 * ld;
+          }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem reusable by the next tile
+        __syncwarp();
+      } else if (!NORMALIZE && interior && !diag_tile && p.vec_ok) {
         OutT* drow_ptr = out + (long long)(arow - p.c_row0) * p.ld + (tile.y - p.c_col0);
         OutT* mptr = out + (long long)tile.y * p.ld + arow;  // mirror: K[col][row], one row of K per tile column
         const long long ld = p.ld;
@@ -331,6 +400,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       t_work += clock64() - c_s;
     }
     if (p.prof && warp == 4 && lane == 0) { p.prof[blockIdx.x * 8 + 0] = w_tfull; p.prof[blockIdx.x * 8 + 1] = t_work; }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all TMA stores landed
   }
 
   tc_fence_before();

@@ -168,6 +168,30 @@ def test_head_tail_split_is_exact_for_every_threshold(T, monkeypatch, eng):
             _same(est.transform(Yd), d["out"][key]["transform"])
 
 
+@pytest.mark.parametrize("n", [1000, 1003, 260])
+def test_fp32_output_paths_equal_fp64(eng, n):
+    """fp32 K (TMA-store epilogue when rows are 16-byte aligned, vector-store epilogue otherwise)
+    must hold the same integers as the fp64 K, in square, row-block and rectangular mode."""
+    from grakel_b200.packing import pack, label_ids
+    X = gen(n, 14, 11)
+    b = pack(X, "wl", len_ok=lambda m: m >= 2)
+    ids, _ = label_ids(b.labels, None)
+    eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, ids)
+    eng.wl_features(3)
+    K64, d64, _ = eng.gram(n)
+    for kw in ({}, {"dense_all": True}, {"full_tiles": True}):
+        K32, _, _ = eng.gram(n, dtype=np.float32, **kw)
+        assert np.array_equal(K32.astype(np.float64), K64), kw
+    rb, re_ = n // 3, n // 3 + 300 if n > 600 else n // 3 + 50
+    Kr, _, _ = eng.gram(n, dtype=np.float32, row_range=(rb, re_))
+    assert np.array_equal(Kr.astype(np.float64), K64[rb:re_])
+    nf = n - 128
+    Kt64, _, yd = eng.gram(n, n_fit=nf)
+    Kt32, _, _ = eng.gram(n, n_fit=nf, dtype=np.float32)
+    assert np.array_equal(Kt32.astype(np.float64), Kt64) and Kt64.shape == (128, nf)
+    assert np.array_equal(yd, d64[nf:])
+
+
 def test_vertex_histogram_is_level0():
     k = _k()
     X = gen(60, 12, 5)
