@@ -153,7 +153,7 @@ int gk_destroy(gk_handle* h) {
                         &h->flags, &h->block_sums, &h->scalars, &h->ft_keys, &h->ft_cnt, &h->colcnt,
                         &h->colmin, &h->colmax, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
-                        &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_graph_off, &h->fattr, &h->tiles,
+                        &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
                         &h->K, &h->K_stage};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
@@ -530,6 +530,8 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   }
 
   size_t dict_cap = std::max<size_t>(h->sp_dict_cap, 1 << 16);
+  size_t dkey_cap = 1 << 18;
+  bool real_mode = false;
   size_t ft_cap = std::max<size_t>(next_pow2((size_t)std::max<int64_t>(h->V, 1024) * 16), 1 << 20);
   DevScalars* sc = h->scalars.as<DevScalars>();
   GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
@@ -548,11 +550,13 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     GK_CUDA(cudaMemsetAsync(h->ft_keys.p, 0xFF, ft_cap * 8, h->stream));
     GK_CUDA(cudaMemsetAsync(h->ft_cnt.p, 0, ft_cap * 4, h->stream));
     SpParams p;
+    memset(&p, 0, sizeof(p));
     p.graph_ptr = h->graph_ptr.as<int>();
     p.row_ptr = h->row_ptr.as<int>();
     p.col_idx = h->col_idx.as<int>();
     p.weights = (h->has_weights && !use_u16) ? h->weights.as<double>() : nullptr;
     p.labels = with_labels ? h->labels0.as<int>() : nullptr;
+    p.n_labels = with_labels ? std::max(h->n_labels0, 1) : 1;
     p.keep = d_keep;
     p.dict_keys = h->sp_dict_keys.as<unsigned long long>();
     p.dict_mask = (unsigned)(dict_cap - 1);
@@ -562,6 +566,39 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     p.sc = sc;
     p.st = fst;
     p.gdist = h->sp_dist.p;
+    if (real_mode) {
+      // non-integer path lengths: (1) fp64 Floyd-Warshall of every graph into global memory + a
+      // dictionary of the distinct distance bit patterns, (2) histogram keyed by (lu, lv, id(d))
+      GK_TRY(h->sp_dist.ensure((size_t)std::max<long long>(off_all, 1) * 8));
+      GK_TRY(h->sp_dkeys.ensure(dkey_cap * 8));
+      GK_CUDA(cudaMemsetAsync(h->sp_dkeys.p, 0xFF, dkey_cap * 8, h->stream));
+      SpParams pa = p;
+      pa.gdist = h->sp_dist.p;
+      pa.goff = d_goff_all;
+      pa.dict_keys = h->sp_dkeys.as<unsigned long long>();
+      pa.dict_mask = (unsigned)(dkey_cap - 1);
+      pa.keep = nullptr;
+      const size_t smem_a = max_small_nn * 8 + 16;
+      GK_CUDA(cudaFuncSetAttribute(spattr_apsp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_a, 16)));
+      if (!small.empty()) {
+        pa.glist = lists.as<int>();
+        pa.dist_in_global = 0;
+        spattr_apsp<double><<<(int)small.size(), SP_THREADS, smem_a, h->stream>>>(pa);
+        LAUNCH_CHECK(h);
+      }
+      if (!big.empty()) {
+        pa.glist = lists.as<int>() + small.size();
+        pa.dist_in_global = 1;
+        spattr_apsp<double><<<(int)big.size(), SP_THREADS, 16, h->stream>>>(pa);
+        LAUNCH_CHECK(h);
+      }
+      SpParams pb = p;
+      pb.gdist = h->sp_dist.p;
+      pb.goff = d_goff_all;
+      sp_hist_from_dist<<<(int)N, SP_THREADS, SP_LOCAL_SLOTS * 12, h->stream>>>(pb, h->sp_dkeys.as<unsigned long long>(),
+                                                                              (unsigned)(dkey_cap - 1));
+      LAUNCH_CHECK(h);
+    } else {
     if (!small.empty()) {
       p.glist = lists.as<int>();
       p.n_list = (int)small.size();
@@ -576,7 +613,7 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
       const int W = 1 << i;
       int nmax = 0;
       for (int g : bfs[i]) nmax = std::max(nmax, ex->graph_ptr[g + 1] - ex->graph_ptr[g]);
-      const size_t smem = SP_LOCAL_SLOTS * 12 + (size_t)nmax * W * 8 + (size_t)nmax * 4 + 16;
+      const size_t smem = SP_LOCAL_SLOTS * 12 + (size_t)nmax * W * 8 + (size_t)16 * W * 8 + (size_t)nmax * 4 + 16;
       p.glist = lists.as<int>() + bfs_off[i];
       p.n_list = (int)bfs[i].size();
       p.dist_in_global = 0;
@@ -606,12 +643,14 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
       else sp_apsp_hist<double><<<(int)big.size(), SP_THREADS, smem_big, h->stream>>>(p);
       LAUNCH_CHECK(h);
     }
+    }  // integer-distance mode
     DevScalars* hs;
     GK_TRY(read_scalars(h, &hs));
-    if (hs->sp_nonint) {
-      return fail(GK_ERR_UNSUPPORTED,
-                  "gk_sp_features: non-integer (or >= 2^24) shortest-path length; only integer-valued edge weights "
-                  "are supported on the device path");
+    if (hs->sp_nonint && !real_mode) { real_mode = true; --attempt; continue; }  // switch to exact float keys
+    if (real_mode && (hs->ft_overflow & 2u) && dkey_cap < (1u << 24)) {
+      // either dictionary may have overflowed; grow the distance dictionary first
+      dkey_cap *= 8;
+      if (dkey_cap > (1u << 24)) dkey_cap = 1u << 24;
     }
     if (hs->ft_overflow & 2u) { dict_cap *= 8; continue; }
     if (hs->ft_overflow & 1u) { ft_cap *= 4; continue; }

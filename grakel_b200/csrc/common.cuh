@@ -159,6 +159,7 @@ struct gk_handle {
   gk::DevBuf sp_dist;      // global-memory distance matrices for graphs too large for smem
   gk::DevBuf sp_dict_keys; // (lu,lv,d) -> column dictionary
   gk::DevBuf sp_dict_ids;
+  gk::DevBuf sp_dkeys;     // real-valued weights: dictionary of distance bit patterns
   size_t sp_dict_cap = 0;
   gk::DevBuf sp_graph_off; // per-graph offset into sp_dist (for gk_sp_distances)
   int sp_flags = 0;

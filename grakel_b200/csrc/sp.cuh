@@ -45,6 +45,7 @@ struct SpParams {
   const int* labels;       // dense ids or NULL (with_labels = False)
   const int* glist;        // graphs handled by this launch (NULL = all, blockIdx.x)
   int n_list;
+  int n_labels;            // size of the label alphabet (1 when with_labels = False)
   void* gdist;             // global distance scratch (large graphs / keep_dist)
   const long long* goff;   // element offset of graph g inside gdist
   int dist_in_global;      // 1: run FW in gdist instead of shared memory
@@ -120,10 +121,18 @@ sp_bfs_hist(SpParams p) {
   unsigned long long* lkeys = reinterpret_cast<unsigned long long*>(sp_smem);
   unsigned* lcnt = reinterpret_cast<unsigned*>(sp_smem + SP_LOCAL_SLOTS * 8);
   unsigned long long* adj = reinterpret_cast<unsigned long long*>(sp_smem + SP_LOCAL_SLOTS * 12);  // [n][W]
-  int* lab = reinterpret_cast<int*>(adj + (size_t)n * W);                                          // [n]
+  unsigned long long* lmask = adj + (size_t)n * W;                                                  // [L][W] (direct mode)
+  // Small alphabets (L <= 16): the CTA-local histogram is DIRECT-indexed by (ls, lv, level) --
+  // one shared-memory atomicAdd per (source, level, label class) with the class population count,
+  // instead of a hashed CAS + add per vertex pair (shared atomics cost ~2 cycles per lane).
+  const int L = p.n_labels;
+  const bool direct = L <= 11;  // >= 16 levels in the direct table; deeper levels go to the global table
+  const int dcap = direct ? SP_LOCAL_SLOTS / (L * L) : 0;  // levels covered by the direct table
+  int* lab = reinterpret_cast<int*>(lmask + (direct ? (size_t)L * W : 0));                          // [n]
   const int tid = threadIdx.x;
   for (int i = tid; i < SP_LOCAL_SLOTS; i += blockDim.x) { lkeys[i] = EMPTY64; lcnt[i] = 0; }
   for (int i = tid; i < n * W; i += blockDim.x) adj[i] = 0ULL;
+  if (direct) for (int i = tid; i < L * W; i += blockDim.x) lmask[i] = 0ULL;
   for (int i = tid; i < n; i += blockDim.x) lab[i] = p.labels ? p.labels[v0 + i] : 0;
   __syncthreads();
   const int e0 = p.row_ptr[v0], e1 = p.row_ptr[v0 + n];
@@ -137,6 +146,8 @@ sp_bfs_hist(SpParams p) {
     const int w = p.col_idx[k] - v0;
     if (w != lo) atomicOr(&adj[(size_t)lo * W + (w >> 6)], 1ULL << (w & 63));
   }
+  if (direct)
+    for (int v = tid; v < n; v += blockDim.x) atomicOr(&lmask[(size_t)lab[v] * W + (v >> 6)], 1ULL << (v & 63));
   __syncthreads();
   double* keep = p.keep ? p.keep + p.goff[g] : nullptr;
   for (int s = tid; s < n; s += blockDim.x) {
@@ -150,28 +161,44 @@ sp_bfs_hist(SpParams p) {
       for (int v = 0; v < n; ++v) keep[(size_t)s * n + v] = __longlong_as_double(0x7ff0000000000000LL);
       keep[(size_t)s * n + s] = 0.0;
     }
-    const unsigned long long ls = (unsigned long long)(unsigned)lab[s];
+    const int lsi = lab[s];
+    const unsigned long long ls = (unsigned long long)(unsigned)lsi;
     unsigned level = 1;
     while (true) {
       bool any = false;
 #pragma unroll
-      for (int w = 0; w < W; ++w) nx[w] = 0ULL;
+      for (int w = 0; w < W; ++w) { nx[w] = 0ULL; any |= fr[w] != 0ULL; }
+      if (!any) break;
+      const bool use_direct = direct && (int)level <= dcap;
+      if (use_direct) {  // class population counts of the new frontier
+        for (int l = 0; l < L; ++l) {
+          int c = 0;
+#pragma unroll
+          for (int w = 0; w < W; ++w) c += __popcll(fr[w] & lmask[(size_t)l * W + w]);
+          if (c) atomicAdd(&lcnt[(lsi * L + l) * dcap + (int)level - 1], (unsigned)c);
+        }
+      }
 #pragma unroll
       for (int w = 0; w < W; ++w) {
         unsigned long long bits = fr[w];
-        any |= bits != 0ULL;
         while (bits) {
           const int b = __ffsll((long long)bits) - 1;
           bits &= bits - 1;
           const int v = (w << 6) + b;
-          const unsigned long long key = (ls << 44) | ((unsigned long long)(unsigned)lab[v] << 24) | level;
-          sp_local_add(lkeys, lcnt, p, g, key);
+          if (!use_direct) {
+            const unsigned long long key = (ls << 44) | ((unsigned long long)(unsigned)lab[v] << 24) | level;
+            if (direct) {  // level beyond the direct table: lcnt holds direct counters, bypass the CTA table
+              const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
+              sp_feature_add(p, g, col, 1u);
+            } else {
+              sp_local_add(lkeys, lcnt, p, g, key);
+            }
+          }
           if (keep) keep[(size_t)s * n + v] = (double)level;
 #pragma unroll
           for (int x = 0; x < W; ++x) nx[x] |= adj[(size_t)v * W + x];
         }
       }
-      if (!any) break;
 #pragma unroll
       for (int w = 0; w < W; ++w) { nx[w] &= ~vis[w]; vis[w] |= nx[w]; fr[w] = nx[w]; }
       ++level;
@@ -179,10 +206,18 @@ sp_bfs_hist(SpParams p) {
   }
   __syncthreads();
   for (int i = tid; i < SP_LOCAL_SLOTS; i += blockDim.x) {
-    const unsigned long long key = lkeys[i];
-    if (key == EMPTY64) continue;
+    unsigned long long key;
+    const unsigned c = lcnt[i];
+    if (direct) {  // slot i = (ls * L + lv) * dcap + (level - 1)
+      if (!c || i >= L * L * dcap) continue;
+      const int pair = i / dcap, lev = i - pair * dcap + 1;
+      key = ((unsigned long long)(pair / L) << 44) | ((unsigned long long)(pair % L) << 24) | (unsigned long long)lev;
+    } else {
+      key = lkeys[i];
+      if (key == EMPTY64) continue;
+    }
     const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
-    sp_feature_add(p, g, col, lcnt[i]);
+    sp_feature_add(p, g, col, c);
   }
 }
 

@@ -68,6 +68,44 @@ spattr_apsp(SpParams p) {
   }
 }
 
+// Real-valued edge weights: histogram of (l(u), l(v), id(d(u,v))) from distance matrices kept
+// in global memory, where id() is the slot of the distance's bit pattern in the global distance
+// dictionary filled by spattr_apsp<double> (exact float equality, shortest_path.py:472, 511).
+__global__ void __launch_bounds__(SP_THREADS)
+sp_hist_from_dist(SpParams p, const unsigned long long* __restrict__ dkeys, unsigned dmask) {
+  extern __shared__ __align__(16) unsigned char sp_smem[];
+  const int g = blockIdx.x;
+  const int v0 = p.graph_ptr[g];
+  const int n = p.graph_ptr[g + 1] - v0;
+  if (n <= 0) return;
+  unsigned long long* lkeys = reinterpret_cast<unsigned long long*>(sp_smem);
+  unsigned* lcnt = reinterpret_cast<unsigned*>(sp_smem + SP_LOCAL_SLOTS * 8);
+  const double* dist = reinterpret_cast<const double*>(p.gdist) + p.goff[g];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < SP_LOCAL_SLOTS; i += SP_THREADS) { lkeys[i] = EMPTY64; lcnt[i] = 0; }
+  __syncthreads();
+  const long long nn = (long long)n * n;
+  for (long long i = tid; i < nn; i += SP_THREADS) {
+    const int u = (int)(i / n), w = (int)(i - (long long)u * n);
+    const double d = dist[i];
+    if (p.keep) p.keep[p.goff[g] + i] = d;
+    if (u == w || !(d < 1.0e300)) continue;
+    const unsigned long long dk = (unsigned long long)__double_as_longlong(d);
+    unsigned slot = (unsigned)(mix64(dk) >> 13) & dmask;
+    while (dkeys[slot] != dk) slot = (slot + 1) & dmask;
+    const unsigned long long lu = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + u] : 0ULL;
+    const unsigned long long lv = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + w] : 0ULL;
+    sp_local_add(lkeys, lcnt, p, g, (lu << 44) | (lv << 24) | (unsigned long long)slot);
+  }
+  __syncthreads();
+  for (int i = tid; i < SP_LOCAL_SLOTS; i += SP_THREADS) {
+    const unsigned long long key = lkeys[i];
+    if (key == EMPTY64) continue;
+    const int col = sp_dict_slot(p.dict_keys, p.dict_mask, key, p.sc);
+    sp_feature_add(p, g, col, lcnt[i]);
+  }
+}
+
 // Phase C: F_g[blk] += a_i (x) a_j for every ordered pair at distance with block id blk.
 // One CTA per graph, thread t owns element (t / da, t % da) of every block; F lives in
 // shared memory (blocks processed in chunks of `chunk` distances if they do not fit).

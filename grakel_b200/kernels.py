@@ -338,6 +338,14 @@ class ShortestPath(Kernel):
         block = pack(X, "sp", need_labels=wl, len_ok=lambda n: n in (2, 3) or (n == 1 and not wl),
                      want_weights=True, fw_zero_is_absent=self.algorithm_type == "floyd_warshall",
                      type_error_msg="each element of X must have at least one and at most 3 elements\n")
+        if block.weights is not None and np.any(block.weights != np.rint(block.weights)):
+            # Feature keys compare path lengths by exact float equality (shortest_path.py:472, 511), and the
+            # reference's own Dijkstra and Floyd-Warshall disagree in the last bit on real weights.  The device
+            # runs the k-ordered fp64 Floyd-Warshall, so only that semantics is reproduced bit for bit.
+            fw = self.algorithm_type == "floyd_warshall" or (self.algorithm_type == "auto" and block.all_adjacency)
+            if not fw:
+                raise NotImplementedError("non-integer edge weights are supported with Floyd-Warshall semantics only "
+                                          "(adjacency input or algorithm_type='floyd_warshall')")
         if self._method_calling in (1, 2):
             self._nx = block.n_graphs
             if wl:

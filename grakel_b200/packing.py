@@ -117,15 +117,14 @@ def _edges_of(g, kind):
 class Block:
     """Packed CSR block of a graph list (host, numpy)."""
 
-    __slots__ = ("n_graphs", "graph_ptr", "row_ptr", "col_idx", "weights", "labels", "attrs")
-
-    def __init__(self, graph_ptr, row_ptr, col_idx, weights, labels, attrs=None):
+    def __init__(self, graph_ptr, row_ptr, col_idx, weights, labels, attrs=None, all_adjacency=False):
         self.graph_ptr = np.ascontiguousarray(graph_ptr, dtype=np.int32)
         self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
         self.col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
         self.weights = weights
         self.labels = labels  # list of Python objects (len V) or None
         self.attrs = attrs
+        self.all_adjacency = all_adjacency  # every graph came as an adjacency matrix ("auto" -> Floyd-Warshall)
         self.n_graphs = len(self.graph_ptr) - 1
 
     @property
@@ -146,7 +145,7 @@ class Block:
             w = np.concatenate([wa, wb])
         lab = None if a.labels is None or b.labels is None else list(a.labels) + list(b.labels)
         at = None if a.attrs is None or b.attrs is None else np.concatenate([a.attrs, b.attrs])
-        return Block(gp, rp, ci, w, lab, at)
+        return Block(gp, rp, ci, w, lab, at, a.all_adjacency and b.all_adjacency)
 
 
 def iter_elements(X, len_ok, type_error_msg=None):
@@ -197,6 +196,7 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
     attr_rows = [] if attributes else None
     deg_total = 0
     any_weight = False
+    all_adjacency = True
     for idx, g, L in iter_elements(X, len_ok, type_error_msg):
         kind = classify(g)
         if kind is None:
@@ -241,6 +241,7 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
             any_weight = any_weight or bool(len(ww) and np.any(ww != 1.0))
             deg_total += len(ii)
         else:
+            all_adjacency = False
             verts, edges = _edges_of(g, kind)
             if mode == "wl":
                 if not L:
@@ -302,7 +303,7 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
             raise ValueError("node attributes must all have the same length")
     if graph_ptr[-1] >= 2 ** 31 or len(col_idx) >= 2 ** 31:
         raise ValueError("graph block exceeds int32 indexing")
-    return Block(np.asarray(graph_ptr), row_ptr, col_idx, weights, labels, attrs)
+    return Block(np.asarray(graph_ptr), row_ptr, col_idx, weights, labels, attrs, all_adjacency)
 
 
 def label_ids(labels, known=None, sort_new=True):

@@ -78,13 +78,16 @@ def test_fit_then_transform_with_unseen_labels(tag):
     _run_case(gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"]), d["out"])
 
 
-def test_real_weights_raise_not_guess():
+def test_real_weights_floyd_warshall_semantics():
+    """Real-valued weights: path lengths are compared by exact float equality, so the device must
+    reproduce the reference's fp64 k-ordered Floyd-Warshall bit for bit (adjacency input / forced
+    FW); the Dijkstra flavour differs in the last bit inside the reference itself and is refused."""
     d = gio.load(os.path.join(G, "fit_transform.json.gz"))["realw"]
-    X = gio.dec_dataset(d["X"])
+    X, Y = gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"])
+    out = {k: v for k, v in d["out"].items() if "dijkstra" not in k}
+    _run_case(X, Y, out)
     with pytest.raises(NotImplementedError):
-        _k().ShortestPath().fit_transform(X)
-    # WL ignores weights: still exact
-    _same(_k().WeisfeilerLehman(n_iter=2).fit_transform(X), d["out"]["wl_h2_u"]["fit_transform"])
+        _k().ShortestPath(algorithm_type="dijkstra").fit_transform(X)
 
 
 def test_mutag_goldens():
@@ -190,6 +193,27 @@ def test_fp32_output_paths_equal_fp64(eng, n):
     Kt32, _, _ = eng.gram(n, n_fit=nf, dtype=np.float32)
     assert np.array_equal(Kt32.astype(np.float64), Kt64) and Kt64.shape == (128, nf)
     assert np.array_equal(yd, d64[nf:])
+
+
+def test_wide_counts_take_the_exact_integer_path():
+    """A feature count above 256 is not exact in bf16: the engine must switch to the exact
+    u64 CUDA-core Gram on its own (gram_path 2) and still match the oracle bit for bit."""
+    k = _k()
+    rs = np.random.RandomState(5)
+    X = []
+    for n in (400, 350, 30, 500):
+        A = (rs.rand(n, n) < 0.01).astype(float)
+        A = ((A + A.T) > 0).astype(float)
+        np.fill_diagonal(A, 0)
+        X.append([A, {i: int(i % 2) for i in range(n)}])  # two labels -> counts of 200+ per graph
+    wl = k.WeisfeilerLehman(n_iter=2)
+    K = wl.fit_transform(X)
+    assert int(wl.stats_.max_count) > 256 and int(wl.stats_.gram_path) == 2
+    _same(K, WLOracle(n_iter=2).fit_transform(X))
+    sp = k.ShortestPath()
+    Ks = sp.fit_transform(X[2:3] + X[:1])
+    assert int(sp.stats_.gram_path) == 2
+    _same(Ks, SPOracle().fit_transform(X[2:3] + X[:1]))
 
 
 def test_vertex_histogram_is_level0():
