@@ -256,6 +256,13 @@ def main():
                "api": "gk_wl_fit_transform (C-ABI), pinned host CSR in, pinned fp64 K out",
                "last_step_ms": {"h2d+pack": es.ms_h2d, "features": es.ms_features, "columns+panel": es.ms_panel,
                                 "gemm": es.ms_gemm, "tail": es.ms_tail, "d2h": es.ms_d2h}}
+        # host-side breakdown of one e2e step (wall clock, separate C calls)
+        tb = {}
+        t0 = time.perf_counter(); eng.pack(gp_p, rp_p, ci_p, lab_p); tb["pack_csr(host scans + H2D)"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); s_ = eng.wl_features(H); tb["wl_features"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); eng.gram(n, out=Kh, dtype=np.float64, row_range=(rb, re_) if world > 1 else None, stats=s_, want_diag=False)
+        tb["gram + D2H"] = (time.perf_counter() - t0) * 1e3
+        e2e["host_wall_ms"] = tb
         if rank == 0 and world == 1 and n == N_GRAPHS:
             assert float(Kh.sum()) == 22925628586.0, "K checksum differs from the reference golden"
 

@@ -200,68 +200,17 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
   if (V >= (1LL << 26)) return fail(GK_ERR_ARG, "gk_pack_csr: more than 2^26 vertices in one block");
   const int64_t E = V ? row_ptr[V] : 0;
   if (E < 0 || (E > 0 && !col_idx)) return fail(GK_ERR_ARG, "gk_pack_csr: bad row_ptr / col_idx");
-  // host-side scans (one pass, branch-light so the compiler vectorises the inner loops):
-  // degrees, graph sizes, neighbours stay inside their graph
-  int max_deg = 0, max_n = 0;
-  long long hist[6] = {0, 0, 0, 0, 0, 0};  // degree <= 4, 8, 16, 32, more
+  // graph sizes (N small); every per-vertex / per-edge scan runs on the device below
+  int max_n = 0;
   for (int64_t g = 0; g < N; ++g) {
-    const int v0 = graph_ptr[g], v1 = graph_ptr[g + 1];
-    if (v1 < v0 || v1 > V) return fail(GK_ERR_ARG, "gk_pack_csr: graph_ptr not monotone");
-    max_n = std::max(max_n, v1 - v0);
-    int bad = 0;
-    for (int v = v0; v < v1; ++v) {
-      const int d = row_ptr[v + 1] - row_ptr[v];
-      bad |= d < 0;
-      max_deg = std::max(max_deg, d);
-      hist[d <= 4 ? 0 : d <= 8 ? 1 : d <= 16 ? 2 : d <= 32 ? 3 : 4]++;
-    }
-    if (bad) return fail(GK_ERR_ARG, "gk_pack_csr: row_ptr not monotone");
-    if (v1 > v0) {
-      int lo = v0, hi = v0;
-      for (int64_t e = row_ptr[v0]; e < row_ptr[v1]; ++e) {
-        lo = std::min(lo, col_idx[e]);
-        hi = std::max(hi, col_idx[e]);
-      }
-      if (lo < v0 || hi >= v1) return fail(GK_ERR_ARG, "gk_pack_csr: edge leaves its graph");
-    }
+    const int n = graph_ptr[g + 1] - graph_ptr[g];
+    if (n < 0 || graph_ptr[g + 1] > V) return fail(GK_ERR_ARG, "gk_pack_csr: graph_ptr not monotone");
+    max_n = std::max(max_n, n);
   }
-  int n_labels0 = 0;
-  if (labels) {
-    for (int64_t v = 0; v < V; ++v) {
-      if (labels[v] < 0) return fail(GK_ERR_ARG, "gk_pack_csr: negative label id");
-      n_labels0 = std::max(n_labels0, labels[v] + 1);
-    }
-  }
-  bool unit = true;
-  if (weights) {
-    for (int64_t e = 0; e < E; ++e) {
-      if (!(weights[e] >= 0.0)) return fail(GK_ERR_UNSUPPORTED, "gk_pack_csr: negative or NaN edge weight");
-      if (weights[e] != 1.0) unit = false;
-    }
-  }
-  // WL signature kernel choice: one thread per vertex for degree <= 8 (cost ~1 lane), else
-  // 16 or 32 lanes per vertex; vertices above the width take the warp-per-vertex kernel.
-  {
-    const long long above8 = hist[2] + hist[3] + hist[4], above16 = hist[3] + hist[4], above32 = hist[4];
-    const long long c8 = (long long)V * 1 + above8 * 32, c16 = (long long)V * 16 + above16 * 32,
-                    c32 = (long long)V * 32 + above32 * 32;
-    h->group_width = 8;
-    long long best = c8;
-    if (c16 < best) { best = c16; h->group_width = 16; }
-    if (c32 < best) { best = c32; h->group_width = 32; }
-  }
-  std::vector<int> large;
-  for (int64_t v = 0; v < V; ++v)
-    if (row_ptr[v + 1] - row_ptr[v] > h->group_width) large.push_back((int)v);
-
   h->N = N; h->V = V; h->E = E;
-  h->n_labels0 = n_labels0;
   h->has_weights = weights != nullptr;
-  h->unit_weights = unit;
   h->attr_dim = attrs ? attr_dim : 0;
-  h->max_degree = max_deg;
   h->max_graph_size = max_n;
-  h->n_large = (int64_t)large.size();
   h->features_ready = false;
   h->feature_kind = 0;
   HandleExtra* ex = extra_of(h);
@@ -272,6 +221,7 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
   GK_TRY(h->row_ptr.ensure((V + 1) * 4));
   GK_TRY(h->col_idx.ensure(std::max<int64_t>(E, 1) * 4));
   GK_TRY(h->vgraph.ensure(std::max<int64_t>(V, 1) * 4));
+  GK_TRY(h->large_list.ensure(std::max<int64_t>(V, 1) * 4 + 64));
   GK_CUDA(cudaMemcpyAsync(h->graph_ptr.p, graph_ptr, (N + 1) * 4, cudaMemcpyHostToDevice, h->stream));
   GK_CUDA(cudaMemcpyAsync(h->row_ptr.p, row_ptr, (V + 1) * 4, cudaMemcpyHostToDevice, h->stream));
   if (E) GK_CUDA(cudaMemcpyAsync(h->col_idx.p, col_idx, E * 4, cudaMemcpyHostToDevice, h->stream));
@@ -287,17 +237,53 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
     GK_TRY(h->attrs.ensure((size_t)V * attr_dim * 8));
     GK_CUDA(cudaMemcpyAsync(h->attrs.p, attrs, (size_t)V * attr_dim * 8, cudaMemcpyHostToDevice, h->stream));
   }
-  if (!large.empty()) {
-    GK_TRY(h->large_list.ensure(large.size() * 4));
-    GK_CUDA(cudaMemcpyAsync(h->large_list.p, large.data(), large.size() * 4, cudaMemcpyHostToDevice, h->stream));
-  }
+  // device-side statistics + validation (degree histogram, bounds, labels, weights)
+  int* d_scan = reinterpret_cast<int*>(h->scalars.as<DevScalars>()) ;  // reuse the scalar block as 16 ints
+  GK_CUDA(cudaMemsetAsync(d_scan, 0, 64, h->stream));
+  int hscan[16] = {0};
   if (V) {
     fill_vgraph<<<cdiv(V, 256), 256, 0, h->stream>>>((int)V, (int)N, h->graph_ptr.as<int>(), h->vgraph.as<int>());
     LAUNCH_CHECK(h);
+    pack_scan<<<cdiv(V, 256), 256, 0, h->stream>>>((int)V, (int)E, h->graph_ptr.as<int>(), h->vgraph.as<int>(),
+                                                   h->row_ptr.as<int>(), h->col_idx.as<int>(),
+                                                   labels ? h->labels0.as<int>() : nullptr, d_scan);
+    LAUNCH_CHECK(h);
+    if (weights && E) {
+      pack_scan_weights<<<h->sm_count * 4, 256, 0, h->stream>>>(E, h->weights.as<double>(), d_scan);
+      LAUNCH_CHECK(h);
+    }
+    GK_CUDA(cudaMemcpyAsync(h->h_scalars.p, d_scan, 64, cudaMemcpyDeviceToHost, h->stream));
+    GK_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(hscan, h->h_scalars.p, 64);
+  }
+  if (hscan[6] & 1) return fail(GK_ERR_ARG, "gk_pack_csr: row_ptr not monotone");
+  if (hscan[6] & 2) return fail(GK_ERR_ARG, "gk_pack_csr: edge leaves its graph");
+  if (hscan[6] & 4) return fail(GK_ERR_ARG, "gk_pack_csr: negative label id");
+  if (hscan[8] & 2) return fail(GK_ERR_UNSUPPORTED, "gk_pack_csr: negative or NaN edge weight");
+  h->n_labels0 = labels ? hscan[7] + 1 : 0;
+  h->unit_weights = !(hscan[8] & 1);
+  h->max_degree = hscan[5];
+  // WL signature kernel choice: one thread per vertex for degree <= 8 (cost ~1 lane), else
+  // 16 or 32 lanes per vertex; vertices above the width take the warp-per-vertex kernel.
+  {
+    const long long above8 = (long long)hscan[2] + hscan[3] + hscan[4], above16 = (long long)hscan[3] + hscan[4],
+                    above32 = hscan[4];
+    const long long c8 = (long long)V * 1 + above8 * 32, c16 = (long long)V * 16 + above16 * 32,
+                    c32 = (long long)V * 32 + above32 * 32;
+    h->group_width = 8;
+    h->n_large = above8;
+    long long best = c8;
+    if (c16 < best) { best = c16; h->group_width = 16; h->n_large = above16; }
+    if (c32 < best) { best = c32; h->group_width = 32; h->n_large = above32; }
+  }
+  if (h->n_large) {
+    GK_CUDA(cudaMemsetAsync(d_scan, 0, 4, h->stream));
+    pack_large_list<<<cdiv(V, 256), 256, 0, h->stream>>>((int)V, h->row_ptr.as<int>(), h->group_width,
+                                                         h->large_list.as<int>(), d_scan);
+    LAUNCH_CHECK(h);
   }
   GK_CUDA(cudaEventRecord(h->tev[1], h->stream));
-  // the source buffers (including the local `large` vector) must outlive the copies
-  GK_CUDA(cudaStreamSynchronize(h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));  // caller buffers may be reused once we return
   return GK_OK;
 }
 

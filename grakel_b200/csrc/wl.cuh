@@ -438,6 +438,61 @@ wl_insert_level0(int V, const int* __restrict__ lab, const int* __restrict__ vgr
   ft_account(did, g, old, is_new, st, blockIdx.x);
 }
 
+// CSR statistics + validation on the device (replaces host loops over V and E in gk_pack_csr):
+// out[0..4] degree histogram (<=4, <=8, <=16, <=32, more), out[5] max degree, out[6] error bits
+// (1 = negative degree, 2 = neighbour outside its graph, 4 = negative label), out[7] max label.
+__global__ void __launch_bounds__(256)
+pack_scan(int V, int E, const int* __restrict__ graph_ptr, const int* __restrict__ vgraph,
+          const int* __restrict__ row_ptr, const int* __restrict__ col_idx, const int* __restrict__ labels,
+          int* out) {
+  __shared__ int sh[8];
+  if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V) {
+    const int b = row_ptr[v], d = row_ptr[v + 1] - b;
+    int err = (d < 0 || b < 0 || (long long)b + d > E) ? 1 : 0;
+    const int g = vgraph[v];
+    const int v0 = graph_ptr[g], v1 = graph_ptr[g + 1];
+    for (int e = 0; e < d && !err; ++e) {
+      const int w = col_idx[b + e];
+      if (w < v0 || w >= v1) err |= 2;
+    }
+    int lab = 0;
+    if (labels) { lab = labels[v]; if (lab < 0) err |= 4; }
+    atomicAdd(&sh[(d > 4) + (d > 8) + (d > 16) + (d > 32)], 1);
+    atomicMax(&sh[5], d);
+    if (err) atomicOr(&sh[6], err);
+    atomicMax(&sh[7], lab);
+  }
+  __syncthreads();
+  if (threadIdx.x < 5 && sh[threadIdx.x]) atomicAdd(&out[threadIdx.x], sh[threadIdx.x]);
+  if (threadIdx.x == 5) atomicMax(&out[5], sh[5]);
+  if (threadIdx.x == 6 && sh[6]) atomicOr(&out[6], sh[6]);
+  if (threadIdx.x == 7) atomicMax(&out[7], sh[7]);
+}
+
+// edge weights: out[8] bit 1 = some weight != 1, bit 2 = negative or NaN weight
+__global__ void __launch_bounds__(256)
+pack_scan_weights(long long E, const double* __restrict__ w, int* out) {
+  int f = 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const double x = w[e];
+    if (!(x >= 0.0)) f |= 2;
+    if (x != 1.0) f |= 1;
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(&out[8], f);
+}
+
+// vertices whose degree exceeds the chosen lane width -> list for wl_sig_large (order irrelevant)
+__global__ void __launch_bounds__(256)
+pack_large_list(int V, const int* __restrict__ row_ptr, int width, int* __restrict__ list, int* counter) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  if (row_ptr[v + 1] - row_ptr[v] > width) list[atomicAdd(counter, 1)] = v;
+}
+
 // vertex -> graph id by binary search in graph_ptr
 __global__ void __launch_bounds__(256)
 fill_vgraph(int V, int N, const int* __restrict__ graph_ptr, int* __restrict__ vgraph) {
