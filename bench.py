@@ -35,7 +35,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_GRAPHS, NBAR, H, SEED = 10000, 40, 5, 0
-CPU_SAMPLE = 2000  # graphs in the bounded CPU sample
+CPU_SAMPLE = 6000  # graphs in the bounded CPU sample (~10 s of CPU work per step on the box's host)
+CPU_THREADS = H + 1  # the reference parallelises over WL levels (joblib threading, weisfeiler_lehman.py:279-285)
 
 
 def pack_workload(n_graphs):
@@ -115,35 +116,61 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_arm(n_sample, steps=1, warmup=0):
-    """The CPU oracle port on a prefix of the workload; returns (pairs/s, seconds/step)."""
+def measured_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    (profiles/traffic.json), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        for k, v in d.items():
+            if isinstance(v, dict) and key in k:
+                return v["dram_read_bytes"] + v["dram_write_bytes"]
+    except Exception:
+        pass
+    return None
+
+
+def cpu_threads():
+    return max(1, min(CPU_THREADS, os.cpu_count() or 1))
+
+
+def cpu_arm(steps=1, budget_s=12.0, n_max=CPU_SAMPLE):
+    """The CPU oracle port on a prefix of the workload, one thread per WL level like the
+    reference's best configuration (n_jobs).  The prefix length is chosen from a timed
+    1 500-graph probe (cost ~ n^2) so that `steps` steps take about `budget_s` seconds in
+    total, capped at `n_max` graphs.  Returns (pairs/s, seconds/step, n_sample)."""
     from oracle.gk_oracle import WLOracle, gen
-    X = gen(n_sample, NBAR, SEED)
-    for _ in range(warmup):
-        WLOracle(n_iter=H).fit_transform(X[: max(50, n_sample // 10)])
+    X = gen(n_max, NBAR, SEED)
+    nj = cpu_threads()
+    probe = min(1500, n_max)
+    t = time.perf_counter()
+    WLOracle(n_iter=H, n_jobs=nj).fit_transform(X[:probe])  # also the warm-up
+    t_probe = time.perf_counter() - t
+    n_sample = int(min(n_max, max(probe, probe * np.sqrt(budget_s / max(steps, 1) / t_probe))))
+    n_sample -= n_sample % 100
+    X = X[:n_sample]
     ts = []
     for _ in range(steps):
         t = time.perf_counter()
-        K = WLOracle(n_iter=H).fit_transform(X)
+        K = WLOracle(n_iter=H, n_jobs=nj).fit_transform(X)
         ts.append(time.perf_counter() - t)
-    assert K.shape == (n_sample, n_sample)
+        assert K.shape == (n_sample, n_sample)
+        del K
     t = float(np.mean(ts))
-    return n_sample * n_sample / t, t
+    return n_sample * n_sample / t, t, n_sample
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n = CPU_SAMPLE
-    val, t = cpu_arm(n, steps=args.steps, warmup=min(args.warmup, 1))
-    cores = 1
+    val, t, n = cpu_arm(steps=args.steps, budget_s=100.0)
+    cores = cpu_threads()
     line = {
         "impl": "reference", "metric": "graph-pairs/sec, N x N WL-subtree (h=5) Gram", "value": val,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"config2: {N_GRAPHS} ER graphs (avg {NBAR} nodes, 7 labels, seed {SEED}), WL-subtree h={H}",
-                   "parallelism": "host CPU, 1 thread (the reference's default n_jobs=None)"},
+                   "parallelism": f"host CPU, {cores} threads (one per WL level, the reference's n_jobs threading)"},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"first {n} of the {N_GRAPHS} graphs ({n * n} ordered pairs per step); "
                                    f"host has {os.cpu_count()} logical cores"},
@@ -305,8 +332,14 @@ def main():
         "gpu_launches": launches,
         "roofline": {"kernel": "gram_tc_kernel<float,false> (tcgen05 bf16 SYRK)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "peak_source": peak_src, "flops_per_launch": flops, "ms_per_launch": g_ms,
+                     "traffic": measured_traffic("hybrid") if (world == 1 and n == N_GRAPHS) else None,
+                     "traffic_unit": "bytes/launch (ncu dram read+write, profiles/traffic.json)",
+                     "peak_source": peak_src, "flops_per_launch": flops, "ms_per_launch": g_ms,
                      "share_of_step": g_ms / ms_step},
+        "roofline_store": {"kernel": "gram_tc_kernel epilogue (K written once, fp32)", "bound": "hbm",
+                           "achieved": (re_ - rb if world > 1 else n) * n * 4 / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0,
+                           "peak": peak_hbm, "unit": "GB/s",
+                           "frac": ((re_ - rb if world > 1 else n) * n * 4 / (g_ms * 1e-3) / 1e9 / peak_hbm) if g_ms > 0 else 0.0},
         "stages_ms": {"wl_features": float(np.mean(feat_ms)), "columns+panel": float(np.mean(panel_ms)),
                       "gram_gemm": g_ms, "tail_pairs": float(np.mean(tail_ms)), "wall_ms_per_step": wall_ms / args.steps},
         "head_tail": {"threshold_T": int(st.threshold), "head_columns": Dc, "tail_columns": int(st.n_tail_columns),
@@ -314,10 +347,10 @@ def main():
         "dense_gemm_mode": dense,
     }
     if not args.no_cpu and world == 1:
-        val, t = cpu_arm(CPU_SAMPLE)
-        line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": 1, "kind": "port",
-                                "sample": f"first {CPU_SAMPLE} of the {n} graphs, {t:.1f} s on one host thread "
-                                          f"({os.cpu_count()} logical cores on the box)"}
+        val, t, n_cpu = cpu_arm(steps=1, budget_s=12.0)
+        line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": cpu_threads(), "kind": "port",
+                                "sample": f"first {n_cpu} of the {n} graphs, {t:.1f} s with {cpu_threads()} host threads "
+                                          f"(one per WL level; {os.cpu_count()} logical cores on the box)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -68,6 +68,7 @@ _SYMBOLS = {
                                       C.c_int64, _P, C.POINTER(GkStats)]),
     "gk_event_record": (C.c_int, [_P, C.c_int32]),
     "gk_event_elapsed": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    "gk_profiler_range": (C.c_int, [C.c_int32]),
     "gk_selftest_gram": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P]),
 }
 
@@ -244,6 +245,9 @@ class Engine:
         ms = C.c_float()
         self._check(self.lib.gk_event_elapsed(self.h, a, b, C.byref(ms)))
         return ms.value
+
+    def profiler_range(self, on):
+        self._check(self.lib.gk_profiler_range(1 if on else 0))
 
     def sync(self):
         self._check(self.lib.gk_sync(self.h))

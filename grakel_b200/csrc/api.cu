@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <cuda_profiler_api.h>
+
 #include "common.cuh"
 #include "features.cuh"
 #include "gram_tc.cuh"
@@ -183,6 +185,12 @@ int gk_event_elapsed(gk_handle* h, int32_t a, int32_t b, float* ms) {
   if (!h || !ms || a < 0 || a >= 16 || b < 0 || b >= 16) return fail(GK_ERR_ARG, "gk_event_elapsed: bad args");
   GK_CUDA(cudaEventSynchronize(h->ev[b]));
   GK_CUDA(cudaEventElapsedTime(ms, h->ev[a], h->ev[b]));
+  return GK_OK;
+}
+
+// ncu/nsys capture range (tools/profile_step.py runs under `--profile-from-start off`)
+int gk_profiler_range(int32_t on) {
+  GK_CUDA(on ? cudaProfilerStart() : cudaProfilerStop());
   return GK_OK;
 }
 

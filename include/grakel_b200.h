@@ -160,6 +160,10 @@ int gk_sp_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr
 int gk_event_record(gk_handle* h, int32_t slot);            /* slot in [0,16) */
 int gk_event_elapsed(gk_handle* h, int32_t a, int32_t b, float* ms);
 
+/* cudaProfilerStart / cudaProfilerStop (on != 0 / on == 0): lets a profiler capture one
+ * steady-state pass (tools/profile_step.py under `ncu --profile-from-start off`). */
+int gk_profiler_range(int32_t on);
+
 /* Self-test of the tensor-core Gram on a dense count matrix (tests only):
  * counts[n*d] (uint16), out_tc / out_simt [n*n] fp64. */
 int gk_selftest_gram(gk_handle* h, int64_t n, int64_t d, const uint16_t* counts, double* out_tc,

@@ -283,11 +283,14 @@ class _VH:
 # Weisfeiler-Lehman subtree  (weisfeiler_lehman.py:117-555)
 # --------------------------------------------------------------------------
 class WLOracle:
-    def __init__(self, n_iter=5, normalize=False):
+    def __init__(self, n_iter=5, normalize=False, n_jobs=None):
         if type(n_iter) is not int or n_iter <= 0:
             raise TypeError("'n_iter' must be a positive integer")
         self.h = n_iter
         self.normalize = normalize
+        # weisfeiler_lehman.py:279-285: with n_jobs the reference hands one task per level
+        # (base kernel fit_transform) to a joblib *threading* pool; same structure here.
+        self.n_jobs = n_jobs
 
     @staticmethod
     def _signature(own, nbr_labels):
@@ -306,9 +309,18 @@ class WLOracle:
         self.inv = {0: inv0}
         count = len(inv0)
         L = [{v: inv0[lab] for v, lab in l.items()} for l in L]
-        self.levels = [_VH().fit(L)]
+        pool = None
+        if self.n_jobs is not None and self.n_jobs != 1:
+            from concurrent.futures import ThreadPoolExecutor
+            import os as _os
+            pool = ThreadPoolExecutor(max_workers=self.n_jobs if self.n_jobs > 0 else (_os.cpu_count() or 1))
+
+        def level_task(Lc):
+            vh = _VH().fit(Lc)
+            return vh, vh.gram()
+
+        tasks = [pool.submit(level_task, L) if pool else level_task(L)]
         level_labels = [[dict(l) for l in L]] if return_levels else None
-        Ks = [self.levels[0].gram()]
         for it in range(1, self.h + 1):  # weisfeiler_lehman.py:223-258
             # The reference collects the credential set, sorts it and numbers it (:243-246);
             # K only depends on the partition, so ids are handed out at first sight here
@@ -330,9 +342,13 @@ class WLOracle:
             L = newL
             if return_levels:
                 level_labels.append([dict(l) for l in L])
-            vh = _VH().fit(L)
-            self.levels.append(vh)
-            Ks.append(vh.gram())
+            tasks.append(pool.submit(level_task, L) if pool else level_task(L))
+        done = [t.result() if pool else t for t in tasks]
+        if pool:
+            pool.shutdown()
+        self.levels = [vh for vh, _ in done]
+        Ks = [k for _, k in done]
+        del done, tasks
         K = np.sum(Ks, axis=0)  # weisfeiler_lehman.py:270
         self.level_labels = level_labels
         self.xdiag = np.diagonal(K).copy()
