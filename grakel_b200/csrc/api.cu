@@ -12,6 +12,7 @@
 #include "sp.cuh"
 #include "spattr.cuh"
 #include "wl.cuh"
+#include "wl_fused.cuh"
 
 namespace gk {
 thread_local std::string g_last_error;
@@ -88,6 +89,7 @@ using namespace gk;
 // extra host-side state that does not belong in the POD-ish handle header
 struct HandleExtra {
   std::vector<int> graph_ptr;
+  std::vector<int> graph_eptr;  // first edge of each graph (row_ptr[graph_ptr[g]])
   std::vector<long long> sp_goff;
 };
 static std::vector<std::pair<gk_handle*, HandleExtra*>> g_extra;
@@ -156,7 +158,7 @@ int gk_destroy(gk_handle* h) {
                         &h->colmin, &h->colmax, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
-                        &h->K, &h->K_stage};
+                        &h->K, &h->K_stage, &h->wlf_buf};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
@@ -223,6 +225,8 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
   h->feature_kind = 0;
   HandleExtra* ex = extra_of(h);
   ex->graph_ptr.assign(graph_ptr, graph_ptr + N + 1);
+  ex->graph_eptr.resize(N + 1);
+  for (int64_t g = 0; g <= N; ++g) ex->graph_eptr[g] = V ? row_ptr[graph_ptr[g]] : 0;
 
   GK_CUDA(cudaEventRecord(h->tev[0], h->stream));
   GK_TRY(h->graph_ptr.ensure((N + 1) * 4));
@@ -360,11 +364,65 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   GK_TRY(h->flags.ensure(V * 4));
   const int nb = cdiv(V, 256);
   GK_TRY(h->block_sums.ensure((size_t)nb * 4));
-  h->ht_cap = next_pow2((size_t)V * 2);
-  GK_TRY(h->ht_keys.ensure(h->ht_cap * 8));
-  GK_TRY(h->ht_rep.ensure(h->ht_cap * 4));
-  const size_t ft_level_cap = next_pow2((size_t)V * 2);  // one L2-sized sub-table per level
-  h->ft_cap = ft_level_cap * (size_t)L;
+  h->ht_cap = std::max<size_t>(next_pow2((size_t)V * 2), 1024);
+  GK_TRY(h->ht_keys.ensure(h->ht_cap * 8 * 2));  // two tables: the fused kernel alternates between levels
+  GK_TRY(h->ht_rep.ensure(h->ht_cap * 4 * 2));
+  const size_t ft_level_cap = std::max<size_t>(next_pow2((size_t)V * 2), 1024);  // one L2-sized sub-table per level
+  // Fused persistent kernel (wl_fused.cuh) whenever the graphs can be cut into shared-memory tiles of
+  // whole graphs; otherwise (a graph above the tile capacity) the multi-kernel path below.
+  bool fused = true;
+  if (const char* e = getenv("GRAKEL_B200_WL_FUSED")) fused = atoi(e) != 0;
+  const int G = std::min(h->sm_count, 1024);
+  int n_tiles = 0;
+  if (fused) {
+    HandleExtra* ex = extra_of(h);
+    std::vector<int> tv, ct(G + 1, 0);
+    bool ok = false;
+    for (int per = std::max<int64_t>(1, std::max((V + (int64_t)G * WLF_TILE_V - 1) / ((int64_t)G * WLF_TILE_V),
+                                                 (E + (int64_t)G * WLF_TILE_E - 1) / ((int64_t)G * WLF_TILE_E)));
+         per <= 4096 && !ok; per *= 2) {
+      // G * per tiles of whole graphs, balanced by vertex count
+      const int T = G * per;
+      tv.assign(T + 1, 0);
+      size_t g = 0;
+      for (int t = 1; t < T; ++t) {
+        const long long want = (long long)V * t / T;
+        while (g < (size_t)h->N && ex->graph_ptr[g] < want) ++g;
+        tv[t] = (int)g;
+      }
+      tv[T] = (int)h->N;
+      ok = true;
+      for (int t = 0; t < T && ok; ++t) {
+        const int nv = ex->graph_ptr[tv[t + 1]] - ex->graph_ptr[tv[t]];
+        const int ne = ex->graph_eptr[tv[t + 1]] - ex->graph_eptr[tv[t]];
+        if (nv > WLF_TILE_V || ne > WLF_TILE_E) ok = false;
+      }
+      if (ok) {
+        n_tiles = T;
+        for (int t = 0; t <= T; ++t) tv[t] = ex->graph_ptr[tv[t]];  // graph index -> first vertex
+        for (int c = 0; c <= G; ++c) ct[c] = c * per;
+        long long max_cta = 0;
+        for (int c = 0; c < G; ++c) max_cta = std::max<long long>(max_cta, tv[ct[c + 1]] - tv[ct[c]]);
+        if (max_cta >= (1 << WLF_RANK_BITS)) ok = false;
+      }
+      if (h->max_graph_size > WLF_TILE_V) break;
+    }
+    fused = ok;
+    if (fused) {
+      // layout of wlf_buf (ints): [tile_vbeg (T+1) | cta_tile (G+1) | cta_count (G) | barrier]
+      const size_t n_int = (size_t)(n_tiles + 1) + (G + 1) + G + 1;
+      GK_TRY(h->wlf_buf.ensure(n_int * 4));
+      GK_TRY(h->h_tiles.ensure(((size_t)n_tiles + G + 2) * 4));
+      int* hp = h->h_tiles.as<int>();
+      memcpy(hp, tv.data(), (size_t)(n_tiles + 1) * 4);
+      memcpy(hp + n_tiles + 1, ct.data(), (size_t)(G + 1) * 4);
+      GK_CUDA(cudaMemcpyAsync(h->wlf_buf.p, hp, ((size_t)n_tiles + G + 2) * 4, cudaMemcpyHostToDevice, h->stream));
+      GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
+    }
+  }
+  // feature block: the multi-kernel path fills one open-addressing sub-table per level, the fused
+  // kernel appends at most V entries per level to the same arrays used as a COO list
+  h->ft_cap = fused ? std::max<size_t>((size_t)V * L, 1) : ft_level_cap * (size_t)L;
   if (h->ft_cap > (1ULL << 31)) return fail(GK_ERR_ARG, "gk_wl_features: feature table too large");
   GK_TRY(h->ft_keys.ensure(h->ft_cap * 8));
   GK_TRY(h->ft_cnt.ensure(h->ft_cap * 4));
@@ -378,7 +436,70 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     const unsigned long long seed = mix64(0x5851F42D4C957F2DULL + 0x9E3779B97F4A7C15ULL * (unsigned long long)retries);
     GK_TRY(init_scalars(h, h->n_labels0));
     FeatStats fst;
-    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)nb * L, &fst));
+    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)std::max(nb, G) * L, &fst));
+    if (fused) {
+      // one persistent cooperative kernel for all levels; it appends (graph, column, count) entries
+      // to ft_keys / ft_cnt used as a compact COO list
+      if (L > 1) GK_CUDA(cudaMemsetAsync(h->ht_keys.as<unsigned long long>() + h->ht_cap, 0xFF, h->ht_cap * 8, h->stream));
+      int* wb = h->wlf_buf.as<int>();
+      int* d_cta_tile = wb + n_tiles + 1;
+      int* d_cta_count = d_cta_tile + G + 1;
+      unsigned* d_barrier = reinterpret_cast<unsigned*>(d_cta_count + G);
+      GK_CUDA(cudaMemsetAsync(d_barrier, 0, 4, h->stream));
+      WlFusedParams fp;
+      memset(&fp, 0, sizeof(fp));
+      fp.V = (int)V; fp.L = L;
+      fp.graph_ptr = h->graph_ptr.as<int>();
+      fp.row_ptr = h->row_ptr.as<int>(); fp.col_idx = h->col_idx.as<int>(); fp.vgraph = h->vgraph.as<int>();
+      fp.labels0 = h->labels0.as<int>(); fp.tile_vbeg = wb; fp.cta_tile = d_cta_tile; fp.cta_count = d_cta_count;
+      fp.barrier = d_barrier;
+      fp.labels_all = labels_all; fp.sig_nbr = h->sig_nbr.as<int>(); fp.slot_of = h->slot_of.as<int>();
+      fp.rank_pack = h->flags.as<int>();
+      fp.table = h->ht_keys.as<unsigned long long>();
+      fp.ht_mask = (unsigned)(h->ht_cap - 1);
+      fp.coo_keys = h->ft_keys.as<unsigned long long>(); fp.coo_cnt = h->ft_cnt.as<unsigned>();
+      fp.seed = seed; fp.st = fst; fp.sc = sc;
+      const bool prof = getenv("GRAKEL_B200_PROF") != nullptr;
+      if (prof) {
+        GK_TRY(h->K_stage.ensure((size_t)G * L * 128));
+        GK_CUDA(cudaMemsetAsync(h->K_stage.p, 0, (size_t)G * L * 128, h->stream));
+        fp.prof = h->K_stage.as<long long>();
+      }
+      void* args[] = {&fp};
+      GK_CUDA(cudaLaunchCooperativeKernel((void*)wl_fused_kernel, dim3(G), dim3(WLF_THREADS), args, WLF_SMEM, h->stream));
+      LAUNCH_CHECK(h);
+      if (prof) {
+        std::vector<long long> pr((size_t)G * L * 16);
+        GK_CUDA(cudaMemcpyAsync(pr.data(), h->K_stage.p, pr.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        GK_CUDA(cudaStreamSynchronize(h->stream));
+        long long t0 = pr[0];
+        for (int b = 0; b < G; ++b) t0 = std::min(t0, pr[(size_t)b * L * 16]);
+        fprintf(stderr, "[wl_fused prof] ns since kernel start; per level: phase = avg over CTAs of its duration (max)\n");
+        for (int lv = 0; lv < L; ++lv) {
+          const char* names[6] = {"A", "wait1", "B", "clear", "wait2", "C"};
+          double avg[6] = {0}, mx[6] = {0};
+          long long end_max = 0;
+          for (int b = 0; b < G; ++b) {
+            const long long* q = &pr[((size_t)b * L + lv) * 16];
+            end_max = std::max(end_max, q[6] - t0);
+            if (lv == 0) { avg[5] += (double)(q[6] - q[0]) / G; mx[5] = std::max(mx[5], (double)(q[6] - q[0])); continue; }
+            for (int k = 0; k < 6; ++k) { const double d = (double)(q[k + 1] - q[k]); avg[k] += d / G; mx[k] = std::max(mx[k], d); }
+          }
+          fprintf(stderr, "  level %d:", lv);
+          for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.1f (%.1f)", names[k], avg[k] / 1e3, mx[k] / 1e3);
+          if (lv) {  // split of phase A (last tile of each CTA): stage | thread-per-vertex | warp-per-vertex | copy-out
+            double sa[4] = {0};
+            for (int b = 0; b < G; ++b) {
+              const long long* q = &pr[((size_t)b * L + lv) * 16];
+              sa[0] += (double)(q[8] - q[0]) / G; sa[1] += (double)(q[9] - q[8]) / G;
+              sa[2] += (double)(q[10] - q[9]) / G; sa[3] += (double)(q[1] - q[10]) / G;
+            }
+            fprintf(stderr, " | A = stage %.1f + thread %.1f + warp %.1f + out %.1f", sa[0] / 1e3, sa[1] / 1e3, sa[2] / 1e3, sa[3] / 1e3);
+          }
+          fprintf(stderr, " | level done at %.1f us\n", end_max / 1e3);
+        }
+      }
+    } else {
     GK_CUDA(cudaMemsetAsync(h->ft_keys.p, 0xFF, h->ft_cap * 8, h->stream));
     GK_CUDA(cudaMemsetAsync(h->ft_cnt.p, 0, h->ft_cap * 4, h->stream));
     GK_CUDA(cudaMemcpyAsync(labels_all, h->labels0.p, V * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -419,6 +540,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
                                                    h->ft_cnt.as<unsigned>(), (unsigned)(ft_level_cap - 1));
       LAUNCH_CHECK(h);
     }
+    }  // multi-kernel path
     DevScalars* hs;
     GK_TRY(read_scalars(h, &hs));
     if (hs->ft_overflow) return fail(GK_ERR_STATE, "gk_wl_features: feature table overflow");
@@ -428,6 +550,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   GK_CUDA(cudaEventSynchronize(h->tev[3]));
   DevScalars* hs = h->h_scalars.as<DevScalars>();
   h->n_columns = hs->level_base[L];
+  if (fused) h->ft_cap = (size_t)hs->sp_coo;  // compact COO list: every slot is an entry
   h->features_ready = true;
   h->feature_kind = 1;
   if (stats) {
@@ -833,7 +956,7 @@ static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_b
   if (ld <= 0) ld = k_cols;
   const int64_t launches0 = h->launches;
   GK_TRY(h->K.ensure((size_t)std::max<int64_t>(k_rows, 1) * k_cols * 8));
-  h->K_rows = k_rows; h->K_cols = k_cols; h->K_dtype = GK_F64;
+  h->K_rows = k_rows; h->K_cols = k_cols; h->K_ld = k_cols; h->K_dtype = GK_F64;
   const int a0 = (int)((square ? 0 : n_fit) + row_begin), a1 = (int)((square ? 0 : n_fit) + row_end);
   GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
   if (k_rows > 0) {
@@ -933,9 +1056,6 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   if (D > h->col_cap) return fail(GK_ERR_STATE, "gk_gram: column statistics missing");
   const int nbc = cdiv(D, 256);
   GK_TRY(h->colslot.ensure(D * 4));
-  GK_TRY(h->tail_cur.ensure(D * 4));
-  GK_TRY(h->col_flags3.ensure(D * sizeof(int3)));
-  GK_TRY(h->col_block_sums.ensure((size_t)nbc * sizeof(int3)));
   GK_TRY(h->colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->h_colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->diag_f64.ensure(N * 8));
@@ -1013,14 +1133,13 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     for (int b = 0; b < HIST_BUCKETS; ++b)
       fprintf(stderr, "  bucket %2d: cols %llu work %llu entries %llu\n", b, hc.hist_cols[b], hc.hist_work[b], hc.hist_entries[b]);
   }
-  col_flags<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, (int)n_fit, h->colcnt.as<unsigned>(), h->colmin.as<int>(),
-                                        h->colmax.as<int>(), T, h->col_flags3.as<int3>(), h->col_block_sums.as<int3>());
-  LAUNCH_CHECK(h);
-  scan_sums3<<<1, 1024, 0, h->stream>>>(nbc, h->col_block_sums.as<int3>());
-  LAUNCH_CHECK(h);
   GK_TRY(h->tail_desc.ensure((size_t)std::max<int64_t>(n_tail_cols, 1) * sizeof(int2)));
-  col_assign<<<nbc, 256, 0, h->stream>>>(D, h->col_flags3.as<int3>(), h->col_block_sums.as<int3>(),
-                                         h->colslot.as<int>(), h->tail_desc.as<int2>());
+  GK_TRY(h->tail_cur.ensure((size_t)std::max<int64_t>(n_tail_cols, 1) * 4));
+  unsigned* col_counters = reinterpret_cast<unsigned*>(cs);  // the histogram has been read: reuse its first words
+  GK_CUDA(cudaMemsetAsync(col_counters, 0, 16, h->stream));
+  col_classify<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, (int)n_fit, h->colcnt.as<unsigned>(), h->colmin.as<int>(),
+                                           h->colmax.as<int>(), T, h->colslot.as<int>(), h->tail_desc.as<int2>(),
+                                           h->tail_cur.as<unsigned>(), col_counters);
   LAUNCH_CHECK(h);
   if (path == 1 && Dc == 0) path = 3;
   h->Dc = Dc;
@@ -1032,11 +1151,14 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     if (!K_out) return fail(GK_ERR_ARG, "gk_gram: GK_OUT_DEVICE without a pointer");
     d_out = K_out;
   } else {
-    GK_TRY(h->K.ensure((size_t)std::max<int64_t>(k_rows, 1) * k_cols * esz));
+    // library-owned K: rows padded to a multiple of 8 elements so that every row is 32-byte aligned
+    // (TMA / 256-bit stores in the GEMM epilogue for any n_fit, e.g. 14 142 graphs on 2 GPUs)
+    h->K_ld = (k_cols + 7) / 8 * 8;
+    GK_TRY(h->K.ensure((size_t)std::max<int64_t>(k_rows, 1) * h->K_ld * esz));
     d_out = h->K.p;
     h->K_rows = k_rows; h->K_cols = k_cols; h->K_dtype = out_dtype;
   }
-  const long long d_ld = (flags & GK_OUT_DEVICE) ? ld : k_cols;
+  const long long d_ld = (flags & GK_OUT_DEVICE) ? ld : h->K_ld;
 
   // panel-row ranges: A rows index K rows, B rows index K columns
   const int a0 = (int)((square ? 0 : n_fit) + row_begin), a1 = (int)((square ? 0 : n_fit) + row_end);
@@ -1062,7 +1184,6 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   if (k_rows > 0) {
     if (has_tail) {
       GK_TRY(h->tail_ent.ensure((size_t)n_tail_ent * sizeof(int2)));
-      GK_CUDA(cudaMemsetAsync(h->tail_cur.p, 0, D * 4, h->stream));
     }
     if (path == 1 || path == 3) {
       const size_t panel_bytes = (size_t)N * std::max<int64_t>(h->Dc_pad, BK) * 2;
@@ -1071,7 +1192,8 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       if (Dc || has_tail) {
         feat_scatter<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
             h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(),
-            h->panel.as<__nv_bfloat16>(), h->Dc_pad, h->tail_cur.as<unsigned>(), h->tail_ent.as<int2>());
+            h->panel.as<__nv_bfloat16>(), h->Dc_pad, h->tail_cur.as<unsigned>(), h->tail_desc.as<int2>(),
+            h->tail_ent.as<int2>());
         LAUNCH_CHECK(h);
       }
     }
@@ -1166,7 +1288,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   // ---- results to the host
   GK_CUDA(cudaEventRecord(h->ev[14], h->stream));
   if (K_out && !(flags & GK_OUT_DEVICE) && k_rows > 0) {
-    GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * esz, d_out, (size_t)k_cols * esz, (size_t)k_cols * esz,
+    GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * esz, d_out, (size_t)d_ld * esz, (size_t)k_cols * esz,
                               (size_t)k_rows, cudaMemcpyDeviceToHost, h->stream));
   }
   if (xdiag) GK_CUDA(cudaMemcpyAsync(xdiag, h->diag_f64.p, n_fit * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1202,7 +1324,7 @@ int gk_fetch(gk_handle* h, void* K_out, int32_t out_dtype, int64_t ld) {
   const size_t esz = out_dtype == GK_F64 ? 8 : 4;
   if (ld <= 0) ld = h->K_cols;
   GK_CUDA(cudaSetDevice(h->dev));
-  GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * esz, h->K.p, (size_t)h->K_cols * esz, (size_t)h->K_cols * esz,
+  GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * esz, h->K.p, (size_t)h->K_ld * esz, (size_t)h->K_cols * esz,
                             (size_t)h->K_rows, cudaMemcpyDeviceToHost, h->stream));
   GK_CUDA(cudaStreamSynchronize(h->stream));
   return GK_OK;

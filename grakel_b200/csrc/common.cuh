@@ -134,6 +134,7 @@ struct gk_handle {
   gk::DevBuf ht_keys, ht_rep;
   size_t ht_cap = 0;
   gk::DevBuf flags, block_sums;
+  gk::DevBuf wlf_buf;  // fused WL kernel: [cta_vbeg (G+1) | cta_count (G) | barrier]
   gk::DevBuf scalars;  // gk::DevScalars
   gk::PinBuf h_scalars;
 
@@ -172,7 +173,7 @@ struct gk_handle {
   gk::DevBuf tiles;  // int2 list
   gk::PinBuf h_tiles;
   gk::DevBuf K;      // device-resident result of the last gk_gram
-  int64_t K_rows = 0, K_cols = 0;
+  int64_t K_rows = 0, K_cols = 0, K_ld = 0;  // K_ld: row pitch in elements (>= K_cols)
   int K_dtype = GK_F32;
   gk::DevBuf K_stage;  // fp64 staging when K is kept as f32 but fetched as f64
 

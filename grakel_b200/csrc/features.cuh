@@ -121,95 +121,68 @@ col_hist(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt
   }
 }
 
-// classification + first half of three scans (head column index, tail column index,
-// tail entry offset).  colslot: >= 0 head index, -1 unused, <= -2 tail (offset = -(v+2)).
+// Classification + slot allocation in ONE pass over the columns (replaces a three-kernel
+// flag / scan / assign pipeline: only ~1.5 % of the columns contribute, so warp-aggregated
+// atomics on three counters are cheaper than scanning 1.6 M columns three times).
+//   colslot[c] >= 0  : head column index in the dense panel
+//   colslot[c] == -1 : column does not contribute to any off-diagonal entry
+//   colslot[c] <= -2 : tail column t = -(colslot+2); tail_desc[t] = {first entry, m}
+// Slot order depends on scheduling; K does not (exact integer arithmetic, see gram_tc.cuh).
+// counters: [0] head columns, [1] tail columns, [2] tail entries (zeroed by the host).
 __global__ void __launch_bounds__(256)
-col_flags(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt, const int* __restrict__ colmin,
-          const int* __restrict__ colmax, int T, int3* __restrict__ flags, int3* __restrict__ block_sums) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int3 f = make_int3(0, 0, 0);
+col_classify(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt, const int* __restrict__ colmin,
+             const int* __restrict__ colmax, int T, int* __restrict__ colslot, int2* __restrict__ tail_desc,
+             unsigned* __restrict__ tail_cur, unsigned* counters) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int kind = 0;
+  unsigned m = 0;
   if (c < D) {
-    const unsigned m = colcnt[c];
+    m = colcnt[c];
     unsigned long long work;
-    if (m && col_contributes(m, square ? 0 : colmin[c], square ? 0 : colmax[c], n_fit, square, &work)) {
-      if (m > (unsigned)T || m >= COL_CAP) f.x = 1;
-      else { f.y = 1; f.z = (int)m; }
-    }
-    flags[c] = f;
+    if (m && col_contributes(m, square ? 0 : colmin[c], square ? 0 : colmax[c], n_fit, square, &work))
+      kind = (m > (unsigned)T || m >= COL_CAP) ? 1 : 2;
   }
-  int t0, t1, t2;
-  block_exclusive_scan_256(f.x, &t0);
-  block_exclusive_scan_256(f.y, &t1);
-  block_exclusive_scan_256(f.z, &t2);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = make_int3(t0, t1, t2);
-}
-
-// exclusive scan of up to ~1M int3 block sums by ONE block of 1024 threads (serial chunk per
-// thread + shuffle scan of the 1024 partials)
-__global__ void __launch_bounds__(1024)
-scan_sums3(int nb, int3* __restrict__ sums) {
-  __shared__ int3 wsum[32];
-  const int chunk = (nb + 1023) / 1024;
-  const int beg = min(nb, (int)threadIdx.x * chunk), end = min(nb, beg + chunk);
-  int3 acc = make_int3(0, 0, 0);
-  for (int i = beg; i < end; ++i) { const int3 v = sums[i]; acc.x += v.x; acc.y += v.y; acc.z += v.z; }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int3 incl = acc;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int x = __shfl_up_sync(0xffffffffu, incl.x, d), y = __shfl_up_sync(0xffffffffu, incl.y, d),
-              z = __shfl_up_sync(0xffffffffu, incl.z, d);
-    if (lane >= d) { incl.x += x; incl.y += y; incl.z += z; }
+  const unsigned hm = __ballot_sync(0xffffffffu, kind == 1), tm = __ballot_sync(0xffffffffu, kind == 2);
+  const unsigned below = (1u << lane) - 1u;
+  int slot = -1;
+  if (hm) {
+    unsigned base = 0;
+    if (lane == __ffs(hm) - 1) base = atomicAdd(&counters[0], (unsigned)__popc(hm));
+    base = __shfl_sync(0xffffffffu, base, __ffs(hm) - 1);
+    if (kind == 1) slot = (int)(base + __popc(hm & below));
   }
-  if (lane == 31) wsum[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    int3 w = wsum[lane];
+  if (tm) {
+    // exclusive prefix of m over the tail lanes of the warp
+    unsigned incl = kind == 2 ? m : 0u;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int x = __shfl_up_sync(0xffffffffu, w.x, d), y = __shfl_up_sync(0xffffffffu, w.y, d),
-                z = __shfl_up_sync(0xffffffffu, w.z, d);
-      if (lane >= d) { w.x += x; w.y += y; w.z += z; }
+      const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
     }
-    wsum[lane] = w;
-  }
-  __syncthreads();
-  int3 run = make_int3(incl.x - acc.x, incl.y - acc.y, incl.z - acc.z);
-  if (wid) { run.x += wsum[wid - 1].x; run.y += wsum[wid - 1].y; run.z += wsum[wid - 1].z; }
-  for (int i = beg; i < end; ++i) {
-    const int3 v = sums[i];
-    sums[i] = run;
-    run.x += v.x; run.y += v.y; run.z += v.z;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-col_assign(long long D, const int3* __restrict__ flags, const int3* __restrict__ block_sums,
-           int* __restrict__ colslot, int2* __restrict__ tail_desc) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int3 f = c < D ? flags[c] : make_int3(0, 0, 0);
-  int t0, t1, t2;
-  const int e0 = block_exclusive_scan_256(f.x, &t0);
-  const int e1 = block_exclusive_scan_256(f.y, &t1);
-  const int e2 = block_exclusive_scan_256(f.z, &t2);
-  const int3 b = block_sums[blockIdx.x];  // already exclusive (scan_sums3)
-  if (c < D) {
-    int slot = -1;
-    if (f.x) slot = b.x + e0;
-    else if (f.y) {
-      const int off = b.z + e2;
-      slot = -(off + 2);
-      tail_desc[b.y + e1] = make_int2(off, f.z);
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned tbase = 0, ebase = 0;
+    if (lane == __ffs(tm) - 1) {
+      tbase = atomicAdd(&counters[1], (unsigned)__popc(tm));
+      ebase = atomicAdd(&counters[2], total);
     }
-    colslot[c] = slot;
+    tbase = __shfl_sync(0xffffffffu, tbase, __ffs(tm) - 1);
+    ebase = __shfl_sync(0xffffffffu, ebase, __ffs(tm) - 1);
+    if (kind == 2) {
+      const int t = (int)(tbase + __popc(tm & below));
+      tail_desc[t] = make_int2((int)(ebase + incl - m), (int)m);
+      tail_cur[t] = 0u;
+      slot = -(t + 2);
+    }
   }
+  if (c < D) colslot[c] = slot;
 }
 
 // pass 2 over the table: head entries -> zeroed bf16 panel, tail entries -> per-column lists
 __global__ void __launch_bounds__(256)
 feat_scatter(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
              const int* __restrict__ colslot, __nv_bfloat16* __restrict__ panel, long long ld,
-             unsigned* __restrict__ tail_cur, int2* __restrict__ tail_ent) {
+             unsigned* __restrict__ tail_cur, const int2* __restrict__ tail_desc, int2* __restrict__ tail_ent) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   unsigned long long k = keys[i];
@@ -221,9 +194,9 @@ feat_scatter(size_t cap, const unsigned long long* __restrict__ keys, const unsi
   if (slot >= 0) {
     panel[(long long)g * ld + slot] = __float2bfloat16_rn((float)cnt[i]);
   } else {
-    const int off = -(slot + 2);
-    const unsigned pos = atomicAdd(&tail_cur[c], 1u);
-    tail_ent[off + pos] = make_int2(g, (int)cnt[i]);
+    const int t = -(slot + 2);
+    const unsigned pos = atomicAdd(&tail_cur[t], 1u);
+    tail_ent[tail_desc[t].x + pos] = make_int2(g, (int)cnt[i]);
   }
 }
 

@@ -246,6 +246,37 @@ def test_high_degree_and_empty_edge_graphs():
         _same(k.ShortestPath().fit_transform(X[:4]), SPOracle().fit_transform(X[:4]))
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_wl_fused_and_multikernel_paths_agree(fused, monkeypatch, eng):
+    """The persistent cooperative WL kernel (wl_fused.cuh) and the per-level kernels (wl.cuh)
+    must produce the same labels (first-occurrence ids), level sizes and Gram matrix -- on a
+    sparse set (thread-per-vertex signatures), on a set with hubs of degree > 32 (warp path)
+    and on a block smaller than the grid (empty CTA ranges)."""
+    monkeypatch.setenv("GRAKEL_B200_WL_FUSED", fused)
+    k = _k()
+    rs = np.random.RandomState(11)
+    dense = []
+    for n in (70, 33, 150, 12):
+        A = (rs.rand(n, n) < 0.3).astype(float)
+        A = ((A + A.T) > 0).astype(float)
+        np.fill_diagonal(A, 0)
+        dense.append([A, {i: int(rs.randint(3)) for i in range(n)}])
+    for X, h in ((gen(300, 18, 7), 4), (dense, 3), (gen(3, 6, 2), 2)):
+        wl = k.WeisfeilerLehman(n_iter=h)
+        K = wl.fit_transform(X)
+        o = WLOracle(n_iter=h)
+        Ko, levels = o.fit_transform(X, return_levels=True)
+        _same(K, Ko)
+        parts = wl_partitions(levels)
+        V = wl.X.block.n_vertices
+        for lv in range(1, h + 1):
+            dev = eng.wl_labels(lv, V).astype(np.int64)
+            assert np.array_equal(dev, parts[lv]), f"level {lv} labels differ (fused={fused})"
+        assert list(wl.stats_.level_dims[1:h + 1]) == [int(parts[lv].max()) + 1 for lv in range(1, h + 1)]
+        # fit then transform goes through the same kernel with n_fit < n_graphs
+        _same(k.WeisfeilerLehman(n_iter=h).fit(X[:-1]).transform(X[-1:]), WLOracle(n_iter=h).fit_transform(X)[-1:, :-1])
+
+
 # --------------------------------------------------------------- SP
 def test_apsp_known_answers(eng):
     """grakel/tests/test_graph.py:40,62-65 and doc/documentation/introduction.rst:313-343."""
