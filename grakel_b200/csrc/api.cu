@@ -136,6 +136,9 @@ int gk_create(int device_ordinal, gk_handle** out) {
   h->dev = device_ordinal;
   h->sm_count = prop.multiProcessorCount;
   GK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  GK_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  GK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  GK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   for (auto& e : h->ev) GK_CUDA(cudaEventCreate(&e));
   for (auto& e : h->tev) GK_CUDA(cudaEventCreate(&e));
   GK_TRY(h->scalars.ensure(sizeof(DevScalars)));
@@ -167,6 +170,9 @@ int gk_destroy(gk_handle* h) {
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->tev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->stream2);
+  cudaEventDestroy(h->ev_fork);
+  cudaEventDestroy(h->ev_join);
   drop_extra(h);
   delete h;
   return GK_OK;
@@ -364,7 +370,8 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   GK_TRY(h->flags.ensure(V * 4));
   const int nb = cdiv(V, 256);
   GK_TRY(h->block_sums.ensure((size_t)nb * 4));
-  h->ht_cap = std::max<size_t>(next_pow2((size_t)V * 2), 1024);
+  // load factor <= 0.25: the insert loop of a warp runs as long as its longest probe sequence
+  h->ht_cap = std::max<size_t>(next_pow2((size_t)V * 4), 1024);
   GK_TRY(h->ht_keys.ensure(h->ht_cap * 8 * 2));  // two tables: the fused kernel alternates between levels
   GK_TRY(h->ht_rep.ensure(h->ht_cap * 4 * 2));
   const size_t ft_level_cap = std::max<size_t>(next_pow2((size_t)V * 2), 1024);  // one L2-sized sub-table per level
@@ -550,7 +557,6 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   GK_CUDA(cudaEventSynchronize(h->tev[3]));
   DevScalars* hs = h->h_scalars.as<DevScalars>();
   h->n_columns = hs->level_base[L];
-  if (fused) h->ft_cap = (size_t)hs->sp_coo;  // compact COO list: every slot is an entry
   h->features_ready = true;
   h->feature_kind = 1;
   if (stats) {
@@ -725,12 +731,26 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
       else sp_apsp_hist<double><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
       LAUNCH_CHECK(h);
     }
+    // the (up to four) word-width classes are independent: odd classes run on the side stream so
+    // that the tail of one launch overlaps the next (they only share atomically updated tables)
+    bool forked = false;
     for (int i = 0; i < 4; ++i) {
       if (bfs[i].empty()) continue;
       const int W = 1 << i;
+      cudaStream_t st = h->stream;
+      if (i & 1) {
+        if (!forked) {
+          GK_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+          GK_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+          forked = true;
+        }
+        st = h->stream2;
+      }
       int nmax = 0;
       for (int g : bfs[i]) nmax = std::max(nmax, ex->graph_ptr[g + 1] - ex->graph_ptr[g]);
-      const size_t smem = SP_LOCAL_SLOTS * 12 + (size_t)nmax * W * 8 + (size_t)16 * W * 8 + (size_t)nmax * 4 + 16;
+      const bool direct = p.n_labels <= SP_DIRECT_MAX_LABELS;
+      const size_t smem = (direct ? SP_LOCAL_SLOTS * 4 : SP_LOCAL_SLOTS * 12) + (size_t)nmax * W * 8 + (size_t)16 * W * 8 +
+                          (size_t)nmax * 4 + 16;
       p.glist = lists.as<int>() + bfs_off[i];
       p.n_list = (int)bfs[i].size();
       p.dist_in_global = 0;
@@ -743,12 +763,16 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
         default: GK_CUDA(cudaFuncSetAttribute(sp_bfs_hist<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
       }
       switch (W) {
-        case 1: sp_bfs_hist<1><<<(int)bfs[i].size(), threads, smem, h->stream>>>(p); break;
-        case 2: sp_bfs_hist<2><<<(int)bfs[i].size(), threads, smem, h->stream>>>(p); break;
-        case 4: sp_bfs_hist<4><<<(int)bfs[i].size(), threads, smem, h->stream>>>(p); break;
-        default: sp_bfs_hist<8><<<(int)bfs[i].size(), threads, smem, h->stream>>>(p); break;
+        case 1: sp_bfs_hist<1><<<(int)bfs[i].size(), threads, smem, st>>>(p); break;
+        case 2: sp_bfs_hist<2><<<(int)bfs[i].size(), threads, smem, st>>>(p); break;
+        case 4: sp_bfs_hist<4><<<(int)bfs[i].size(), threads, smem, st>>>(p); break;
+        default: sp_bfs_hist<8><<<(int)bfs[i].size(), threads, smem, st>>>(p); break;
       }
       LAUNCH_CHECK(h);
+    }
+    if (forked) {
+      GK_CUDA(cudaEventRecord(h->ev_join, h->stream2));
+      GK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
     if (!big.empty()) {
       if (keep) return fail(GK_ERR_UNSUPPORTED, "gk_sp_features: KEEP_DIST with graphs beyond the shared-memory budget");

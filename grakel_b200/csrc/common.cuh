@@ -112,6 +112,8 @@ struct gk_handle {
   int dev = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: independent kernels of one phase run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[16] = {};
   cudaEvent_t tev[8] = {};  // internal stage timers
 

@@ -17,6 +17,7 @@ namespace gk {
 
 constexpr int SP_LOCAL_SLOTS = 2048;  // per-CTA (key -> count) aggregation table
 constexpr int SP_THREADS = 256;
+constexpr int SP_DIRECT_MAX_LABELS = 11;  // sp_bfs_hist: direct (ls, lv, level) counters up to this alphabet size
 
 template <typename T> struct DistTraits;
 template <> struct DistTraits<unsigned short> {
@@ -118,19 +119,21 @@ sp_bfs_hist(SpParams p) {
   const int v0 = p.graph_ptr[g];
   const int n = p.graph_ptr[g + 1] - v0;
   if (n <= 0) return;
-  unsigned long long* lkeys = reinterpret_cast<unsigned long long*>(sp_smem);
-  unsigned* lcnt = reinterpret_cast<unsigned*>(sp_smem + SP_LOCAL_SLOTS * 8);
-  unsigned long long* adj = reinterpret_cast<unsigned long long*>(sp_smem + SP_LOCAL_SLOTS * 12);  // [n][W]
-  unsigned long long* lmask = adj + (size_t)n * W;                                                  // [L][W] (direct mode)
-  // Small alphabets (L <= 16): the CTA-local histogram is DIRECT-indexed by (ls, lv, level) --
+  // Small alphabets (L <= 11): the CTA-local histogram is DIRECT-indexed by (ls, lv, level) --
   // one shared-memory atomicAdd per (source, level, label class) with the class population count,
   // instead of a hashed CAS + add per vertex pair (shared atomics cost ~2 cycles per lane).
+  // The direct table needs counters only, so the 16 KB key array is not allocated in that mode
+  // (3x more resident CTAs per SM): layout [keys (hashed mode only) | counts | adj | lmask | labels].
   const int L = p.n_labels;
-  const bool direct = L <= 11;  // >= 16 levels in the direct table; deeper levels go to the global table
+  const bool direct = L <= SP_DIRECT_MAX_LABELS;  // >= 16 levels in the direct table; deeper levels go to the global table
   const int dcap = direct ? SP_LOCAL_SLOTS / (L * L) : 0;  // levels covered by the direct table
+  unsigned long long* lkeys = reinterpret_cast<unsigned long long*>(sp_smem);
+  unsigned* lcnt = reinterpret_cast<unsigned*>(sp_smem + (direct ? 0 : SP_LOCAL_SLOTS * 8));
+  unsigned long long* adj = reinterpret_cast<unsigned long long*>(sp_smem + (direct ? SP_LOCAL_SLOTS * 4 : SP_LOCAL_SLOTS * 12));  // [n][W]
+  unsigned long long* lmask = adj + (size_t)n * W;                                                  // [L][W] (direct mode)
   int* lab = reinterpret_cast<int*>(lmask + (direct ? (size_t)L * W : 0));                          // [n]
   const int tid = threadIdx.x;
-  for (int i = tid; i < SP_LOCAL_SLOTS; i += blockDim.x) { lkeys[i] = EMPTY64; lcnt[i] = 0; }
+  for (int i = tid; i < SP_LOCAL_SLOTS; i += blockDim.x) { if (!direct) lkeys[i] = EMPTY64; lcnt[i] = 0; }
   for (int i = tid; i < n * W; i += blockDim.x) adj[i] = 0ULL;
   if (direct) for (int i = tid; i < L * W; i += blockDim.x) lmask[i] = 0ULL;
   for (int i = tid; i < n; i += blockDim.x) lab[i] = p.labels ? p.labels[v0 + i] : 0;

@@ -32,9 +32,12 @@ namespace gk {
 constexpr int WLF_THREADS = 1024;
 constexpr int WLF_TILE_V = 4096;    // vertices per tile (u16 local indices)
 constexpr int WLF_TILE_E = 16384;   // edges per tile
+constexpr int WLF_VPT = WLF_TILE_V / WLF_THREADS;  // vertices per thread and tile (register batches)
+constexpr int WLF_AGG = 8192;       // per-tile column -> graph-count aggregation table (shared memory)
 constexpr int WLF_RANK_BITS = 20;   // rank_pack = cta << 20 | rank of the representative inside its CTA
-constexpr int WLF_SMEM = (WLF_TILE_V + 1) * 4 /*rp_s*/ + WLF_TILE_E * 2 /*col_s*/ + WLF_TILE_V * 4 /*lab_s*/ +
-                         WLF_TILE_E * 4 /*sig_s*/ + 16;
+constexpr int WLF_SMEM = (WLF_TILE_V + 1) * 4 /*rp_s*/ + 4 /*pad*/ + WLF_TILE_V * 8 /*key_s*/ + WLF_TILE_V * 4 /*lab_s*/ +
+                         WLF_TILE_E * 4 /*sig_s | agg*/ + WLF_TILE_E * 2 /*col_s*/ + 16;
+static_assert(WLF_AGG * 8 <= WLF_TILE_E * 4, "aggregation table must fit in the sig_s region");
 
 struct WlFusedParams {
   int V, L;
@@ -57,7 +60,7 @@ struct WlFusedParams {
   unsigned* barrier;  // zeroed by the host before the launch
   unsigned long long seed;
   FeatStats st;
-  DevScalars* sc;   // sc->sp_coo is the COO append counter
+  DevScalars* sc;
   long long* prof;  // optional [grid][L][16] globaltimer stamps (GRAKEL_B200_PROF), else NULL
 };
 
@@ -110,22 +113,27 @@ __device__ __forceinline__ int wlf_block_scan(int x, int* total, int* s_warp /*[
   return off + incl - x;
 }
 
-// packed-table insert: returns the slot whose word carries this signature's tag
-__device__ __forceinline__ unsigned wlf_insert(unsigned long long* tab, unsigned mask, unsigned long long key, int v) {
-  const unsigned long long mine = (key & 0xFFFFFFFF00000000ULL) | (unsigned)v;
-  unsigned slot = (unsigned)((key & 0xFFFFFFFFULL) * 0x9E3779B1ULL >> 8) & mask;
-  while (true) {
-    unsigned long long w = __ldcg(&tab[slot]);
-    if (w == EMPTY64) {
-      w = atomicCAS(&tab[slot], EMPTY64, mine);
-      if (w == EMPTY64) return slot;
-    }
-    if ((w >> 32) == (key >> 32)) {
-      if ((unsigned)w > (unsigned)v) atomicMin(&tab[slot], mine);
-      return slot;
-    }
-    slot = (slot + 1) & mask;
-  }
+// ---- signature hashes (32-bit arithmetic; two independent lanes -> {tag, home slot}).
+// Equal signatures have equal degree, hence always take the same code path, so the
+// thread-per-vertex path (sequential over the sorted labels) and the warp path (sum of
+// positional terms) may use different functions.  Exactness never depends on the hash:
+// every vertex is verified against its representative and a clash makes the host retry.
+__device__ __forceinline__ unsigned wlf_fmix(unsigned h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ unsigned long long wlf_finish(unsigned a, unsigned c, int own, int deg, unsigned long long seed) {
+  a = wlf_fmix(a ^ ((unsigned)own * 0x9E3779B1u) ^ (unsigned)seed);
+  c = wlf_fmix(c + (unsigned)own * 0x7FEB352Du + (unsigned)deg * 0x846CA68Bu + (unsigned)(seed >> 32));
+  return (((unsigned long long)a << 32) | c) >> 1;  // never EMPTY64
+}
+__device__ __forceinline__ void wlf_seq_step(unsigned& a, unsigned& c, int x) {
+  a = (a ^ (unsigned)x) * 0x9E3779B1u; a ^= a >> 15;
+  c = (c + (unsigned)x) * 0x85EBCA77u; c ^= c >> 13;
+}
+__device__ __forceinline__ void wlf_pos_term(unsigned& a, unsigned& c, int x, int pos, unsigned long long seed) {
+  a += wlf_fmix((unsigned)x * 0x9E3779B1u + (unsigned)pos * 0x85EBCA77u + (unsigned)seed);
+  c += wlf_fmix(((unsigned)x ^ 0x5bd1e995u) * 0xC2B2AE3Du + (unsigned)pos * 0x27D4EB2Fu + (unsigned)(seed >> 32));
 }
 
 // stage one tile: CSR slice (row offsets relative to the tile, neighbours as tile-local u16)
@@ -140,44 +148,73 @@ __device__ __forceinline__ void wlf_stage(const WlFusedParams& p, int v0, int nv
     for (int i = tid; i < nv; i += WLF_THREADS) lab_s[i] = lab_src[v0 + i];
 }
 
-// feature entries of one tile from the labels in lab_s: vertex i emits (graph, base + label, count)
-// iff it is the first vertex of its graph carrying that label.
-__device__ __forceinline__ void wlf_emit(const WlFusedParams& p, int v0, int nv, const int* lab_s, long long base,
-                                         int* s_warp, int* s_bcast, unsigned& mx, unsigned& n_new) {
+// Feature entries of one tile from the labels in lab_s: vertex i emits (graph, base + label, count)
+// iff it is the first vertex of its graph carrying that label (labels compared inside the graph in
+// shared memory).  One COO reservation per tile; the per-column graph counts are aggregated in a
+// shared-memory table first, so a column shared by every graph costs one global atomic per tile.
+__device__ __forceinline__ void wlf_emit(const WlFusedParams& p, int v0, int nv, const int* lab_s, unsigned* agg,
+                                         long long base, size_t coo_off, int* s_warp, unsigned& mx, unsigned& n_new) {
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int i0 = 0; i0 < nv; i0 += WLF_THREADS) {
-    const int i = i0 + tid;
-    int emit = 0, g = -1;
-    unsigned cnt = 0;
-    int l = 0;
-    if (i < nv) {
-      g = p.vgraph[v0 + i];
-      const int gs = p.graph_ptr[g] - v0, ge = p.graph_ptr[g + 1] - v0;
-      l = lab_s[i];
+  for (int s = tid; s < WLF_AGG * 2; s += WLF_THREADS) agg[s] = (s & 1) ? 0u : 0xFFFFFFFFu;  // {column, graphs}
+  int g[WLF_VPT], l[WLF_VPT], gs[WLF_VPT], ge[WLF_VPT];
+  unsigned cnt[WLF_VPT];
+  bool emit[WLF_VPT];
+#pragma unroll
+  for (int k = 0; k < WLF_VPT; ++k) {
+    const int i = tid + k * WLF_THREADS;
+    g[k] = i < nv ? p.vgraph[v0 + i] : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < WLF_VPT; ++k) {
+    gs[k] = ge[k] = 0;
+    if (g[k] >= 0) { gs[k] = p.graph_ptr[g[k]] - v0; ge[k] = p.graph_ptr[g[k] + 1] - v0; }
+  }
+  int n_emit = 0;
+#pragma unroll
+  for (int k = 0; k < WLF_VPT; ++k) {
+    const int i = tid + k * WLF_THREADS;
+    cnt[k] = 0;
+    emit[k] = false;
+    l[k] = 0;
+    if (g[k] >= 0) {
+      l[k] = lab_s[i];
       bool first = true;
-      for (int u = gs; u < ge; ++u) {
-        const bool same = lab_s[u] == l;
-        cnt += same ? 1u : 0u;
+      for (int u = gs[k]; u < ge[k]; ++u) {
+        const bool same = lab_s[u] == l[k];
+        cnt[k] += same ? 1u : 0u;
         first = first && !(same && u < i);
       }
-      emit = first ? 1 : 0;
+      emit[k] = first;
+      n_emit += first ? 1 : 0;
     }
-    int total;
-    const int ex = wlf_block_scan(emit, &total, s_warp);
-    if (tid == 0) *s_bcast = total ? (int)atomicAdd(&p.sc->sp_coo, (unsigned long long)total) : 0;
-    __syncthreads();
-    const int off = *s_bcast;
-    if (emit) {
-      const unsigned long long col = (unsigned long long)(base + l);
-      p.coo_keys[off + ex] = ((unsigned long long)(unsigned)g << 32) | col;
-      p.coo_cnt[off + ex] = cnt;
-      if (__ldcg(&p.st.colcnt[col]) < COL_CAP) atomicAdd(&p.st.colcnt[col], 1u);
-      mx = max(mx, cnt);
+  }
+  // Every (tile, level) owns a fixed region of the COO arrays, [coo_off, coo_off + nv): at most one
+  // entry per vertex, so no global reservation (an atomic round trip that stalls the whole CTA) is
+  // needed; the unused remainder is filled with EMPTY64 keys, which every consumer skips.
+  int total;
+  int ex = wlf_block_scan(n_emit, &total, s_warp);  // also orders the agg initialisation before its use
+  const size_t off = coo_off;
+  for (int i = total + tid; i < nv; i += WLF_THREADS) p.coo_keys[off + i] = EMPTY64;
+#pragma unroll
+  for (int k = 0; k < WLF_VPT; ++k) {
+    if (emit[k]) {
+      const unsigned col = (unsigned)(base + l[k]);
+      p.coo_keys[off + ex] = ((unsigned long long)(unsigned)g[k] << 32) | col;
+      p.coo_cnt[off + ex] = cnt[k];
+      ++ex;
+      mx = max(mx, cnt[k]);
       n_new += 1u;
+      unsigned slot = (col * 0x9E3779B1u >> 12) & (WLF_AGG - 1);
+      while (true) {
+        unsigned prev = agg[2 * slot];
+        if (prev == 0xFFFFFFFFu) prev = atomicCAS(&agg[2 * slot], 0xFFFFFFFFu, col);
+        if (prev == 0xFFFFFFFFu || prev == col) { atomicAdd(&agg[2 * slot + 1], 1u); break; }
+        slot = (slot + 1) & (WLF_AGG - 1);
+      }
     }
     // exact self similarity: sum of squared counts per graph (runs of equal g inside the warp)
-    unsigned long long val = emit ? (unsigned long long)cnt * cnt : 0ULL;
-    const int gg = g;
+    unsigned long long val = emit[k] ? (unsigned long long)cnt[k] * cnt[k] : 0ULL;
+    const int gg = g[k];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const unsigned long long y = __shfl_down_sync(0xffffffffu, val, d);
@@ -185,22 +222,28 @@ __device__ __forceinline__ void wlf_emit(const WlFusedParams& p, int v0, int nv,
       if (lane + d < 32 && gy == gg) val += y;
     }
     const int gprev = __shfl_up_sync(0xffffffffu, gg, 1);
-    if (g >= 0 && (lane == 0 || gprev != gg) && val) atomicAdd(&p.st.diag[g], val);
-    __syncthreads();  // s_bcast is reused by the next round
+    if (gg >= 0 && (lane == 0 || gprev != gg) && val) atomicAdd(&p.st.diag[gg], val);
   }
+  __syncthreads();
+  for (int s = tid; s < WLF_AGG; s += WLF_THREADS) {
+    const unsigned col = agg[2 * s];
+    if (col != 0xFFFFFFFFu) atomicAdd(&p.st.colcnt[col], agg[2 * s + 1]);
+  }
+  __syncthreads();  // agg is reused by the next tile
 }
 
 __global__ void __launch_bounds__(WLF_THREADS, 1)
 wl_fused_kernel(WlFusedParams p) {
   extern __shared__ __align__(16) unsigned char wlf_smem[];
   int* rp_s = reinterpret_cast<int*>(wlf_smem);
-  int* lab_s = rp_s + (WLF_TILE_V + 1);
+  unsigned long long* key_s = reinterpret_cast<unsigned long long*>(rp_s + (WLF_TILE_V + 2));
+  int* lab_s = reinterpret_cast<int*>(key_s + WLF_TILE_V);
   int* sig_s = lab_s + WLF_TILE_V;
+  unsigned* agg = reinterpret_cast<unsigned*>(sig_s);  // phase [C] only
   unsigned short* col_s = reinterpret_cast<unsigned short*>(sig_s + WLF_TILE_E);
   __shared__ int s_warp[32];
   __shared__ int s_prefix[1024];  // exclusive scan of the CTA counts (grid <= 1024)
   __shared__ unsigned s_red[64];
-  __shared__ int s_bcast;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int G = gridDim.x, b = blockIdx.x;
   const int t_beg = p.cta_tile[b], t_end = p.cta_tile[b + 1];
@@ -237,7 +280,7 @@ wl_fused_kernel(WlFusedParams p) {
     wlf_stage(p, v0, nv, 0, 0, p.labels0, rp_s, col_s, lab_s, false);
     for (int i = tid; i < nv; i += WLF_THREADS) p.labels_all[v0 + i] = p.labels0[v0 + i];
     __syncthreads();
-    wlf_emit(p, v0, nv, lab_s, 0, s_warp, &s_bcast, mx, n_new);
+    wlf_emit(p, v0, nv, lab_s, agg, 0, (size_t)v0, s_warp, mx, n_new);
   }
   level_base = p.sc->level_base[1];  // = number of level-0 labels (set by the host)
   flush_partials(0);
@@ -257,7 +300,7 @@ wl_fused_kernel(WlFusedParams p) {
       wlf_stage(p, v0, nv, e0, ne, lab_in, rp_s, col_s, lab_s, true);
       __syncthreads();
       WLF_STAMP(lv, 8);
-      // one thread per vertex of degree <= 8: 19-comparator network in registers
+      // [A1] one thread per vertex of degree <= 8: 19-comparator network in registers
       for (int i = tid; i < nv; i += WLF_THREADS) {
         const int beg = rp_s[i];
         const int deg = rp_s[i + 1] - beg;
@@ -279,19 +322,20 @@ wl_fused_kernel(WlFusedParams p) {
         GK_CSWAP(x2, x4) GK_CSWAP(x3, x5)
         GK_CSWAP(x3, x4)
         const int xs[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
-        unsigned long long tt = 0;
+        unsigned ha = 0x243F6A88u, hc = 0x85A308D3u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (j < deg) {
             sig_s[beg + j] = xs[j];
-            tt += sig_term(xs[j], j, p.seed);
+            wlf_seq_step(ha, hc, xs[j]);
           }
         }
-        p.slot_of[v0 + i] = (int)wlf_insert(tab, p.ht_mask, sig_final(tt, lab_s[i], deg, p.seed), v0 + i);
+        key_s[i] = wlf_finish(ha, hc, lab_s[i], deg, p.seed);
       }
       if (p.prof) { __syncthreads(); WLF_STAMP(lv, 9); }
-      // higher degrees: one warp per vertex, all-ascending bitonic network in the vertex's own
-      // shared-memory segment (valid for any length: exchanges with the virtual +inf tail are no-ops)
+      // [A2] higher degrees: one warp per vertex.  <= 32: one label per lane, bitonic network on
+      // shuffles; above: all-ascending bitonic network in the vertex's own shared-memory segment
+      // (valid for any length: exchanges with the virtual +inf tail are no-ops).
       for (int i0 = wid * 32; i0 < nv; i0 += WLF_THREADS) {
         const int iv = i0 + lane;
         const bool big = iv < nv && (rp_s[iv + 1] - rp_s[iv]) > 8;
@@ -301,40 +345,105 @@ wl_fused_kernel(WlFusedParams p) {
           m &= m - 1;
           const int beg = rp_s[i], deg = rp_s[i + 1] - beg;
           int* seg = sig_s + beg;
-          for (int j = lane; j < deg; j += 32) seg[j] = lab_s[col_s[beg + j]];
-          __syncwarp();
-          int n2 = 1;
-          while (n2 < deg) n2 <<= 1;
-          for (int k = 2; k <= n2; k <<= 1) {
-            for (int j = lane; j < deg; j += 32) {
-              const int q = j ^ (k - 1);
-              if (q > j && q < deg) {
-                const int a = seg[j], c = seg[q];
-                if (a > c) { seg[j] = c; seg[q] = a; }
+          unsigned ha = 0, hc = 0;
+          if (deg <= 32) {
+            int x = lane < deg ? lab_s[col_s[beg + lane]] : 0x7fffffff;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+              for (int j = k >> 1; j > 0; j >>= 1) {
+                const int y = __shfl_xor_sync(0xffffffffu, x, j);
+                const bool up = (lane & k) == 0;
+                const bool lower = (lane & j) == 0;
+                x = (lower == up) ? min(x, y) : max(x, y);
               }
             }
+            if (lane < deg) {
+              seg[lane] = x;
+              wlf_pos_term(ha, hc, x, lane, p.seed);
+            }
+          } else {
+            for (int j = lane; j < deg; j += 32) seg[j] = lab_s[col_s[beg + j]];
             __syncwarp();
-            for (int s = k >> 2; s > 0; s >>= 1) {
+            int n2 = 1;
+            while (n2 < deg) n2 <<= 1;
+            for (int k = 2; k <= n2; k <<= 1) {
               for (int j = lane; j < deg; j += 32) {
-                const int q = j ^ s;
+                const int q = j ^ (k - 1);
                 if (q > j && q < deg) {
                   const int a = seg[j], c = seg[q];
                   if (a > c) { seg[j] = c; seg[q] = a; }
                 }
               }
               __syncwarp();
+              for (int s = k >> 2; s > 0; s >>= 1) {
+                for (int j = lane; j < deg; j += 32) {
+                  const int q = j ^ s;
+                  if (q > j && q < deg) {
+                    const int a = seg[j], c = seg[q];
+                    if (a > c) { seg[j] = c; seg[q] = a; }
+                  }
+                }
+                __syncwarp();
+              }
             }
+            for (int j = lane; j < deg; j += 32) wlf_pos_term(ha, hc, seg[j], j, p.seed);
           }
-          unsigned long long tt = 0;
-          for (int j = lane; j < deg; j += 32) tt += sig_term(seg[j], j, p.seed);
 #pragma unroll
-          for (int s = 16; s > 0; s >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, s);
-          if (lane == 0)
-            p.slot_of[v0 + i] = (int)wlf_insert(tab, p.ht_mask, sig_final(tt, lab_s[i], deg, p.seed), v0 + i);
+          for (int s = 16; s > 0; s >>= 1) {
+            ha += __shfl_xor_sync(0xffffffffu, ha, s);
+            hc += __shfl_xor_sync(0xffffffffu, hc, s);
+          }
+          if (lane == 0) key_s[i] = wlf_finish(ha, hc, lab_s[i], deg, p.seed);
         }
       }
       __syncthreads();
       WLF_STAMP(lv, 10);
+      // [A3] insert every vertex of the tile; the (<= 4) probes of a thread are issued together
+      {
+        unsigned long long key[WLF_VPT], w[WLF_VPT];
+        unsigned slot[WLF_VPT];
+        bool act[WLF_VPT];
+#pragma unroll
+        for (int k = 0; k < WLF_VPT; ++k) {
+          const int i = tid + k * WLF_THREADS;
+          act[k] = i < nv;
+          key[k] = act[k] ? key_s[i] : 0ULL;
+          slot[k] = (unsigned)((key[k] & 0xFFFFFFFFULL) * 0x9E3779B1ULL >> 8) & p.ht_mask;
+        }
+        bool any = true;
+        while (any) {
+          // CAS first (no read-before-CAS): a new signature costs ONE L2 round trip; an existing one
+          // gets the slot's word back from the failed CAS.  Same-address CASes of a popular signature
+          // serialise in the L2 slice at about one per clock, which is cheaper than a second round trip
+          // for every vertex.
+#pragma unroll
+          for (int k = 0; k < WLF_VPT; ++k) {
+            const unsigned long long mine = (key[k] & 0xFFFFFFFF00000000ULL) | (unsigned)(v0 + tid + k * WLF_THREADS);
+            w[k] = act[k] ? atomicCAS(&tab[slot[k]], EMPTY64, mine) : 0ULL;
+          }
+          any = false;
+#pragma unroll
+          for (int k = 0; k < WLF_VPT; ++k) {
+            if (!act[k]) continue;
+            const int v = v0 + tid + k * WLF_THREADS;
+            const unsigned long long mine = (key[k] & 0xFFFFFFFF00000000ULL) | (unsigned)v;
+            if (w[k] == EMPTY64) { act[k] = false; continue; }  // the CAS installed our word
+            if ((w[k] >> 32) == (key[k] >> 32)) {
+              if ((unsigned)w[k] > (unsigned)v) atomicMin(&tab[slot[k]], mine);
+              act[k] = false;
+              continue;
+            }
+            slot[k] = (slot[k] + 1) & p.ht_mask;
+            any = true;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < WLF_VPT; ++k) {
+          const int i = tid + k * WLF_THREADS;
+          if (i < nv) p.slot_of[v0 + i] = (int)slot[k];
+        }
+      }
       // sorted neighbour labels to global memory (coalesced): other CTAs verify against them
       for (int k = tid; k < ne; k += WLF_THREADS) p.sig_nbr[e0 + k] = sig_s[k];
     }
@@ -347,18 +456,53 @@ wl_fused_kernel(WlFusedParams p) {
     int carry = 0;
     for (int t = t_beg; t < t_end; ++t) {
       const int v0 = p.tile_vbeg[t], nv = p.tile_vbeg[t + 1] - v0;
-      for (int i0 = 0; i0 < nv; i0 += WLF_THREADS) {
-        const int v = v0 + i0 + tid;
+      int r[WLF_VPT];
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        r[k] = i < nv ? p.slot_of[v0 + i] : 0;
+      }
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        if (i < nv) r[k] = (int)(unsigned)__ldcg(&tab[r[k]]);
+      }
+      // verification against the representative: its CSR row and label are fetched for all (<= 4)
+      // vertices of the thread at once, then up to 8 sorted neighbour labels per side in one batch
+      int bv[WLF_VPT], dv[WLF_VPT], br[WLF_VPT], dr[WLF_VPT], lo[WLF_VPT], lr[WLF_VPT];
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        bv[k] = dv[k] = br[k] = dr[k] = lo[k] = lr[k] = 0;
+        if (i < nv && r[k] != v0 + i) {
+          bv[k] = p.row_ptr[v0 + i]; dv[k] = p.row_ptr[v0 + i + 1] - bv[k];
+          br[k] = p.row_ptr[r[k]]; dr[k] = p.row_ptr[r[k] + 1] - br[k];
+          lo[k] = lab_in[v0 + i]; lr[k] = __ldcg(&lab_in[r[k]]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        if (k * WLF_THREADS >= nv) break;  // uniform
+        const int v = v0 + i;
         int f = 0;
-        if (i0 + tid < nv) {
-          const int r = (int)(unsigned)__ldcg(&tab[p.slot_of[v]]);
-          p.slot_of[v] = r;
-          f = (r == v);
+        if (i < nv) {
+          p.slot_of[v] = r[k];
+          f = (r[k] == v);
           if (!f) {
-            const int bv = p.row_ptr[v], dv = p.row_ptr[v + 1] - bv;
-            const int br = p.row_ptr[r], dr = p.row_ptr[r + 1] - br;
-            bool same = (dv == dr) && (lab_in[v] == __ldcg(&lab_in[r]));
-            for (int j = 0; same && j < dv; ++j) same = p.sig_nbr[bv + j] == __ldcg(&p.sig_nbr[br + j]);
+            bool same = (dv[k] == dr[k]) && (lo[k] == lr[k]);
+            if (same && dv[k] <= 8) {
+              int a[8], c[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                a[j] = j < dv[k] ? p.sig_nbr[bv[k] + j] : 0;
+                c[j] = j < dv[k] ? __ldcg(&p.sig_nbr[br[k] + j]) : 0;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) same = same && (a[j] == c[j]);
+            } else {
+              for (int j = 0; same && j < dv[k]; ++j) same = p.sig_nbr[bv[k] + j] == __ldcg(&p.sig_nbr[br[k] + j]);
+            }
             if (!same) atomicOr(&p.sc->collision, 1u);
           }
         }
@@ -390,16 +534,28 @@ wl_fused_kernel(WlFusedParams p) {
       __syncthreads();
       for (int t = t_beg; t < t_end; ++t) {
         const int v0 = p.tile_vbeg[t], nv = p.tile_vbeg[t + 1] - v0;
-        for (int i = tid; i < nv; i += WLF_THREADS) {
-          const int v = v0 + i;
-          const int r = p.slot_of[v];
-          const int rp = __ldcg(&p.rank_pack[r]);
-          const int id = s_prefix[rp >> WLF_RANK_BITS] + (rp & ((1 << WLF_RANK_BITS) - 1));
-          lab_out[v] = id;
-          lab_s[i] = id;
+        int r[WLF_VPT];
+#pragma unroll
+        for (int k = 0; k < WLF_VPT; ++k) {
+          const int i = tid + k * WLF_THREADS;
+          r[k] = i < nv ? p.slot_of[v0 + i] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < WLF_VPT; ++k) {
+          const int i = tid + k * WLF_THREADS;
+          if (i < nv) r[k] = __ldcg(&p.rank_pack[r[k]]);
+        }
+#pragma unroll
+        for (int k = 0; k < WLF_VPT; ++k) {
+          const int i = tid + k * WLF_THREADS;
+          if (i < nv) {
+            const int id = s_prefix[r[k] >> WLF_RANK_BITS] + (r[k] & ((1 << WLF_RANK_BITS) - 1));
+            lab_out[v0 + i] = id;
+            lab_s[i] = id;
+          }
         }
         __syncthreads();
-        wlf_emit(p, v0, nv, lab_s, level_base, s_warp, &s_bcast, mx, n_new);
+        wlf_emit(p, v0, nv, lab_s, agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
       }
       if (b == 0 && tid == 0) {
         p.sc->level_dims[lv] = total;
