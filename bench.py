@@ -197,6 +197,9 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
+    # rank 0 prints exactly one JSON line on stdout: keep NCCL's version banner off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)

@@ -1100,7 +1100,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
 
   // ---- head / tail split.  force_T: 1 = every contributing column dense.
   const double flops_per_col = square ? (double)k_rows * (double)(N + 1) : 2.0 * (double)k_rows * (double)k_cols;
-  const double store_seconds = (double)k_rows * (double)k_cols * (double)esz * (square && k_rows == N ? 1.0 : 1.0) / 5.0e12;
+  const double store_seconds = (double)k_rows * (double)k_cols * (double)esz / 6.5e12;  // K written once (debug print only)
   int force_T = (flags & (GK_GRAM_SIMT | GK_DENSE_ALL)) ? 1 : -1;
   if (force_T < 0) {  // testing knob: GRAKEL_B200_FORCE_T=<threshold>
     const char* e = getenv("GRAKEL_B200_FORCE_T");
@@ -1122,9 +1122,11 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   if ((flags & GK_GRAM_SIMT) || max_count > 256 || max_diag >= (1LL << 24)) { path = 2; force_T = 1; }
   int T = 1;
   {
-    // T = 2^k minimising  max(t_store, head_cols * flops_per_col / rate) + tail_updates * t_atomic
-    const double rate = 1.2e15;      // dense bf16 rate gram_tc_kernel sustains (flop/s)
-    const double t_atomic = 2.0e-11; // amortised cost of one scattered pair update of K (L2 RED throughput)
+    // T = 2^k minimising  head_cols * flops_per_col / rate + tail_updates * t_atomic
+    // calibration (B200, profiles/r01b_*): dense mode sustains 1.5e15 flop/s; 4.36 M scattered fp32 atomics
+    // take 152 us (random 32-byte sectors of a matrix that does not fit in L2: DRAM-bound)
+    const double rate = 1.5e15;      // dense bf16 rate gram_tc_kernel sustains (flop/s)
+    const double t_atomic = 3.5e-11; // amortised cost of one scattered pair update of K
     double best = -1.0;
     for (int k = 0; k <= HIST_BUCKETS - 2; ++k) {
       double head_cols = 0, tail_upd = 0;
@@ -1132,8 +1134,10 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
         if (b > k) head_cols += (double)hc.hist_cols[b];
         else tail_upd += (double)hc.hist_work[b];
       }
-      double t_dense = head_cols * flops_per_col / rate;
-      if (head_cols > 0 && t_dense < store_seconds) t_dense = store_seconds;
+      // measured (T = 64 vs 32 at config 2): the GEMM's time is additive in its store floor and its MMA
+      // work -- operand loads and epilogue stores share the L2 -- so the constant store term does not
+      // change the argmin and only the two variable terms are compared
+      const double t_dense = head_cols * flops_per_col / rate;
       const double t = t_dense + tail_upd * t_atomic;
       if (best < 0 || t < best) { best = t; T = 1 << k; }
     }

@@ -26,8 +26,11 @@ def all_gather_rows(k_local, n_rows: int, group=None):
     world = dist.get_world_size(group)
     per = (n_rows + world - 1) // world
     n_cols = k_local.shape[1]
-    pad = torch.zeros((per, n_cols), dtype=k_local.dtype, device=k_local.device)
-    pad[: k_local.shape[0]] = k_local
+    if k_local.shape[0] == per and k_local.is_contiguous():
+        pad = k_local  # already block-sized (rows past this rank's range are sliced off below): no copy
+    else:
+        pad = torch.zeros((per, n_cols), dtype=k_local.dtype, device=k_local.device)
+        pad[: k_local.shape[0]] = k_local
     out = torch.empty((world * per, n_cols), dtype=k_local.dtype, device=k_local.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return out[:n_rows]
