@@ -114,6 +114,7 @@ struct gk_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream: independent kernels of one phase run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_stage[2] = {};  // D2H staging buffers of deliver_widen
   cudaEvent_t ev[16] = {};
   cudaEvent_t tev[8] = {};  // internal stage timers
 

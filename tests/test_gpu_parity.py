@@ -277,6 +277,23 @@ def test_wl_fused_and_multikernel_paths_agree(fused, monkeypatch, eng):
         _same(k.WeisfeilerLehman(n_iter=h).fit(X[:-1]).transform(X[-1:]), WLOracle(n_iter=h).fit_transform(X)[-1:, :-1])
 
 
+def test_fp32_transport_with_host_widening_is_exact(monkeypatch):
+    """GRAKEL_B200_WIDEN=1: K crosses PCIe as fp32 and is widened to float64 by the library's host
+    threads (chunked, double-buffered) -- must be bit-identical to the fp64 transport, also for row
+    counts that are not a multiple of the chunk or of the worker count."""
+    k = _k()
+    for n, nbar in ((257, 10), (1031, 8)):
+        X = gen(n, nbar, 9)
+        monkeypatch.delenv("GRAKEL_B200_WIDEN", raising=False)
+        K0 = k.WeisfeilerLehman(n_iter=2).fit_transform(X)
+        monkeypatch.setenv("GRAKEL_B200_WIDEN", "1")
+        K1 = k.WeisfeilerLehman(n_iter=2).fit_transform(X)
+        assert K1.dtype == np.float64
+        _same(K1, K0)
+        Kt = k.WeisfeilerLehman(n_iter=2).fit(X[:-5]).transform(X[-5:])
+        _same(Kt, K0[-5:, :-5])
+
+
 # --------------------------------------------------------------- SP
 def test_apsp_known_answers(eng):
     """grakel/tests/test_graph.py:40,62-65 and doc/documentation/introduction.rst:313-343."""
