@@ -3,8 +3,9 @@
 
 Workload (N=1, and every rank at N>1): BASELINE config 2 -- 10 000 synthetic
 Erdos-Renyi labelled graphs (avg 40 nodes, 7 labels, seed 0), WL-subtree h=5.
-A "step" is one pass of the hot path over that batch: WL relabel of all graphs,
-feature block, dense bf16 panel, tcgen05 Gram GEMM, diagonal / output.
+A "step" is one pass of the hot path over that batch: WL relabel of all graphs
+(one persistent kernel), feature block, dense bf16 head panel, tcgen05 Gram GEMM,
+exact sparse tail, diagonal / output.
 
   value      pairs/s with the packed CSR already resident in HBM and K left in HBM
              (CUDA events on the engine's stream, max over ranks)
