@@ -57,9 +57,11 @@ _SYMBOLS = {
     "gk_wl_features": (C.c_int, [_P, C.c_int32, C.POINTER(GkStats)]),
     "gk_sp_features": (C.c_int, [_P, C.c_int32, C.POINTER(GkStats)]),
     "gk_spattr_features": (C.c_int, [_P, C.POINTER(GkStats)]),
+    "gk_wl_sp_features": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(GkStats)]),
     "gk_gram": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int32, C.c_int64, _P, _P,
                           C.POINTER(GkStats)]),
     "gk_fetch": (C.c_int, [_P, _P, C.c_int32, C.c_int64]),
+    "gk_set_row_map": (C.c_int, [_P, C.c_int64, _P]),
     "gk_wl_labels": (C.c_int, [_P, C.c_int32, _P]),
     "gk_sp_distances": (C.c_int, [_P, C.c_int64, _P]),
     "gk_wl_fit_transform": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int64,
@@ -153,6 +155,11 @@ class Engine:
             self._check(self.lib.gk_pack_csr(self.h, len(gp) - 1, _ptr(gp), _ptr(rp), _ptr(ci), _ptr(lab), _ptr(w),
                                              _ptr(at), ad))
 
+    def set_row_map(self, n_rows, row_of_graph):
+        m = None if row_of_graph is None else _i32(row_of_graph)
+        with self._lock:
+            self._check(self.lib.gk_set_row_map(self.h, int(n_rows), _ptr(m)))
+
     def wl_features(self, n_iter):
         st = GkStats()
         with self._lock:
@@ -164,6 +171,13 @@ class Engine:
         flags = (GK_SP_WITH_LABELS if with_labels else 0) | (GK_SP_KEEP_DIST if keep_dist else 0)
         with self._lock:
             self._check(self.lib.gk_sp_features(self.h, flags, C.byref(st)))
+        return st
+
+    def wl_sp_features(self, n_iter, keep_dist=False):
+        st = GkStats()
+        flags = GK_SP_WITH_LABELS | (GK_SP_KEEP_DIST if keep_dist else 0)
+        with self._lock:
+            self._check(self.lib.gk_wl_sp_features(self.h, int(n_iter), flags, C.byref(st)))
         return st
 
     def spattr_features(self):

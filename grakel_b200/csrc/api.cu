@@ -170,7 +170,7 @@ int gk_destroy(gk_handle* h) {
                         &h->colmin, &h->colmax, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
-                        &h->K, &h->K_stage, &h->wlf_buf};
+                        &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
@@ -239,6 +239,7 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
   h->max_graph_size = max_n;
   h->features_ready = false;
   h->feature_kind = 0;
+  h->n_rows = 0;  // a new block starts without a row map
   HandleExtra* ex = extra_of(h);
   ex->graph_ptr.assign(graph_ptr, graph_ptr + N + 1);
   ex->graph_eptr.resize(N + 1);
@@ -592,13 +593,31 @@ int gk_wl_labels(gk_handle* h, int32_t level, int32_t* out) {
 }
 
 // ---------------------------------------------------------------------------
-int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
+// Shortest-path features.  wl_iter < 0: the ShortestPath kernel on the packed labels.
+// wl_iter >= 0: WeisfeilerLehman(base_graph_kernel=ShortestPath) -- the graphs are relabelled for
+// wl_iter rounds first (gk_wl_features), then the labelled path histogram of EVERY level goes into one
+// feature block: label ids are made level-unique (id + first column of the level), so the levels use
+// disjoint columns and one Gram equals the reference's sum of per-level matrices
+// (weisfeiler_lehman.py:260-270 with shortest_path.py:370-410 as the base kernel).
+static int sp_features_impl(gk_handle* h, int32_t flags, int32_t wl_iter, gk_stats* stats) {
   if (!h) return fail(GK_ERR_ARG, "null handle");
   if (h->N <= 0) return fail(GK_ERR_STATE, "gk_sp_features: no graphs packed");
   GK_CUDA(cudaSetDevice(h->dev));
   const bool with_labels = flags & GK_SP_WITH_LABELS;
   if (with_labels && !h->labels0.p) return fail(GK_ERR_ARG, "gk_sp_features: vertex labels are required");
-  if (with_labels && h->n_labels0 >= (1 << 20)) return fail(GK_ERR_UNSUPPORTED, "gk_sp_features: more than 2^20 distinct labels");
+  std::vector<long long> level_base(1, 0);  // first label id of each pass
+  int n_pass = 1;
+  long long n_labels_total = h->n_labels0;
+  if (wl_iter >= 0) {
+    if (!with_labels) return fail(GK_ERR_ARG, "gk_wl_sp_features: the base kernel needs vertex labels");
+    gk_stats wst;
+    GK_TRY(gk_wl_features(h, wl_iter, &wst));
+    n_pass = wl_iter + 1;
+    level_base.assign(n_pass + 1, 0);
+    for (int l = 0; l < n_pass; ++l) level_base[l + 1] = level_base[l] + wst.level_dims[l];
+    n_labels_total = level_base[n_pass];
+  }
+  if (with_labels && n_labels_total >= (1 << 20)) return fail(GK_ERR_UNSUPPORTED, "gk_sp_features: more than 2^20 distinct labels");
   const bool use_u16 = (!h->has_weights || h->unit_weights) && h->max_graph_size < 16000;
   const size_t esz = use_u16 ? 2 : 8;
   HandleExtra* ex = extra_of(h);
@@ -665,7 +684,7 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   size_t dict_cap = std::max<size_t>(h->sp_dict_cap, 1 << 16);
   size_t dkey_cap = 1 << 18;
   bool real_mode = false;
-  size_t ft_cap = std::max<size_t>(next_pow2((size_t)std::max<int64_t>(h->V, 1024) * 16), 1 << 20);
+  size_t ft_cap = std::max<size_t>(next_pow2((size_t)std::max<int64_t>(h->V, 1024) * 16 * (size_t)std::min(n_pass, 4)), 1 << 20);
   DevScalars* sc = h->scalars.as<DevScalars>();
   GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
   for (int attempt = 0;; ++attempt) {
@@ -689,7 +708,7 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     p.col_idx = h->col_idx.as<int>();
     p.weights = (h->has_weights && !use_u16) ? h->weights.as<double>() : nullptr;
     p.labels = with_labels ? h->labels0.as<int>() : nullptr;
-    p.n_labels = with_labels ? std::max(h->n_labels0, 1) : 1;
+    p.n_labels = with_labels ? (int)std::max<long long>(n_labels_total, 1) : 1;
     p.keep = d_keep;
     p.dict_keys = h->sp_dict_keys.as<unsigned long long>();
     p.dict_mask = (unsigned)(dict_cap - 1);
@@ -699,6 +718,11 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     p.sc = sc;
     p.st = fst;
     p.gdist = h->sp_dist.p;
+    for (int pass = 0; pass < n_pass; ++pass) {
+    if (wl_iter >= 0) {
+      p.labels = h->labels_all.as<int>() + (size_t)pass * h->V;
+      p.label_offset = (int)level_base[pass];
+    }
     if (real_mode) {
       // non-integer path lengths: (1) fp64 Floyd-Warshall of every graph into global memory + a
       // dictionary of the distinct distance bit patterns, (2) histogram keyed by (lu, lv, id(d))
@@ -795,6 +819,7 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
       LAUNCH_CHECK(h);
     }
     }  // integer-distance mode
+    }  // passes (WL levels)
     DevScalars* hs;
     GK_TRY(read_scalars(h, &hs));
     if (hs->sp_nonint && !real_mode) { real_mode = true; --attempt; continue; }  // switch to exact float keys
@@ -824,6 +849,13 @@ int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     stats->ms_features = ev_ms(h->tev[2], h->tev[3]);
   }
   return GK_OK;
+}
+
+int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats) { return sp_features_impl(h, flags, -1, stats); }
+
+int gk_wl_sp_features(gk_handle* h, int32_t n_iter, int32_t flags, gk_stats* stats) {
+  if (n_iter < 0) return fail(GK_ERR_ARG, "gk_wl_sp_features: n_iter out of range");
+  return sp_features_impl(h, flags | GK_SP_WITH_LABELS, n_iter, stats);
 }
 
 int gk_sp_distances(gk_handle* h, int64_t g, double* out) {
@@ -1221,9 +1253,11 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   if (!h) return fail(GK_ERR_ARG, "null handle");
   if (!h->features_ready) return fail(GK_ERR_STATE, "gk_gram: no feature block (call gk_wl_features / gk_sp_features)");
   if (out_dtype != GK_F32 && out_dtype != GK_F64) return fail(GK_ERR_ARG, "gk_gram: bad out_dtype");
-  const int64_t N = h->N;
+  const int64_t N = h->n_rows > 0 ? h->n_rows : h->N;  // rows of the feature block (gk_set_row_map)
+  const int* d_row_map = h->n_rows > 0 ? h->row_map.as<int>() : nullptr;
   if (n_fit <= 0 || n_fit > N) return fail(GK_ERR_ARG, "gk_gram: n_fit out of range");
   if (h->feature_kind == 3) {
+    if (d_row_map) return fail(GK_ERR_UNSUPPORTED, "gk_gram: row map with ShortestPathAttr features");
     GK_CUDA(cudaSetDevice(h->dev));
     return gram_spattr(h, n_fit, flags, row_begin, row_end, K_out, out_dtype, ld, xdiag, ydiag, stats);
   }
@@ -1251,7 +1285,15 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   GK_TRY(h->h_colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->diag_f64.ensure(N * 8));
   GK_CUDA(cudaMemsetAsync(&sc->n_entries, 0, sizeof(unsigned long long) * 3 + sizeof(long long), h->stream));
-  diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, h->diag_u64.as<unsigned long long>(),
+  const unsigned long long* d_diag_u64 = h->diag_u64.as<unsigned long long>();
+  if (d_row_map) {
+    GK_TRY(h->diag_rows.ensure(N * 8));
+    GK_CUDA(cudaMemsetAsync(h->diag_rows.p, 0, N * 8, h->stream));
+    diag_remap<<<cdiv(h->N, 256), 256, 0, h->stream>>>((int)h->N, d_row_map, d_diag_u64, h->diag_rows.as<unsigned long long>());
+    LAUNCH_CHECK(h);
+    d_diag_u64 = h->diag_rows.as<unsigned long long>();
+  }
+  diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, d_diag_u64,
                                                    h->diag_f64.as<double>(), (int)h->n_part,
                                                    h->part_max.as<unsigned>(), h->part_new.as<unsigned>(), sc);
   LAUNCH_CHECK(h);
@@ -1260,7 +1302,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     GK_TRY(h->colmax.ensure(D * 4));
     GK_CUDA(cudaMemsetAsync(h->colmin.p, 0x7F, D * 4, h->stream));
     GK_CUDA(cudaMemsetAsync(h->colmax.p, 0xFF, D * 4, h->stream));
-    feat_minmax<<<h->sm_count * 16, 256, 0, h->stream>>>(h->ft_cap, h->ft_keys.as<unsigned long long>(),
+    feat_minmax<<<h->sm_count * 16, 256, 0, h->stream>>>(h->ft_cap, h->ft_keys.as<unsigned long long>(), d_row_map,
                                                          h->colmin.as<int>(), h->colmax.as<int>());
     LAUNCH_CHECK(h);
   }
@@ -1398,7 +1440,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       if (Dc) GK_CUDA(cudaMemsetAsync(h->panel.p, 0, panel_bytes, h->stream));
       if (Dc || has_tail) {
         feat_scatter<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
-            h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(),
+            h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(), d_row_map,
             h->panel.as<__nv_bfloat16>(), h->Dc_pad, h->tail_cur.as<unsigned>(), h->tail_desc.as<int2>(),
             h->tail_ent.as<int2>());
         LAUNCH_CHECK(h);
@@ -1450,7 +1492,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       GK_TRY(h->panel.ensure(panel_bytes));
       GK_CUDA(cudaMemsetAsync(h->panel.p, 0, panel_bytes, h->stream));
       feat_fill_panel_u32<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
-          h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(),
+          h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(), d_row_map,
           h->panel.as<unsigned>(), std::max<int64_t>(Dc, 1));
       LAUNCH_CHECK(h);
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
@@ -1525,6 +1567,23 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     stats->ms_d2h = ev_ms(h->ev[14], h->ev[15]);
     stats->ms_total = ev_ms(h->tev[4], h->ev[15]);
   }
+  return GK_OK;
+}
+
+int gk_set_row_map(gk_handle* h, int64_t n_rows, const int32_t* row_of_graph) {
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  if (h->N <= 0) return fail(GK_ERR_STATE, "gk_set_row_map: no graphs packed");
+  GK_CUDA(cudaSetDevice(h->dev));
+  if (n_rows <= 0 || !row_of_graph) {  // back to the identity
+    h->n_rows = 0;
+    return GK_OK;
+  }
+  for (int64_t g = 0; g < h->N; ++g)
+    if (row_of_graph[g] < 0 || row_of_graph[g] >= n_rows) return fail(GK_ERR_ARG, "gk_set_row_map: row index out of range");
+  GK_TRY(h->row_map.ensure(h->N * 4));
+  GK_CUDA(cudaMemcpyAsync(h->row_map.p, row_of_graph, h->N * 4, cudaMemcpyHostToDevice, h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  h->n_rows = n_rows;
   return GK_OK;
 }
 

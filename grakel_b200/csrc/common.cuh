@@ -156,6 +156,8 @@ struct gk_handle {
   gk::DevBuf tail_desc, tail_ent, tail_cur;
   gk::PinBuf h_colstats;
   gk::DevBuf diag_u64, diag_f64;
+  gk::DevBuf row_map, diag_rows;  // gk_set_row_map: packed graph -> row of K (0 rows = identity)
+  int64_t n_rows = 0;
   gk::DevBuf panel;
   int64_t Dc = 0, Dc_pad = 0;
 

@@ -40,15 +40,26 @@ struct ColStats {           // device-side, zeroed per gk_gram
 // (hash) order the running extrema converge after O(log m) updates per column, so the
 // L2-read filter removes almost all atomics even for columns present in every graph.
 __global__ void __launch_bounds__(256)
-feat_minmax(size_t cap, const unsigned long long* __restrict__ keys, int* colmin, int* colmax) {
+feat_minmax(size_t cap, const unsigned long long* __restrict__ keys, const int* __restrict__ row_map, int* colmin,
+            int* colmax) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned long long k = keys[i];
     if (k == EMPTY64) continue;
-    const int g = (int)(k >> 32);
+    const int g = row_map ? row_map[(int)(k >> 32)] : (int)(k >> 32);
     const unsigned c = (unsigned)k;
     if (__ldcg(&colmin[c]) > g) atomicMin(&colmin[c], g);
     if (__ldcg(&colmax[c]) < g) atomicMax(&colmax[c], g);
   }
+}
+
+// Row map (gk_set_row_map): several packed graphs feed one row of K (CoreFramework: the k-core
+// subgraphs of a graph).  Their feature columns are disjoint, so a row's self similarity is the sum
+// of its packed graphs' self similarities.
+__global__ void __launch_bounds__(256)
+diag_remap(int n_packed, const int* __restrict__ row_map, const unsigned long long* __restrict__ diag,
+           unsigned long long* diag_rows) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_packed && diag[g]) atomicAdd(&diag_rows[row_map[g]], diag[g]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -181,8 +192,9 @@ col_classify(long long D, int square, int n_fit, const unsigned* __restrict__ co
 // pass 2 over the table: head entries -> zeroed bf16 panel, tail entries -> per-column lists
 __global__ void __launch_bounds__(256)
 feat_scatter(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
-             const int* __restrict__ colslot, __nv_bfloat16* __restrict__ panel, long long ld,
-             unsigned* __restrict__ tail_cur, const int2* __restrict__ tail_desc, int2* __restrict__ tail_ent) {
+             const int* __restrict__ colslot, const int* __restrict__ row_map, __nv_bfloat16* __restrict__ panel,
+             long long ld, unsigned* __restrict__ tail_cur, const int2* __restrict__ tail_desc,
+             int2* __restrict__ tail_ent) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   unsigned long long k = keys[i];
@@ -190,7 +202,7 @@ feat_scatter(size_t cap, const unsigned long long* __restrict__ keys, const unsi
   const unsigned c = (unsigned)k;
   const int slot = colslot[c];
   if (slot == -1) return;
-  const int g = (int)(k >> 32);
+  const int g = row_map ? row_map[(int)(k >> 32)] : (int)(k >> 32);
   if (slot >= 0) {
     panel[(long long)g * ld + slot] = __float2bfloat16_rn((float)cnt[i]);
   } else {
@@ -203,14 +215,16 @@ feat_scatter(size_t cap, const unsigned long long* __restrict__ keys, const unsi
 // same, into a u32 panel (exact CUDA-core Gram; no tail in that mode)
 __global__ void __launch_bounds__(256)
 feat_fill_panel_u32(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
-                    const int* __restrict__ colslot, unsigned* __restrict__ panel, long long ld) {
+                    const int* __restrict__ colslot, const int* __restrict__ row_map, unsigned* __restrict__ panel,
+                    long long ld) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   unsigned long long k = keys[i];
   if (k == EMPTY64) return;
   const int dc = colslot[(unsigned)k];
   if (dc < 0) return;
-  panel[(long long)(k >> 32) * ld + dc] = cnt[i];
+  const int g = row_map ? row_map[(int)(k >> 32)] : (int)(k >> 32);
+  panel[(long long)g * ld + dc] = cnt[i];
 }
 
 // Tail contraction: one warp per tail column, all ordered pairs of its entries.

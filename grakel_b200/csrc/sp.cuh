@@ -44,6 +44,7 @@ struct SpParams {
   const int* col_idx;
   const double* weights;   // NULL = unit
   const int* labels;       // dense ids or NULL (with_labels = False)
+  int label_offset;        // added to every label (WL levels share one dictionary: ids are made level-unique)
   const int* glist;        // graphs handled by this launch (NULL = all, blockIdx.x)
   int n_list;
   int n_labels;            // size of the label alphabet (1 when with_labels = False)
@@ -136,7 +137,7 @@ sp_bfs_hist(SpParams p) {
   for (int i = tid; i < SP_LOCAL_SLOTS; i += blockDim.x) { if (!direct) lkeys[i] = EMPTY64; lcnt[i] = 0; }
   for (int i = tid; i < n * W; i += blockDim.x) adj[i] = 0ULL;
   if (direct) for (int i = tid; i < L * W; i += blockDim.x) lmask[i] = 0ULL;
-  for (int i = tid; i < n; i += blockDim.x) lab[i] = p.labels ? p.labels[v0 + i] : 0;
+  for (int i = tid; i < n; i += blockDim.x) lab[i] = p.labels ? p.labels[v0 + i] + p.label_offset : 0;
   __syncthreads();
   const int e0 = p.row_ptr[v0], e1 = p.row_ptr[v0 + n];
   // edge list -> bitmask rows (vertex of edge k found by binary search in row_ptr)
@@ -283,7 +284,7 @@ sp_apsp_hist(SpParams p) {
   }
   // labelled path-length histogram (shortest_path.py:470-490)
   for (int u = warp; u < n; u += NW) {
-    const unsigned long long lu = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + u] : 0ULL;
+    const unsigned long long lu = p.labels ? (unsigned long long)(unsigned)(p.labels[v0 + u] + p.label_offset) : 0ULL;
     const T* ru = dist + (long long)u * n;
     for (int w = lane; w < n; w += 32) {
       if (w == u) continue;
@@ -296,7 +297,7 @@ sp_apsp_hist(SpParams p) {
         di = (unsigned)d;
         if ((double)di != (double)d || d >= 16777216.0) { atomicOr(&p.sc->sp_nonint, 1u); continue; }
       }
-      const unsigned long long lv = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + w] : 0ULL;
+      const unsigned long long lv = p.labels ? (unsigned long long)(unsigned)(p.labels[v0 + w] + p.label_offset) : 0ULL;
       const unsigned long long key = (lu << 44) | (lv << 24) | (unsigned long long)di;
       sp_local_add(lkeys, lcnt, p, g, key);
     }

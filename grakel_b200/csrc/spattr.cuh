@@ -93,8 +93,8 @@ sp_hist_from_dist(SpParams p, const unsigned long long* __restrict__ dkeys, unsi
     const unsigned long long dk = (unsigned long long)__double_as_longlong(d);
     unsigned slot = (unsigned)(mix64(dk) >> 13) & dmask;
     while (dkeys[slot] != dk) slot = (slot + 1) & dmask;
-    const unsigned long long lu = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + u] : 0ULL;
-    const unsigned long long lv = p.labels ? (unsigned long long)(unsigned)p.labels[v0 + w] : 0ULL;
+    const unsigned long long lu = p.labels ? (unsigned long long)(unsigned)(p.labels[v0 + u] + p.label_offset) : 0ULL;
+    const unsigned long long lv = p.labels ? (unsigned long long)(unsigned)(p.labels[v0 + w] + p.label_offset) : 0ULL;
     sp_local_add(lkeys, lcnt, p, g, (lu << 44) | (lv << 24) | (unsigned long long)slot);
   }
   __syncthreads();

@@ -195,6 +195,71 @@ class VertexHistogram(Kernel):
 
 
 # ------------------------------------------------------------------------------
+def _edge_label_values(X):
+    """Edge-label values per element, with the element checks of EdgeHistogram.parse_input
+    (edge_histogram.py:76-103): elements must have exactly three members (graph, node labels,
+    edge labels) or be `Graph` objects; only the VALUES of the edge-label dictionary are used."""
+    if not isinstance(X, Iterable):
+        raise TypeError("input must be an iterable\n")
+    out = []
+    for idx, x in enumerate(iter(X)):
+        if isinstance(x, Graph):
+            if not x.edge_labels:
+                raise ValueError("Graph does not have any labels for edges.")
+            L = x.edge_labels
+        else:
+            is_iter = isinstance(x, Iterable)
+            if is_iter:
+                x = list(x)
+            if not (is_iter and len(x) in (0, 3)):
+                raise TypeError("each element of X must be either a graph object or a list with at least a graph like "
+                                "object and node labels dict \n")
+            if len(x) == 0:
+                warnings.warn("Ignoring empty element on index: " + str(idx))
+                continue
+            L = x[2]
+        out.append(list(L.values()))
+    if not out:
+        raise ValueError("parsed input is empty")
+    return out
+
+
+class EdgeHistogram(Kernel):
+    """Edge histogram kernel (edge_histogram.py:23-212): K = Phi Phi^T with
+    Phi[g, l] = number of edge-label entries of g equal to l.  On the device this is the
+    vertex-histogram path over a block whose "vertices" are the edge-label entries."""
+
+    _levels = 0
+
+    def __init__(self, n_jobs=None, normalize=False, verbose=False, sparse="auto"):
+        super().__init__(n_jobs=n_jobs, normalize=normalize, verbose=verbose)
+        self.sparse = sparse
+        self._initialized.update({"sparse": True})
+
+    def initialize(self):
+        if not self._initialized["n_jobs"]:  # edge_histogram.py:48-52
+            if self.n_jobs is not None:
+                warnings.warn("no implemented parallelization for EdgeHistogram")
+            self._initialized["n_jobs"] = True
+
+    def parse_input(self, X):
+        values = _edge_label_values(X)
+        sizes = np.concatenate([[0], np.cumsum([len(v) for v in values])])
+        labels = [l for v in values for l in v]
+        block = Block(sizes, np.zeros(int(sizes[-1]) + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), None, labels)
+        if self._method_calling in (1, 2):
+            ids, dictionary = label_ids(labels, None, sort_new=False)
+            self._labels = dictionary
+            self.sparse_ = True
+            return Fitted(block, ids, dictionary)
+        ids, _ = label_ids(labels, self.X.dictionary, sort_new=False)
+        return Fitted(block, ids, self.X.dictionary)
+
+    def _device_features(self, eng):
+        return eng.wl_features(self._levels)
+
+
+# ------------------------------------------------------------------------------
 class WeisfeilerLehman(Kernel):
     """Weisfeiler-Lehman subtree kernel (weisfeiler_lehman.py:23-555).
 
@@ -231,9 +296,16 @@ class WeisfeilerLehman(Kernel):
                     raise ValueError("If the second argument of base kernel exists, it must be a dictionary between "
                                      "parameters names and values")
                 params.pop("normalize", None)
-            if base is not VertexHistogram:
-                raise NotImplementedError("grakel_b200 runs the WL *subtree* kernel (base_graph_kernel="
-                                          "VertexHistogram); other base kernels are outside the device hot path")
+            if base not in (VertexHistogram, EdgeHistogram, ShortestPath):
+                raise NotImplementedError("grakel_b200 runs WeisfeilerLehman over VertexHistogram (the subtree kernel), "
+                                          "EdgeHistogram or ShortestPath; other base kernels are outside the device "
+                                          "hot path")
+            if base is ShortestPath:
+                if not params.get("with_labels", True):
+                    raise NotImplementedError("WeisfeilerLehman over ShortestPath(with_labels=False) ignores the WL "
+                                              "labels; use (n_iter + 1) * ShortestPath(with_labels=False)")
+                if params.get("algorithm_type", "auto") not in ("auto", "floyd_warshall", "dijkstra"):
+                    raise ValueError('Unsupported "algorithm_type"')
             params["normalize"] = False
             params["verbose"] = self.verbose
             params["n_jobs"] = None
@@ -246,20 +318,45 @@ class WeisfeilerLehman(Kernel):
             self._n_iter = self.n_iter + 1
             self._initialized["n_iter"] = True
 
+    def _pack_for_base(self, X, len_ok):
+        """One block per base kernel: the subtree kernel needs the adjacency structure only, the
+        shortest-path base also the edge weights; the edge-histogram base never looks at the graph --
+        its block has one "vertex" per edge-label entry and no edges, so that every WL round reproduces
+        the same partition and K = (n_iter + 1) * K_EH, exactly what the reference computes by fitting
+        one EdgeHistogram per level on unchanged edge labels (weisfeiler_lehman.py:157-169, 260-270)."""
+        base = self._base_graph_kernel
+        if base is EdgeHistogram:
+            if not isinstance(X, Iterable):
+                raise TypeError("input must be an iterable\n")
+            X = list(X)
+            pack(X, "wl", len_ok=len_ok)  # the reference builds the Graph + node labels first: same errors
+            values = _edge_label_values(X)
+            sizes = np.concatenate([[0], np.cumsum([len(v) for v in values])])
+            return Block(sizes, np.zeros(int(sizes[-1]) + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), None,
+                         [l for v in values for l in v])
+        if base is ShortestPath:
+            # the base kernel receives the edge DICTIONARY of every graph (weisfeiler_lehman.py:188, 218):
+            # Dijkstra semantics whatever the input spelling; labels are the WL vertex set
+            block = pack(X, "wl", len_ok=len_ok, want_weights=True)
+            if block.weights is not None and np.any(block.weights != np.rint(block.weights)):
+                raise NotImplementedError("non-integer edge weights are supported with Floyd-Warshall semantics only")
+            return block
+        return pack(X, "wl", len_ok=len_ok)
+
     def parse_input(self, X):
         if self._method_calling in (1, 2):
             if hasattr(self, "_X_diag"):
                 delattr(self, "_X_diag")
             if not isinstance(X, Iterable):
                 raise TypeError("input must be an iterable\n")
-            block = pack(X, "wl", len_ok=lambda n: n >= 2)  # weisfeiler_lehman.py:152
+            block = self._pack_for_base(X, lambda n: n >= 2)  # weisfeiler_lehman.py:152
             self._nx = block.n_graphs
             ids, dictionary = label_ids(block.labels, None, sort_new=True)  # :199-206
             self._inv_labels = {0: dictionary}
             return Fitted(block, ids, dictionary)
         if self._method_calling != 3:
             raise ValueError("method call must be called either from fit or fit-transform")
-        block = pack(X, "wl", len_ok=lambda n: n in (2, 3))  # :367
+        block = self._pack_for_base(X, lambda n: n in (2, 3))  # :367
         ids, _ = label_ids(block.labels, self._inv_labels[0], sort_new=True)  # :417-418
         return Fitted(block, ids, self._inv_labels[0])
 
@@ -299,6 +396,8 @@ class WeisfeilerLehman(Kernel):
         return K
 
     def _device_features(self, eng):
+        if self._base_graph_kernel is ShortestPath:
+            return eng.wl_sp_features(self._n_iter - 1)
         return eng.wl_features(self._n_iter - 1)
 
 

@@ -22,6 +22,8 @@
  *   gk_sp_features       Graph.build_shortest_path_matrix / floyd_warshall / dijkstra
  *                        (graph.py:588-687, 1712-1794) + ShortestPath.parse_input
  *                        pair histogram (shortest_path.py:468-490).
+ *   gk_wl_sp_features    the WL level loop with ShortestPath as base kernel
+ *                        (weisfeiler_lehman.py:260-270, "WL-SP" of doc/benchmarks).
  *   gk_spattr_features   ShortestPathAttr.parse_input + the bilinear pair kernel
  *                        (shortest_path.py:77-164) as an explicit feature map.
  *   gk_gram              VertexHistogram._calculate_kernel_matrix
@@ -124,6 +126,11 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
 int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats);
 int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats);
 int gk_spattr_features(gk_handle* h, gk_stats* stats);
+/* WeisfeilerLehman(base_graph_kernel=ShortestPath), weisfeiler_lehman.py:260-270 over
+ * shortest_path.py:370-410: n_iter WL rounds, then the labelled shortest-path histogram of every
+ * level in one feature block (level-unique label ids => disjoint columns), so that one gk_gram
+ * returns the sum of the per-level matrices. */
+int gk_wl_sp_features(gk_handle* h, int32_t n_iter, int32_t flags, gk_stats* stats);
 
 /* Gram matrix of the current feature block.
  *   n_fit == n_graphs : K is [n_graphs x n_graphs]                      (fit_transform)
@@ -135,6 +142,14 @@ int gk_spattr_features(gk_handle* h, gk_stats* stats);
 int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64_t row_end,
             void* K_out, int32_t out_dtype, int64_t ld, double* xdiag, double* ydiag,
             gk_stats* stats);
+
+/* Row map: packed graph g contributes to row row_of_graph[g] of K (n_rows rows in total; gk_gram's
+ * n_fit / row ranges / diagonals then count rows).  Used by CoreFramework (core_framework.py:177-223):
+ * the k-core subgraphs of every graph are packed as separate graphs with level-tagged labels (their
+ * feature columns are therefore disjoint) and mapped back to their graph's row, so one Gram equals the
+ * reference's scatter-add of one base-kernel matrix per core level.  Cleared by gk_pack_csr;
+ * n_rows <= 0 restores the identity. */
+int gk_set_row_map(gk_handle* h, int64_t n_rows, const int32_t* row_of_graph);
 
 /* Copy rows of the device-resident K of the last gk_gram to the host. */
 int gk_fetch(gk_handle* h, void* K_out, int32_t out_dtype, int64_t ld);

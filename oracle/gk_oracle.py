@@ -280,17 +280,80 @@ class _VH:
 
 
 # --------------------------------------------------------------------------
+# Edge histogram  (edge_histogram.py:23-212)
+# --------------------------------------------------------------------------
+class EHOracle:
+    """Counts of the VALUES of each element's edge-label dictionary (edge_histogram.py:76-112);
+    the graph itself is never consulted.  Elements are [graph, node_labels, edge_labels]."""
+
+    def __init__(self, normalize=False):
+        self.normalize = normalize
+
+    @staticmethod
+    def _label_dicts(X):
+        out = []
+        for x in X:
+            x = list(x)
+            if len(x) == 0:
+                continue
+            if len(x) != 3:
+                raise TypeError("each element of X must be either a graph object or a list with at least a graph like "
+                                "object and node labels dict \n")
+            out.append(dict(enumerate(x[2].values())))
+        if not out:
+            raise ValueError("parsed input is empty")
+        return out
+
+    def fit_transform(self, X):
+        self.vh = _VH().fit(self._label_dicts(X))
+        K = self.vh.gram()
+        self.xdiag = self.vh.xdiag()
+        if self.normalize:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = K / np.sqrt(np.outer(self.xdiag, self.xdiag))
+        return K
+
+    def transform(self, Y):
+        K = self.vh.transform(self._label_dicts(Y))
+        self.ydiag = self.vh.ydiag()
+        if self.normalize:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = K / np.sqrt(np.outer(self.ydiag, self.xdiag))
+        return K
+
+
+# --------------------------------------------------------------------------
 # Weisfeiler-Lehman subtree  (weisfeiler_lehman.py:117-555)
 # --------------------------------------------------------------------------
 class WLOracle:
-    def __init__(self, n_iter=5, normalize=False, n_jobs=None):
+    def __init__(self, n_iter=5, normalize=False, n_jobs=None, base="subtree"):
         if type(n_iter) is not int or n_iter <= 0:
             raise TypeError("'n_iter' must be a positive integer")
         self.h = n_iter
         self.normalize = normalize
+        # base kernel fitted on every level's relabelled graphs (weisfeiler_lehman.py:260-270):
+        # "subtree" = VertexHistogram (default), "edge_histogram", "shortest_path"
+        if base not in ("subtree", "edge_histogram", "shortest_path"):
+            raise ValueError("unknown base kernel")
+        self.base = base
         # weisfeiler_lehman.py:279-285: with n_jobs the reference hands one task per level
         # (base kernel fit_transform) to a joblib *threading* pool; same structure here.
         self.n_jobs = n_jobs
+
+    def _make_base(self):
+        return EHOracle() if self.base == "edge_histogram" else SPOracle(with_labels=True)
+
+    @staticmethod
+    def _level_elements(Gs, L, extras):
+        """What the reference hands to the base kernel of a level: (edge dictionary, level labels)
+        + the edge labels when the element had them (weisfeiler_lehman.py:218, 256)."""
+        out = []
+        for g, l, e in zip(Gs, L, extras):
+            ed = {u: dict(d) for u, d in g.ed.items()}
+            for v in l:
+                ed.setdefault(v, {})
+            out.append([ed, dict(l)] + ([e] if e is not None else []))
+        return out
 
     @staticmethod
     def _signature(own, nbr_labels):
@@ -315,9 +378,20 @@ class WLOracle:
             import os as _os
             pool = ThreadPoolExecutor(max_workers=self.n_jobs if self.n_jobs > 0 else (_os.cpu_count() or 1))
 
+        extras = []
+        for x in X:  # edge labels travel unchanged to every level (weisfeiler_lehman.py:157-169)
+            x = list(x)
+            if len(x) == 0:
+                continue
+            extras.append(x[2] if len(x) > 2 else None)
+        self._fit_extras = extras
+
         def level_task(Lc):
-            vh = _VH().fit(Lc)
-            return vh, vh.gram()
+            if self.base == "subtree":
+                vh = _VH().fit(Lc)
+                return vh, vh.gram()
+            bk = self._make_base()
+            return bk, bk.fit_transform(self._level_elements(Gs, Lc, extras))
 
         tasks = [pool.submit(level_task, L) if pool else level_task(L)]
         level_labels = [[dict(l) for l in L]] if return_levels else None
@@ -367,7 +441,19 @@ class WLOracle:
         fresh = sorted({v for l in L for v in l.values() if v not in inv0})
         new0 = {lab: i for i, lab in enumerate(fresh, nl)}  # weisfeiler_lehman.py:417-418
         L = [{v: (inv0[lab] if lab in inv0 else new0[lab]) for v, lab in l.items()} for l in L]
-        Ks = [self.levels[0].transform(L)]
+        yextras = []
+        for x in Y:
+            x = list(x)
+            if len(x) == 0:
+                continue
+            yextras.append(x[2] if len(x) > 2 else None)
+
+        def level_transform(it, Lc):
+            if self.base == "subtree":
+                return self.levels[it].transform(Lc)
+            return self.levels[it].transform(self._level_elements(Gs, Lc, yextras))
+
+        Ks = [level_transform(0, L)]
         for it in range(1, self.h + 1):  # :435-476
             nl += len(self.inv[it])
             inv = self.inv[it]
@@ -381,9 +467,9 @@ class WLOracle:
                 sigs.append(s)
             new = {sig: i for i, sig in enumerate(sorted(unseen), nl)}
             L = [{v: (inv[s] if s in inv else new[s]) for v, s in sg.items()} for sg in sigs]
-            Ks.append(self.levels[it].transform(L))
+            Ks.append(level_transform(it, L))
         K = np.sum(Ks, axis=0)
-        self.ydiag = np.sum([lv.ydiag() for lv in self.levels], axis=0)
+        self.ydiag = np.sum([lv.ydiag() if self.base == "subtree" else lv.ydiag for lv in self.levels], axis=0)
         if self.normalize:  # :494-498
             with np.errstate(divide="ignore", invalid="ignore"):
                 K = np.nan_to_num(K / np.sqrt(np.outer(self.ydiag, self.xdiag)))
@@ -570,4 +656,30 @@ def gen(N, nbar, seed, nl=7, attr=0, as_adj=False):
                 g[(x, y)] = 1
                 g[(y, x)] = 1
             out.append([g, L])
+    return out
+
+
+def gen_edge_labelled(N, nbar, seed, nl=5, n_el=3):
+    """Like gen(), plus an edge-label dictionary {(a, b): l, (b, a): l} per graph (third element)."""
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(N):
+        n = int(rs.randint(nbar // 2, nbar + nbar // 2 + 1))
+        p = 4.0 / max(n - 1, 1)
+        iu = np.triu_indices(n, 1)
+        m = rs.rand(len(iu[0])) < p
+        g, el = {}, {}
+        for a, b in zip(iu[0][m].tolist(), iu[1][m].tolist()):
+            l = int(rs.randint(n_el))
+            g[(a, b)] = 1
+            g[(b, a)] = 1
+            el[(a, b)] = l
+            el[(b, a)] = l
+        if not g:
+            g[(0, 1)] = 1
+            g[(1, 0)] = 1
+            el[(0, 1)] = 0
+            el[(1, 0)] = 0
+        L = {i: int(rs.randint(nl)) for i in range(n)}
+        out.append([g, L, el])
     return out
