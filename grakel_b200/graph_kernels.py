@@ -4,6 +4,8 @@
     "weisfeiler_lehman" / "WL"  (framework; base "vertex_histogram"/"subtree_wl"/"VH"/"ST-WL")
     "vertex_histogram" / "subtree_wl" / "VH" / "ST-WL"
     "shortest_path" / "SP"      (+ with_labels, algorithm_type, as_attributes)
+    "edge_histogram" / "EH"
+    "core_framework" / "CORE"   (framework; base "shortest_path" or "weisfeiler_lehman" ...)
 
 Any other reference kernel name raises NotImplementedError (not ValueError, which
 the reference reserves for unknown names).  The Nystroem option is host-side
@@ -18,17 +20,20 @@ from sklearn.base import BaseEstimator, TransformerMixin
 from sklearn.utils import check_random_state
 from sklearn.utils.validation import check_is_fitted
 
-from .kernels import ShortestPath, ShortestPathAttr, VertexHistogram, WeisfeilerLehman
+from .core_framework import CoreFramework
+from .kernels import EdgeHistogram, ShortestPath, ShortestPathAttr, VertexHistogram, WeisfeilerLehman
 
 _VH = ("vertex_histogram", "subtree_wl", "VH", "ST-WL")
 _SP = ("shortest_path", "SP")
 _WL = ("weisfeiler_lehman", "WL")
+_EH = ("edge_histogram", "EH")
+_CORE = ("core_framework", "CORE")
 # names the reference knows but that are outside the hot path (graph_kernels.py:38-64)
-_OTHER = {"edge_histogram", "EH", "random_walk", "RW", "graphlet_sampling", "GR", "subgraph_matching", "SM",
+_OTHER = {"random_walk", "RW", "graphlet_sampling", "GR", "subgraph_matching", "SM",
           "multiscale_laplacian", "ML", "lovasz_theta", "LOVT", "svm_theta", "SVMT", "neighborhood_hash", "NH",
           "neighborhood_subgraph_pairwise_distance", "NSPD", "odd_sth", "ODD", "propagation", "PR",
           "pyramid_match", "PM", "graph_hopper", "GH", "weisfeiler_lehman_optimal_assignment", "WL-OA",
-          "hadamard_code", "HC", "core_framework", "CORE"}
+          "hadamard_code", "HC"}
 default_n_components = 100
 
 
@@ -126,12 +131,14 @@ class GraphKernel(BaseEstimator, TransformerMixin):
                 warnings.warn("Overriding global kernel attribute " + str(key) + " with " + str(val) +
                               ". Please set this attribute as an argument of GraphKernel.")
             kernel[key] = val
-        if name in _VH or name in _SP:
+        if name in _VH or name in _SP or name in _EH:
             if len(kernel_list) != 0:
                 warnings.warn("Kernel List not empty while reaching a base-kernel - the rest kernel names will be "
                               "ignored")
             if name in _VH:
                 return VertexHistogram, kernel
+            if name in _EH:
+                return EdgeHistogram, kernel
             if kernel.pop("as_attributes", False):
                 return ShortestPathAttr, kernel
             return ShortestPath, kernel
@@ -139,6 +146,10 @@ class GraphKernel(BaseEstimator, TransformerMixin):
             if len(kernel_list):
                 kernel["base_graph_kernel"] = self.make_kernel_(kernel_list, {})
             return WeisfeilerLehman, kernel
+        if name in _CORE:  # graph_kernels.py:527-531
+            if len(kernel_list):
+                kernel["base_graph_kernel"] = self.make_kernel_(kernel_list, {})
+            return CoreFramework, kernel
         if name in _OTHER:
             raise NotImplementedError("kernel '" + str(name) + "' is outside the device hot path of grakel_b200 "
                                       "(WL-subtree, vertex histogram, shortest path)")

@@ -19,7 +19,11 @@ def _features(n_graphs, vgraph, cols, D):
     return csr_matrix((d, (r, c)), shape=(n_graphs, D))
 
 
-def _finish(Phi, n_graphs, n_fit, normalize, nan_to_num):
+def _finish(Phi, n_graphs, n_fit, normalize, nan_to_num, rows=None, n_rows=None):
+    if rows is not None:  # gk_set_row_map: packed graph g feeds row rows[g] (disjoint columns per source)
+        P = csr_matrix((np.ones(len(rows)), (np.asarray(rows), np.arange(len(rows)))), shape=(n_rows, Phi.shape[0]))
+        Phi = csr_matrix(P.dot(Phi))
+        n_graphs = n_rows
     X = Phi[:n_fit]
     diag = np.asarray(Phi.multiply(Phi).sum(axis=1)).ravel()
     if n_fit == n_graphs:
@@ -53,9 +57,9 @@ def wl_levels(block, ids, n_iter):
     return levels
 
 
-def wl_gram_block(block, ids, n_iter, n_fit=None, normalize=False):
+def wl_gram_block(block, ids, n_iter, n_fit=None, normalize=False, rows=None, n_rows=None):
     N = block.n_graphs
-    n_fit = N if n_fit is None else n_fit
+    n_fit = (N if rows is None else n_rows) if n_fit is None else n_fit
     vgraph = np.repeat(np.arange(N), np.diff(block.graph_ptr))
     levels = wl_levels(block, ids, n_iter)
     cols, base = [], 0
@@ -63,7 +67,7 @@ def wl_gram_block(block, ids, n_iter, n_fit=None, normalize=False):
         cols.append(lab + base)
         base += int(lab.max()) + 1 if len(lab) else 0
     Phi = _features(N, np.tile(vgraph, len(levels)), np.concatenate(cols), base)
-    return _finish(Phi, N, n_fit, normalize, True)
+    return _finish(Phi, N, n_fit, normalize, True, rows, n_rows)
 
 
 def apsp_block(block, g):
@@ -81,21 +85,32 @@ def apsp_block(block, g):
     return D
 
 
-def sp_gram_block(block, ids, n_fit=None, with_labels=True, normalize=False):
+def sp_gram_block(block, ids, n_fit=None, with_labels=True, normalize=False, rows=None, n_rows=None, wl_iter=None,
+                  nan_to_num=False):
+    """ShortestPath features; with `wl_iter` the gk_wl_sp_features model: the labelled path
+    histogram of every WL level with level-unique label ids in one feature block."""
     N = block.n_graphs
-    n_fit = N if n_fit is None else n_fit
+    n_fit = (N if rows is None else n_rows) if n_fit is None else n_fit
+    if wl_iter is None:
+        label_sets = [np.asarray(ids, dtype=np.int64)] if with_labels else [None]
+    else:
+        label_sets, base = [], 0
+        for lab in wl_levels(block, ids, wl_iter):
+            label_sets.append(lab + base)
+            base += int(lab.max()) + 1 if len(lab) else 0
     enum = {}
-    rows, cols = [], []
+    frows, cols = [], []
     for g in range(N):
         D = apsp_block(block, g)
         v0 = int(block.graph_ptr[g])
         n = D.shape[0]
-        for u in range(n):
-            for v in range(n):
-                if u == v or not np.isfinite(D[u, v]):
-                    continue
-                key = (int(ids[v0 + u]), int(ids[v0 + v]), D[u, v]) if with_labels else D[u, v]
-                rows.append(g)
-                cols.append(enum.setdefault(key, len(enum)))
-    Phi = _features(N, np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64), max(len(enum), 1))
-    return _finish(Phi, N, n_fit, normalize, False)
+        for lab in label_sets:
+            for u in range(n):
+                for v in range(n):
+                    if u == v or not np.isfinite(D[u, v]):
+                        continue
+                    key = (int(lab[v0 + u]), int(lab[v0 + v]), D[u, v]) if lab is not None else D[u, v]
+                    frows.append(g)
+                    cols.append(enum.setdefault(key, len(enum)))
+    Phi = _features(N, np.asarray(frows, dtype=np.int64), np.asarray(cols, dtype=np.int64), max(len(enum), 1))
+    return _finish(Phi, N, n_fit, normalize, nan_to_num or wl_iter is not None, rows, n_rows)
