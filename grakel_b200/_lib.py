@@ -58,6 +58,7 @@ _SYMBOLS = {
     "gk_sp_features": (C.c_int, [_P, C.c_int32, C.POINTER(GkStats)]),
     "gk_spattr_features": (C.c_int, [_P, C.POINTER(GkStats)]),
     "gk_wl_sp_features": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(GkStats)]),
+    "gk_wl_oa_features": (C.c_int, [_P, C.c_int32, C.POINTER(GkStats)]),
     "gk_gram": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int32, C.c_int64, _P, _P,
                           C.POINTER(GkStats)]),
     "gk_fetch": (C.c_int, [_P, _P, C.c_int32, C.c_int64]),
@@ -164,6 +165,12 @@ class Engine:
         st = GkStats()
         with self._lock:
             self._check(self.lib.gk_wl_features(self.h, int(n_iter), C.byref(st)))
+        return st
+
+    def wl_oa_features(self, n_iter):
+        st = GkStats()
+        with self._lock:
+            self._check(self.lib.gk_wl_oa_features(self.h, int(n_iter), C.byref(st)))
         return st
 
     def sp_features(self, with_labels=True, keep_dist=False):

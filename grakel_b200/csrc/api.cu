@@ -21,6 +21,7 @@
 #include "spattr.cuh"
 #include "wl.cuh"
 #include "wl_fused.cuh"
+#include "wl_oa.cuh"
 
 namespace gk {
 thread_local std::string g_last_error;
@@ -170,7 +171,7 @@ int gk_destroy(gk_handle* h) {
                         &h->colmin, &h->colmax, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
-                        &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows};
+                        &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
@@ -580,6 +581,65 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     stats->kernel_launches = h->launches - launches0;
     stats->ms_features = ev_ms(h->tev[2], h->tev[3]);
   }
+  return GK_OK;
+}
+
+// WL-OA: the WL feature block, then its unary expansion (wl_oa.cuh); one gk_gram of the expanded
+// block is the histogram-intersection matrix of weisfeiler_lehman_optimal_assignment.py:257-266.
+int gk_wl_oa_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
+  gk_stats local;
+  gk_stats* st = stats ? stats : &local;
+  GK_TRY(gk_wl_features(h, n_iter, st));
+  h->features_ready = false;
+  const int64_t launches0 = h->launches;
+  const int64_t D = std::max<int64_t>(h->n_columns, 1);
+  const size_t out_cap = std::max<size_t>((size_t)h->V * (size_t)h->n_levels, 1);  // one entry per (vertex, level)
+  if (out_cap > (1ULL << 31)) return fail(GK_ERR_ARG, "gk_wl_oa_features: feature block too large");
+  GK_TRY(h->oa_keys.ensure(out_cap * 8));
+  GK_TRY(h->oa_cnt.ensure(out_cap * 4));
+  GK_TRY(h->oa_colcnt.ensure((out_cap + 1) * 4));
+  GK_TRY(h->colmin.ensure(D * 4));  // scratch until the next gk_gram: largest count / first threshold column
+  GK_TRY(h->colmax.ensure(D * 4));
+  GK_TRY(h->colstats.ensure(std::max(sizeof(ColStats), sizeof(OaCursors))));
+  GK_TRY(h->h_colstats.ensure(std::max(sizeof(ColStats), sizeof(OaCursors))));
+  OaCursors* cur = h->colstats.as<OaCursors>();
+  unsigned* colmaxcnt = h->colmin.as<unsigned>();
+  unsigned* colbase = h->colmax.as<unsigned>();
+  GK_CUDA(cudaMemsetAsync(cur, 0, sizeof(OaCursors), h->stream));
+  GK_CUDA(cudaMemsetAsync(colmaxcnt, 0, D * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->oa_keys.p, 0xFF, out_cap * 8, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->oa_colcnt.p, 0, (out_cap + 1) * 4, h->stream));
+  GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, h->N * 8, h->stream));
+  oa_colmax<<<h->sm_count * 8, 256, 0, h->stream>>>(h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(),
+                                                    colmaxcnt);
+  LAUNCH_CHECK(h);
+  oa_colbase<<<cdiv(D, 256), 256, 0, h->stream>>>(D, colmaxcnt, colbase, cur);
+  LAUNCH_CHECK(h);
+  oa_expand<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+      h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), colbase, out_cap,
+      h->oa_keys.as<unsigned long long>(), h->oa_cnt.as<unsigned>(), cur, h->oa_colcnt.as<unsigned>(),
+      h->diag_u64.as<unsigned long long>(), h->scalars.as<DevScalars>());
+  LAUNCH_CHECK(h);
+  h->n_part = 1;
+  oa_finish<<<1, 1, 0, h->stream>>>(cur, h->part_max.as<unsigned>(), h->part_new.as<unsigned>());
+  LAUNCH_CHECK(h);
+  GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, cur, sizeof(OaCursors), cudaMemcpyDeviceToHost, h->stream));
+  DevScalars* hs;
+  GK_TRY(read_scalars(h, &hs));
+  GK_CUDA(cudaEventRecord(h->tev[3], h->stream));
+  GK_CUDA(cudaEventSynchronize(h->tev[3]));
+  if (hs->ft_overflow) return fail(GK_ERR_STATE, "gk_wl_oa_features: expanded feature block overflow");
+  const OaCursors hc = *h->h_colstats.as<OaCursors>();
+  std::swap(h->ft_keys, h->oa_keys);
+  std::swap(h->ft_cnt, h->oa_cnt);
+  std::swap(h->colcnt, h->oa_colcnt);
+  h->ft_cap = out_cap;
+  h->col_cap = (int64_t)out_cap + 1;
+  h->n_columns = (int64_t)hc.n_cols;
+  h->features_ready = true;
+  st->n_columns = h->n_columns;
+  st->kernel_launches += h->launches - launches0;
+  st->ms_features = ev_ms(h->tev[2], h->tev[3]);
   return GK_OK;
 }
 

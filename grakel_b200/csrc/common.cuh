@@ -148,6 +148,7 @@ struct gk_handle {
   bool features_ready = false;
   int feature_kind = 0;  // 1 = WL, 2 = SP, 3 = SP-attr (dense fp32 features)
 
+  gk::DevBuf oa_keys, oa_cnt, oa_colcnt;  // WL-OA: unary-expanded block, swapped with ft_keys / ft_cnt / colcnt
   // ---- columns / panel / diag
   gk::DevBuf colcnt, colmin, colmax, colslot, col_flags3, col_block_sums, colstats;
   int64_t col_cap = 0;  // allocated length of the per-column arrays

@@ -1,0 +1,106 @@
+// Weisfeiler-Lehman optimal assignment (weisfeiler_lehman_optimal_assignment.py:78-279) as a Gram.
+//
+// The reference builds, per graph, the vector Hs[j, c] = number of vertices of j that carry WL label c
+// at c's level (the hierarchy walk of :203-209 adds 1 to every ancestor of a vertex's last-level
+// label), i.e. exactly the WL feature block of all levels, and then fills K with an O(N^2) Python loop
+// of histogram intersections  K[i, j] = sum_c min(Hs[i, c], Hs[j, c])  (:257-266).
+//
+// min(a, b) = sum_{t >= 1} [a >= t][b >= t]  for non-negative integers, so the intersection kernel is
+// the DOT PRODUCT of the unary ("thermometer") expansions: column c with count k becomes the k columns
+// (c, 1) ... (c, k), each holding 1.  The expanded block has exactly one entry per (vertex, level) --
+// (h + 1) V entries, barely more than the nnz of the count block -- and feeds the same head / tail Gram
+// as the subtree kernel (features.cuh, gram_tc.cuh): high-frequency threshold columns go through the
+// tcgen05 GEMM, the long tail through exact pair updates, self similarities are sums of 1 = (h + 1) n_j,
+// and the transform rule "drop the columns X does not have" (:433) is the rectangular column filter.
+// Everything stays integer-exact.
+#pragma once
+#include "common.cuh"
+#include "wl.cuh"
+
+namespace gk {
+
+struct OaCursors {
+  unsigned long long n_cols;     // columns of the expanded block
+  unsigned long long n_entries;  // entries of the expanded block
+};
+
+// pass 1: largest count of every column (L2-read filter: most updates do not raise the maximum)
+__global__ void __launch_bounds__(256)
+oa_colmax(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt, unsigned* colmax) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    if (k == EMPTY64) continue;
+    const unsigned c = (unsigned)k, n = cnt[i];
+    if (__ldcg(&colmax[c]) < n) atomicMax(&colmax[c], n);
+  }
+}
+
+// pass 2: first threshold column of every column.  Warp-aggregated allocation from one cursor: the
+// order of the expanded columns depends on scheduling, K does not (exact integer arithmetic).
+__global__ void __launch_bounds__(256)
+oa_colbase(long long D, const unsigned* __restrict__ colmax, unsigned* __restrict__ colbase, OaCursors* cur) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const unsigned m = c < D ? colmax[c] : 0u;
+  unsigned incl = m;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && total) base = atomicAdd(&cur->n_cols, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (c < D) colbase[c] = (unsigned)(base + incl - m);
+}
+
+// pass 3: entry (graph, c, k) -> k entries (graph, colbase[c] + t, 1), t < k; statistics of the new
+// block (graphs per column, self similarity = number of entries of the graph) maintained on the fly.
+__global__ void __launch_bounds__(256)
+oa_expand(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
+          const unsigned* __restrict__ colbase, size_t out_cap, unsigned long long* __restrict__ out_keys,
+          unsigned* __restrict__ out_cnt, OaCursors* cur, unsigned* colcnt, unsigned long long* diag, DevScalars* sc) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  unsigned long long k = EMPTY64;
+  unsigned n = 0;
+  if (i < cap) {
+    k = keys[i];
+    if (k != EMPTY64) n = cnt[i];
+  }
+  unsigned incl = n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;  // warp-uniform
+  unsigned long long pos = 0;
+  if (lane == 31) pos = atomicAdd(&cur->n_entries, (unsigned long long)total);
+  pos = __shfl_sync(0xffffffffu, pos, 31) + incl - n;
+  // self similarity: one atomic per (warp, graph) -- COO entries of a graph are adjacent
+  const unsigned g = n ? (unsigned)(k >> 32) : 0xffffffffu;
+  const unsigned peers = __match_any_sync(0xffffffffu, g);
+  unsigned gsum = 0;
+  for (unsigned m = peers; m; m &= m - 1) gsum += __shfl_sync(peers, n, __ffs(m) - 1);
+  if (n && lane == __ffs(peers) - 1) atomicAdd(&diag[g], (unsigned long long)gsum);
+  if (!n) return;
+  if (pos + n > out_cap) { sc->ft_overflow = 1u; return; }
+  const unsigned b = colbase[(unsigned)k];
+  const unsigned long long hi = k & 0xffffffff00000000ULL;
+  for (unsigned t = 0; t < n; ++t) {
+    out_keys[pos + t] = hi | (unsigned long long)(b + t);
+    out_cnt[pos + t] = 1u;
+    if (__ldcg(&colcnt[b + t]) < COL_CAP) atomicAdd(&colcnt[b + t], 1u);
+  }
+}
+
+// per-CTA partials of the feature kernels, as diag_finish folds them: one "CTA", largest count 1
+__global__ void oa_finish(const OaCursors* cur, unsigned* part_max, unsigned* part_new) {
+  part_max[0] = cur->n_entries ? 1u : 0u;
+  part_new[0] = (unsigned)cur->n_entries;
+}
+
+}  // namespace gk

@@ -6,6 +6,7 @@
     "shortest_path" / "SP"      (+ with_labels, algorithm_type, as_attributes)
     "edge_histogram" / "EH"
     "core_framework" / "CORE"   (framework; base "shortest_path" or "weisfeiler_lehman" ...)
+    "weisfeiler_lehman_optimal_assignment" / "WL-OA"
 
 Any other reference kernel name raises NotImplementedError (not ValueError, which
 the reference reserves for unknown names).  The Nystroem option is host-side
@@ -21,19 +22,20 @@ from sklearn.utils import check_random_state
 from sklearn.utils.validation import check_is_fitted
 
 from .core_framework import CoreFramework
-from .kernels import EdgeHistogram, ShortestPath, ShortestPathAttr, VertexHistogram, WeisfeilerLehman
+from .kernels import (EdgeHistogram, ShortestPath, ShortestPathAttr, VertexHistogram, WeisfeilerLehman,
+                      WeisfeilerLehmanOptimalAssignment)
 
 _VH = ("vertex_histogram", "subtree_wl", "VH", "ST-WL")
 _SP = ("shortest_path", "SP")
 _WL = ("weisfeiler_lehman", "WL")
 _EH = ("edge_histogram", "EH")
 _CORE = ("core_framework", "CORE")
+_WLOA = ("weisfeiler_lehman_optimal_assignment", "WL-OA")
 # names the reference knows but that are outside the hot path (graph_kernels.py:38-64)
 _OTHER = {"random_walk", "RW", "graphlet_sampling", "GR", "subgraph_matching", "SM",
           "multiscale_laplacian", "ML", "lovasz_theta", "LOVT", "svm_theta", "SVMT", "neighborhood_hash", "NH",
           "neighborhood_subgraph_pairwise_distance", "NSPD", "odd_sth", "ODD", "propagation", "PR",
-          "pyramid_match", "PM", "graph_hopper", "GH", "weisfeiler_lehman_optimal_assignment", "WL-OA",
-          "hadamard_code", "HC"}
+          "pyramid_match", "PM", "graph_hopper", "GH", "hadamard_code", "HC"}
 default_n_components = 100
 
 
@@ -131,7 +133,7 @@ class GraphKernel(BaseEstimator, TransformerMixin):
                 warnings.warn("Overriding global kernel attribute " + str(key) + " with " + str(val) +
                               ". Please set this attribute as an argument of GraphKernel.")
             kernel[key] = val
-        if name in _VH or name in _SP or name in _EH:
+        if name in _VH or name in _SP or name in _EH or name in _WLOA:
             if len(kernel_list) != 0:
                 warnings.warn("Kernel List not empty while reaching a base-kernel - the rest kernel names will be "
                               "ignored")
@@ -139,6 +141,8 @@ class GraphKernel(BaseEstimator, TransformerMixin):
                 return VertexHistogram, kernel
             if name in _EH:
                 return EdgeHistogram, kernel
+            if name in _WLOA:  # graph_kernels.py:540-541
+                return WeisfeilerLehmanOptimalAssignment, kernel
             if kernel.pop("as_attributes", False):
                 return ShortestPathAttr, kernel
             return ShortestPath, kernel

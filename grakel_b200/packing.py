@@ -189,6 +189,10 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
     mode = 'sp' : vertex set = range(n) (adjacency) or the sorted symbols that occur
                   in an edge (dictionary input; graph.py:1613-1631), labels indexed in
                   that order (graph.py:390-394).
+    mode = 'wloa': vertex set = the keys of the reference's edge DICTIONARY -- range(n) for
+                  adjacency input, the endpoints of the listed edges otherwise; labelled vertices
+                  without any edge never reach the histogram
+                  (weisfeiler_lehman_optimal_assignment.py:179, 203-209).
     """
     graph_ptr = [0]
     rp_parts, ci_parts, w_parts = [], [], []
@@ -259,7 +263,12 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
                     dst.append(loc[v])  # KeyError like the reference's L[j][n]
                     ww.append(w)
             else:
-                sv = sorted(verts)
+                if mode == "wloa":  # keys of the edge dictionary = endpoints of listed edges (any order)
+                    sv = list(dict.fromkeys(x for e in edges for x in e))
+                    if kind == "dict_dict":  # {u: {}} keeps u as a key (graph.py:1660-1667); {u: []} does not
+                        sv = list(dict.fromkeys(list(g.keys()) + sv))
+                else:
+                    sv = sorted(verts)
                 loc = {k: i for i, k in enumerate(sv)}
                 verts_n = len(sv)
                 if need_labels:

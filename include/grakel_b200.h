@@ -24,6 +24,9 @@
  *                        pair histogram (shortest_path.py:468-490).
  *   gk_wl_sp_features    the WL level loop with ShortestPath as base kernel
  *                        (weisfeiler_lehman.py:260-270, "WL-SP" of doc/benchmarks).
+ *   gk_wl_oa_features    WeisfeilerLehmanOptimalAssignment.parse_input + the O(N^2) Python loop of
+ *                        histogram intersections (weisfeiler_lehman_optimal_assignment.py:78-229,
+ *                        257-266, 433-437).
  *   gk_spattr_features   ShortestPathAttr.parse_input + the bilinear pair kernel
  *                        (shortest_path.py:77-164) as an explicit feature map.
  *   gk_gram              VertexHistogram._calculate_kernel_matrix
@@ -131,6 +134,12 @@ int gk_spattr_features(gk_handle* h, gk_stats* stats);
  * level in one feature block (level-unique label ids => disjoint columns), so that one gk_gram
  * returns the sum of the per-level matrices. */
 int gk_wl_sp_features(gk_handle* h, int32_t n_iter, int32_t flags, gk_stats* stats);
+
+/* WeisfeilerLehmanOptimalAssignment (weisfeiler_lehman_optimal_assignment.py:78-279): the WL feature
+ * block of all levels in unary ("thermometer") form -- column c with count k becomes k columns holding 1
+ * -- so that gk_gram's dot products are the histogram intersections sum_c min(Hs[i,c], Hs[j,c]) of
+ * :257-266 / :433-437, the self similarities the row sums of :459-461, exactly (integers). */
+int gk_wl_oa_features(gk_handle* h, int32_t n_iter, gk_stats* stats);
 
 /* Gram matrix of the current feature block.
  *   n_fit == n_graphs : K is [n_graphs x n_graphs]                      (fit_transform)

@@ -476,6 +476,112 @@ class WLOracle:
         return K
 
 
+# --------------------------------------------------------------------------
+# Weisfeiler-Lehman optimal assignment  (weisfeiler_lehman_optimal_assignment.py:19-481)
+# --------------------------------------------------------------------------
+class WLOAOracle:
+    """WL-OA: the WL label hierarchy + histogram intersection.
+
+    parse_input (:78-229) relabels like WeisfeilerLehman but numbers the labels of ALL levels in one
+    running counter and records each label's parent (the vertex's previous label, :221-229); a graph's
+    vector Hs[j] counts, for every vertex, each label on the path from its last-level label up to the
+    root (:203-209) -- i.e. the number of vertices of j that carry that label at that label's level.
+    K[i, j] = sum_c min(Hs[i, c], Hs[j, c]) (:257-266); transform slices Hs_y[:, :X.shape[1]] (:433) and
+    Y_diag uses every Y column (:459-461)."""
+
+    def __init__(self, n_iter=5, normalize=False):
+        if type(n_iter) is not int or n_iter <= 0:
+            raise TypeError("'n_iter' must be a positive integer")
+        self.h = n_iter
+        self.normalize = normalize
+
+    def _vectors(self, Gs, L, width):
+        """:203-209 / :419-425 -- walk every vertex's label up the hierarchy ('omega' is 1 throughout)."""
+        Hs = np.zeros((len(Gs), width))
+        for j, l in enumerate(L):
+            for lab in l.values():
+                cur = lab
+                while cur is not None:
+                    Hs[j, cur] += 1
+                    cur = self.parent[cur]
+        return Hs
+
+    @staticmethod
+    def _intersect(A, B):
+        K = np.empty((A.shape[0], B.shape[0]))
+        for i in range(A.shape[0]):
+            K[i] = np.minimum(A[i][None, :], B).sum(axis=1)  # :263 / :437
+        return K
+
+    def fit_transform(self, X):
+        Gs = _parse(X)
+        L = [dict(g.labels) for g in Gs]
+        self._fit_graphs = Gs
+        self.parent = {}
+        inv0 = {lab: i for i, lab in enumerate(sorted({v for l in L for v in l.values()}))}  # :157-161
+        for i in inv0.values():
+            self.parent[i] = None  # children of 'root'
+        count = len(inv0)
+        self.inv = {0: inv0}
+        L = [{v: inv0[lab] for v, lab in l.items()} for l in L]
+        for it in range(1, self.h + 1):  # :173-200
+            sigs, fresh = [], set()
+            for g, l in zip(Gs, L):
+                s = {v: WLOracle._signature(l[v], [l[n] for n in nb.keys()]) for v, nb in g.ed.items()}  # keys of the edge dictionary only
+                fresh.update(s.values())
+                sigs.append(s)
+            inv = {}
+            for sig in sorted(fresh):  # :186-190 (sorted by credential; the order does not enter K)
+                inv[sig] = count
+                self.parent[count] = sig[0]
+                count += 1
+            L = [{v: inv[s] for v, s in sg.items()} for sg in sigs]
+            self.inv[it] = inv
+        self.n_fit_labels = count
+        self.X = self._vectors(Gs, L, count + 1)  # + the (always empty) 'root' column, :204
+        K = self._intersect(self.X, self.X)
+        self.xdiag = np.diagonal(K).copy()
+        if self.normalize:  # :268-272
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = np.nan_to_num(K / np.sqrt(np.outer(self.xdiag, self.xdiag)))
+        return K
+
+    def transform(self, Y):
+        Gs = _parse(Y)
+        L = [dict(g.labels) for g in Gs]
+        inv0 = self.inv[0]
+        parent = dict(self.parent)
+        count = self.n_fit_labels  # :355
+        new0 = {}
+        for lab in sorted({v for l in L for v in l.values() if v not in inv0}):  # :356-359
+            new0[lab] = count
+            parent[count] = None
+            count += 1
+        L = [{v: (inv0[lab] if lab in inv0 else new0[lab]) for v, lab in l.items()} for l in L]
+        for it in range(1, self.h + 1):  # :370-400
+            inv = self.inv[it]
+            sigs, unseen = [], set()
+            for g, l in zip(Gs, L):
+                s = {v: WLOracle._signature(l[v], [l[n] for n in nb.keys()]) for v, nb in g.ed.items()}  # keys of the edge dictionary only
+                unseen.update(x for x in s.values() if x not in inv)
+                sigs.append(s)
+            new = {}
+            for sig in sorted(unseen):
+                new[sig] = count
+                parent[count] = sig[0]
+                count += 1
+            L = [{v: (inv[s] if s in inv else new[s]) for v, s in sg.items()} for sg in sigs]
+        keep, self.parent = self.parent, parent
+        Hs = self._vectors(Gs, L, count + 1)
+        self.parent = keep
+        K = self._intersect(Hs[:, : self.X.shape[1]], self.X)  # :433-437
+        self.ydiag = Hs.sum(axis=1)  # :459-461 (min of a row with itself, all columns)
+        if self.normalize:  # :440-444
+            with np.errstate(divide="ignore", invalid="ignore"):
+                K = np.nan_to_num(K / np.sqrt(np.outer(self.ydiag, self.xdiag)))
+        return K
+
+
 def wl_partitions(level_labels):
     """Canonical (first-occurrence) renumbering of each level's labels, vertices
     taken graph by graph in sorted-vertex order.  Two implementations agree on
@@ -683,3 +789,24 @@ def gen_edge_labelled(N, nbar, seed, nl=5, n_el=3):
         L = {i: int(rs.randint(nl)) for i in range(n)}
         out.append([g, L, el])
     return out
+
+
+def oa_sets():
+    """Fit / transform sets of the WL-OA goldens (tests/golden/make_golden_oa.py): seeded sparse graphs
+    (two labels, ~60 % of the ER edges removed: paths, small trees, isolated vertices -- credentials stay
+    shared between graphs at every level), a few one-directional edges, plus level-0 labels the fitted
+    set has never seen."""
+    X = gen(40, 12, 11, nl=2)
+    rs = np.random.RandomState(5)
+    for i, (g, _l) in enumerate(X):
+        for (a, b) in [e for e in sorted(g) if e[0] < e[1]]:
+            r = rs.rand()
+            if r < 0.6:
+                del g[(a, b)], g[(b, a)]
+            elif r < 0.65 and i % 3 == 0:
+                del g[(b, a)]  # directed
+    fit, new = X[:28], X[28:]
+    for _g, l in new[::2]:
+        for v in list(l)[::4]:
+            l[v] = 7 + int(rs.randint(2))  # labels 7, 8 do not occur in `fit`
+    return fit, new

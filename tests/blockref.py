@@ -70,6 +70,27 @@ def wl_gram_block(block, ids, n_iter, n_fit=None, normalize=False, rows=None, n_
     return _finish(Phi, N, n_fit, normalize, True, rows, n_rows)
 
 
+def wl_oa_gram_block(block, ids, n_iter, n_fit=None, normalize=False):
+    """gk_wl_oa_features model: unary expansion of the WL count block -- the k-th vertex of a graph
+    carrying column c lands in column (c, k) -- then the ordinary Gram (dot products of 0/1 rows =
+    histogram intersections)."""
+    N = block.n_graphs
+    n_fit = N if n_fit is None else n_fit
+    vgraph = np.repeat(np.arange(N), np.diff(block.graph_ptr))
+    seen = Counter()
+    enum = {}
+    rows, cols = [], []
+    base = 0
+    for lab in wl_levels(block, ids, n_iter):
+        for g, c in zip(vgraph.tolist(), (lab + base).tolist()):
+            seen[(g, c)] += 1
+            rows.append(g)
+            cols.append(enum.setdefault((c, seen[(g, c)]), len(enum)))
+        base += int(lab.max()) + 1 if len(lab) else 0
+    Phi = _features(N, np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64), max(len(enum), 1))
+    return _finish(Phi, N, n_fit, normalize, True)
+
+
 def apsp_block(block, g):
     v0, v1 = int(block.graph_ptr[g]), int(block.graph_ptr[g + 1])
     n = v1 - v0

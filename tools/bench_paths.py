@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Secondary measurements (not the driver's bench line): BASELINE configs 3 (ShortestPath,
-5 000 graphs, avg 60 nodes) and 5 (ShortestPathAttr, 2 000 graphs, d=16) on one GPU,
+5 000 graphs, avg 60 nodes) and 5 (ShortestPathAttr, 2 000 graphs, d=16), and WL-OA on the graphs of
+config 2, on one GPU,
 CSR resident in HBM -> K resident in HBM, CUDA events on the engine's stream."""
 import json
 import os
@@ -72,6 +73,30 @@ def main():
     out["config5_spattr"] = {"graphs": n, "feature_dim": D, "distance_blocks": int(st.level_dims[0]), "ms_per_step": ms,
                              "pairs_per_s": n * n / (ms * 1e-3), "ms_features": st.ms_features, "ms_gram_fp64": st.ms_gemm,
                              "gram_fp64_tflops": 2.0 * n * n * D / (st.ms_gemm * 1e-3) / 1e12}
+    # ---- WL-OA on the graphs of config 2: unary-expanded WL block, same Gram
+    X = gen(10000, 40, 0)
+    b = pack(X, "wloa", len_ok=lambda k: k >= 2)
+    ids, _ = label_ids(b.labels, None, sort_new=True)
+    eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, ids)
+    n = b.n_graphs
+
+    def step_oa():
+        st = eng.wl_oa_features(5)
+        eng.gram(n, out=False, dtype=np.float32, stats=st, want_diag=False)
+        return st
+
+    ms, st = timed(eng, step_oa)
+    from oracle.gk_oracle import WLOAOracle  # CPU leg of this secondary measurement
+    m = 150
+    t = time.perf_counter()
+    WLOAOracle(n_iter=5).fit_transform(X[:m])
+    t_cpu = time.perf_counter() - t
+    out["config2_wloa"] = {
+        "graphs": n, "vertices": int(b.graph_ptr[-1]), "ms_per_step": ms, "pairs_per_s": n * n / (ms * 1e-3),
+        "ms_features(WL + unary expansion)": st.ms_features, "ms_columns+panel": st.ms_panel, "ms_gemm": st.ms_gemm,
+        "ms_tail": st.ms_tail, "unary_columns": int(st.n_columns), "unary_entries": int(st.n_entries),
+        "head_columns": int(st.n_dense_columns), "threshold_T": int(st.threshold), "tail_updates": int(st.tail_updates),
+        "cpu_port": {"graphs": m, "seconds": t_cpu, "pairs_per_s": m * m / t_cpu, "kind": "port, 1 thread"}}
     print(json.dumps(out))
 
 

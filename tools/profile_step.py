@@ -23,7 +23,7 @@ from grakel_b200 import _lib  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="wl,dense,sp", help="comma list of wl,dense,sp,spattr")
+    ap.add_argument("--what", default="wl,dense,sp", help="comma list of wl,dense,sp,spattr,wloa")
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
     what = set(args.what.split(","))
@@ -62,6 +62,17 @@ def main():
             st = eng.spattr_features()
             eng.gram(b5.n_graphs, out=False, dtype=np.float64, stats=st, want_diag=False)
         jobs.append(spattr)
+    if "wloa" in what:
+        from grakel_b200.packing import label_ids, pack
+        from oracle.gk_oracle import gen  # workload generator only
+        bo = pack(gen(10000, 40, 0), "wloa", len_ok=lambda k: k >= 2)
+        ido, _ = label_ids(bo.labels, None, sort_new=True)
+
+        def wloa():
+            eng.pack(bo.graph_ptr, bo.row_ptr, bo.col_idx, ido)
+            st = eng.wl_oa_features(H)
+            eng.gram(bo.n_graphs, out=False, dtype=np.float32, stats=st, want_diag=False)
+        jobs.append(wloa)
     for j in jobs:
         for _ in range(args.warmup):
             j()
