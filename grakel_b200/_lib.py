@@ -73,6 +73,11 @@ _SYMBOLS = {
     "gk_event_elapsed": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "gk_profiler_range": (C.c_int, [C.c_int32]),
     "gk_selftest_gram": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "gk_tu_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(_P)]),
+    "gk_tu_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "gk_tu_pack": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gk_tu_fill": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gk_tu_close": (C.c_int, [_P]),
 }
 
 _lib = None

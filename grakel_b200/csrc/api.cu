@@ -22,6 +22,7 @@
 #include "wl.cuh"
 #include "wl_fused.cuh"
 #include "wl_oa.cuh"
+#include "tu_reader.h"
 
 namespace gk {
 thread_local std::string g_last_error;
@@ -1657,6 +1658,67 @@ int gk_fetch(gk_handle* h, void* K_out, int32_t out_dtype, int64_t ld) {
   GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * esz, h->K.p, (size_t)h->K_ld * esz, (size_t)h->K_cols * esz,
                             (size_t)h->K_rows, cudaMemcpyDeviceToHost, h->stream));
   GK_CUDA(cudaStreamSynchronize(h->stream));
+  return GK_OK;
+}
+
+// --------------------------------------------------------------------------- TU files -> CSR (host only)
+int gk_tu_open(const char* dir, const char* name, int32_t flags, gk_tu** out) {
+  if (!dir || !name || !out) return fail(GK_ERR_ARG, "gk_tu_open: null argument");
+  std::string err;
+  const int r = gk::tu::open(dir, name, flags, out, &err);
+  return r == GK_OK ? GK_OK : fail(r, "gk_tu_open: " + err);
+}
+
+int gk_tu_info(const gk_tu* t, int64_t* info) {
+  if (!t || !info) return fail(GK_ERR_ARG, "gk_tu_info: null argument");
+  info[0] = t->n_graphs; info[1] = t->n_nodes; info[2] = (int64_t)t->eu.size();
+  info[3] = !t->node_label.empty(); info[4] = !t->el.empty(); info[5] = !t->classes.empty();
+  info[6] = t->attr_dim; info[7] = 0;
+  return GK_OK;
+}
+
+int gk_tu_pack(gk_tu* t, int32_t mode, int64_t* n_vertices, int64_t* n_edges) {
+  if (!t) return fail(GK_ERR_ARG, "gk_tu_pack: null handle");
+  std::string err;
+  const int r = gk::tu::pack(t, mode, &err);
+  if (r != GK_OK) return fail(r, "gk_tu_pack: " + err);
+  if (n_vertices) *n_vertices = (int64_t)t->vnode.size();
+  if (n_edges) *n_edges = (int64_t)t->col_idx.size();
+  return GK_OK;
+}
+
+int gk_tu_fill(const gk_tu* t, int32_t* graph_ptr, int32_t* row_ptr, int32_t* col_idx, int32_t* node_labels,
+               int32_t* edge_labels, double* attrs, int32_t* classes, int32_t* node_of_vertex) {
+  if (!t) return fail(GK_ERR_ARG, "gk_tu_fill: null handle");
+  if (t->mode < 0) return fail(GK_ERR_STATE, "gk_tu_fill: call gk_tu_pack first");
+  const size_t V = t->vnode.size();
+  if (graph_ptr) memcpy(graph_ptr, t->graph_ptr.data(), t->graph_ptr.size() * 4);
+  if (row_ptr) memcpy(row_ptr, t->row_ptr.data(), t->row_ptr.size() * 4);
+  if (col_idx && !t->col_idx.empty()) memcpy(col_idx, t->col_idx.data(), t->col_idx.size() * 4);
+  if (node_labels) {
+    if (t->vlabel.empty() && V) return fail(GK_ERR_STATE, "gk_tu_fill: the dataset has no node labels");
+    if (V) memcpy(node_labels, t->vlabel.data(), V * 4);
+  }
+  if (edge_labels) {
+    if (t->el.empty()) return fail(GK_ERR_STATE, "gk_tu_fill: the dataset has no edge labels");
+    if (!t->elabel.empty()) memcpy(edge_labels, t->elabel.data(), t->elabel.size() * 4);
+  }
+  if (attrs) {
+    if (!t->attr_dim) return fail(GK_ERR_STATE, "gk_tu_fill: node attributes were not loaded (GK_TU_ATTR_NODES)");
+    for (size_t v = 0; v < V; ++v)
+      memcpy(attrs + v * t->attr_dim, t->node_attr.data() + (size_t)t->vnode[v] * t->attr_dim, (size_t)t->attr_dim * 8);
+  }
+  if (classes) {
+    if (t->classes.empty()) return fail(GK_ERR_STATE, "gk_tu_fill: the dataset has no graph classes");
+    memcpy(classes, t->classes.data(), t->classes.size() * 4);
+  }
+  if (node_of_vertex)
+    for (size_t v = 0; v < V; ++v) node_of_vertex[v] = t->vnode[v] + 1;
+  return GK_OK;
+}
+
+int gk_tu_close(gk_tu* t) {
+  delete t;
   return GK_OK;
 }
 

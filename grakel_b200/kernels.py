@@ -172,15 +172,21 @@ class VertexHistogram(Kernel):
             known = None
         else:
             known = self.X.dictionary
-        sizes, labels = [0], []
-        for _, _g, L in iter_elements(X, lambda n: n in (2, 3)):
-            vals = list(L.values())
-            labels.extend(vals)
-            sizes.append(sizes[-1] + len(vals))
-        if len(sizes) == 1:
-            raise ValueError("parsed input is empty")
-        block = Block(np.asarray(sizes), np.zeros(sizes[-1] + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), None,
-                      labels)
+        if isinstance(X, Block):  # packed input (datasets.read_tu): only the label multisets matter
+            X.require("wl")
+            block = Block(X.graph_ptr, np.zeros(X.n_vertices + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), None,
+                          X.labels)
+            labels = X.labels
+        else:
+            sizes, labels = [0], []
+            for _, _g, L in iter_elements(X, lambda n: n in (2, 3)):
+                vals = list(L.values())
+                labels.extend(vals)
+                sizes.append(sizes[-1] + len(vals))
+            if len(sizes) == 1:
+                raise ValueError("parsed input is empty")
+            block = Block(np.asarray(sizes), np.zeros(sizes[-1] + 1, dtype=np.int64), np.zeros(0, dtype=np.int64),
+                          None, labels)
         if known is None:
             ids, new = label_ids(labels, None, sort_new=False)
             dictionary = new
@@ -325,6 +331,10 @@ class WeisfeilerLehman(Kernel):
         the same partition and K = (n_iter + 1) * K_EH, exactly what the reference computes by fitting
         one EdgeHistogram per level on unchanged edge labels (weisfeiler_lehman.py:157-169, 260-270)."""
         base = self._base_graph_kernel
+        if isinstance(X, Block):  # packed input (datasets.read_tu)
+            if base is EdgeHistogram:
+                raise NotImplementedError("packed blocks carry no edge-label entries; pass the list of graphs")
+            return X.require("wl")
         if base is EdgeHistogram:
             if not isinstance(X, Iterable):
                 raise TypeError("input must be an iterable\n")
@@ -347,7 +357,7 @@ class WeisfeilerLehman(Kernel):
         if self._method_calling in (1, 2):
             if hasattr(self, "_X_diag"):
                 delattr(self, "_X_diag")
-            if not isinstance(X, Iterable):
+            if not isinstance(X, (Iterable, Block)):
                 raise TypeError("input must be an iterable\n")
             block = self._pack_for_base(X, lambda n: n >= 2)  # weisfeiler_lehman.py:152
             self._nx = block.n_graphs
@@ -385,7 +395,7 @@ class WeisfeilerLehman(Kernel):
         check_is_fitted(self, ["X", "_nx", "_inv_labels"])
         if X is None:
             raise ValueError("transform input cannot be None")
-        if not isinstance(X, Iterable):
+        if not isinstance(X, (Iterable, Block)):
             raise ValueError("input must be an iterable\n")
         Y = self.parse_input(X)
         K, xdiag, ydiag = self._run(Block.concat(self.X.block, Y.block), np.concatenate([self.X.ids, Y.ids]),
@@ -436,9 +446,12 @@ class WeisfeilerLehmanOptimalAssignment(Kernel):
         if self._method_calling in (1, 2):
             if hasattr(self, "_X_diag"):
                 delattr(self, "_X_diag")
-            if not isinstance(X, Iterable):
+            if isinstance(X, Block):  # packed input (datasets.read_tu)
+                block = X.require("sp", "wloa")
+            elif not isinstance(X, Iterable):
                 raise TypeError("input must be an iterable\n")
-            block = pack(X, "wloa", len_ok=lambda n: n >= 2, type_error_msg=msg)  # :113
+            else:
+                block = pack(X, "wloa", len_ok=lambda n: n >= 2, type_error_msg=msg)  # :113
             self._nx = block.n_graphs
             ids, dictionary = label_ids(block.labels, None, sort_new=True)  # :157-161
             self._inv_labels = {0: dictionary}
@@ -446,10 +459,13 @@ class WeisfeilerLehmanOptimalAssignment(Kernel):
             return Fitted(block, ids, dictionary)
         if self._method_calling != 3:
             raise ValueError("method call must be called either from fit or fit-transform")
-        try:
-            block = pack(X, "wloa", len_ok=lambda n: n in (2, 3), type_error_msg=msg)  # :323
-        except TypeError as e:  # transform raises ValueError for malformed elements (:344-346)
-            raise ValueError("each element of X must have at least one and at most 3 elements\n") from e
+        if isinstance(X, Block):
+            block = X.require("sp", "wloa")
+        else:
+            try:
+                block = pack(X, "wloa", len_ok=lambda n: n in (2, 3), type_error_msg=msg)  # :323
+            except TypeError as e:  # transform raises ValueError for malformed elements (:344-346)
+                raise ValueError("each element of X must have at least one and at most 3 elements\n") from e
         ids, _ = label_ids(block.labels, self._inv_labels[0], sort_new=True)  # :356-359
         return Fitted(block, ids, self._inv_labels[0])
 
@@ -469,7 +485,7 @@ class WeisfeilerLehmanOptimalAssignment(Kernel):
         check_is_fitted(self, ["X", "_nx", "_hierarchy", "_inv_labels"])
         if X is None:
             raise ValueError("transform input cannot be None")
-        if not isinstance(X, Iterable):
+        if not isinstance(X, (Iterable, Block)):
             raise ValueError("input must be an iterable\n")
         Y = self.parse_input(X)
         K, xdiag, ydiag = self._run(Block.concat(self.X.block, Y.block), np.concatenate([self.X.ids, Y.ids]),
@@ -516,9 +532,12 @@ class ShortestPath(Kernel):
         # Floyd-Warshall treats a 0 entry as "no edge" (graph.py:1786); Dijkstra walks every
         # listed edge.  "auto" picks FW for adjacency input and Dijkstra for dictionaries, so
         # zero-weight dictionary edges only disappear when FW is forced.
-        block = pack(X, "sp", need_labels=wl, len_ok=lambda n: n in (2, 3) or (n == 1 and not wl),
-                     want_weights=True, fw_zero_is_absent=self.algorithm_type == "floyd_warshall",
-                     type_error_msg="each element of X must have at least one and at most 3 elements\n")
+        if isinstance(X, Block):  # packed input (datasets.read_tu): unit weights, dictionary semantics
+            block = X.require("sp", labels=wl)
+        else:
+            block = pack(X, "sp", need_labels=wl, len_ok=lambda n: n in (2, 3) or (n == 1 and not wl),
+                         want_weights=True, fw_zero_is_absent=self.algorithm_type == "floyd_warshall",
+                         type_error_msg="each element of X must have at least one and at most 3 elements\n")
         if block.weights is not None and np.any(block.weights != np.rint(block.weights)):
             # Feature keys compare path lengths by exact float equality (shortest_path.py:472, 511), and the
             # reference's own Dijkstra and Floyd-Warshall disagree in the last bit on real weights.  The device
@@ -596,6 +615,10 @@ class ShortestPathAttr(Kernel):
         if self.metric is not np.dot:
             raise NotImplementedError("grakel_b200 evaluates ShortestPathAttr through its bilinear feature map, which "
                                       "is only valid for the default metric=np.dot")
+        if isinstance(X, Block):  # packed input (datasets.read_tu(prefer_attr_nodes=True))
+            if X.require("sp", labels=False).attrs is None:
+                raise ValueError("Graph does not have any labels for vertices.")
+            return Fitted(X, None, {})
         block = pack(X, "sp", need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=True,
                      fw_zero_is_absent=self.algorithm_type == "floyd_warshall", attributes=True,
                      type_error_msg="each element of X must be either a graph or an iterable with at least 2 and at "

@@ -126,6 +126,7 @@ class Block:
         self.attrs = attrs
         self.all_adjacency = all_adjacency  # every graph came as an adjacency matrix ("auto" -> Floyd-Warshall)
         self.n_graphs = len(self.graph_ptr) - 1
+        self.mode = None  # vertex-set rule the block was packed with: 'wl' | 'sp' | 'wloa' (pack / datasets.read_tu)
 
     @property
     def n_vertices(self):
@@ -143,9 +144,27 @@ class Block:
             wa = a.weights if a.weights is not None else np.ones(ea)
             wb = b.weights if b.weights is not None else np.ones(len(b.col_idx))
             w = np.concatenate([wa, wb])
-        lab = None if a.labels is None or b.labels is None else list(a.labels) + list(b.labels)
+        if a.labels is None or b.labels is None:
+            lab = None
+        elif isinstance(a.labels, np.ndarray) and isinstance(b.labels, np.ndarray):
+            lab = np.concatenate([a.labels, b.labels])
+        else:
+            lab = list(a.labels) + list(b.labels)
         at = None if a.attrs is None or b.attrs is None else np.concatenate([a.attrs, b.attrs])
-        return Block(gp, rp, ci, w, lab, at, a.all_adjacency and b.all_adjacency)
+        out = Block(gp, rp, ci, w, lab, at, a.all_adjacency and b.all_adjacency)
+        out.mode = a.mode if a.mode == b.mode else None
+        return out
+
+    def require(self, *modes, labels=True):
+        """Packed-input fast path of the estimators: the block must carry the vertex set the kernel walks."""
+        if self.mode not in modes:
+            raise ValueError("this block was packed for another kernel (vertex set %r, needed %s): see "
+                             "grakel_b200.datasets.read_tu(kernel=...)" % (self.mode, " or ".join(map(repr, modes))))
+        if labels and self.labels is None:
+            raise ValueError("Graph does not have any labels for vertices.")
+        if self.n_graphs == 0:
+            raise ValueError("parsed input is empty")
+        return self
 
 
 def iter_elements(X, len_ok, type_error_msg=None):
@@ -312,7 +331,9 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
             raise ValueError("node attributes must all have the same length")
     if graph_ptr[-1] >= 2 ** 31 or len(col_idx) >= 2 ** 31:
         raise ValueError("graph block exceeds int32 indexing")
-    return Block(np.asarray(graph_ptr), row_ptr, col_idx, weights, labels, attrs, all_adjacency)
+    out = Block(np.asarray(graph_ptr), row_ptr, col_idx, weights, labels, attrs, all_adjacency)
+    out.mode = mode
+    return out
 
 
 def label_ids(labels, known=None, sort_new=True):
@@ -325,6 +346,17 @@ def label_ids(labels, known=None, sort_new=True):
     order when `sort_new` is False (ShortestPath only uses labels as dict keys).
     Returns (int32 ids, dictionary of the labels that were new)."""
     known = {} if known is None else known
+    if isinstance(labels, np.ndarray) and labels.dtype.kind in "iu":  # packed blocks (datasets.read_tu): vectorised
+        uniq, first, inv = np.unique(labels, return_index=True, return_inverse=True)
+        order = np.arange(len(uniq)) if sort_new else np.argsort(first, kind="stable")
+        fresh, ids_of = {}, np.empty(len(uniq), dtype=np.int32)
+        for j in order.tolist():
+            l = int(uniq[j])
+            if l in known:
+                ids_of[j] = known[l]
+            else:
+                ids_of[j] = fresh[l] = len(known) + len(fresh)
+        return ids_of[inv].astype(np.int32, copy=False), fresh
     fresh = {}
     seen = set()
     for l in labels:

@@ -180,6 +180,31 @@ int gk_sp_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr
                         const double* weights, int32_t sp_flags, int32_t flags, void* K_out,
                         int32_t out_dtype, int64_t ld, double* diag, gk_stats* stats);
 
+/* ---- TU-format dataset files -> packed CSR block (host side; no device work).
+ * Replaces grakel/datasets/base.py:135-290 (read_data: <name>_graph_indicator.txt, _A.txt, _node_labels.txt,
+ * _node_attributes.txt, _edge_labels.txt, _graph_labels.txt parsed into per-graph Python sets and dicts) and
+ * the per-graph Graph parsing that follows it (graph.py:147-230, 982-1053): the arrays gk_tu_fill writes are
+ * exactly what gk_pack_csr takes.  Edge semantics as in read_data: an edge line belongs to the graph of its
+ * source, GK_TU_SYMMETRIC adds the reverse edge (base.py:216-218), duplicates collapse, the last edge-label
+ * line of a pair wins (:262-266). */
+typedef struct gk_tu gk_tu;
+#define GK_TU_SYMMETRIC 1      /* read_data(is_symmetric=True) */
+#define GK_TU_ATTR_NODES 2     /* read_data(prefer_attr_nodes=True): node attributes instead of node labels */
+#define GK_TU_DEGREE_LABELS 4  /* read_data(produce_labels_nodes=True) when there is no node-label file */
+/* vertex set of the packed block */
+#define GK_TU_LABELLED_NODES 0 /* every labelled node: what WeisfeilerLehman / VertexHistogram walk */
+#define GK_TU_EDGE_NODES 1     /* nodes that occur in an edge: ShortestPath(+Attr) and WL-OA (edge-dictionary keys) */
+int gk_tu_open(const char* dir, const char* name, int32_t flags, gk_tu** out);
+/* info[0..7] = graphs, nodes, edge lines, has node labels, has edge labels, has classes, attribute dim, 0 */
+int gk_tu_info(const gk_tu* t, int64_t* info);
+/* choose the vertex set, build the CSR; returns the sizes of the arrays gk_tu_fill writes */
+int gk_tu_pack(gk_tu* t, int32_t mode, int64_t* n_vertices, int64_t* n_edges);
+/* graph_ptr[graphs+1], row_ptr[V+1], col_idx[E] (GLOBAL vertex ids, rows sorted), node_labels[V] (raw integer
+ * labels), edge_labels[E], attrs[V*dim], classes[graphs], node_of_vertex[V] (1-based file node id); any may be NULL */
+int gk_tu_fill(const gk_tu* t, int32_t* graph_ptr, int32_t* row_ptr, int32_t* col_idx, int32_t* node_labels,
+               int32_t* edge_labels, double* attrs, int32_t* classes, int32_t* node_of_vertex);
+int gk_tu_close(gk_tu* t);
+
 /* CUDA-event timing on the handle's stream (bench.py). */
 int gk_event_record(gk_handle* h, int32_t slot);            /* slot in [0,16) */
 int gk_event_elapsed(gk_handle* h, int32_t a, int32_t b, float* ms);

@@ -810,3 +810,70 @@ def oa_sets():
         for v in list(l)[::4]:
             l[v] = 7 + int(rs.randint(2))  # labels 7, 8 do not occur in `fit`
     return fit, new
+
+
+# --------------------------------------------------------------------------
+# TU-format dataset files  (datasets/base.py:135-290)
+# --------------------------------------------------------------------------
+def read_data_oracle(path, name, is_symmetric=False, prefer_attr_nodes=False, produce_labels_nodes=False):
+    """Restatement of `read_data`: -> ([[set of (u, v), {node: label}, {(u, v): edge label}], ...], classes or
+    None).  Graph ids and node ids are the 1-based ids of the files; an edge line belongs to the graph of its
+    source (:213-215), `is_symmetric` adds the reverse to the graph of the target (:216-218)."""
+    import os as _os
+    if _os.path.isdir(_os.path.join(path, name)):  # ./<name>/<name>_A.txt (:181-191)
+        path = _os.path.join(path, name)
+    base = _os.path.join(path, name + "_")
+
+    def lines(suffix):
+        fn = base + suffix
+        if not _os.path.exists(fn):
+            return None
+        with open(fn) as f:
+            return [ln[:-1] if ln.endswith("\n") else ln for ln in f]
+
+    ngc, graphs, nlab, elab = {}, {}, {}, {}
+    for i, ln in enumerate(lines("graph_indicator.txt"), 1):  # :203-211
+        g = int(ln)
+        ngc[i] = g
+        graphs.setdefault(g, set()); nlab.setdefault(g, {}); elab.setdefault(g, {})
+    elc = {}
+    for i, ln in enumerate(lines("A.txt"), 1):  # :214-220
+        a, b = (int(x) for x in ln.replace(" ", "").split(","))
+        elc[i] = (a, b)
+        graphs[ngc[a]].add((a, b))
+        if is_symmetric:
+            graphs[ngc[b]].add((b, a))
+    attr, nl = lines("node_attributes.txt"), lines("node_labels.txt")
+    if prefer_attr_nodes and attr is not None:  # :223-232
+        for i, ln in enumerate(attr, 1):
+            nlab[ngc[i]][i] = [float(x) for x in ln.replace(" ", "").split(",")]
+    elif nl is not None:  # :234-240
+        for i, ln in enumerate(nl, 1):
+            nlab[ngc[i]][i] = int(ln)
+    elif produce_labels_nodes:  # :241-243
+        for g in graphs:
+            nlab[g] = dict(Counter(s for (s, d) in graphs[g] if s != d))
+    el = lines("edge_labels.txt")
+    if el is not None:  # :259-267
+        for i, ln in enumerate(el, 1):
+            a, b = elc[i]
+            elab[ngc[a]][(a, b)] = int(ln)
+            if is_symmetric:
+                elab[ngc[b]][(b, a)] = int(ln)
+    data = [[graphs[g], nlab[g], elab[g]] for g in range(1, len(graphs) + 1)]  # :274-276
+    cl = lines("graph_labels.txt")
+    return data, (None if cl is None else np.array([int(x) for x in cl], dtype=int))
+
+
+def tu_digest(elements, mode):
+    """Canonical digest of what a kernel sees in read_data's elements: per graph the sorted (node, label) pairs of
+    its vertex set and its sorted edge list.  mode 'wl': vertices = label keys; 'sp': vertices = edge endpoints."""
+    import hashlib
+    h = hashlib.sha1()
+    for g, l, _e in elements:
+        verts = sorted(l) if mode == "wl" else sorted({x for e in g for x in e})
+        edges = sorted((a, b) for (a, b) in g if mode != "wl" or a in l)
+        lab = [l[v] for v in verts]
+        lab = [int(x) if not isinstance(x, list) else tuple(float(y) for y in x) for x in lab]
+        h.update(repr((verts, lab, edges)).encode())
+    return h.hexdigest()
