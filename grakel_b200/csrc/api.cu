@@ -1524,6 +1524,10 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
           !getenv("GRAKEL_B200_NO_TMA_STORE")) {
         GK_TRY(make_out_map(&tmC, d_out, k_cols, k_rows, d_ld));
         p.tma_store = 1;
+        if (p.mirror) {  // full square: the mirrored half goes through the same tensor map
+          const char* e = getenv("GRAKEL_B200_MIRROR_TMA");
+          if (!e || atoi(e) != 0) p.mirror = 2;
+        }
       }
       p.tiles = h->tiles.as<int2>();
       p.n_tiles = (int)n_tiles;

@@ -41,7 +41,7 @@ struct GramParams {
   int c_row0, c_col0;  // K[row - c_row0][col - c_col0]
   void* out;
   long long ld;
-  int mirror;          // also store the transposed element (symmetric case)
+  int mirror;          // also store the transposed element (symmetric case): 1 = row stores, 2 = TMA store of a transposed tile
   int fix_diag;        // K[g][g] = diag[g] (self similarity over ALL columns)
   int nan_to_num;
   int vec_ok;          // 32-byte aligned rows: 256-bit vector stores allowed
@@ -290,7 +290,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j)
               if (arow == bcol0 + j) v[j] = __float_as_uint(dself);
           }
-          const uint32_t buf = my_buf + (uint32_t)((c0 >> 5) & 1) * EPI_BUF_BYTES;
+          // buffers: without the TMA mirror the two staging tiles alternate between column blocks; with it
+          // tile 0 stages the direct block and tile 1 the transposed one.  Either way the bulk group that
+          // last read the tile about to be overwritten is the second newest, hence wait_group.read 1.
+          const uint32_t buf = p.mirror == 2 ? my_buf : my_buf + (uint32_t)((c0 >> 5) & 1) * EPI_BUF_BYTES;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's previous store
           __syncwarp();
           const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
@@ -307,7 +310,27 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_2d(&tmC, buf, bcol0 - p.c_col0, arow0 - p.c_row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (p.mirror && row_ok) {
+          if (p.mirror == 2) {
+            // Mirrored block K[bcol0 + r][arow0 + c] = v_c[r]: transposed into the second staging tile (lane c
+            // writes column c; with the 128-byte swizzle the 32 lanes of one st.shared hit 32 distinct banks)
+            // and stored by ONE bulk request instead of 32 row stores of 128 bytes.  TMA clips at the edges.
+            const uint32_t mbuf = my_buf + EPI_BUF_BYTES;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            const uint32_t cbase = mbuf + (uint32_t)((lane & 3) << 2);
+            const uint32_t cq = (uint32_t)(lane >> 2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t a = cbase + (uint32_t)j * 128u + ((cq ^ (uint32_t)(j & 7)) << 4);
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v[j]) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, mbuf, arow0 - p.c_col0, bcol0 - p.c_row0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else if (p.mirror && row_ok) {
             if (bcol0 + 32 <= p.b_row_end) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) { *reinterpret_cast<uint32_t*>(mptr) = v[j]; mptr += ld; }
