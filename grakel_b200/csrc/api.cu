@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "features.cuh"
 #include "gram_tc.cuh"
+#include "gram_tc2.cuh"
 #include "sp.cuh"
 #include "spattr.cuh"
 #include "wl.cuh"
@@ -158,6 +159,7 @@ int gk_create(int device_ordinal, gk_handle** out) {
   GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
   *out = h;
   return GK_OK;
 }
@@ -1292,14 +1294,14 @@ static void launch_empty(gk_handle* h, int a0, int a1, int b0, int b1, const Gra
 
 // Build the tile list: bands of 12 row tiles, column-major inside a band, so that the
 // ~148 tiles in flight cover a compact block of the output and share panel rows in L2.
-static void build_tiles(std::vector<int2>& tiles, int a0, int a1, int b0, int b1, bool upper_only) {
-  const int n_m = cdiv(a1 - a0, BM), n_n = cdiv(b1 - b0, BN);
-  const int BAND = 12;
+static void build_tiles(std::vector<int2>& tiles, int a0, int a1, int b0, int b1, bool upper_only, int bm = BM) {
+  const int n_m = cdiv(a1 - a0, bm), n_n = cdiv(b1 - b0, BN);
+  const int BAND = 12 * BM / bm;
   for (int m0 = 0; m0 < n_m; m0 += BAND) {
     const int m1 = std::min(n_m, m0 + BAND);
     for (int j = 0; j < n_n; ++j) {
       for (int i = m0; i < m1; ++i) {
-        const int ar = a0 + i * BM, br = b0 + j * BN;
+        const int ar = a0 + i * bm, br = b0 + j * BN;
         if (upper_only && br + BN - 1 < ar) continue;  // tile entirely below the diagonal
         tiles.push_back(make_int2(ar, br));
       }
@@ -1508,8 +1510,14 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       }
     }
     if (path == 1) {
+      // CTA-pair kernel (gram_tc2.cuh: cta_group::2, 256 x 256 tiles) for fp32 un-normalised output through
+      // TMA stores: 1 831 vs 1 515 TFLOP/s in dense mode, 0.201 vs 0.228 ms in head mode on the same box
+      // (profiles/r01g_bench_cta{2,1}.json).  GRAKEL_B200_CTA2=0 selects the one-CTA kernel.
+      const char* e_cta2 = getenv("GRAKEL_B200_CTA2");
+      const bool cta2 = !(e_cta2 && atoi(e_cta2) == 0) && dev_dtype == GK_F32 && !norm_in_epilogue &&
+                        ((uintptr_t)d_out) % 16 == 0 && (d_ld * 4) % 16 == 0 && !getenv("GRAKEL_B200_NO_TMA_STORE");
       std::vector<int2> tiles;
-      build_tiles(tiles, a0, a1, b0, b1, mirror);
+      build_tiles(tiles, a0, a1, b0, b1, mirror, cta2 ? BM2 : BM);
       n_tiles = (int64_t)tiles.size();
       GK_TRY(h->h_tiles.ensure(tiles.size() * sizeof(int2)));
       memcpy(h->h_tiles.p, tiles.data(), tiles.size() * sizeof(int2));
@@ -1532,15 +1540,16 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       p.tiles = h->tiles.as<int2>();
       p.n_tiles = (int)n_tiles;
       p.num_k_blocks = (int)(h->Dc_pad / BK);
-      const int grid = (int)std::min<int64_t>(n_tiles, h->sm_count);
-      const bool prof = getenv("GRAKEL_B200_PROF") != nullptr;
+      const int grid = cta2 ? 2 * (int)std::min<int64_t>(n_tiles, h->sm_count / 2) : (int)std::min<int64_t>(n_tiles, h->sm_count);
+      const bool prof = !cta2 && getenv("GRAKEL_B200_PROF") != nullptr;
       if (prof) {
         GK_TRY(h->K_stage.ensure((size_t)grid * 64));
         GK_CUDA(cudaMemsetAsync(h->K_stage.p, 0, (size_t)grid * 64, h->stream));
         p.prof = h->K_stage.as<long long>();
       }
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
-      if (dev_dtype == GK_F64) { if (norm_in_epilogue) launch_tc<double, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<double, false>(h, tmA, tmB, tmC, p, grid); }
+      if (cta2) gram_tc2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM, h->stream>>>(tmA, tmC, p);
+      else if (dev_dtype == GK_F64) { if (norm_in_epilogue) launch_tc<double, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<double, false>(h, tmA, tmB, tmC, p, grid); }
       else { if (norm_in_epilogue) launch_tc<float, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<float, false>(h, tmA, tmB, tmC, p, grid); }
       LAUNCH_CHECK(h);
       if (prof) {

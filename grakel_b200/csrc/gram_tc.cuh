@@ -148,6 +148,98 @@ __device__ __forceinline__ OutT epilogue_value(float acc, int arow, int bcol, do
   }
 }
 
+// Epilogue of one 128 x 256 accumulator for fp32, un-normalised output through TMA stores (shared by the
+// one-CTA and the CTA-pair kernel).  `tile` = {first A row of THIS CTA's 128 rows, first B row}; `acc` = TMEM
+// address of the accumulator's first column in this warp's lane quarter; `my_buf` = the warp's two staging tiles.
+__device__ __forceinline__ void epi_tma_store_tile(const GramParams& p, const CUtensorMap* tmC_ptr, int2 tile,
+                                                   uint32_t acc, int ew, int lane, uint32_t my_buf) {
+  using OutT = float;
+  const CUtensorMap& tmC = *tmC_ptr;
+  OutT* __restrict__ out = reinterpret_cast<OutT*>(p.out);
+  const int row = ew * 32 + lane;
+  const int arow = tile.x + row;
+  const bool row_ok = arow < p.a_row_end;
+  const bool diag_tile = p.fix_diag && (tile.x < tile.y + BN) && (tile.y < tile.x + BM);
+  // Direct block: registers -> 128B-swizzled smem tile -> ONE TMA store per 32x32 block (the
+  // SM->L2 path is bound by write requests: 1 bulk request instead of 128).  TMA clips at the
+  // matrix edge, so partial tiles need no predicates.  Mirrored block: coalesced 128-byte
+  // stores straight from registers (lanes = consecutive rows of the tile).
+  const int arow0 = tile.x + ew * 32;
+  float dself = 0.f;
+  if (diag_tile && row_ok) dself = (float)p.diag[arow];
+  OutT* mptr = out + (long long)tile.y * p.ld + arow;
+  const long long ld = p.ld;
+  const bool rows_in = arow0 < p.a_row_end;  // warp-uniform: any row of this warp's block inside
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t v[32];
+    tc_ld32(acc + (uint32_t)c0, v);
+    const int bcol0 = tile.y + c0;
+    if (bcol0 >= p.b_row_end || !rows_in) { mptr += 32 * ld; continue; }  // warp-uniform
+    if (diag_tile) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (arow == bcol0 + j) v[j] = __float_as_uint(dself);
+    }
+    // buffers: without the TMA mirror the two staging tiles alternate between column blocks; with it
+    // tile 0 stages the direct block and tile 1 the transposed one.  Either way the bulk group that
+    // last read the tile about to be overwritten is the second newest, hence wait_group.read 1.
+    const uint32_t buf = p.mirror == 2 ? my_buf : my_buf + (uint32_t)((c0 >> 5) & 1) * EPI_BUF_BYTES;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's previous store
+    __syncwarp();
+    const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t a = rowaddr + (uint32_t)((q ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * q]), "r"(v[4 * q + 1]),
+                   "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                   : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&tmC, buf, bcol0 - p.c_col0, arow0 - p.c_row0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (p.mirror == 2) {
+      // Mirrored block K[bcol0 + r][arow0 + c] = v_c[r]: transposed into the second staging tile (lane c
+      // writes column c; with the 128-byte swizzle the 32 lanes of one st.shared hit 32 distinct banks)
+      // and stored by ONE bulk request instead of 32 row stores of 128 bytes.  TMA clips at the edges.
+      const uint32_t mbuf = my_buf + EPI_BUF_BYTES;
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      const uint32_t cbase = mbuf + (uint32_t)((lane & 3) << 2);
+      const uint32_t cq = (uint32_t)(lane >> 2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t a = cbase + (uint32_t)j * 128u + ((cq ^ (uint32_t)(j & 7)) << 4);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v[j]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmC, mbuf, arow0 - p.c_col0, bcol0 - p.c_row0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else if (p.mirror && row_ok) {
+      if (bcol0 + 32 <= p.b_row_end) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { *reinterpret_cast<uint32_t*>(mptr) = v[j]; mptr += ld; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (bcol0 + j < p.b_row_end) *reinterpret_cast<uint32_t*>(mptr) = v[j];
+          mptr += ld;
+        }
+      }
+    } else {
+      mptr += 32 * ld;
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem reusable by the next tile
+  __syncwarp();
+}
+
 template <typename OutT, bool NORMALIZE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -268,85 +360,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool interior = (tile.x + BM <= p.a_row_end) && (tile.y + BN <= p.b_row_end);
       const bool diag_tile = p.fix_diag && (tile.x < tile.y + BN) && (tile.y < tile.x + BM);
       if (sizeof(OutT) == 4 && !NORMALIZE && p.tma_store) {
-        // Direct block: registers -> 128B-swizzled smem tile -> ONE TMA store per 32x32 block (the
-        // SM->L2 path is bound by write requests: 1 bulk request instead of 128).  TMA clips at the
-        // matrix edge, so partial tiles need no predicates.  Mirrored block: coalesced 128-byte
-        // stores straight from registers (lanes = consecutive rows of the tile).
-        const uint32_t my_buf = epi_base + (uint32_t)ew * (2u * EPI_BUF_BYTES);
-        const int arow0 = tile.x + ew * 32;
-        float dself = 0.f;
-        if (diag_tile && row_ok) dself = (float)p.diag[arow];
-        OutT* mptr = out + (long long)tile.y * p.ld + arow;
-        const long long ld = p.ld;
-        const bool rows_in = arow0 < p.a_row_end;  // warp-uniform: any row of this warp's block inside
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c0), v);
-          const int bcol0 = tile.y + c0;
-          if (bcol0 >= p.b_row_end || !rows_in) { mptr += 32 * ld; continue; }  // warp-uniform
-          if (diag_tile) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (arow == bcol0 + j) v[j] = __float_as_uint(dself);
-          }
-          // buffers: without the TMA mirror the two staging tiles alternate between column blocks; with it
-          // tile 0 stages the direct block and tile 1 the transposed one.  Either way the bulk group that
-          // last read the tile about to be overwritten is the second newest, hence wait_group.read 1.
-          const uint32_t buf = p.mirror == 2 ? my_buf : my_buf + (uint32_t)((c0 >> 5) & 1) * EPI_BUF_BYTES;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's previous store
-          __syncwarp();
-          const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t a = rowaddr + (uint32_t)((q ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * q]), "r"(v[4 * q + 1]),
-                         "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
-                         : "memory");
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, buf, bcol0 - p.c_col0, arow0 - p.c_row0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          if (p.mirror == 2) {
-            // Mirrored block K[bcol0 + r][arow0 + c] = v_c[r]: transposed into the second staging tile (lane c
-            // writes column c; with the 128-byte swizzle the 32 lanes of one st.shared hit 32 distinct banks)
-            // and stored by ONE bulk request instead of 32 row stores of 128 bytes.  TMA clips at the edges.
-            const uint32_t mbuf = my_buf + EPI_BUF_BYTES;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-            const uint32_t cbase = mbuf + (uint32_t)((lane & 3) << 2);
-            const uint32_t cq = (uint32_t)(lane >> 2);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const uint32_t a = cbase + (uint32_t)j * 128u + ((cq ^ (uint32_t)(j & 7)) << 4);
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v[j]) : "memory");
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmC, mbuf, arow0 - p.c_col0, bcol0 - p.c_row0);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          } else if (p.mirror && row_ok) {
-            if (bcol0 + 32 <= p.b_row_end) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { *reinterpret_cast<uint32_t*>(mptr) = v[j]; mptr += ld; }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (bcol0 + j < p.b_row_end) *reinterpret_cast<uint32_t*>(mptr) = v[j];
-                mptr += ld;
-              }
-            }
-          } else {
-            mptr += 32 * ld;
-          }
-        }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem reusable by the next tile
-        __syncwarp();
+        epi_tma_store_tile(p, &tmC, tile, tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN), ew, lane,
+                           epi_base + (uint32_t)ew * (2u * EPI_BUF_BYTES));
       } else if (!NORMALIZE && interior && !diag_tile && p.vec_ok) {
         OutT* drow_ptr = out + (long long)(arow - p.c_row0) * p.ld + (tile.y - p.c_col0);
         OutT* mptr = out + (long long)tile.y * p.ld + arow;  // mirror: K[col][row], one row of K per tile column

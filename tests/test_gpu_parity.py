@@ -195,6 +195,34 @@ def test_fp32_output_paths_equal_fp64(eng, n):
     assert np.array_equal(yd, d64[nf:])
 
 
+@pytest.mark.parametrize("n", [1000, 260, 3000])
+def test_cta_pair_gemm_equals_one_cta_gemm(eng, n, monkeypatch):
+    """gram_tc2_kernel (tcgen05 cta_group::2, 256 x 256 tiles per two-CTA cluster; GRAKEL_B200_CTA2=0 turns it off) must
+    write the same fp32 integers as the one-CTA kernel and as the fp64 matrix: square (mirrored SYRK tiles),
+    every column dense, full tiles, a row block, and the rectangular transform shape."""
+    from grakel_b200.packing import pack, label_ids
+    X = gen(n, 14, 17)
+    b = pack(X, "wl", len_ok=lambda m: m >= 2)
+    ids, _ = label_ids(b.labels, None)
+    eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, ids)
+    eng.wl_features(3)
+    K64, _, _ = eng.gram(n)
+    nf = n - 136
+    Kt64, _, _ = eng.gram(n, n_fit=nf)
+    rb, re_ = n // 3, n // 3 + (700 if n > 2000 else 100)
+    st = _k()._lib.GkStats()
+    for cta2 in ("1", "0"):  # the default (CTA pairs) and the one-CTA kernel
+        monkeypatch.setenv("GRAKEL_B200_CTA2", cta2)
+        for kw in ({}, {"dense_all": True}, {"full_tiles": True}):
+            K32, _, _ = eng.gram(n, dtype=np.float32, stats=st, **kw)
+            assert np.array_equal(K32.astype(np.float64), K64), (cta2, kw)
+        assert int(st.gram_path) == 1
+        Kr, _, _ = eng.gram(n, dtype=np.float32, row_range=(rb, re_))
+        assert np.array_equal(Kr.astype(np.float64), K64[rb:re_])
+        Kt32, _, _ = eng.gram(n, n_fit=nf, dtype=np.float32)
+        assert np.array_equal(Kt32.astype(np.float64), Kt64)
+
+
 def test_wide_counts_take_the_exact_integer_path():
     """A feature count above 256 is not exact in bf16: the engine must switch to the exact
     u64 CUDA-core Gram on its own (gram_path 2) and still match the oracle bit for bit."""
