@@ -11,7 +11,7 @@ exact sparse tail, diagonal / output.
              (CUDA events on the engine's stream, max over ranks)
   e2e        pairs/s through the C-ABI one-call entry point gk_wl_fit_transform with
              PINNED HOST buffers: CSR H2D and the fp64 K D2H inside the timed region
-  roofline   the tcgen05 Gram GEMM: algorithmic flops N(N+1)*D_c (upper-triangular
+  roofline   the tcgen05 Gram GEMM (CTA-pair kernel): algorithmic flops N(N+1)*D_c (upper-triangular
              tiles) / CUDA-event duration vs the measured bf16 peak
   cpu_baseline / --impl reference
              the CPU oracle port (oracle/gk_oracle.py, pinned to the real reference's
@@ -38,6 +38,12 @@ sys.path.insert(0, ROOT)
 N_GRAPHS, NBAR, H, SEED = 10000, 40, 5, 0
 CPU_SAMPLE = 6000  # graphs in the bounded CPU sample (~10 s of CPU work per step on the box's host)
 CPU_THREADS = H + 1  # the reference parallelises over WL levels (joblib threading, weisfeiler_lehman.py:279-285)
+
+
+# the Gram GEMM gk_gram launches for fp32 output (grakel_b200/csrc/api.cu): CTA pairs unless switched off
+GEMM_KERNEL = ("gram_tc_kernel<float,false> (tcgen05 cta_group::1 bf16 SYRK, 128x256 tiles)"
+               if os.environ.get("GRAKEL_B200_CTA2", "1") == "0" else
+               "gram_tc2_kernel (tcgen05 cta_group::2 bf16 SYRK, 256x256 tile per two-CTA cluster)")
 
 
 def pack_workload(n_graphs):
@@ -334,7 +340,7 @@ def main():
         "clocks": clk.summary(),
         "e2e": e2e,
         "gpu_launches": launches,
-        "roofline": {"kernel": "gram_tc_kernel<float,false> (tcgen05 bf16 SYRK)", "bound": "tensor",
+        "roofline": {"kernel": GEMM_KERNEL, "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "traffic": measured_traffic("hybrid") if (world == 1 and n == N_GRAPHS) else None,
                      "traffic_unit": "bytes/launch (ncu dram read+write, profiles/traffic.json)",

@@ -616,9 +616,9 @@ int gk_wl_oa_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   oa_colmax<<<h->sm_count * 8, 256, 0, h->stream>>>(h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(),
                                                     colmaxcnt);
   LAUNCH_CHECK(h);
-  oa_colbase<<<cdiv(D, 256), 256, 0, h->stream>>>(D, colmaxcnt, colbase, cur);
+  oa_colbase<<<cdiv(D, OA_THREADS), OA_THREADS, 0, h->stream>>>(D, colmaxcnt, colbase, cur);
   LAUNCH_CHECK(h);
-  oa_expand<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+  oa_expand<<<cdiv((long long)h->ft_cap, OA_THREADS), OA_THREADS, 0, h->stream>>>(
       h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), colbase, out_cap,
       h->oa_keys.as<unsigned long long>(), h->oa_cnt.as<unsigned>(), cur, h->oa_colcnt.as<unsigned>(),
       h->diag_u64.as<unsigned long long>(), h->scalars.as<DevScalars>());

@@ -35,29 +35,51 @@ oa_colmax(size_t cap, const unsigned long long* __restrict__ keys, const unsigne
   }
 }
 
-// pass 2: first threshold column of every column.  Warp-aggregated allocation from one cursor: the
-// order of the expanded columns depends on scheduling, K does not (exact integer arithmetic).
-__global__ void __launch_bounds__(256)
-oa_colbase(long long D, const unsigned* __restrict__ colmax, unsigned* __restrict__ colbase, OaCursors* cur) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const unsigned m = c < D ? colmax[c] : 0u;
-  unsigned incl = m;
+constexpr int OA_THREADS = 1024;
+
+// Block-wide reservation from one global cursor: exclusive offset of this thread's `n` items.  ONE atomic per
+// block -- returning atomics on a single address serialise in their L2 slice (a warp-aggregated version of
+// oa_expand spent ~200 us in 74 k of them, profiles/r01h_full_summary.md).  All threads of the block must call.
+__device__ __forceinline__ unsigned long long oa_block_reserve(unsigned n, unsigned long long* cursor) {
+  __shared__ unsigned s_tot[32];
+  __shared__ unsigned long long s_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned incl = n;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += y;
   }
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned long long base = 0;
-  if (lane == 31 && total) base = atomicAdd(&cur->n_cols, (unsigned long long)total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  if (c < D) colbase[c] = (unsigned)(base + incl - m);
+  if (lane == 31) s_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const unsigned t = lane < (int)(blockDim.x >> 5) ? s_tot[lane] : 0u;
+    unsigned i2 = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, i2, d);
+      if (lane >= d) i2 += y;
+    }
+    s_tot[lane] = i2 - t;  // exclusive offset of warp `lane`
+    if (lane == 31) s_base = i2 ? atomicAdd(cursor, (unsigned long long)i2) : 0ULL;
+  }
+  __syncthreads();
+  return s_base + s_tot[wid] + incl - n;
+}
+
+// pass 2: first threshold column of every column.  The order of the expanded columns depends on
+// scheduling, K does not (exact integer arithmetic).
+__global__ void __launch_bounds__(OA_THREADS)
+oa_colbase(long long D, const unsigned* __restrict__ colmax, unsigned* __restrict__ colbase, OaCursors* cur) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned m = c < D ? colmax[c] : 0u;
+  const unsigned long long base = oa_block_reserve(m, &cur->n_cols);
+  if (c < D) colbase[c] = (unsigned)base;
 }
 
 // pass 3: entry (graph, c, k) -> k entries (graph, colbase[c] + t, 1), t < k; statistics of the new
 // block (graphs per column, self similarity = number of entries of the graph) maintained on the fly.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(OA_THREADS)
 oa_expand(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
           const unsigned* __restrict__ colbase, size_t out_cap, unsigned long long* __restrict__ out_keys,
           unsigned* __restrict__ out_cnt, OaCursors* cur, unsigned* colcnt, unsigned long long* diag, DevScalars* sc) {
@@ -69,17 +91,7 @@ oa_expand(size_t cap, const unsigned long long* __restrict__ keys, const unsigne
     k = keys[i];
     if (k != EMPTY64) n = cnt[i];
   }
-  unsigned incl = n;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += y;
-  }
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;  // warp-uniform
-  unsigned long long pos = 0;
-  if (lane == 31) pos = atomicAdd(&cur->n_entries, (unsigned long long)total);
-  pos = __shfl_sync(0xffffffffu, pos, 31) + incl - n;
+  const unsigned long long pos = oa_block_reserve(n, &cur->n_entries);
   // self similarity: one atomic per (warp, graph) -- COO entries of a graph are adjacent
   const unsigned g = n ? (unsigned)(k >> 32) : 0xffffffffu;
   const unsigned peers = __match_any_sync(0xffffffffu, g);
