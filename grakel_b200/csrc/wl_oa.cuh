@@ -79,10 +79,18 @@ oa_colbase(long long D, const unsigned* __restrict__ colmax, unsigned* __restric
 
 // pass 3: entry (graph, c, k) -> k entries (graph, colbase[c] + t, 1), t < k; statistics of the new
 // block (graphs per column, self similarity = number of entries of the graph) maintained on the fly.
+// Graphs-per-column counts are aggregated in a shared-memory table first: a threshold column of a
+// level-0 label is held by thousands of graphs, and same-address global atomics retire one after the
+// other at ~28 ns each (the un-aggregated version spent 230 us in chains of up to 8 192 of them,
+// profiles/r01i_launches_wloa.csv); per block a hot column now costs one global atomic.
+constexpr int OA_AGG = 4096;  // slots of the per-block (column -> graphs) table
+
 __global__ void __launch_bounds__(OA_THREADS)
 oa_expand(size_t cap, const unsigned long long* __restrict__ keys, const unsigned* __restrict__ cnt,
           const unsigned* __restrict__ colbase, size_t out_cap, unsigned long long* __restrict__ out_keys,
           unsigned* __restrict__ out_cnt, OaCursors* cur, unsigned* colcnt, unsigned long long* diag, DevScalars* sc) {
+  __shared__ unsigned agg_col[OA_AGG], agg_cnt[OA_AGG];
+  for (int s = threadIdx.x; s < OA_AGG; s += OA_THREADS) { agg_col[s] = 0xFFFFFFFFu; agg_cnt[s] = 0u; }
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   unsigned long long k = EMPTY64;
@@ -91,21 +99,39 @@ oa_expand(size_t cap, const unsigned long long* __restrict__ keys, const unsigne
     k = keys[i];
     if (k != EMPTY64) n = cnt[i];
   }
-  const unsigned long long pos = oa_block_reserve(n, &cur->n_entries);
+  const unsigned long long pos = oa_block_reserve(n, &cur->n_entries);  // its barriers also order the table init
   // self similarity: one atomic per (warp, graph) -- COO entries of a graph are adjacent
   const unsigned g = n ? (unsigned)(k >> 32) : 0xffffffffu;
   const unsigned peers = __match_any_sync(0xffffffffu, g);
   unsigned gsum = 0;
   for (unsigned m = peers; m; m &= m - 1) gsum += __shfl_sync(peers, n, __ffs(m) - 1);
   if (n && lane == __ffs(peers) - 1) atomicAdd(&diag[g], (unsigned long long)gsum);
-  if (!n) return;
-  if (pos + n > out_cap) { sc->ft_overflow = 1u; return; }
-  const unsigned b = colbase[(unsigned)k];
-  const unsigned long long hi = k & 0xffffffff00000000ULL;
-  for (unsigned t = 0; t < n; ++t) {
-    out_keys[pos + t] = hi | (unsigned long long)(b + t);
-    out_cnt[pos + t] = 1u;
-    if (__ldcg(&colcnt[b + t]) < COL_CAP) atomicAdd(&colcnt[b + t], 1u);
+  if (n) {
+    if (pos + n > out_cap) {
+      sc->ft_overflow = 1u;
+    } else {
+      const unsigned b = colbase[(unsigned)k];
+      const unsigned long long hi = k & 0xffffffff00000000ULL;
+      for (unsigned t = 0; t < n; ++t) {
+        const unsigned col = b + t;
+        out_keys[pos + t] = hi | (unsigned long long)col;
+        out_cnt[pos + t] = 1u;
+        unsigned slot = (col * 0x9E3779B1u >> 14) & (OA_AGG - 1);
+        bool done = false;
+        for (int probe = 0; probe < 16 && !done; ++probe) {
+          unsigned prev = agg_col[slot];
+          if (prev == 0xFFFFFFFFu) prev = atomicCAS(&agg_col[slot], 0xFFFFFFFFu, col);
+          if (prev == 0xFFFFFFFFu || prev == col) { atomicAdd(&agg_cnt[slot], 1u); done = true; }
+          else slot = (slot + 1) & (OA_AGG - 1);
+        }
+        if (!done && __ldcg(&colcnt[col]) < COL_CAP) atomicAdd(&colcnt[col], 1u);  // table crowded: straight to global
+      }
+    }
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < OA_AGG; s += OA_THREADS) {
+    const unsigned col = agg_col[s];
+    if (col != 0xFFFFFFFFu && __ldcg(&colcnt[col]) < COL_CAP) atomicAdd(&colcnt[col], agg_cnt[s]);
   }
 }
 
