@@ -204,9 +204,12 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
-    # rank 0 prints exactly one JSON line on stdout: keep NCCL's version banner off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints exactly one JSON line on stdout.  Libraries write there too (NCCL prints its version banner
+    # at NCCL_DEBUG=VERSION and above, straight to file descriptor 1), so descriptor 1 is pointed at stderr for the
+    # whole run and the JSON line goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
@@ -361,7 +364,7 @@ def main():
         line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": cpu_threads(), "kind": "port",
                                 "sample": f"first {n_cpu} of the {n} graphs, {t:.1f} s with {cpu_threads()} host threads "
                                           f"(one per WL level; {os.cpu_count()} logical cores on the box)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

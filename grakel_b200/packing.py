@@ -20,6 +20,7 @@ from __future__ import annotations
 import numbers
 import warnings
 from collections.abc import Iterable
+from itertools import chain
 
 import numpy as np
 
@@ -199,6 +200,57 @@ def _adjacency_array(g):
     return A
 
 
+_INT_TYPES = {int, np.int64, np.int32}
+_NUM_TYPES = {int, float, bool, np.float64, np.float32, np.int64, np.int32}
+
+
+def _fast_edge_dict(g, L, mode, need_labels):
+    """Vectorised packing of the common spelling {(u, v): w} with integer vertex symbols: every per-edge step
+    runs inside C iterators (itertools / map / numpy.fromiter) instead of Python byte code.  Returns
+    (n_vertices, src, dst, weights, label list) with the slow path's semantics, or None whenever anything is
+    unusual (other symbol types, unlabelled or foreign vertices, ...): the caller then takes the general path,
+    which also produces the reference's errors."""
+    E = len(g)
+    if E == 0 or set(map(type, g)) != {tuple} or set(map(len, g)) != {2}:
+        return None
+    if not set(map(type, g.values())) <= _NUM_TYPES:
+        return None
+    if not set(map(type, chain.from_iterable(g))) <= _INT_TYPES:
+        return None
+    flat = np.fromiter(chain.from_iterable(g), dtype=np.int64, count=2 * E)
+    src, dst = flat[0::2], flat[1::2]
+    ww = np.fromiter(g.values(), dtype=np.float64, count=E)
+    lab_list = None
+    if mode == "wl":  # vertex set = label keys; only a contiguous integer range keeps the index arithmetic trivial
+        if not L or type(L) is not dict:
+            return None
+        keys = list(L)
+        n = len(keys)
+        k0 = keys[0]
+        if type(k0) is not int or keys != list(range(k0, k0 + n)):
+            return None
+        if int(flat.min()) < k0 or int(flat.max()) >= k0 + n:
+            return None  # an unlabelled source is skipped, an unlabelled target is a KeyError: general path
+        src, dst = src - k0, dst - k0
+        lab_list = list(L.values())
+    else:  # 'sp' / 'wloa': vertex set = the symbols that occur in an edge, sorted
+        sv = np.unique(flat)
+        n = len(sv)
+        if int(sv[0]) == 0 and int(sv[-1]) == n - 1:
+            pass  # already 0..n-1
+        else:
+            src, dst = np.searchsorted(sv, src), np.searchsorted(sv, dst)
+        if need_labels:
+            if not L or type(L) is not dict:
+                return None
+            try:
+                lab_list = list(map(L.__getitem__, sv.tolist()))
+            except KeyError:
+                return None
+    order = np.lexsort((dst, src))
+    return n, src[order], dst[order], ww[order], lab_list
+
+
 def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=False,
          fw_zero_is_absent=False, attributes=False, type_error_msg=None):
     """Pack an iterable of reference-style elements.
@@ -221,6 +273,23 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
     any_weight = False
     all_adjacency = True
     for idx, g, L in iter_elements(X, len_ok, type_error_msg):
+        base = graph_ptr[-1]
+        fast = None
+        if type(g) is dict and not attributes and not fw_zero_is_absent:
+            fast = _fast_edge_dict(g, L, mode, need_labels)
+        if fast is not None:
+            all_adjacency = False
+            verts_n, ii, jj, ww, lab_list = fast
+            counts = np.bincount(ii, minlength=verts_n)
+            rp_parts.append(deg_total + np.cumsum(counts))
+            ci_parts.append(jj + base)
+            w_parts.append(ww)
+            any_weight = any_weight or bool(np.any(ww != 1.0))
+            deg_total += len(ii)
+            if need_labels:
+                labels.extend(lab_list)
+            graph_ptr.append(base + verts_n)
+            continue
         kind = classify(g)
         if kind is None:
             raise ValueError("Unsupported input type. For more information check the documentation, concerning "
