@@ -191,3 +191,67 @@ def test_no_gpu_means_loud_failure():
         pytest.skip("GPU present")
     with pytest.raises(Exception):
         WeisfeilerLehman(n_iter=1).fit_transform([[{(0, 1): 1, (1, 0): 1}, {0: 1, 1: 2}]])
+
+
+# ------------------------------------------------------------------ vectorised packer fast path
+def _blocks_equal(a, b, same_order=True):
+    if same_order:
+        return (np.array_equal(a.graph_ptr, b.graph_ptr) and np.array_equal(a.row_ptr, b.row_ptr)
+                and np.array_equal(a.col_idx, b.col_idx) and list(a.labels or []) == list(b.labels or [])
+                and ((a.weights is None) == (b.weights is None))
+                and (a.weights is None or np.array_equal(a.weights, b.weights)))
+    # vertex order inside a graph may differ: compare the labelled edge multisets per graph
+    if not np.array_equal(a.graph_ptr, b.graph_ptr):
+        return False
+    for blk in (a, b):
+        blk._canon = []
+        for g in range(blk.n_graphs):
+            v0, v1 = blk.graph_ptr[g], blk.graph_ptr[g + 1]
+            es = sorted((blk.labels[v], blk.labels[blk.col_idx[k]]) for v in range(v0, v1)
+                        for k in range(blk.row_ptr[v], blk.row_ptr[v + 1]))
+            blk._canon.append((sorted(blk.labels[v0:v1]), es))
+    return a._canon == b._canon
+
+
+@pytest.mark.parametrize("mode", ["wl", "sp", "wloa"])
+def test_fast_edge_dict_path_equals_the_general_packer(mode, monkeypatch):
+    """{(u, v): w} inputs with integer symbols take a vectorised path (packing._fast_edge_dict); it must build the
+    block the general path builds, and hand every unusual element back to it."""
+    from grakel_b200 import packing
+    from oracle.gk_oracle import gen
+    rs = np.random.RandomState(3)
+    X = gen(60, 14, 5)
+    for i, (g, l) in enumerate(X):  # weights, a shifted id range, directed edges, dropped edges
+        if i % 4 == 1:
+            for e in list(g):
+                g[e] = float(rs.randint(1, 4))
+        if i % 4 == 2:
+            X[i][0] = {(a + 7, b + 7): w for (a, b), w in g.items()}
+            X[i][1] = {v + 7: lab for v, lab in l.items()}
+        if i % 4 == 3:
+            for e in [e for e in sorted(g) if rs.rand() < 0.3]:
+                del g[e]
+    X = [x for x in X if len(x[0])]
+    odd = [
+        [{("a", "b"): 1, ("b", "a"): 1}, {"a": 0, "b": 1}],           # symbols that are not integers
+        [{(0, 1): 1, (1, 0): 1}, {0: 5, 1: 6, 3: 7}],                 # label keys with a gap
+        [{(0, 1): 1, (1, 2): 1}, {1: 5, 0: 6, 2: 7}],                 # label keys out of order
+        [{(0, 1): 1.0, (5, 0): 1.0, (1, 0): 2.0}, {0: 1, 1: 2, 5: 3}],
+    ]
+    kw = dict(len_ok=lambda n: n >= 2, want_weights=True)
+    fast = packing.pack(X + odd, mode, **kw)
+    calls = []
+    real = packing._fast_edge_dict
+    monkeypatch.setattr(packing, "_fast_edge_dict", lambda *a: calls.append(1) or None)
+    slow = packing.pack(X + odd, mode, **kw)
+    assert len(calls) == len(X) + len(odd)
+    assert _blocks_equal(fast, slow, same_order=mode != "wloa")
+    monkeypatch.setattr(packing, "_fast_edge_dict", real)
+    taken = sum(real(g, l, mode, True) is not None for g, l in X)
+    assert taken == len(X)  # the regular elements really go through the fast path
+    assert real(odd[0][0], odd[0][1], mode, True) is None
+    # an unlabelled vertex: the fast path declines, the general path raises / skips exactly as before
+    bad = [[{(0, 1): 1, (1, 0): 1}, {0: 1}]]
+    assert real(bad[0][0], bad[0][1], mode, True) is None
+    with pytest.raises(KeyError):
+        packing.pack(bad, mode, **kw)
