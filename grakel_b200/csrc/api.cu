@@ -174,7 +174,7 @@ int gk_destroy(gk_handle* h) {
                         &h->colmin, &h->colmax, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
-                        &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt};
+                        &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt, &h->wl_single};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
@@ -439,7 +439,8 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       memcpy(hp, tv.data(), (size_t)(n_tiles + 1) * 4);
       memcpy(hp + n_tiles + 1, ct.data(), (size_t)(G + 1) * 4);
       GK_CUDA(cudaMemcpyAsync(h->wlf_buf.p, hp, ((size_t)n_tiles + G + 2) * 4, cudaMemcpyHostToDevice, h->stream));
-      GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
+      GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
+      GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
     }
   }
   // feature block: the multi-kernel path fills one open-addressing sub-table per level, the fused
@@ -477,6 +478,15 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       fp.barrier = d_barrier;
       fp.labels_all = labels_all; fp.sig_nbr = h->sig_nbr.as<int>(); fp.slot_of = h->slot_of.as<int>();
       fp.rank_pack = h->flags.as<int>();
+      // singleton shortcut (wl_fused.cuh, SKIP): opt-in with GRAKEL_B200_WL_SKIP=1 until it has been through the
+      // GPU parity suite (tools/run_r01l.sh)
+      const char* e_skip = getenv("GRAKEL_B200_WL_SKIP");
+      const bool wl_skip = e_skip && atoi(e_skip) != 0;
+      if (wl_skip) {
+        GK_TRY(h->wl_single.ensure((size_t)V));
+        GK_CUDA(cudaMemsetAsync(h->wl_single.p, 0, (size_t)V, h->stream));
+        fp.single = h->wl_single.as<unsigned char>();
+      }
       fp.table = h->ht_keys.as<unsigned long long>();
       fp.ht_mask = (unsigned)(h->ht_cap - 1);
       fp.coo_keys = h->ft_keys.as<unsigned long long>(); fp.coo_cnt = h->ft_cnt.as<unsigned>();
@@ -488,7 +498,8 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
         fp.prof = h->K_stage.as<long long>();
       }
       void* args[] = {&fp};
-      GK_CUDA(cudaLaunchCooperativeKernel((void*)wl_fused_kernel, dim3(G), dim3(WLF_THREADS), args, WLF_SMEM, h->stream));
+      GK_CUDA(cudaLaunchCooperativeKernel(wl_skip ? (void*)wl_fused_kernel<true> : (void*)wl_fused_kernel<false>, dim3(G),
+                                          dim3(WLF_THREADS), args, WLF_SMEM, h->stream));
       LAUNCH_CHECK(h);
       if (prof) {
         std::vector<long long> pr((size_t)G * L * 16);

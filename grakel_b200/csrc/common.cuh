@@ -138,6 +138,7 @@ struct gk_handle {
   size_t ht_cap = 0;
   gk::DevBuf flags, block_sums;
   gk::DevBuf wlf_buf;  // fused WL kernel: [cta_vbeg (G+1) | cta_count (G) | barrier]
+  gk::DevBuf wl_single;  // fused WL kernel, singleton shortcut: one byte per vertex
   gk::DevBuf scalars;  // gk::DevScalars
   gk::PinBuf h_scalars;
 

@@ -52,6 +52,7 @@ struct WlFusedParams {
   int* sig_nbr;          // [E] sorted neighbour labels of the current level
   int* slot_of;          // [V] hash slot, then representative vertex
   int* rank_pack;        // [V] valid for representatives
+  unsigned char* single; // [V] SKIP variant: the vertex's label of the previous level is held by no other vertex
   int* cta_count;        // [grid]
   unsigned long long* table;  // 2 x (ht_mask + 1) packed {tag, representative} words
   unsigned ht_mask;
@@ -153,7 +154,8 @@ __device__ __forceinline__ void wlf_stage(const WlFusedParams& p, int v0, int nv
 // shared memory).  One COO reservation per tile; the per-column graph counts are aggregated in a
 // shared-memory table first, so a column shared by every graph costs one global atomic per tile.
 __device__ __forceinline__ void wlf_emit(const WlFusedParams& p, int v0, int nv, const int* lab_s, unsigned* agg,
-                                         long long base, size_t coo_off, int* s_warp, unsigned& mx, unsigned& n_new) {
+                                         long long base, size_t coo_off, int* s_warp, unsigned& mx, unsigned& n_new,
+                                         const unsigned char* single = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31;
   for (int s = tid; s < WLF_AGG * 2; s += WLF_THREADS) agg[s] = (s & 1) ? 0u : 0xFFFFFFFFu;  // {column, graphs}
   int g[WLF_VPT], l[WLF_VPT], gs[WLF_VPT], ge[WLF_VPT];
@@ -176,7 +178,12 @@ __device__ __forceinline__ void wlf_emit(const WlFusedParams& p, int v0, int nv,
     cnt[k] = 0;
     emit[k] = false;
     l[k] = 0;
-    if (g[k] >= 0) {
+    if (g[k] >= 0 && single && single[v0 + i]) {  // label unique in the whole data set: one entry, count 1
+      l[k] = lab_s[i];
+      cnt[k] = 1;
+      emit[k] = true;
+      n_emit += 1;
+    } else if (g[k] >= 0) {
       l[k] = lab_s[i];
       bool first = true;
       for (int u = gs[k]; u < ge[k]; ++u) {
@@ -232,6 +239,13 @@ __device__ __forceinline__ void wlf_emit(const WlFusedParams& p, int v0, int nv,
   __syncthreads();  // agg is reused by the next tile
 }
 
+// SKIP = true: vertices whose previous label is a singleton class (no other vertex of the data set carries it) are
+// not hashed, inserted or verified again -- their next label is necessarily a singleton too (the signature contains
+// the own label) -- and their feature entry is (graph, column, 1) without the in-graph count.  From level 3 on
+// that is 96 % of the vertices of BASELINE config 2.  The table word gains a "single" bit below the (then 30-bit)
+// tag: the installing CAS sets it, the first matching vertex clears it with the atomicMin that also elects the
+// smaller representative.  SKIP = false is the kernel as measured in profiles/r01c..r01h.
+template <bool SKIP>
 __global__ void __launch_bounds__(WLF_THREADS, 1)
 wl_fused_kernel(WlFusedParams p) {
   extern __shared__ __align__(16) unsigned char wlf_smem[];
@@ -305,6 +319,7 @@ wl_fused_kernel(WlFusedParams p) {
         const int beg = rp_s[i];
         const int deg = rp_s[i + 1] - beg;
         if (deg > 8) continue;
+        if constexpr (SKIP) { if (p.single[v0 + i]) continue; }
         int x0, x1, x2, x3, x4, x5, x6, x7;
         x0 = 0 < deg ? lab_s[col_s[beg + 0]] : 0x7fffffff;
         x1 = 1 < deg ? lab_s[col_s[beg + 1]] : 0x7fffffff;
@@ -338,7 +353,8 @@ wl_fused_kernel(WlFusedParams p) {
       // (valid for any length: exchanges with the virtual +inf tail are no-ops).
       for (int i0 = wid * 32; i0 < nv; i0 += WLF_THREADS) {
         const int iv = i0 + lane;
-        const bool big = iv < nv && (rp_s[iv + 1] - rp_s[iv]) > 8;
+        bool big = iv < nv && (rp_s[iv + 1] - rp_s[iv]) > 8;
+        if constexpr (SKIP) { if (big && p.single[v0 + iv]) big = false; }
         unsigned m = __ballot_sync(0xffffffffu, big);
         while (m) {
           const int i = i0 + __ffs(m) - 1;
@@ -408,6 +424,7 @@ wl_fused_kernel(WlFusedParams p) {
         for (int k = 0; k < WLF_VPT; ++k) {
           const int i = tid + k * WLF_THREADS;
           act[k] = i < nv;
+          if constexpr (SKIP) { if (act[k] && p.single[v0 + i]) act[k] = false; }
           key[k] = act[k] ? key_s[i] : 0ULL;
           slot[k] = (unsigned)((key[k] & 0xFFFFFFFFULL) * 0x9E3779B1ULL >> 8) & p.ht_mask;
         }
@@ -419,7 +436,8 @@ wl_fused_kernel(WlFusedParams p) {
           // for every vertex.
 #pragma unroll
           for (int k = 0; k < WLF_VPT; ++k) {
-            const unsigned long long mine = (key[k] & 0xFFFFFFFF00000000ULL) | (unsigned)(v0 + tid + k * WLF_THREADS);
+            unsigned long long mine = (key[k] & 0xFFFFFFFF00000000ULL) | (unsigned)(v0 + tid + k * WLF_THREADS);
+            if constexpr (SKIP) mine |= 1ULL << 32;  // {30-bit tag | single = 1 | vertex}
             w[k] = act[k] ? atomicCAS(&tab[slot[k]], EMPTY64, mine) : 0ULL;
           }
           any = false;
@@ -429,7 +447,16 @@ wl_fused_kernel(WlFusedParams p) {
             const int v = v0 + tid + k * WLF_THREADS;
             const unsigned long long mine = (key[k] & 0xFFFFFFFF00000000ULL) | (unsigned)v;
             if (w[k] == EMPTY64) { act[k] = false; continue; }  // the CAS installed our word
-            if ((w[k] >> 32) == (key[k] >> 32)) {
+            if constexpr (SKIP) {
+              if ((w[k] >> 33) == (key[k] >> 33)) {
+                const unsigned rep = (unsigned)w[k];
+                // a second member: clear the single bit and keep the smaller representative in one atomicMin
+                if (((w[k] >> 32) & 1ULL) || rep > (unsigned)v)
+                  atomicMin(&tab[slot[k]], (key[k] & 0xFFFFFFFE00000000ULL) | (unsigned)min(rep, (unsigned)v));
+                act[k] = false;
+                continue;
+              }
+            } else if ((w[k] >> 32) == (key[k] >> 32)) {
               if ((unsigned)w[k] > (unsigned)v) atomicMin(&tab[slot[k]], mine);
               act[k] = false;
               continue;
@@ -462,10 +489,23 @@ wl_fused_kernel(WlFusedParams p) {
         const int i = tid + k * WLF_THREADS;
         r[k] = i < nv ? p.slot_of[v0 + i] : 0;
       }
+      bool sgl[WLF_VPT];  // SKIP: the vertex's label of THIS level is a singleton class
 #pragma unroll
       for (int k = 0; k < WLF_VPT; ++k) {
         const int i = tid + k * WLF_THREADS;
-        if (i < nv) r[k] = (int)(unsigned)__ldcg(&tab[r[k]]);
+        sgl[k] = false;
+        if constexpr (SKIP) {
+          if (i < nv) {
+            if (p.single[v0 + i]) { r[k] = v0 + i; sgl[k] = true; }  // never inserted: its own representative
+            else {
+              const unsigned long long word = __ldcg(&tab[r[k]]);
+              r[k] = (int)(unsigned)word;
+              sgl[k] = ((word >> 32) & 1ULL) && r[k] == v0 + i;
+            }
+          }
+        } else {
+          if (i < nv) r[k] = (int)(unsigned)__ldcg(&tab[r[k]]);
+        }
       }
       // verification against the representative: its CSR row and label are fetched for all (<= 4)
       // vertices of the thread at once, then up to 8 sorted neighbour labels per side in one batch
@@ -488,6 +528,7 @@ wl_fused_kernel(WlFusedParams p) {
         int f = 0;
         if (i < nv) {
           p.slot_of[v] = r[k];
+          if constexpr (SKIP) p.single[v] = sgl[k] ? 1 : 0;
           f = (r[k] == v);
           if (!f) {
             bool same = (dv[k] == dr[k]) && (lo[k] == lr[k]);
@@ -555,7 +596,7 @@ wl_fused_kernel(WlFusedParams p) {
           }
         }
         __syncthreads();
-        wlf_emit(p, v0, nv, lab_s, agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
+        wlf_emit(p, v0, nv, lab_s, agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new, SKIP ? p.single : nullptr);
       }
       if (b == 0 && tid == 0) {
         p.sc->level_dims[lv] = total;
