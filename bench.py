@@ -353,6 +353,14 @@ def main():
                            "achieved": (re_ - rb if world > 1 else n) * n * 4 / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0,
                            "peak": peak_hbm, "unit": "GB/s",
                            "frac": ((re_ - rb if world > 1 else n) * n * 4 / (g_ms * 1e-3) / 1e9 / peak_hbm) if g_ms > 0 else 0.0},
+        # the other large kernel of a step, against the HBM roof with SURVEY 8(d)'s algorithmic bytes: K1 relabel
+        # (12V + 4E + 4) + K2 compaction 16V per iteration, K3 histogram 4V + 8 nnz_i per level.  It is bound by
+        # dependent L2 operations and two grid barriers per level, not by bytes -- the fraction says so.
+        "roofline_relabel": (lambda b, ms: {"kernel": "wl_fused_kernel (all WL levels, one persistent launch)", "bound": "hbm",
+                                            "algorithmic_bytes": b, "ms_per_launch": ms, "achieved": b / (ms * 1e-3) / 1e9,
+                                            "peak": peak_hbm, "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / peak_hbm,
+                                            "share_of_step": ms / ms_step})(
+            float(H * (12 * V + 4 * E + 4 + 16 * V) + (H + 1) * 4 * V + 8 * int(st.n_entries)), float(np.mean(feat_ms))),
         "stages_ms": {"wl_features": float(np.mean(feat_ms)), "columns+panel": float(np.mean(panel_ms)),
                       "gram_gemm": g_ms, "tail_pairs": float(np.mean(tail_ms)), "wall_ms_per_step": wall_ms / args.steps},
         "head_tail": {"threshold_T": int(st.threshold), "head_columns": Dc, "tail_columns": int(st.n_tail_columns),
