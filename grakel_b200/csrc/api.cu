@@ -478,10 +478,10 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       fp.barrier = d_barrier;
       fp.labels_all = labels_all; fp.sig_nbr = h->sig_nbr.as<int>(); fp.slot_of = h->slot_of.as<int>();
       fp.rank_pack = h->flags.as<int>();
-      // singleton shortcut (wl_fused.cuh, SKIP): opt-in with GRAKEL_B200_WL_SKIP=1 until it has been through the
-      // GPU parity suite (tools/run_r01l.sh)
+      // singleton shortcut (wl_fused.cuh, SKIP): 0.293 vs 0.336 ms for all six levels of config 2, full GPU suite green
+      // with it (profiles/r01l_*); GRAKEL_B200_WL_SKIP=0 selects the kernel without it
       const char* e_skip = getenv("GRAKEL_B200_WL_SKIP");
-      const bool wl_skip = e_skip && atoi(e_skip) != 0;
+      const bool wl_skip = !(e_skip && atoi(e_skip) == 0);
       if (wl_skip) {
         GK_TRY(h->wl_single.ensure((size_t)V));
         GK_CUDA(cudaMemsetAsync(h->wl_single.p, 0, (size_t)V, h->stream));
