@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -45,8 +46,10 @@ namespace gk {
 namespace tu {
 
 struct FileBuf {
-  std::vector<char> data;
+  std::unique_ptr<char[]> buf;  // not zero-filled: every byte is overwritten by fread / the sentinel
+  size_t size = 0;              // file bytes + the sentinel newline
   bool present = false;
+  const char* begin() const { return buf.get(); }
 };
 
 inline bool slurp(const std::string& path, FileBuf* fb, std::string* err) {
@@ -59,11 +62,12 @@ inline bool slurp(const std::string& path, FileBuf* fb, std::string* err) {
   fseek(f, 0, SEEK_END);
   const long n = ftell(f);
   fseek(f, 0, SEEK_SET);
-  fb->data.resize((size_t)std::max<long>(n, 0) + 1);
-  const size_t got = n > 0 ? fread(fb->data.data(), 1, (size_t)n, f) : 0;
+  fb->size = (size_t)std::max<long>(n, 0) + 1;
+  fb->buf.reset(new char[fb->size]);
+  const size_t got = n > 0 ? fread(fb->buf.get(), 1, (size_t)n, f) : 0;
   fclose(f);
   if ((long)got != n) { *err = "short read on " + path; return false; }
-  fb->data[(size_t)n] = '\n';  // sentinel: every line ends
+  fb->buf[(size_t)n] = '\n';  // sentinel: every line ends
   fb->present = true;
   return true;
 }
@@ -107,51 +111,18 @@ inline bool parse_int_range(const char* p, const char* end, int per_line, std::v
   return true;
 }
 
-// Large files are cut at newlines and parsed by a few threads; on any error the file is parsed again
-// sequentially so that the message carries the exact line number.
+// Output vectors are reserved from the file size (first-touch page faults, not parsing, dominate otherwise).
 inline bool parse_ints(const FileBuf& fb, int per_line, std::vector<int32_t>* out0, std::vector<int32_t>* out1,
                        const std::string& what, std::string* err) {
-  const char* base = fb.data.data();
-  const size_t size = fb.data.size();  // includes the sentinel newline
-  const size_t est = size / (per_line == 2 ? 10 : 3) + 16;
-  unsigned T = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-  if (size < (1u << 20)) T = 1;
-  if (T > 1) {
-    std::vector<size_t> cut(T + 1, 0);
-    cut[T] = size;
-    for (unsigned i = 1; i < T; ++i) {
-      const char* q = (const char*)memchr(base + size * i / T, '\n', size - size * i / T);
-      cut[i] = q ? (size_t)(q - base) + 1 : size;
-    }
-    std::vector<std::vector<int32_t>> a(T), b(T);
-    std::vector<std::string> errs(T);
-    std::vector<char> oks(T, 1);
-    std::vector<std::thread> th;
-    for (unsigned i = 0; i < T; ++i)
-      th.emplace_back([&, i]() {
-        a[i].reserve(est / T);
-        if (per_line == 2) b[i].reserve(est / T);
-        if (cut[i] < cut[i + 1]) oks[i] = parse_int_range(base + cut[i], base + cut[i + 1], per_line, &a[i], &b[i], what, &errs[i]);
-      });
-    for (auto& t : th) t.join();
-    bool ok = true;
-    for (unsigned i = 0; i < T; ++i) ok = ok && oks[i];
-    if (ok) {
-      for (unsigned i = 0; i < T; ++i) {
-        out0->insert(out0->end(), a[i].begin(), a[i].end());
-        if (per_line == 2) out1->insert(out1->end(), b[i].begin(), b[i].end());
-      }
-      return true;
-    }
-  }
+  const size_t est = fb.size / (per_line == 2 ? 8 : 2) + 16;
   out0->reserve(est);
   if (per_line == 2) out1->reserve(est);
-  return parse_int_range(base, base + size, per_line, out0, out1, what, err);
+  return parse_int_range(fb.begin(), fb.begin() + fb.size, per_line, out0, out1, what, err);
 }
 
 inline bool parse_floats(const FileBuf& fb, std::vector<double>* out, int32_t* dim, const std::string& what, std::string* err) {
-  const char* p = fb.data.data();
-  const char* end = p + fb.data.size() - 1;
+  const char* p = fb.begin();
+  const char* end = p + fb.size - 1;
   long line = 0;
   *dim = 0;
   while (p < end) {
@@ -183,21 +154,32 @@ inline int open(const char* dir, const char* name, int32_t flags, gk_tu** out, s
   const std::string base = std::string(dir) + "/" + name + "_";
   gk_tu* t = new gk_tu();
   t->flags = flags;
-  FileBuf fi, fa, fn, fna, fe, fg;
-  bool ok = slurp(base + "graph_indicator.txt", &fi, err) && slurp(base + "A.txt", &fa, err) &&
-            slurp(base + "node_labels.txt", &fn, err) && slurp(base + "edge_labels.txt", &fe, err) &&
-            slurp(base + "graph_labels.txt", &fg, err);
-  if (ok && (flags & GK_TU_ATTR_NODES)) ok = slurp(base + "node_attributes.txt", &fna, err);
-  if (ok && !fi.present) { *err = "missing " + base + "graph_indicator.txt"; ok = false; }
+  // the edge list (by far the largest file) is read and parsed on the calling thread, everything else on a helper
+  bool ok_side = true, has_indicator = false;
+  std::string err_side;
+  std::thread side([&]() {
+    FileBuf fi, fn, fna, fe, fg;
+    std::vector<int32_t> dummy;
+    bool ok = slurp(base + "graph_indicator.txt", &fi, &err_side) && slurp(base + "node_labels.txt", &fn, &err_side) &&
+              slurp(base + "edge_labels.txt", &fe, &err_side) && slurp(base + "graph_labels.txt", &fg, &err_side);
+    if (ok && (flags & GK_TU_ATTR_NODES)) ok = slurp(base + "node_attributes.txt", &fna, &err_side);
+    has_indicator = fi.present;
+    if (ok && fi.present) ok = parse_ints(fi, 1, &t->indicator, &dummy, "graph_indicator", &err_side);
+    // read_data only opens the label file when it does not take the attributes (base.py:223-240)
+    if (ok && fn.present && !fna.present) ok = parse_ints(fn, 1, &t->node_label, &dummy, "node_labels", &err_side);
+    if (ok && fe.present) ok = parse_ints(fe, 1, &t->el, &dummy, "edge_labels", &err_side);
+    if (ok && fg.present) ok = parse_ints(fg, 1, &t->classes, &dummy, "graph_labels", &err_side);
+    if (ok && fna.present) ok = parse_floats(fna, &t->node_attr, &t->attr_dim, "node_attributes", &err_side);
+    ok_side = ok;
+  });
+  FileBuf fa;
+  bool ok = slurp(base + "A.txt", &fa, err);
+  if (ok && fa.present) ok = parse_ints(fa, 2, &t->eu, &t->ev, "A", err);
+  fa.buf.reset();
+  side.join();
+  if (ok_side && !has_indicator) { err_side = "missing " + base + "graph_indicator.txt"; ok_side = false; }
+  if (!ok_side) { *err = err_side; ok = false; }  // the indicator / label files are reported first, like a sequential read
   if (ok && !fa.present) { *err = "missing " + base + "A.txt"; ok = false; }
-  std::vector<int32_t> dummy;
-  if (ok) ok = parse_ints(fi, 1, &t->indicator, &dummy, "graph_indicator", err);
-  if (ok) ok = parse_ints(fa, 2, &t->eu, &t->ev, "A", err);
-  // read_data only opens the label file when it does not take the attributes (base.py:223-240)
-  if (ok && fn.present && !fna.present) ok = parse_ints(fn, 1, &t->node_label, &dummy, "node_labels", err);
-  if (ok && fe.present) ok = parse_ints(fe, 1, &t->el, &dummy, "edge_labels", err);
-  if (ok && fg.present) ok = parse_ints(fg, 1, &t->classes, &dummy, "graph_labels", err);
-  if (ok && fna.present) ok = parse_floats(fna, &t->node_attr, &t->attr_dim, "node_attributes", err);
   if (ok) {
     t->n_nodes = (int64_t)t->indicator.size();
     int32_t gmax = 0;
@@ -223,63 +205,77 @@ inline int open(const char* dir, const char* name, int32_t flags, gk_tu** out, s
   return GK_OK;
 }
 
-struct DirEdge {
-  int32_t u, v, lab;
-  uint32_t seq;  // write order in the reference: line e forward = 2e, reverse = 2e + 1
-};
-
 // mode GK_TU_LABELLED_NODES: vertex set = the keys of the node-label dictionary (what WeisfeilerLehman walks,
 //   weisfeiler_lehman.py:234) -- every node of the graph when a label / attribute file exists;
 // mode GK_TU_EDGE_NODES: vertex set = the nodes that occur in an edge of their graph (ShortestPath's
 //   sorted edge symbols, graph.py:1613-1631; the edge-dictionary keys WL-OA walks).
+//
+// Edges are bucketed by source with a STABLE counting sort in the reference's write order (line e forward, then
+// its reverse when symmetric) and each short row is sorted by target with a stable insertion sort, so the last
+// element of a run of equal targets is the last write of that pair: duplicates collapse and the last edge label
+// wins (base.py:262-266) without carrying sequence numbers around.
 inline int pack(gk_tu* t, int32_t mode, std::string* err) {
   if (mode != GK_TU_LABELLED_NODES && mode != GK_TU_EDGE_NODES) { *err = "gk_tu_pack: unknown mode"; return GK_ERR_ARG; }
   const int64_t n = t->n_nodes;
   const bool sym = t->flags & GK_TU_SYMMETRIC;
   const bool has_el = !t->el.empty();
-  std::vector<DirEdge> de;
-  de.reserve(t->eu.size() * (sym ? 2 : 1));
-  for (size_t e = 0; e < t->eu.size(); ++e) {
+  const size_t L = t->eu.size();
+  const int32_t* ind = t->indicator.data();
+  std::vector<uint32_t> start(n + 1, 0);
+  for (size_t e = 0; e < L; ++e) {
     const int32_t u = t->eu[e], v = t->ev[e];
-    if (t->indicator[u] != t->indicator[v]) {
+    if (ind[u] != ind[v]) {
       *err = "A: line " + std::to_string(e + 1) + " joins nodes of different graphs (the reference raises KeyError on it)";
       return GK_ERR_ARG;
     }
-    const int32_t lab = has_el ? t->el[e] : 0;
-    de.push_back({u, v, lab, (uint32_t)(2 * e)});
-    if (sym) de.push_back({v, u, lab, (uint32_t)(2 * e + 1)});
+    start[u + 1] += 1;
+    if (sym) start[v + 1] += 1;
   }
-  {  // sort by (u, v, write order): counting sort on the source, then each (short) row on its own
-    std::vector<uint32_t> start(n + 1, 0);
-    for (const auto& e : de) start[e.u + 1] += 1;
-    for (int64_t i = 0; i < n; ++i) start[i + 1] += start[i];
-    std::vector<DirEdge> tmp(de.size());
+  for (int64_t i = 0; i < n; ++i) start[i + 1] += start[i];
+  const size_t M = start[n];
+  std::unique_ptr<int32_t[]> rv(new int32_t[M ? M : 1]), rl(has_el ? new int32_t[M ? M : 1] : nullptr);
+  {
     std::vector<uint32_t> cur(start.begin(), start.end() - 1);
-    for (const auto& e : de) tmp[cur[e.u]++] = e;
-    de.swap(tmp);
-    for (int64_t i = 0; i < n; ++i) {
-      const uint32_t lo = start[i], hi = start[i + 1];
-      if (hi - lo > 32) {
-        std::sort(de.begin() + lo, de.begin() + hi, [](const DirEdge& a, const DirEdge& b) {
-          if (a.v != b.v) return a.v < b.v;
-          return a.seq < b.seq;
-        });
-      } else {
-        for (uint32_t x = lo + 1; x < hi; ++x) {  // insertion sort: rows are a handful of edges
-          const DirEdge e = de[x];
-          uint32_t y = x;
-          while (y > lo && (de[y - 1].v > e.v || (de[y - 1].v == e.v && de[y - 1].seq > e.seq))) { de[y] = de[y - 1]; --y; }
-          de[y] = e;
-        }
+    for (size_t e = 0; e < L; ++e) {
+      const int32_t u = t->eu[e], v = t->ev[e];
+      uint32_t k = cur[u]++;
+      rv[k] = v;
+      if (has_el) rl[k] = t->el[e];
+      if (sym) {
+        k = cur[v]++;
+        rv[k] = u;
+        if (has_el) rl[k] = t->el[e];
       }
     }
   }
-  size_t w = 0;  // keep the LAST write of every (u, v)
-  for (size_t i = 0; i < de.size(); ++i) {
-    if (i + 1 < de.size() && de[i + 1].u == de[i].u && de[i + 1].v == de[i].v) continue;
-    de[w++] = de[i];
+  // sort every row by target (stable), then keep the last element of each run of equal targets
+  std::vector<uint32_t> deg(n, 0);
+  std::vector<std::pair<int32_t, int32_t>> tmp;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t lo = start[i], hi = start[i + 1];
+    if (hi - lo > 48) {
+      tmp.resize(hi - lo);
+      for (uint32_t x = lo; x < hi; ++x) tmp[x - lo] = {rv[x], has_el ? rl[x] : 0};
+      std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first < b.first; });
+      for (uint32_t x = lo; x < hi; ++x) { rv[x] = tmp[x - lo].first; if (has_el) rl[x] = tmp[x - lo].second; }
+    } else {
+      for (uint32_t x = lo + 1; x < hi; ++x) {
+        const int32_t v = rv[x], l = has_el ? rl[x] : 0;
+        uint32_t y = x;
+        while (y > lo && rv[y - 1] > v) { rv[y] = rv[y - 1]; if (has_el) rl[y] = rl[y - 1]; --y; }
+        rv[y] = v;
+        if (has_el) rl[y] = l;
+      }
+    }
+    uint32_t w = lo;
+    for (uint32_t x = lo; x < hi; ++x) {
+      if (x + 1 < hi && rv[x + 1] == rv[x]) continue;  // a later write of the same pair follows
+      rv[w] = rv[x];
+      if (has_el) rl[w] = rl[x];
+      ++w;
+    }
+    deg[i] = w - lo;
   }
-  de.resize(w);
   // node labels: file, or (GK_TU_DEGREE_LABELS, no file) out-degree without self loops -- nodes of degree 0 stay
   // unlabelled (base.py:239-241: Counter over the sources of the edge set)
   std::vector<int32_t> label;
@@ -292,48 +288,51 @@ inline int pack(gk_tu* t, int32_t mode, std::string* err) {
     std::fill(labelled.begin(), labelled.end(), 1);
   } else if (t->flags & GK_TU_DEGREE_LABELS) {
     label.assign(n, 0);
-    for (const auto& e : de)
-      if (e.u != e.v) { label[e.u] += 1; labelled[e.u] = 1; }
+    for (int64_t i = 0; i < n; ++i)
+      for (uint32_t x = start[i]; x < start[i] + deg[i]; ++x)
+        if (rv[x] != (int32_t)i) { label[i] += 1; labelled[i] = 1; }
   }
   std::vector<char> keep(n, 0);
   if (mode == GK_TU_LABELLED_NODES) {
     keep = labelled;
   } else {
-    for (const auto& e : de) { keep[e.u] = 1; keep[e.v] = 1; }
+    for (int64_t i = 0; i < n; ++i)
+      for (uint32_t x = start[i]; x < start[i] + deg[i]; ++x) { keep[i] = 1; keep[rv[x]] = 1; }
   }
   // vertices grouped by graph, node order inside a graph (stable counting sort)
   t->graph_ptr.assign(t->n_graphs + 1, 0);
   for (int64_t i = 0; i < n; ++i)
-    if (keep[i]) t->graph_ptr[t->indicator[i] + 1] += 1;
+    if (keep[i]) t->graph_ptr[ind[i] + 1] += 1;
   for (int64_t g = 0; g < t->n_graphs; ++g) t->graph_ptr[g + 1] += t->graph_ptr[g];
   const int64_t V = t->graph_ptr[t->n_graphs];
   std::vector<int32_t> pos(n, -1), cursor(t->graph_ptr.begin(), t->graph_ptr.end() - 1);
   t->vnode.assign(V, 0);
   for (int64_t i = 0; i < n; ++i)
-    if (keep[i]) { pos[i] = cursor[t->indicator[i]]++; t->vnode[pos[i]] = (int32_t)i; }
+    if (keep[i]) { pos[i] = cursor[ind[i]]++; t->vnode[pos[i]] = (int32_t)i; }
   // CSR over the kept vertices.  An edge whose source is not a vertex is never visited by the reference
   // (weisfeiler_lehman.py:234 walks labelled vertices only); a target that is not a vertex is its KeyError.
   t->row_ptr.assign(V + 1, 0);
-  size_t kept_edges = 0;
-  for (const auto& e : de) {
-    if (pos[e.u] < 0) continue;
-    if (pos[e.v] < 0) {
-      *err = "node " + std::to_string(e.v + 1) + " is the target of an edge but has no label (the reference raises KeyError)";
-      return GK_ERR_ARG;
-    }
-    t->row_ptr[pos[e.u] + 1] += 1;
-    ++kept_edges;
+  for (int64_t i = 0; i < n; ++i) {
+    if (pos[i] < 0) continue;
+    for (uint32_t x = start[i]; x < start[i] + deg[i]; ++x)
+      if (pos[rv[x]] < 0) {
+        *err = "node " + std::to_string(rv[x] + 1) + " is the target of an edge but has no label (the reference raises KeyError)";
+        return GK_ERR_ARG;
+      }
+    t->row_ptr[pos[i] + 1] = (int32_t)deg[i];
   }
   for (int64_t v = 0; v < V; ++v) t->row_ptr[v + 1] += t->row_ptr[v];
+  const size_t kept_edges = (size_t)t->row_ptr[V];
   t->col_idx.assign(kept_edges, 0);
   t->elabel.assign(has_el ? kept_edges : 0, 0);
-  std::vector<int32_t> fill(t->row_ptr.begin(), t->row_ptr.end() - 1);
-  // `de` is sorted by (u, v) and positions are monotone in the node id inside a graph, so every row comes out sorted
-  for (const auto& e : de) {
-    if (pos[e.u] < 0) continue;
-    const int32_t k = fill[pos[e.u]]++;
-    t->col_idx[k] = pos[e.v];
-    if (has_el) t->elabel[k] = e.lab;
+  // positions are monotone in the node id inside a graph, so rows sorted by node id stay sorted
+  for (int64_t v = 0; v < V; ++v) {
+    const int32_t i = t->vnode[v];
+    int32_t k = t->row_ptr[v];
+    for (uint32_t x = start[i]; x < start[i] + deg[i]; ++x, ++k) {
+      t->col_idx[k] = pos[rv[x]];
+      if (has_el) t->elabel[k] = rl[x];
+    }
   }
   t->vlabel.clear();
   if (!label.empty()) {
