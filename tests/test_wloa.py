@@ -181,3 +181,33 @@ def test_gpu_wloa_full_size_properties():
     pick = np.random.RandomState(3).choice(len(X), 48, replace=False)
     _eq(K[np.ix_(pick, pick)], WLOAOracle(n_iter=5).fit_transform([X[i] for i in pick]))
     assert e.stats_.n_entries == 6 * int(n.sum())  # one unary entry per (vertex, level)
+
+
+# ------------------------------------------------------------------ two independent restatements agree
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_wloa_oracle_equals_histogram_intersection_of_the_wl_oracle(seed):
+    """WL-OA = histogram intersection of the WL-subtree feature vectors of all levels, on the vertices that touch an
+    edge.  Rebuild it from the (separately pinned) WL oracle's per-level labels and compare with WLOAOracle."""
+    from collections import Counter
+    from oracle.gk_oracle import WLOracle
+    rs = np.random.RandomState(seed)
+    X = gen(24, 10, 100 + seed, nl=3)
+    for g, _l in X:  # thin the graphs: isolated vertices and one-directional edges appear
+        for e in [e for e in sorted(g) if rs.rand() < 0.35]:
+            del g[e]
+    X = [x for x in X if len(x[0])]
+    h = 3
+    # the WL oracle walks every labelled vertex; restrict it to the edge-dictionary vertices first
+    Xr = []
+    for g, l in X:
+        verts = {x for e in g for x in e}
+        Xr.append([g, {v: l[v] for v in verts}])
+    _, levels = WLOracle(n_iter=h).fit_transform(Xr, return_levels=True)
+    feats = []
+    for j in range(len(Xr)):
+        c = Counter()
+        for lv in range(h + 1):
+            c.update((lv, lab) for lab in levels[lv][j].values())
+        feats.append(c)
+    K = np.array([[sum(min(n, b[k]) for k, n in a.items() if k in b) for b in feats] for a in feats], dtype=float)
+    _eq(WLOAOracle(n_iter=h).fit_transform(X), K)
