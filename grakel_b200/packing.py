@@ -24,6 +24,11 @@ from itertools import chain
 
 import numpy as np
 
+try:  # CPython-level packer for the commonest spelling (csrc/fastpack.c, built by csrc/build.sh); optional
+    from . import _fastpack
+except Exception:  # pragma: no cover
+    _fastpack = None
+
 try:  # scipy is a hard dependency of the reference; optional here
     from scipy.sparse import issparse
 except Exception:  # pragma: no cover
@@ -265,6 +270,19 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
                   without any edge never reach the histogram
                   (weisfeiler_lehman_optimal_assignment.py:179, 203-209).
     """
+    if (_fastpack is not None and type(X) is list and X and not attributes and not fw_zero_is_absent
+            and all(type(x) in (list, tuple) and len(x) >= 2 and len_ok(len(x)) for x in X)):
+        # whole-input fast path: {(u, v): w} graphs with integer symbols, walked with the CPython API; it declines
+        # (None) on anything unusual and the general loop below decides -- and raises -- as before
+        res = _fastpack.pack_edge_dicts(X, 0 if mode == "wl" else 1, 1 if need_labels else 0)
+        if res is not None:
+            gp, rp, ci, ww, labs, any_w = res
+            out = Block(np.frombuffer(gp, dtype=np.int32).copy(), np.frombuffer(rp, dtype=np.int32).copy(),
+                        np.frombuffer(ci, dtype=np.int32).copy(),
+                        np.frombuffer(ww, dtype=np.float64).copy() if (want_weights and any_w) else None,
+                        labs if need_labels else None, None, False)
+            out.mode = mode
+            return out
     graph_ptr = [0]
     rp_parts, ci_parts, w_parts = [], [], []
     labels = [] if need_labels else None

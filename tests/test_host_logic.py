@@ -239,6 +239,15 @@ def test_fast_edge_dict_path_equals_the_general_packer(mode, monkeypatch):
         [{(0, 1): 1.0, (5, 0): 1.0, (1, 0): 2.0}, {0: 1, 1: 2, 5: 3}],
     ]
     kw = dict(len_ok=lambda n: n >= 2, want_weights=True)
+    cmod = packing._fastpack
+    assert cmod is not None, "grakel_b200/_fastpack was not built (grakel_b200/csrc/build.sh)"
+    # the CPython-level packer (csrc/fastpack.c) takes the regular elements in one call ...
+    cres = cmod.pack_edge_dicts(X, 0 if mode == "wl" else 1, 1)
+    assert cres is not None
+    cblock = packing.pack(X, mode, **kw)
+    assert cmod.pack_edge_dicts(X + odd, 0 if mode == "wl" else 1, 1) is None  # ... and declines the odd ones
+    monkeypatch.setattr(packing, "_fastpack", None)
+    assert _blocks_equal(cblock, packing.pack(X, mode, **kw))  # == the numpy fast path, bit for bit
     fast = packing.pack(X + odd, mode, **kw)
     calls = []
     real = packing._fast_edge_dict
@@ -246,6 +255,7 @@ def test_fast_edge_dict_path_equals_the_general_packer(mode, monkeypatch):
     slow = packing.pack(X + odd, mode, **kw)
     assert len(calls) == len(X) + len(odd)
     assert _blocks_equal(fast, slow, same_order=mode != "wloa")
+    assert _blocks_equal(cblock, packing.pack(X, mode, **kw), same_order=mode != "wloa")  # == the general path
     monkeypatch.setattr(packing, "_fast_edge_dict", real)
     taken = sum(real(g, l, mode, True) is not None for g, l in X)
     assert taken == len(X)  # the regular elements really go through the fast path
@@ -253,5 +263,11 @@ def test_fast_edge_dict_path_equals_the_general_packer(mode, monkeypatch):
     # an unlabelled vertex: the fast path declines, the general path raises / skips exactly as before
     bad = [[{(0, 1): 1, (1, 0): 1}, {0: 1}]]
     assert real(bad[0][0], bad[0][1], mode, True) is None
+    assert cmod.pack_edge_dicts(bad, 0 if mode == "wl" else 1, 1) is None
+    monkeypatch.setattr(packing, "_fastpack", cmod)
     with pytest.raises(KeyError):
         packing.pack(bad, mode, **kw)
+    # inputs the C packer must leave alone: floats as symbols, bool keys, a non-dict graph, huge ints, empty graph
+    for weird in ([[{(0.0, 1.0): 1}, {0.0: 1, 1.0: 2}]], [[{(0, 1): "x"}, {0: 1, 1: 2}]], [[[(0, 1)], {0: 1, 1: 2}]],
+                  [[{(0, 2 ** 70): 1}, {0: 1, 2 ** 70: 2}]], [[{}, {0: 1}]], [[{(0, 1, 2): 1}, {0: 1, 1: 2}]]):
+        assert cmod.pack_edge_dicts(weird, 0 if mode == "wl" else 1, 1) is None
