@@ -10,7 +10,9 @@ from .kernels import (EdgeHistogram, Kernel, ShortestPath, ShortestPathAttr, Ver
                       WeisfeilerLehmanOptimalAssignment)
 from .core_framework import CoreFramework
 from .graph_kernels import GraphKernel
+from ._lib import default_device, set_default_device
 
 __version__ = "0.1.0"
 __all__ = ["Graph", "Kernel", "GraphKernel", "WeisfeilerLehman", "VertexHistogram", "ShortestPath",
-           "ShortestPathAttr", "EdgeHistogram", "CoreFramework", "WeisfeilerLehmanOptimalAssignment"]
+           "ShortestPathAttr", "EdgeHistogram", "CoreFramework", "WeisfeilerLehmanOptimalAssignment", "set_default_device",
+           "default_device"]

@@ -78,6 +78,9 @@ _SYMBOLS = {
     "gk_tu_pack": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gk_tu_fill": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gk_tu_close": (C.c_int, [_P]),
+    "gk_host_alloc": (C.c_int, [C.c_int64, C.POINTER(_P)]),
+    "gk_host_free": (C.c_int, [_P, C.c_int64]),
+    "gk_selftest_deliver": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, _P, _P, C.c_int32, _P]),
 }
 
 _lib = None
@@ -115,6 +118,36 @@ def _ptr(a):
 
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class _HostBlock:
+    """Owner of one gk_host_alloc mapping; the ndarray returned to the user keeps it alive through `.base`."""
+
+    def __init__(self, lib, nbytes):
+        p = _P()
+        if lib.gk_host_alloc(nbytes, C.byref(p)) != 0:
+            raise MemoryError("gk_host_alloc(%d) failed: %s" % (nbytes, lib.gk_last_error().decode()))
+        self._lib, self.ptr, self.nbytes = lib, p.value, nbytes
+        self.__array_interface__ = {"data": (self.ptr, False), "shape": (nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.gk_host_free(self.ptr, self.nbytes)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def host_matrix(rows, cols, dtype=np.float64):
+    """Fresh C-order (rows, cols) ndarray in a huge-page-backed, pooled host mapping (gk_host_alloc); small
+    results come from numpy directly."""
+    dt = np.dtype(dtype)
+    nbytes = int(rows) * int(cols) * dt.itemsize
+    if nbytes < (8 << 20) or os.environ.get("GRAKEL_B200_HOST_ALLOC", "1") == "0":
+        return np.empty((rows, cols), dtype=dt)
+    block = _HostBlock(load_library(), nbytes)
+    return np.asarray(block).view(dt).reshape(rows, cols)
 
 
 class Engine:
@@ -222,7 +255,7 @@ class Engine:
                 assert K.dtype == dt and K.flags.c_contiguous and K.shape == (re_ - rb, n_fit)
                 kptr = _ptr(K)
         else:
-            K = np.empty((re_ - rb, n_fit), dtype=dt)
+            K = host_matrix(re_ - rb, n_fit, dt)
             kptr = _ptr(K)
         xd = np.empty(n_fit, dtype=np.float64) if want_diag else None
         yd = np.empty(n_graphs - n_fit, dtype=np.float64) if (want_diag and not square) else None
@@ -264,6 +297,15 @@ class Engine:
             self._check(self.lib.gk_selftest_gram(self.h, n, d, _ptr(counts), _ptr(a), _ptr(b)))
         return a, b
 
+    def selftest_deliver(self, src, mode=0, diag=None, nan_to_num=False):
+        """Host-only: fp32 matrix -> float64 through the delivery code of gk_gram (no device work)."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        rows, cols = src.shape
+        dst = np.full((rows, cols), np.nan)
+        dg = None if diag is None else np.ascontiguousarray(diag, dtype=np.float64)
+        self._check(self.lib.gk_selftest_deliver(int(mode), rows, cols, _ptr(src), _ptr(dg), 1 if nan_to_num else 0, _ptr(dst)))
+        return dst
+
     def event_record(self, slot):
         self._check(self.lib.gk_event_record(self.h, slot))
 
@@ -281,14 +323,91 @@ class Engine:
 
 _engines = {}
 _engines_lock = threading.Lock()
+_default_device = None
+
+
+def set_default_device(device):
+    """Device ordinal new estimator runs use (default: GRAKEL_B200_DEVICE, else LOCAL_RANK, else 0)."""
+    global _default_device
+    _default_device = None if device is None else int(device)
+
+
+def default_device():
+    if _default_device is not None:
+        return _default_device
+    return int(os.environ.get("GRAKEL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
 def get_engine(device=None):
+    """The process-wide engine of a device (bench / tools / tests that drive the C-ABI step by step)."""
     if device is None:
-        device = int(os.environ.get("GRAKEL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        device = default_device()
     with _engines_lock:
         e = _engines.get(device)
         if e is None:
             e = Engine(device)
             _engines[device] = e
         return e
+
+
+class _EnginePool:
+    """Engines of one device handed out to estimator runs: a run holds one engine (one handle + stream) for its
+    pack -> features -> gram sequence, so estimators used from several Python threads (sklearn's threading
+    backend) run concurrently on separate streams instead of serialising on one handle.  At most
+    GRAKEL_B200_MAX_ENGINES (default 4) engines per device; further threads wait for a free one."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = []
+        self.count = 0
+        self.cv = threading.Condition()
+        self.limit = max(1, int(os.environ.get("GRAKEL_B200_MAX_ENGINES", "4")))
+
+    def acquire(self):
+        with self.cv:
+            while True:
+                if self.free:
+                    return self.free.pop()
+                if self.count < self.limit:
+                    self.count += 1
+                    break
+                self.cv.wait()
+        try:
+            # the first engine of the pool is the process-wide one, so step-by-step users share its buffers
+            return get_engine(self.device) if self.count == 1 else Engine(self.device)
+        except Exception:
+            with self.cv:
+                self.count -= 1
+                self.cv.notify()
+            raise
+
+    def release(self, eng):
+        with self.cv:
+            self.free.append(eng)
+            self.cv.notify()
+
+
+_pools = {}
+
+
+class engine:
+    """`with engine(device) as eng:` -- exclusive use of one engine of the device for the duration."""
+
+    def __init__(self, device=None):
+        self.device = default_device() if device is None else int(device)
+        self.eng = None
+
+    def __enter__(self):
+        with _engines_lock:
+            pool = _pools.get(self.device)
+            if pool is None:
+                pool = _pools[self.device] = _EnginePool(self.device)
+        self.pool = pool
+        self.eng = pool.acquire()
+        self.eng._lock.acquire()
+        return self.eng
+
+    def __exit__(self, *exc):
+        self.eng._lock.release()
+        self.pool.release(self.eng)
+        return False

@@ -186,8 +186,7 @@ class CoreFramework(Kernel):
         return eng.wl_features(b._n_iter - 1)
 
     def _run_cores(self, block, ids, rows, n_rows, n_fit, want_matrix=True):
-        eng = _lib.get_engine()
-        with eng._lock:
+        with _lib.engine(getattr(self, "device_", None)) as eng:
             eng.pack(block.graph_ptr, block.row_ptr, block.col_idx, ids, block.weights, block.attrs)
             eng.set_row_map(n_rows, rows)
             self.stats_ = self._device_features(eng)

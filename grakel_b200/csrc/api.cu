@@ -180,6 +180,7 @@ int gk_destroy(gk_handle* h) {
   h->h_colstats.release();
   h->h_tiles.release();
   h->h_stage.release();
+  h->h_diag.release();
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->tev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -1131,161 +1132,11 @@ static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_b
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
-// Host delivery of an fp32 device matrix into the caller's float64 array: rows are copied in
-// chunks into two pinned staging buffers; while chunk c+1 is on the PCIe bus, the pool widens
-// chunk c into the destination with streaming stores.
-namespace {
-class HostPool {
- public:
-  explicit HostPool(int n) : stop_(false), gen_(0), pending_(0) {
-    // Workers stay on the NUMA node of the thread that creates the pool (the one that also allocates
-    // and touches the pinned staging buffers): remote-socket workers made the widening slower with
-    // every added thread on the 2-socket GPU hosts.
-    std::vector<int> cpus = local_node_cpus();
-    for (int i = 0; i < n; ++i) {
-      th_.emplace_back([this, i] { run(i); });
-      if (!cpus.empty()) {
-        cpu_set_t set;
-        CPU_ZERO(&set);
-        for (int c : cpus) CPU_SET(c, &set);
-        pthread_setaffinity_np(th_.back().native_handle(), sizeof(set), &set);
-      }
-    }
-  }
-  static std::vector<int> local_node_cpus() {
-    std::vector<int> out;
-    const int cpu = sched_getcpu();
-    if (cpu < 0) return out;
-    for (int node = 0; node < 64; ++node) {
-      char path[128];
-      snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
-      FILE* f = fopen(path, "r");
-      if (!f) break;
-      char buf[4096] = {0};
-      if (!fgets(buf, sizeof(buf), f)) { fclose(f); continue; }
-      fclose(f);
-      std::vector<int> list;  // "0-15,64-79"
-      for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
-        int a = 0, b = 0;
-        if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; ++c) list.push_back(c); }
-        else if (sscanf(tok, "%d", &a) == 1) list.push_back(a);
-      }
-      if (std::find(list.begin(), list.end(), cpu) != list.end()) return list;
-    }
-    return out;
-  }
-  ~HostPool() {
-    { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
-    cv_.notify_all();
-    for (auto& t : th_) t.join();
-  }
-  int size() const { return (int)th_.size(); }
-  // runs fn(worker_index) on every worker and returns when all are done
-  void run_all(const std::function<void(int)>& fn) {
-    std::lock_guard<std::mutex> one_caller(call_m_);  // engines on different Python threads share the pool
-    std::unique_lock<std::mutex> l(m_);
-    fn_ = &fn;
-    pending_ = (int)th_.size();
-    ++gen_;
-    cv_.notify_all();
-    done_.wait(l, [this] { return pending_ == 0; });
-  }
-
- private:
-  void run(int idx) {
-    unsigned long long seen = 0;
-    for (;;) {
-      const std::function<void(int)>* fn;
-      {
-        std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
-        fn = fn_;
-      }
-      (*fn)(idx);
-      {
-        std::lock_guard<std::mutex> l(m_);
-        if (--pending_ == 0) done_.notify_all();
-      }
-    }
-  }
-  std::vector<std::thread> th_;
-  std::mutex m_, call_m_;
-  std::condition_variable cv_, done_;
-  const std::function<void(int)>* fn_ = nullptr;
-  bool stop_;
-  unsigned long long gen_;
-  int pending_;
-};
-
-HostPool& host_pool() {
-  static HostPool pool([] {
-    int n = std::min(8, (int)std::thread::hardware_concurrency() / 2);
-    if (const char* e = getenv("GRAKEL_B200_HOST_THREADS")) n = atoi(e);
-    return std::max(1, std::min(n, 64));
-  }());
-  return pool;
-}
-
-__attribute__((target("avx2"))) inline void widen_row_avx2(const float* __restrict__ src, double* __restrict__ dst, long long n) {
-  long long j = 0;
-  for (; j < n && (reinterpret_cast<uintptr_t>(dst + j) & 31); ++j) dst[j] = (double)src[j];
-  for (; j + 8 <= n; j += 8) {
-    const __m256 f = _mm256_loadu_ps(src + j);
-    _mm256_stream_pd(dst + j, _mm256_cvtps_pd(_mm256_castps256_ps128(f)));
-    _mm256_stream_pd(dst + j + 4, _mm256_cvtps_pd(_mm256_extractf128_ps(f, 1)));
-  }
-  for (; j < n; ++j) dst[j] = (double)src[j];
-}
-
-inline void widen_row(const float* __restrict__ src, double* __restrict__ dst, long long n) {
-  static const bool avx2 = __builtin_cpu_supports("avx2");
-  if (avx2) return widen_row_avx2(src, dst, n);
-  long long j = 0;
-  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    for (; j + 4 <= n; j += 4) {  // 2 x (2 floats -> 2 doubles), non-temporal: the destination is not read again here
-      const __m128 f = _mm_loadu_ps(src + j);
-      _mm_stream_pd(dst + j, _mm_cvtps_pd(f));
-      _mm_stream_pd(dst + j + 2, _mm_cvtps_pd(_mm_movehl_ps(f, f)));
-    }
-  }
-  for (; j < n; ++j) dst[j] = (double)src[j];
-}
-}  // namespace
-
-static int deliver_widen(gk_handle* h, const float* d_src, long long d_ld, long long rows, long long cols, double* dst,
-                         long long ld) {
-  const long long chunk_rows = std::max<long long>(1, std::min<long long>(rows, (16LL << 20) / std::max<long long>(cols * 4, 1)));
-  const size_t buf_bytes = (size_t)chunk_rows * cols * 4;
-  GK_TRY(h->h_stage.ensure(buf_bytes * 2));
-  float* stage[2] = {h->h_stage.as<float>(), h->h_stage.as<float>() + (size_t)chunk_rows * cols};
-  HostPool& pool = host_pool();
-  const int nt = pool.size();
-  const long long n_chunks = (rows + chunk_rows - 1) / chunk_rows;
-  auto widen_chunk = [&](long long c) {
-    const long long r0 = c * chunk_rows, nr = std::min(chunk_rows, rows - r0);
-    const float* src = stage[c & 1];
-    pool.run_all([&](int w) {
-      const long long a = nr * w / nt, b = nr * (w + 1) / nt;  // one contiguous band per worker
-      for (long long r = a; r < b; ++r) widen_row(src + r * cols, dst + (r0 + r) * ld, cols);
-    });
-  };
-  for (long long c = 0; c < n_chunks; ++c) {
-    const long long r0 = c * chunk_rows, nr = std::min(chunk_rows, rows - r0);
-    GK_CUDA(cudaMemcpy2DAsync(stage[c & 1], (size_t)cols * 4, d_src + r0 * d_ld, (size_t)d_ld * 4, (size_t)cols * 4, (size_t)nr,
-                              cudaMemcpyDeviceToHost, h->stream));
-    GK_CUDA(cudaEventRecord(h->ev_stage[c & 1], h->stream));
-    if (c > 0) {
-      GK_CUDA(cudaEventSynchronize(h->ev_stage[(c - 1) & 1]));
-      widen_chunk(c - 1);  // overlaps the copy of chunk c
-    }
-  }
-  GK_CUDA(cudaEventSynchronize(h->ev_stage[(n_chunks - 1) & 1]));
-  widen_chunk(n_chunks - 1);
-  _mm_sfence();
-  return GK_OK;
-}
+// Host delivery of an fp32 device matrix into the caller's float64 array (host_deliver.h): K is moved as
+// fp32 -- for the symmetric square case only its upper triangle, in row bands of roughly equal area --
+// through a ring of pinned staging buffers; host threads widen each band into the destination rows and
+// write the mirrored half (8 x 8 register transposes) while the next bands are on the PCIe bus.
+#include "host_deliver.h"
 
 template <typename OutT, bool NORM>
 static void launch_tc(gk_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
@@ -1456,15 +1307,15 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   h->Dc = Dc;
   h->Dc_pad = (Dc + BK - 1) / BK * BK;
 
-  // ---- transport type.  Un-normalised tensor-core results are integers < 2^24 (checked above), i.e.
-  // exact in fp32: with GRAKEL_B200_WIDEN=1 a float64 HOST result is produced and moved as fp32 (half
-  // the HBM writes and half the PCIe bytes) and widened by host threads while the next chunk is in
-  // flight (deliver_widen below).  Opt-in: on the 2-socket GPU hosts measured so far the host-side
-  // widening (11.5-19 ms for 800 MB, strongly dependent on thread placement and on what else uses
-  // the host's memory bandwidth) does not reliably beat the plain 800 MB fp64 DMA (14-15 ms).
+  // ---- transport type.  Tensor-core results are integers < 2^24 (checked above), i.e. exact in fp32: a float64
+  // HOST result is produced and moved as fp32 (half the HBM writes; a quarter of the PCIe bytes for the
+  // symmetric case, whose upper triangle alone is copied) and widened -- and, if asked, normalised in fp64 --
+  // by host threads while the next band is in flight (host_deliver.h).  GRAKEL_B200_WIDEN=0 restores the
+  // plain fp64 D2H copy of a device-side fp64 result.
   const char* widen_env = getenv("GRAKEL_B200_WIDEN");
-  const bool widen_on_host = K_out && !(flags & GK_OUT_DEVICE) && out_dtype == GK_F64 && !normalize && path != 2 &&
-                             widen_env && atoi(widen_env) != 0;
+  const bool widen_on_host = K_out && !(flags & GK_OUT_DEVICE) && out_dtype == GK_F64 && path != 2 &&
+                             !(widen_env && atoi(widen_env) == 0);
+  const bool host_norm = widen_on_host && normalize;
   const int32_t dev_dtype = widen_on_host ? GK_F32 : out_dtype;
   const size_t dev_esz = dev_dtype == GK_F64 ? 8 : 4;
 
@@ -1489,7 +1340,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   const bool full_square = square && row_begin == 0 && row_end == N;
   const bool mirror = full_square && !(flags & GK_FULL_TILES);
   const bool has_tail = path != 2 && n_tail_cols > 0;
-  const bool norm_in_epilogue = normalize && !has_tail;
+  const bool norm_in_epilogue = normalize && !has_tail && !host_norm;
 
   GramParams p;
   memset(&p, 0, sizeof(p));
@@ -1602,7 +1453,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
                                                        (int)n_fit, square ? 1 : 0, (int)row_begin, (int)row_end,
                                                        (float*)d_out, d_ld);
       LAUNCH_CHECK(h);
-      if (normalize) {
+      if (normalize && !host_norm) {
         const double* drow = h->diag_f64.as<double>() + a0;
         const double* dcol = h->diag_f64.as<double>() + b0;
         if (dev_dtype == GK_F64)
@@ -1623,7 +1474,20 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   GK_CUDA(cudaEventRecord(h->ev[14], h->stream));
   if (K_out && !(flags & GK_OUT_DEVICE) && k_rows > 0) {
     if (widen_on_host) {
-      GK_TRY(deliver_widen(h, reinterpret_cast<const float*>(d_out), d_ld, k_rows, k_cols, reinterpret_cast<double*>(K_out), ld));
+      const float* d_k = reinterpret_cast<const float*>(d_out);
+      double* dst = reinterpret_cast<double*>(K_out);
+      DeviceCopier cp{h};
+      if (host_norm) {
+        GK_TRY(h->h_diag.ensure((size_t)N * 8));
+        GK_CUDA(cudaMemcpyAsync(h->h_diag.p, h->diag_f64.p, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
+        GK_CUDA(cudaStreamSynchronize(h->stream));
+        GK_TRY(deliver_rows(cp, d_k, d_ld, k_rows, k_cols, dst, ld, h->h_diag.as<double>() + a0, h->h_diag.as<double>() + b0,
+                            p.nan_to_num));
+      } else if (full_square && !getenv("GRAKEL_B200_NO_TRI")) {
+        GK_TRY(deliver_tri(cp, d_k, d_ld, k_rows, dst, ld));
+      } else {
+        GK_TRY(deliver_rows(cp, d_k, d_ld, k_rows, k_cols, dst, ld, nullptr, nullptr, 0));
+      }
     } else {
       GK_CUDA(cudaMemcpy2DAsync(K_out, (size_t)ld * esz, d_out, (size_t)d_ld * esz, (size_t)k_cols * esz,
                                 (size_t)k_rows, cudaMemcpyDeviceToHost, h->stream));

@@ -114,7 +114,7 @@ struct gk_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream: independent kernels of one phase run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev_stage[2] = {};  // D2H staging buffers of deliver_widen
+  cudaEvent_t ev_stage[4] = {};  // D2H staging ring of host_deliver.h
   cudaEvent_t ev[16] = {};
   cudaEvent_t tev[8] = {};  // internal stage timers
 
@@ -184,6 +184,7 @@ struct gk_handle {
   int K_dtype = GK_F32;
   gk::DevBuf K_stage;  // fp64 staging when K is kept as f32 but fetched as f64
 
-  gk::PinBuf h_stage;  // pinned staging for CSR upload
+  gk::PinBuf h_stage;  // pinned staging ring of the result delivery
+  gk::PinBuf h_diag;   // self similarities on the host (normalisation during the widening)
   int64_t launches = 0;
 };

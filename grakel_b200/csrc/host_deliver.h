@@ -1,0 +1,450 @@
+// Host side of result delivery (included by api.cu only).
+//
+// The reference returns a fresh float64 ndarray on the host (kernel.py:167-204); for BASELINE config 2 that is
+// 800 MB, and a plain fp64 D2H copy (14-15 ms of PCIe) was 92 % of the end-to-end call.  K entries are exact
+// integers below 2^24 on the tensor-core path, so K is produced and moved as fp32 and widened on the host:
+//
+//   deliver_tri   symmetric N x N result: only the upper triangle crosses PCIe (N^2/2 fp32 = a quarter of the
+//                 fp64 bytes), in row bands of about equal area through a ring of pinned staging buffers.  For a
+//                 band [r0, r1) the staging buffer holds columns [r0, N); workers own column ranges of it, widen
+//                 their part into rows r0..r1 of the destination and write its transpose -- rows >= r1, columns
+//                 r0..r1 -- with 8 x 8 register transposes, so every destination line is written exactly once
+//                 with full-line streaming stores while the next bands are in flight.
+//   deliver_rows  any row block (transform results, row tiles of a multi-GPU job): all columns cross as fp32;
+//                 optional fp64 normalisation K_ij / sqrt(d_i d_j) (+ nan_to_num) during the widening -- the
+//                 same IEEE operations as the reference's numpy expression (kernel.py:198-203).
+//
+// Workers are a persistent pool pinned to the NUMA node of the creating thread; one dispatch per delivery
+// (workers follow the band sequence through two atomics), not one per band.
+#pragma once
+#include <atomic>
+#include <sys/mman.h>
+
+namespace {
+
+class HostPool {
+ public:
+  explicit HostPool(int n) : stop_(false), gen_(0), pending_(0) {
+    // Workers stay on the NUMA node of the thread that creates the pool (the one that also allocates
+    // and touches the pinned staging buffers): remote-socket workers made the widening slower with
+    // every added thread on the 2-socket GPU hosts.
+    std::vector<int> cpus = local_node_cpus();
+    for (int i = 0; i < n; ++i) {
+      th_.emplace_back([this, i] { run(i); });
+      if (!cpus.empty()) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        for (int c : cpus) CPU_SET(c, &set);
+        pthread_setaffinity_np(th_.back().native_handle(), sizeof(set), &set);
+      }
+    }
+  }
+  static std::vector<int> local_node_cpus() {
+    std::vector<int> out;
+    if (const char* e = getenv("GRAKEL_B200_HOST_ANY_NODE"))
+      if (atoi(e) != 0) return out;
+    const int cpu = sched_getcpu();
+    if (cpu < 0) return out;
+    for (int node = 0; node < 64; ++node) {
+      char path[128];
+      snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+      FILE* f = fopen(path, "r");
+      if (!f) break;
+      char buf[4096] = {0};
+      if (!fgets(buf, sizeof(buf), f)) { fclose(f); continue; }
+      fclose(f);
+      std::vector<int> list;  // "0-15,64-79"
+      for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; ++c) list.push_back(c); }
+        else if (sscanf(tok, "%d", &a) == 1) list.push_back(a);
+      }
+      if (std::find(list.begin(), list.end(), cpu) != list.end()) return list;
+    }
+    return out;
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return (int)th_.size(); }
+  // start fn(worker_index) on every worker; wait() returns when all are done.  One delivery at a time.
+  void start(const std::function<void(int)>& fn) {
+    call_m_.lock();  // engines on different threads share the pool
+    std::unique_lock<std::mutex> l(m_);
+    fn_ = &fn;
+    pending_ = (int)th_.size();
+    ++gen_;
+    cv_.notify_all();
+  }
+  void wait() {
+    {
+      std::unique_lock<std::mutex> l(m_);
+      done_.wait(l, [this] { return pending_ == 0; });
+    }
+    call_m_.unlock();
+  }
+  void run_all(const std::function<void(int)>& fn) { start(fn); wait(); }
+
+ private:
+  void run(int idx) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        fn = fn_;
+      }
+      (*fn)(idx);
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_, call_m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  bool stop_;
+  unsigned long long gen_;
+  int pending_;
+};
+
+HostPool& host_pool() {
+  static HostPool pool([] {
+    int n = std::min(24, (int)std::thread::hardware_concurrency() / 2);
+    if (const char* e = getenv("GRAKEL_B200_HOST_THREADS")) n = atoi(e);
+    return std::max(1, std::min(n, 128));
+  }());
+  return pool;
+}
+
+// ---- row widening: n floats -> n doubles, optional normalisation by dr * dc[j]
+__attribute__((target("avx2"))) inline void widen_row_avx2(const float* __restrict__ src, double* __restrict__ dst, long long n) {
+  long long j = 0;
+  for (; j < n && (reinterpret_cast<uintptr_t>(dst + j) & 31); ++j) dst[j] = (double)src[j];
+  for (; j + 8 <= n; j += 8) {
+    const __m256 f = _mm256_loadu_ps(src + j);
+    _mm256_stream_pd(dst + j, _mm256_cvtps_pd(_mm256_castps256_ps128(f)));
+    _mm256_stream_pd(dst + j + 4, _mm256_cvtps_pd(_mm256_extractf128_ps(f, 1)));
+  }
+  for (; j < n; ++j) dst[j] = (double)src[j];
+}
+
+inline double norm_one(double v, double dr, double dc, int nan_to_num) {
+  v = v / std::sqrt(dr * dc);
+  if (nan_to_num) {
+    if (v != v) v = 0.0;
+    else if (std::isinf(v)) v = v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+  }
+  return v;
+}
+
+__attribute__((target("avx2"))) inline void widen_row_norm_avx2(const float* __restrict__ src, double* __restrict__ dst, long long n,
+                                                                double dr, const double* __restrict__ dc, int nan_to_num) {
+  long long j = 0;
+  for (; j < n && (reinterpret_cast<uintptr_t>(dst + j) & 31); ++j) dst[j] = norm_one((double)src[j], dr, dc[j], nan_to_num);
+  const __m256d vdr = _mm256_set1_pd(dr);
+  const __m256d vmax = _mm256_set1_pd(1.7976931348623157e308);
+  for (; j + 4 <= n; j += 4) {
+    __m256d v = _mm256_cvtps_pd(_mm_loadu_ps(src + j));
+    v = _mm256_div_pd(v, _mm256_sqrt_pd(_mm256_mul_pd(vdr, _mm256_loadu_pd(dc + j))));
+    if (nan_to_num) {
+      v = _mm256_and_pd(v, _mm256_cmp_pd(v, v, _CMP_ORD_Q));  // NaN -> +0.0
+      v = _mm256_max_pd(_mm256_min_pd(v, vmax), _mm256_sub_pd(_mm256_setzero_pd(), vmax));  // +-inf -> +-DBL_MAX
+    }
+    _mm256_stream_pd(dst + j, v);
+  }
+  for (; j < n; ++j) dst[j] = norm_one((double)src[j], dr, dc[j], nan_to_num);
+}
+
+inline void widen_row(const float* __restrict__ src, double* __restrict__ dst, long long n) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) return widen_row_avx2(src, dst, n);
+  for (long long j = 0; j < n; ++j) dst[j] = (double)src[j];
+}
+inline void widen_row_norm(const float* __restrict__ src, double* __restrict__ dst, long long n, double dr, const double* dc,
+                           int nan_to_num) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) return widen_row_norm_avx2(src, dst, n, dr, dc, nan_to_num);
+  for (long long j = 0; j < n; ++j) dst[j] = norm_one((double)src[j], dr, dc[j], nan_to_num);
+}
+
+// ---- transposed widening: dst[(j0 + b) * ld + i0 + a] = src[a * pitch + b]  for a < na, b < nb
+__attribute__((target("avx2"))) inline void transpose_widen_avx2(const float* __restrict__ src, long long pitch, long long na, long long nb,
+                                                                 double* __restrict__ dst, long long ld) {
+  long long b = 0;
+  for (; b + 8 <= nb; b += 8) {
+    long long a = 0;
+    for (; a + 8 <= na; a += 8) {
+      const float* s = src + a * pitch + b;
+      __m256 r0 = _mm256_loadu_ps(s), r1 = _mm256_loadu_ps(s + pitch), r2 = _mm256_loadu_ps(s + 2 * pitch),
+             r3 = _mm256_loadu_ps(s + 3 * pitch), r4 = _mm256_loadu_ps(s + 4 * pitch), r5 = _mm256_loadu_ps(s + 5 * pitch),
+             r6 = _mm256_loadu_ps(s + 6 * pitch), r7 = _mm256_loadu_ps(s + 7 * pitch);
+      __m256 t0 = _mm256_unpacklo_ps(r0, r1), t1 = _mm256_unpackhi_ps(r0, r1), t2 = _mm256_unpacklo_ps(r2, r3),
+             t3 = _mm256_unpackhi_ps(r2, r3), t4 = _mm256_unpacklo_ps(r4, r5), t5 = _mm256_unpackhi_ps(r4, r5),
+             t6 = _mm256_unpacklo_ps(r6, r7), t7 = _mm256_unpackhi_ps(r6, r7);
+      r0 = _mm256_shuffle_ps(t0, t2, 0x44); r1 = _mm256_shuffle_ps(t0, t2, 0xEE);
+      r2 = _mm256_shuffle_ps(t1, t3, 0x44); r3 = _mm256_shuffle_ps(t1, t3, 0xEE);
+      r4 = _mm256_shuffle_ps(t4, t6, 0x44); r5 = _mm256_shuffle_ps(t4, t6, 0xEE);
+      r6 = _mm256_shuffle_ps(t5, t7, 0x44); r7 = _mm256_shuffle_ps(t5, t7, 0xEE);
+      __m256 c[8];
+      c[0] = _mm256_permute2f128_ps(r0, r4, 0x20); c[1] = _mm256_permute2f128_ps(r1, r5, 0x20);
+      c[2] = _mm256_permute2f128_ps(r2, r6, 0x20); c[3] = _mm256_permute2f128_ps(r3, r7, 0x20);
+      c[4] = _mm256_permute2f128_ps(r0, r4, 0x31); c[5] = _mm256_permute2f128_ps(r1, r5, 0x31);
+      c[6] = _mm256_permute2f128_ps(r2, r6, 0x31); c[7] = _mm256_permute2f128_ps(r3, r7, 0x31);
+      for (int k = 0; k < 8; ++k) {
+        double* d = dst + (b + k) * ld + a;
+        const __m256d lo = _mm256_cvtps_pd(_mm256_castps256_ps128(c[k])), hi = _mm256_cvtps_pd(_mm256_extractf128_ps(c[k], 1));
+        if ((reinterpret_cast<uintptr_t>(d) & 31) == 0) { _mm256_stream_pd(d, lo); _mm256_stream_pd(d + 4, hi); }
+        else { _mm256_storeu_pd(d, lo); _mm256_storeu_pd(d + 4, hi); }
+      }
+    }
+    for (; a < na; ++a)
+      for (int k = 0; k < 8; ++k) dst[(b + k) * ld + a] = (double)src[a * pitch + b + k];
+  }
+  for (; b < nb; ++b)
+    for (long long a = 0; a < na; ++a) dst[b * ld + a] = (double)src[a * pitch + b];
+}
+
+inline void transpose_widen(const float* __restrict__ src, long long pitch, long long na, long long nb, double* __restrict__ dst,
+                            long long ld) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) return transpose_widen_avx2(src, pitch, na, nb, dst, ld);
+  for (long long b = 0; b < nb; ++b)
+    for (long long a = 0; a < na; ++a) dst[b * ld + a] = (double)src[a * pitch + b];
+}
+
+constexpr int DELIVER_SLOTS = 4;
+
+// where the bands come from: the device (cudaMemcpy2DAsync + one event per staging slot) or, for the
+// host-only self test of the band / transpose logic (gk_selftest_deliver), another host matrix
+struct DeviceCopier {
+  gk_handle* h;
+  char* stage(size_t bytes) { return h->h_stage.ensure(bytes) == GK_OK ? h->h_stage.as<char>() : nullptr; }
+  bool copy(int slot, void* dst, size_t dpitch, const float* src, size_t spitch, size_t width, size_t height) {
+    if (cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return false;
+    return cudaEventRecord(h->ev_stage[slot], h->stream) == cudaSuccess;
+  }
+  bool wait(int slot) { return cudaEventSynchronize(h->ev_stage[slot]) == cudaSuccess; }
+};
+struct HostCopier {
+  std::vector<char> buf;
+  char* stage(size_t bytes) { buf.resize(bytes); return buf.data(); }
+  bool copy(int, void* dst, size_t dpitch, const float* src, size_t spitch, size_t width, size_t height) {
+    for (size_t r = 0; r < height; ++r) memcpy((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+    return true;
+  }
+  bool wait(int) { return true; }
+};
+
+}  // namespace
+
+// Row block [0, rows) x [0, cols) of an fp32 device matrix -> float64 host rows; optional normalisation with host
+// diagonals (drow[r], dcol[c]).  Bands of ~8 MB through the staging ring.
+template <class Copier>
+static int deliver_rows(Copier& cp, const float* d_src, long long d_ld, long long rows, long long cols, double* dst,
+                        long long ld, const double* drow, const double* dcol, int nan_to_num) {
+  const long long band_rows = std::max<long long>(1, std::min<long long>(rows, (8LL << 20) / std::max<long long>(cols * 4, 1)));
+  const size_t slot_bytes = ((size_t)band_rows * cols * 4 + 255) / 256 * 256;
+  char* stage = cp.stage(slot_bytes * DELIVER_SLOTS);
+  if (!stage) return GK_ERR_CUDA;
+  const long long n_bands = (rows + band_rows - 1) / band_rows;
+  HostPool& pool = host_pool();
+  const int nt = pool.size();
+  std::atomic<long long> ready(0);
+  std::vector<std::atomic<int>> done(n_bands);
+  for (auto& d : done) d.store(0);
+  auto enqueue = [&](long long c) -> int {
+    const long long r0 = c * band_rows, nr = std::min(band_rows, rows - r0);
+    if (!cp.copy((int)(c % DELIVER_SLOTS), stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes, (size_t)cols * 4, d_src + r0 * d_ld,
+                 (size_t)d_ld * 4, (size_t)cols * 4, (size_t)nr))
+      return fail(GK_ERR_CUDA, "deliver_rows: D2H copy could not be queued");
+    return GK_OK;
+  };
+  const std::function<void(int)> work = [&](int w) {
+    for (long long c = 0; c < n_bands; ++c) {
+      while (ready.load(std::memory_order_acquire) <= c) {
+        if (ready.load(std::memory_order_relaxed) < 0) return;  // aborted
+        _mm_pause();
+      }
+      const long long r0 = c * band_rows, nr = std::min(band_rows, rows - r0);
+      const float* src = reinterpret_cast<const float*>(stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes);
+      const long long a = nr * w / nt, b = nr * (w + 1) / nt;  // one contiguous run of rows per worker
+      for (long long r = a; r < b; ++r) {
+        if (drow) widen_row_norm(src + r * cols, dst + (r0 + r) * ld, cols, drow[r0 + r], dcol, nan_to_num);
+        else widen_row(src + r * cols, dst + (r0 + r) * ld, cols);
+      }
+      done[c].fetch_add(1, std::memory_order_release);
+    }
+  };
+  int rc = GK_OK;
+  for (long long c = 0; c < std::min<long long>(n_bands, DELIVER_SLOTS) && rc == GK_OK; ++c) rc = enqueue(c);
+  if (rc != GK_OK) return rc;
+  pool.start(work);
+  for (long long c = 0; c < n_bands; ++c) {
+    if (!cp.wait((int)(c % DELIVER_SLOTS))) { rc = fail(GK_ERR_CUDA, "deliver_rows: D2H copy failed"); break; }
+    ready.store(c + 1, std::memory_order_release);
+    if (c >= 1 && c - 1 + DELIVER_SLOTS < n_bands) {  // slot of band c-1 is free once every worker has left it
+      while (done[c - 1].load(std::memory_order_acquire) < nt) _mm_pause();
+      rc = enqueue(c - 1 + DELIVER_SLOTS);
+      if (rc != GK_OK) break;
+    }
+  }
+  if (rc != GK_OK) ready.store(-1, std::memory_order_release);
+  pool.wait();
+  _mm_sfence();
+  return rc;
+}
+
+// Symmetric n x n fp32 device matrix -> full float64 host matrix; only the upper triangle is copied.
+template <class Copier>
+static int deliver_tri(Copier& cp, const float* d_src, long long d_ld, long long n, double* dst, long long ld) {
+  // bands of about `area` elements: rows [r0, r1), columns [r0, n); row counts are multiples of 8
+  long long area = 2LL << 20;  // 8 MB of fp32 per band
+  if (const char* e = getenv("GRAKEL_B200_BAND_MB")) area = std::max(1, atoi(e)) * (1LL << 18);
+  std::vector<long long> start;
+  for (long long r = 0; r < n;) {
+    start.push_back(r);
+    long long nr = std::max<long long>(8, area / (n - r) / 8 * 8);
+    if (r + nr + 8 > n) nr = n - r;  // no sliver at the end
+    r += nr;
+  }
+  start.push_back(n);
+  const long long n_bands = (long long)start.size() - 1;
+  size_t slot_bytes = 0;
+  for (long long c = 0; c < n_bands; ++c)
+    slot_bytes = std::max(slot_bytes, (size_t)(start[c + 1] - start[c]) * (size_t)(n - start[c]) * 4);
+  slot_bytes = (slot_bytes + 255) / 256 * 256;
+  char* stage = cp.stage(slot_bytes * DELIVER_SLOTS);
+  if (!stage) return GK_ERR_CUDA;
+  HostPool& pool = host_pool();
+  const int nt = pool.size();
+  std::atomic<long long> ready(0);
+  std::vector<std::atomic<int>> done(n_bands);
+  for (auto& d : done) d.store(0);
+  auto enqueue = [&](long long c) -> int {
+    const long long r0 = start[c], nr = start[c + 1] - r0, w = n - r0;
+    if (!cp.copy((int)(c % DELIVER_SLOTS), stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes, (size_t)w * 4, d_src + r0 * d_ld + r0,
+                 (size_t)d_ld * 4, (size_t)w * 4, (size_t)nr))
+      return fail(GK_ERR_CUDA, "deliver_tri: D2H copy could not be queued");
+    return GK_OK;
+  };
+  const std::function<void(int)> work = [&](int wk) {
+    for (long long c = 0; c < n_bands; ++c) {
+      while (ready.load(std::memory_order_acquire) <= c) {
+        if (ready.load(std::memory_order_relaxed) < 0) return;
+        _mm_pause();
+      }
+      const long long r0 = start[c], r1 = start[c + 1], nr = r1 - r0, w = n - r0;
+      const float* src = reinterpret_cast<const float*>(stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes);
+      // this worker's columns of the band (relative to r0), in units of 16 so that ranges start on 128-byte lines
+      const long long units = (w + 15) / 16;
+      const long long ca = std::min(w, units * wk / nt * 16), cb = std::min(w, units * (wk + 1) / nt * 16);
+      if (cb > ca) {
+        for (long long r = 0; r < nr; ++r) widen_row(src + r * w + ca, dst + (r0 + r) * ld + r0 + ca, cb - ca);
+        // mirrored part: band columns >= nr are rows r1.. of the destination, columns r0..r1
+        const long long ma = std::max(ca, nr);
+        if (cb > ma) {
+          // 64-column pieces keep the 8 x 8 blocks' source lines in L1 between the passes over the band's rows
+          for (long long j = ma; j < cb; j += 64) {
+            const long long nb = std::min<long long>(64, cb - j);
+            transpose_widen(src + j, w, nr, nb, dst + (r0 + j) * ld + r0, ld);
+          }
+        }
+      }
+      done[c].fetch_add(1, std::memory_order_release);
+    }
+  };
+  int rc = GK_OK;
+  for (long long c = 0; c < std::min<long long>(n_bands, DELIVER_SLOTS) && rc == GK_OK; ++c) rc = enqueue(c);
+  if (rc != GK_OK) return rc;
+  pool.start(work);
+  for (long long c = 0; c < n_bands; ++c) {
+    if (!cp.wait((int)(c % DELIVER_SLOTS))) { rc = fail(GK_ERR_CUDA, "deliver_tri: D2H copy failed"); break; }
+    ready.store(c + 1, std::memory_order_release);
+    if (c >= 1 && c - 1 + DELIVER_SLOTS < n_bands) {
+      while (done[c - 1].load(std::memory_order_acquire) < nt) _mm_pause();
+      rc = enqueue(c - 1 + DELIVER_SLOTS);
+      if (rc != GK_OK) break;
+    }
+  }
+  if (rc != GK_OK) ready.store(-1, std::memory_order_release);
+  pool.wait();
+  _mm_sfence();
+  return rc;
+}
+
+// ---- result buffers for float64 matrices: anonymous mappings with transparent huge pages requested, recycled
+// through a small pool so that a loop of fit_transform calls does not fault 800 MB of fresh pages in every time
+namespace {
+struct HostBlock { void* p; size_t bytes; };
+std::mutex g_hostpool_m;
+std::vector<HostBlock> g_hostpool;
+size_t g_hostpool_bytes = 0;
+size_t hostpool_limit() {
+  static const size_t lim = [] {
+    size_t mb = 2048;
+    if (const char* e = getenv("GRAKEL_B200_HOST_POOL_MB")) mb = (size_t)std::max(0, atoi(e));
+    return mb << 20;
+  }();
+  return lim;
+}
+}  // namespace
+
+extern "C" {
+
+// Host-only self test of the delivery code (no GPU): `src` is an n x n fp32 matrix on the host (symmetric for
+// mode 0).  mode 0: deliver_tri; mode 1: deliver_rows; mode 2: deliver_rows with normalisation by diag.
+int gk_selftest_deliver(int32_t mode, int64_t rows, int64_t cols, const float* src, const double* diag, int32_t nan_to_num,
+                        double* dst) {
+  if (!src || !dst || rows <= 0 || cols <= 0) return fail(GK_ERR_ARG, "gk_selftest_deliver: bad arguments");
+  HostCopier cp;
+  if (mode == 0) {
+    if (rows != cols) return fail(GK_ERR_ARG, "gk_selftest_deliver: mode 0 needs a square matrix");
+    return deliver_tri(cp, src, cols, rows, dst, cols);
+  }
+  return deliver_rows(cp, src, cols, rows, cols, dst, cols, mode == 2 ? diag : nullptr, mode == 2 ? diag : nullptr, nan_to_num);
+}
+
+int gk_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes <= 0) return fail(GK_ERR_ARG, "gk_host_alloc: bad arguments");
+  const size_t want = ((size_t)bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  {
+    std::lock_guard<std::mutex> l(g_hostpool_m);
+    for (size_t i = 0; i < g_hostpool.size(); ++i)
+      if (g_hostpool[i].bytes == want) {
+        *out = g_hostpool[i].p;
+        g_hostpool_bytes -= want;
+        g_hostpool.erase(g_hostpool.begin() + i);
+        return GK_OK;
+      }
+  }
+  void* p = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) return fail(GK_ERR_CUDA, "gk_host_alloc: mmap failed");
+  madvise(p, want, MADV_HUGEPAGE);  // best effort
+  *out = p;
+  return GK_OK;
+}
+
+int gk_host_free(void* p, int64_t bytes) {
+  if (!p || bytes <= 0) return GK_OK;
+  const size_t want = ((size_t)bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  {
+    std::lock_guard<std::mutex> l(g_hostpool_m);
+    if (g_hostpool_bytes + want <= hostpool_limit()) {
+      g_hostpool.push_back({p, want});
+      g_hostpool_bytes += want;
+      return GK_OK;
+    }
+  }
+  munmap(p, want);
+  return GK_OK;
+}
+
+}  // extern "C"

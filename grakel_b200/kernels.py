@@ -71,8 +71,9 @@ class Kernel(BaseEstimator, TransformerMixin):
         if X is None:
             raise ValueError("`transform` input cannot be None")
         Y = self.parse_input(X)
-        K, _, ydiag = self._run(Block.concat(self.X.block, Y.block), np.concatenate([self.X.ids, Y.ids]),
-                                n_fit=self.X.block.n_graphs)
+        K, xdiag, ydiag = self._run(Block.concat(self.X.block, Y.block), np.concatenate([self.X.ids, Y.ids]),
+                                    n_fit=self.X.block.n_graphs)
+        self._X_diag = xdiag  # kernel.py:160-164 computes it on demand; the joint run returns it anyway
         self._Y_diag = ydiag
         self._is_transformed = True
         if self.normalize:
@@ -144,8 +145,7 @@ class Kernel(BaseEstimator, TransformerMixin):
 
     def _run(self, block, ids, n_fit, want_matrix=True):
         """pack -> feature kernels -> Gram, all on the device.  Returns (K, xdiag, ydiag)."""
-        eng = _lib.get_engine()
-        with eng._lock:
+        with _lib.engine(getattr(self, "device_", None)) as eng:
             eng.pack(block.graph_ptr, block.row_ptr, block.col_idx, ids, block.weights, block.attrs)
             self.stats_ = self._device_features(eng)
             K, xd, yd = eng.gram(block.n_graphs, n_fit=n_fit, normalize=bool(self.normalize) and want_matrix,

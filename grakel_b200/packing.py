@@ -18,6 +18,7 @@ vertex ids), one Python label object per vertex, optional fp64 edge weights.
 from __future__ import annotations
 
 import numbers
+import os
 import warnings
 from collections.abc import Iterable
 from itertools import chain
@@ -195,6 +196,14 @@ def iter_elements(X, len_ok, type_error_msg=None):
         yield idx, x[0], (x[1] if len(x) > 1 else None)
 
 
+def _pack_threads():
+    """Worker threads of the CPython-level packer (GRAKEL_B200_PACK_THREADS; default: half the cores, at most 16)."""
+    e = os.environ.get("GRAKEL_B200_PACK_THREADS")
+    if e:
+        return max(1, int(e))
+    return max(1, min(16, (os.cpu_count() or 2) // 2))
+
+
 def _adjacency_array(g):
     if issparse(g):
         A = np.asarray(g.todense())
@@ -272,14 +281,17 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
     """
     if (_fastpack is not None and type(X) is list and X and not attributes and not fw_zero_is_absent
             and all(type(x) in (list, tuple) and len(x) >= 2 and len_ok(len(x)) for x in X)):
-        # whole-input fast path: {(u, v): w} graphs with integer symbols, walked with the CPython API; it declines
-        # (None) on anything unusual and the general loop below decides -- and raises -- as before
-        res = _fastpack.pack_edge_dicts(X, 0 if mode == "wl" else 1, 1 if need_labels else 0)
+        # whole-input fast path: {(u, v): w} graphs with integer symbols, walked with the CPython API on several
+        # threads; it declines (None) on anything unusual and the general loop below decides -- and raises -- as before
+        res = _fastpack.pack_edge_dicts(X, 0 if mode == "wl" else 1, 1 if need_labels else 0, 1 if want_weights else 0,
+                                        _pack_threads())
         if res is not None:
             gp, rp, ci, ww, labs, any_w = res
-            out = Block(np.frombuffer(gp, dtype=np.int32).copy(), np.frombuffer(rp, dtype=np.int32).copy(),
-                        np.frombuffer(ci, dtype=np.int32).copy(),
-                        np.frombuffer(ww, dtype=np.float64).copy() if (want_weights and any_w) else None,
+            if isinstance(labs, bytearray):  # every label is an exact int: int64 values, ids are assigned vectorised
+                labs = np.frombuffer(labs, dtype=np.int64)
+            out = Block(np.frombuffer(gp, dtype=np.int32), np.frombuffer(rp, dtype=np.int32),
+                        np.frombuffer(ci, dtype=np.int32),
+                        np.frombuffer(ww, dtype=np.float64) if (want_weights and any_w and ww is not None) else None,
                         labs if need_labels else None, None, False)
             out.mode = mode
             return out
@@ -433,16 +445,37 @@ def label_ids(labels, known=None, sort_new=True):
     order when `sort_new` is False (ShortestPath only uses labels as dict keys).
     Returns (int32 ids, dictionary of the labels that were new)."""
     known = {} if known is None else known
-    if isinstance(labels, np.ndarray) and labels.dtype.kind in "iu":  # packed blocks (datasets.read_tu): vectorised
-        uniq, first, inv = np.unique(labels, return_index=True, return_inverse=True)
-        order = np.arange(len(uniq)) if sort_new else np.argsort(first, kind="stable")
+    if isinstance(labels, np.ndarray) and labels.dtype.kind in "iu":  # integer labels (fast packer, datasets.read_tu)
+        lo, hi = (int(labels.min()), int(labels.max())) if len(labels) else (0, 0)
+        if len(labels) and hi - lo < (1 << 22):  # small value range: presence table instead of a sort
+            present = np.zeros(hi - lo + 1, dtype=bool)
+            rel = labels - lo
+            present[rel] = True
+            uniq = np.flatnonzero(present) + lo
+            lut = np.zeros(hi - lo + 1, dtype=np.int32)
+            lut[uniq - lo] = np.arange(len(uniq), dtype=np.int32)
+            inv = lut[rel]
+            first = None
+        else:
+            uniq, first, inv = np.unique(labels, return_index=True, return_inverse=True)
+        if not sort_new:
+            if first is None:  # first occurrence of every distinct value
+                first = np.full(len(uniq), len(labels), dtype=np.int64)
+                np.minimum.at(first, inv, np.arange(len(labels)))
+            order = np.argsort(first, kind="stable")
+        else:
+            order = np.arange(len(uniq))
         fresh, ids_of = {}, np.empty(len(uniq), dtype=np.int32)
-        for j in order.tolist():
-            l = int(uniq[j])
-            if l in known:
-                ids_of[j] = known[l]
-            else:
-                ids_of[j] = fresh[l] = len(known) + len(fresh)
+        if not known:
+            ids_of[order] = np.arange(len(uniq), dtype=np.int32)
+            fresh = dict(zip(uniq[order].tolist(), range(len(uniq))))
+        else:
+            for j in order.tolist():
+                l = int(uniq[j])
+                if l in known:
+                    ids_of[j] = known[l]
+                else:
+                    ids_of[j] = fresh[l] = len(known) + len(fresh)
         return ids_of[inv].astype(np.int32, copy=False), fresh
     fresh = {}
     seen = set()

@@ -218,6 +218,20 @@ int gk_profiler_range(int32_t on);
 int gk_selftest_gram(gk_handle* h, int64_t n, int64_t d, const uint16_t* counts, double* out_tc,
                      double* out_simt);
 
+/* ---- float64 result buffers on the host (the reference returns a fresh float64 ndarray, kernel.py:167-204).
+ * gk_host_alloc maps `bytes` of anonymous memory with transparent huge pages requested; gk_host_free returns
+ * the block to a small per-process pool (GRAKEL_B200_HOST_POOL_MB, default 2048; 0 = unmap at once), so a loop
+ * of fit_transform calls re-uses already-faulted pages.  The Python layer wraps the block in an ndarray whose
+ * finaliser calls gk_host_free.  Any host pointer is accepted as K_out of gk_gram; these are just the fast ones. */
+int gk_host_alloc(int64_t bytes, void** out);
+int gk_host_free(void* p, int64_t bytes);
+
+/* Host-only self test of the result delivery (tests only; no device needed): src[rows*cols] fp32 on the host
+ * -> dst[rows*cols] fp64 through the same band / widen / mirror code gk_gram uses after its D2H copies.
+ * mode 0: symmetric square, upper triangle only; 1: all rows; 2: all rows, normalised by diag (+ nan_to_num). */
+int gk_selftest_deliver(int32_t mode, int64_t rows, int64_t cols, const float* src, const double* diag,
+                        int32_t nan_to_num, double* dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,10 +194,15 @@ def test_no_gpu_means_loud_failure():
 
 
 # ------------------------------------------------------------------ vectorised packer fast path
+def _lab_list(blk):
+    """labels as a list of Python objects (the C packer returns an int64 array when every label is an exact int)"""
+    return [] if blk.labels is None else [int(x) if isinstance(x, np.integer) else x for x in list(blk.labels)]
+
+
 def _blocks_equal(a, b, same_order=True):
     if same_order:
         return (np.array_equal(a.graph_ptr, b.graph_ptr) and np.array_equal(a.row_ptr, b.row_ptr)
-                and np.array_equal(a.col_idx, b.col_idx) and list(a.labels or []) == list(b.labels or [])
+                and np.array_equal(a.col_idx, b.col_idx) and _lab_list(a) == _lab_list(b)
                 and ((a.weights is None) == (b.weights is None))
                 and (a.weights is None or np.array_equal(a.weights, b.weights)))
     # vertex order inside a graph may differ: compare the labelled edge multisets per graph
@@ -207,10 +212,149 @@ def _blocks_equal(a, b, same_order=True):
         blk._canon = []
         for g in range(blk.n_graphs):
             v0, v1 = blk.graph_ptr[g], blk.graph_ptr[g + 1]
-            es = sorted((blk.labels[v], blk.labels[blk.col_idx[k]]) for v in range(v0, v1)
+            lab = _lab_list(blk)
+            es = sorted((lab[v], lab[blk.col_idx[k]]) for v in range(v0, v1)
                         for k in range(blk.row_ptr[v], blk.row_ptr[v + 1]))
-            blk._canon.append((sorted(blk.labels[v0:v1]), es))
+            blk._canon.append((sorted(lab[v0:v1]), es))
     return a._canon == b._canon
+
+
+class _BlockrefEngine:
+    """numpy stand-in for the device engine (tests/blockref.py) behind the estimators' _run"""
+
+    def __init__(self):
+        self._lock = __import__("threading").RLock()
+
+    def pack(self, gp, rp, ci, ids, weights, attrs):
+        from grakel_b200.packing import Block
+        self.block, self.ids = Block(gp, rp, ci, weights, None, attrs), ids
+
+    def wl_features(self, n_iter):
+        self.h = n_iter
+        from grakel_b200._lib import GkStats
+        return GkStats()
+
+    def gram(self, n_graphs, n_fit=None, normalize=False, nan_to_num=False, out=None, stats=None, **kw):
+        K, xd, yd = blockref.wl_gram_block(self.block, self.ids, self.h, n_fit=n_fit, normalize=normalize)
+        return (None if out is False else K), xd, (yd if n_fit != n_graphs else None)
+
+
+@pytest.mark.parametrize("kind", ["VH", "EH"])
+def test_histogram_kernels_fit_then_normalized_transform(kind, monkeypatch):
+    """kernel.py:160-164: `fit(X); transform(Y)` with normalize=True needs X's diagonal although fit_transform
+    never ran -- the joint X||Y run returns it (AttributeError on _X_diag before)."""
+    from contextlib import contextmanager
+    from grakel_b200 import EdgeHistogram, VertexHistogram, _lib
+    from oracle.gk_oracle import gen
+    eng = _BlockrefEngine()
+
+    @contextmanager
+    def fake_engine(device=None):
+        yield eng
+    monkeypatch.setattr(_lib, "engine", fake_engine)
+    X, Y = gen(12, 10, 1), gen(5, 10, 2)
+    if kind == "EH":
+        add = lambda Z: [[g, L, {e: (L[e[0]] + L[e[1]]) % 3 for e in g}] for g, L in Z]
+        X, Y = add(X), add(Y)
+        est = EdgeHistogram(normalize=True)
+    else:
+        est = VertexHistogram(normalize=True)
+    K = est.fit(X).transform(Y)
+    assert K.shape == (5, 12) and np.all(np.isfinite(K)) and K.max() <= 1.0 + 1e-12
+    xd, yd = est.diagonal()
+    assert len(xd) == 12 and len(yd) == 5
+    Kfull = type(est)(normalize=True).fit_transform(X + Y)
+    assert np.allclose(Kfull[12:, :12], K)
+
+
+def test_c_packer_threads_labels_and_hubs():
+    """csrc/fastpack.c: any thread count builds the same block; non-int labels come back as the label objects;
+    a hub vertex with unsorted neighbours gets a sorted row (two counting sorts, no quadratic insertion sort)."""
+    from grakel_b200 import packing
+    from oracle.gk_oracle import gen
+    cmod = packing._fastpack
+    assert cmod is not None
+    X = gen(400, 30, 11)
+    for mode_i in (0, 1):
+        ref = cmod.pack_edge_dicts(X, mode_i, 1, 1, 1)
+        for nt in (2, 3, 8, 64):
+            out = cmod.pack_edge_dicts(X, mode_i, 1, 1, nt)
+            assert all(bytes(a) == bytes(b) for a, b in zip(ref[:3], out[:3])) and bytes(ref[4]) == bytes(out[4])
+        assert isinstance(ref[4], bytearray) and ref[3] is None and ref[5] == 0
+    # string labels on some vertices: label objects, in vertex order, identical to the general path
+    Xs = [[g, {v: ("c%d" % l if v % 3 == 0 else l) for v, l in L.items()}] for g, L in X]
+    for mode in ("wl", "sp"):
+        fast = packing.pack(Xs, mode, len_ok=lambda n: n >= 2)
+        assert isinstance(fast.labels, list)
+        saved, packing._fastpack = packing._fastpack, None
+        try:
+            slow = packing.pack(Xs, mode, len_ok=lambda n: n >= 2)
+        finally:
+            packing._fastpack = saved
+        assert _blocks_equal(fast, slow)
+    # a star with 5 000 leaves listed in descending order, weights carried along
+    n = 5000
+    g = {}
+    for v in range(n, 0, -1):
+        g[(0, v)] = float(v)
+        g[(v, 0)] = 1.0
+    hub = [[g, {v: v % 5 for v in range(n + 1)}]] * 3
+    blk = packing.pack(hub, "wl", len_ok=lambda n: n >= 2, want_weights=True)
+    for k in range(3):
+        v0 = k * (n + 1)
+        row = blk.col_idx[blk.row_ptr[v0]:blk.row_ptr[v0 + 1]] - v0
+        assert np.array_equal(row, np.arange(1, n + 1))
+        assert np.array_equal(blk.weights[blk.row_ptr[v0]:blk.row_ptr[v0 + 1]], np.arange(1, n + 1, dtype=float))
+
+
+def test_label_ids_integer_arrays_match_the_object_path():
+    from grakel_b200.packing import label_ids
+    rs = np.random.RandomState(4)
+    for labels in (rs.randint(-5, 40, size=3000), rs.randint(0, 2 ** 40, size=500), np.array([7], dtype=np.int64)):
+        for sort_new in (True, False):
+            ids_a, new_a = label_ids(labels.astype(np.int64), None, sort_new)
+            ids_o, new_o = label_ids([int(x) for x in labels], None, sort_new)
+            assert np.array_equal(ids_a, ids_o) and new_a == new_o and list(new_a) == list(new_o)
+            known = {int(x): i for i, x in enumerate(sorted(set(labels.tolist()))[::2])}
+            ids_a, new_a = label_ids(labels.astype(np.int64), known, sort_new)
+            ids_o, new_o = label_ids([int(x) for x in labels], known, sort_new)
+            assert np.array_equal(ids_a, ids_o) and new_a == new_o
+
+
+def test_host_delivery_bands_widen_and_mirror():
+    """host_deliver.h without a device: fp32 -> float64 through the band / widen / 8x8-transpose-mirror code of
+    gk_gram's result delivery, for sizes around every blocking boundary, plus the fp64 normalisation."""
+    from grakel_b200 import _lib
+    lib = _lib.load_library()
+
+    class Host:  # selftest_deliver needs no handle
+        pass
+    e = Host()
+    e.lib = lib
+    e._check = lambda rc: (_ for _ in ()).throw(RuntimeError(lib.gk_last_error().decode())) if rc else None
+    deliver = lambda *a, **k: _lib.Engine.selftest_deliver(e, *a, **k)
+    rs = np.random.RandomState(0)
+    for n in (1, 7, 8, 9, 33, 100, 257, 1000, 2049):
+        A = rs.randint(0, 1 << 24, size=(n, n)).astype(np.float32)
+        A = np.triu(A) + np.triu(A, 1).T
+        assert np.array_equal(deliver(A, 0), A.astype(np.float64)), n
+        assert np.array_equal(deliver(A, 1), A.astype(np.float64)), n
+        d = rs.randint(0, 50, size=n).astype(np.float64)
+        with np.errstate(all="ignore"):
+            ref = A.astype(np.float64) / np.sqrt(np.outer(d, d))  # kernel.py:198-203
+        assert np.array_equal(deliver(A, 2, diag=d), ref, equal_nan=True), n
+        assert np.array_equal(deliver(A, 2, diag=d, nan_to_num=True), np.nan_to_num(ref)), n
+    R = rs.rand(300, 777).astype(np.float32)
+    assert np.array_equal(deliver(R, 1), R.astype(np.float64))
+    # pooled result buffers: fresh, writable, C-order; a freed block is handed out again
+    import gc
+    K = _lib.host_matrix(2000, 2000)
+    assert K.flags.c_contiguous and K.flags.writeable and K.dtype == np.float64 and K.shape == (2000, 2000)
+    K[:] = 1.0
+    addr = K.ctypes.data
+    del K
+    gc.collect()
+    assert _lib.host_matrix(2000, 2000).ctypes.data == addr
 
 
 @pytest.mark.parametrize("mode", ["wl", "sp", "wloa"])
