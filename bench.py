@@ -10,12 +10,18 @@ exact sparse tail, diagonal / output.
   value      pairs/s with the packed CSR already resident in HBM and K left in HBM
              (CUDA events on the engine's stream, max over ranks)
   e2e        pairs/s through the C-ABI one-call entry point gk_wl_fit_transform with
-             PINNED HOST buffers: CSR H2D and the fp64 K D2H inside the timed region
+             PINNED HOST buffers: CSR H2D and the float64 K on the host inside the timed region
+             (K crosses PCIe as the fp32 upper triangle and is widened + mirrored by host threads)
+  e2e_api    SURVEY 8(d)'s T_e2e: WeisfeilerLehman(n_iter=5).fit_transform(python list of graphs) ->
+             fresh float64 ndarray, time.perf_counter around the call (packing, H2D, device, delivery)
   roofline   the tcgen05 Gram GEMM (CTA-pair kernel): algorithmic flops N(N+1)*D_c (upper-triangular
-             tiles) / CUDA-event duration vs the measured bf16 peak
+             tiles) / CUDA-event duration vs the measured bf16 BURST peak (a 0.2 ms launch
+             inside a step that is mostly not tensor work)
   cpu_baseline / --impl reference
-             the CPU oracle port (oracle/gk_oracle.py, pinned to the real reference's
-             goldens) on a bounded prefix of the same graphs on the box's host cores
+             the UNMODIFIED reference (ysig/GraKeL installed in baseline/_ref by baseline/build_ref.sh):
+             grakel.WeisfeilerLehman(n_iter=5).fit_transform on a bounded prefix of the same graphs on
+             the box's host cores, with n_jobs=None (library default) and n_jobs=cpu_count (its best
+             setting); the oracle port stands in only if baseline/_ref is missing ("kind": "port")
 
 N > 1 (torchrun): weak scaling -- the graph count grows as 10 000 * sqrt(N) so every rank owns
 the same number of K entries; every rank relabels the (replicated, tiny) CSR block and
@@ -36,8 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_GRAPHS, NBAR, H, SEED = 10000, 40, 5, 0
-CPU_SAMPLE = 6000  # graphs in the bounded CPU sample (~10 s of CPU work per step on the box's host)
-CPU_THREADS = H + 1  # the reference parallelises over WL levels (joblib threading, weisfeiler_lehman.py:279-285)
+CPU_SAMPLE = 3000  # largest prefix the bounded CPU sample may use
 
 
 # the Gram GEMM gk_gram launches for fp32 output (grakel_b200/csrc/api.cu): CTA pairs unless switched off
@@ -119,8 +124,9 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1419.5), d.get("hbm_gbs", 6582.5), "measured (MEASURED_PEAKS.json, sustained bf16)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return d.get("bf16_tflops", 1683.9), d.get("hbm_gbs", 6582.5), \
+            "measured (MEASURED_PEAKS.json, BURST bf16: the GEMM is a 0.2 ms launch inside a mostly non-tensor step)"
+    return 1683.9, 6582.5, "fallback (B200_PROFILING.md)"
 
 
 def measured_traffic(key):
@@ -136,51 +142,118 @@ def measured_traffic(key):
     return None
 
 
-def cpu_threads():
-    return max(1, min(CPU_THREADS, os.cpu_count() or 1))
+def gen_list(n_graphs, nbar=NBAR, seed=SEED):
+    """The seeded generator of SURVEY 8(d) in its Python-list form (what the reference API takes):
+    [{(u, v): 1, (v, u): 1, ...}, {vertex: label}] per graph."""
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n_graphs):
+        n = int(rs.randint(nbar // 2, nbar + nbar // 2 + 1))
+        p = 4.0 / (n - 1)
+        iu = np.triu_indices(n, 1)
+        m = rs.rand(len(iu[0])) < p
+        g = {}
+        for a, b in zip(iu[0][m].tolist(), iu[1][m].tolist()):
+            g[(a, b)] = 1
+            g[(b, a)] = 1
+        out.append([g, {i: int(rs.randint(7)) for i in range(n)}])
+    return out
 
 
-def cpu_arm(steps=1, budget_s=12.0, n_max=CPU_SAMPLE):
-    """The CPU oracle port on a prefix of the workload, one thread per WL level like the
-    reference's best configuration (n_jobs).  The prefix length is chosen from a timed
-    1 500-graph probe (cost ~ n^2) so that `steps` steps take about `budget_s` seconds in
-    total, capped at `n_max` graphs.  Returns (pairs/s, seconds/step, n_sample)."""
-    from oracle.gk_oracle import WLOracle, gen
-    X = gen(n_max, NBAR, SEED)
-    nj = cpu_threads()
-    probe = min(1500, n_max)
-    t = time.perf_counter()
-    WLOracle(n_iter=H, n_jobs=nj).fit_transform(X[:probe])  # also the warm-up
-    t_probe = time.perf_counter() - t
-    n_sample = int(min(n_max, max(probe, probe * np.sqrt(budget_s / max(steps, 1) / t_probe))))
+def host_info():
+    info = {"logical_cores": os.cpu_count()}
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                info["cpu_model"] = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_info
+        info["threadpools"] = [{k: t.get(k) for k in ("user_api", "internal_api", "num_threads")} for t in threadpool_info()]
+    except Exception:
+        pass
+    return info
+
+
+def reference_estimator():
+    """(factory(n_jobs) -> estimator, kind): the real GraKeL from baseline/_ref, else the oracle port."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref, "grakel")):
+        sys.path.insert(0, ref)
+        try:
+            from grakel.kernels import WeisfeilerLehman as RefWL
+            return (lambda nj: RefWL(n_iter=H, n_jobs=nj)), "reference"
+        except Exception as e:  # pragma: no cover
+            print("baseline/_ref import failed (%r): falling back to the oracle port" % (e,), file=sys.stderr)
+            sys.path.remove(ref)
+    from oracle.gk_oracle import WLOracle
+    return (lambda nj: WLOracle(n_iter=H, n_jobs=nj)), "port"
+
+
+def cpu_arm(steps=1, warmup=0, budget_s=12.0, n_max=CPU_SAMPLE):
+    """The reference's CPU fit_transform on a prefix of the workload.  A timed probe (600 graphs, both n_jobs
+    settings) picks the faster setting and the prefix length (cost ~ n^2) so that warmup + steps runs take about
+    `budget_s` seconds, capped at `n_max` graphs.  Returns a dict with pairs/s of the chosen setting, of
+    n_jobs=None on the same prefix, seconds/step, the prefix length and the kind of implementation."""
+    make, kind = reference_estimator()
+    X = gen_list(n_max)
+    ncpu = os.cpu_count() or 1
+    probe = min(600, n_max)
+    tp = {}
+    for nj in (None, ncpu):
+        make(nj).fit_transform(X[:200])  # warm-up (imports, thread pool)
+        t = time.perf_counter()
+        make(nj).fit_transform(X[:probe])
+        tp[nj] = time.perf_counter() - t
+    best = min(tp, key=tp.get)
+    n_sample = int(min(n_max, max(probe, probe * np.sqrt(budget_s / max(steps + warmup, 1) / tp[best]))))
     n_sample -= n_sample % 100
-    X = X[:n_sample]
+    Xs = X[:n_sample]
+    for _ in range(warmup):
+        make(best).fit_transform(Xs)
     ts = []
     for _ in range(steps):
         t = time.perf_counter()
-        K = WLOracle(n_iter=H, n_jobs=nj).fit_transform(X)
+        K = make(best).fit_transform(Xs)
         ts.append(time.perf_counter() - t)
         assert K.shape == (n_sample, n_sample)
         del K
-    t = float(np.mean(ts))
-    return n_sample * n_sample / t, t, n_sample
+    t_best = float(np.mean(ts))
+    t = time.perf_counter()
+    make(ncpu if best is None else None).fit_transform(Xs)  # the other setting, once, on the same prefix
+    t_other = time.perf_counter() - t
+    t_default, t_all = (t_best, t_other) if best is None else (t_other, t_best)
+    return {"value": n_sample * n_sample / t_best, "seconds_per_step": t_best, "n_sample": n_sample, "kind": kind,
+            "n_jobs": "None" if best is None else ncpu,
+            "pairs_per_s_n_jobs_None": n_sample * n_sample / t_default,
+            "pairs_per_s_n_jobs_all": n_sample * n_sample / t_all,
+            "threads_useful": 1 if best is None else min(ncpu, H + 1)}
+
+
+def cpu_baseline_obj(r, n_total):
+    return {"value": r["value"], "unit": "pairs/s", "cores": r["threads_useful"], "kind": r["kind"],
+            "sample": f"first {r['n_sample']} of the {n_total} graphs ({r['n_sample'] ** 2} ordered pairs per step), "
+                      f"{r['seconds_per_step']:.2f} s per fit_transform with n_jobs={r['n_jobs']} (joblib threads over the "
+                      f"{H + 1} WL levels, weisfeiler_lehman.py:279-285)",
+            "n_jobs_None_pairs_per_s": r["pairs_per_s_n_jobs_None"], "n_jobs_all_pairs_per_s": r["pairs_per_s_n_jobs_all"],
+            "host": host_info()}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    val, t, n = cpu_arm(steps=args.steps, budget_s=100.0)
-    cores = cpu_threads()
+    r = cpu_arm(steps=args.steps, warmup=args.warmup, budget_s=110.0, n_max=4000)
+    val, t, n = r["value"], r["seconds_per_step"], r["n_sample"]
     line = {
         "impl": "reference", "metric": "graph-pairs/sec, N x N WL-subtree (h=5) Gram", "value": val,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"config2: {N_GRAPHS} ER graphs (avg {NBAR} nodes, 7 labels, seed {SEED}), WL-subtree h={H}",
-                   "parallelism": f"host CPU, {cores} threads (one per WL level, the reference's n_jobs threading)"},
-        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"first {n} of the {N_GRAPHS} graphs ({n * n} ordered pairs per step); "
-                                   f"host has {os.cpu_count()} logical cores"},
+                   "parallelism": f"host CPU, grakel.WeisfeilerLehman(n_iter={H}, n_jobs={r['n_jobs']}).fit_transform"},
+        "cpu_baseline": cpu_baseline_obj(r, N_GRAPHS),
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -293,7 +366,9 @@ def main():
         e2e = {"value": n * n / float(e2e_t.item()), "unit": "pairs/s",
                "h2d_bytes_per_step": int(gp.nbytes + rp.nbytes + ci.nbytes + lab.nbytes),
                "d2h_bytes_per_step": int(kr * n * 8), "ms_per_step": float(e2e_t.item()) * 1e3,
-               "api": "gk_wl_fit_transform (C-ABI), pinned host CSR in, pinned fp64 K out",
+               "api": "gk_wl_fit_transform (C-ABI), pinned host CSR in, pinned float64 K out (fp32 upper triangle over "
+                      "PCIe, widened + mirrored by host threads)",
+               "pcie_d2h_bytes_per_step": int(n * (n + 1) // 2 * 4) if world == 1 else int(kr * n * 4),
                "last_step_ms": {"h2d+pack": es.ms_h2d, "features": es.ms_features, "columns+panel": es.ms_panel,
                                 "gemm": es.ms_gemm, "tail": es.ms_tail, "d2h": es.ms_d2h}}
         # host-side breakdown of one e2e step (wall clock, separate C calls)
@@ -305,6 +380,38 @@ def main():
         e2e["host_wall_ms"] = tb
         if rank == 0 and world == 1 and n == N_GRAPHS:
             assert float(Kh.sum()) == 22925628586.0, "K checksum differs from the reference golden"
+
+    # ------------------------------------------------ end to end through the Python API (SURVEY 8d T_e2e)
+    e2e_api = None
+    if not args.no_e2e and world == 1 and rank == 0:
+        from grakel_b200 import WeisfeilerLehman
+        _lib.set_default_device(local)
+        t0 = time.perf_counter()
+        X = gen_list(n)
+        t_gen = time.perf_counter() - t0
+        ts = []
+        for i in range(2 + args.steps):
+            t0 = time.perf_counter()
+            est = WeisfeilerLehman(n_iter=H)
+            Ka = est.fit_transform(X)
+            ts.append(time.perf_counter() - t0)
+            if i == 0:
+                assert Ka.dtype == np.float64 and Ka.shape == (n, n) and Ka.flags.c_contiguous
+                if n == N_GRAPHS:
+                    assert float(Ka.sum()) == 22925628586.0, "K checksum (Python API) differs from the reference golden"
+            del Ka
+        # host-side split of one more call
+        from grakel_b200 import packing
+        t0 = time.perf_counter(); blk = packing.pack(X, "wl", len_ok=lambda k: k >= 2); t_pack = time.perf_counter() - t0
+        t0 = time.perf_counter(); packing.label_ids(blk.labels, None, True); t_ids = time.perf_counter() - t0
+        t_api = float(np.mean(ts[2:]))
+        e2e_api = {"value": n * n / t_api, "unit": "pairs/s", "ms_per_step": t_api * 1e3,
+                   "api": f"grakel_b200.WeisfeilerLehman(n_iter={H}).fit_transform(list of [edge dict, label dict]) -> fresh float64 ndarray",
+                   "first_call_ms": ts[0] * 1e3, "min_ms": float(np.min(ts[2:])) * 1e3,
+                   "host_ms": {"pack(list -> CSR)": t_pack * 1e3, "label_ids": t_ids * 1e3},
+                   "result_buffer": "pooled huge-page host mapping (gk_host_alloc); first_call_ms includes faulting it in",
+                   "list_build_ms_not_timed": t_gen * 1e3}
+        del X
 
     if rank != 0:
         if world > 1:
@@ -342,6 +449,7 @@ def main():
                          (n * ((Dc + 63) // 64 * 64) * 2 / 1e6, (re_ - rb if world > 1 else n) * n * 4 / 1e6)},
         "clocks": clk.summary(),
         "e2e": e2e,
+        "e2e_api": e2e_api,
         "gpu_launches": launches,
         "roofline": {"kernel": GEMM_KERNEL, "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
@@ -368,10 +476,7 @@ def main():
         "dense_gemm_mode": dense,
     }
     if not args.no_cpu and world == 1:
-        val, t, n_cpu = cpu_arm(steps=1, budget_s=12.0)
-        line["cpu_baseline"] = {"value": val, "unit": "pairs/s", "cores": cpu_threads(), "kind": "port",
-                                "sample": f"first {n_cpu} of the {n} graphs, {t:.1f} s with {cpu_threads()} host threads "
-                                          f"(one per WL level; {os.cpu_count()} logical cores on the box)"}
+        line["cpu_baseline"] = cpu_baseline_obj(cpu_arm(steps=1, budget_s=12.0), n)
     print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
