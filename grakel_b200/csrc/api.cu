@@ -22,6 +22,7 @@
 #include "spattr.cuh"
 #include "wl.cuh"
 #include "wl_fused.cuh"
+#include "wl_fused2.cuh"
 #include "wl_oa.cuh"
 #include "tu_reader.h"
 
@@ -174,7 +175,8 @@ int gk_destroy(gk_handle* h) {
                         &h->colmin, &h->colmax, &h->colslot, &h->col_flags3, &h->col_block_sums, &h->colstats, &h->tail_desc,
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
-                        &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt, &h->wl_single};
+                        &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt, &h->wl_single,
+                        &h->diag_frozen};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
@@ -388,7 +390,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   GK_TRY(h->block_sums.ensure((size_t)nb * 4));
   // load factor <= 0.25: the insert loop of a warp runs as long as its longest probe sequence
   h->ht_cap = std::max<size_t>(next_pow2((size_t)V * 4), 1024);
-  GK_TRY(h->ht_keys.ensure(h->ht_cap * 8 * 2));  // two tables: the fused kernel alternates between levels
+  GK_TRY(h->ht_keys.ensure(h->ht_cap * 8 * 3));  // three tables: the fused kernel rotates them over the levels
   GK_TRY(h->ht_rep.ensure(h->ht_cap * 4 * 2));
   const size_t ft_level_cap = std::max<size_t>(next_pow2((size_t)V * 2), 1024);  // one L2-sized sub-table per level
   // Fused persistent kernel (wl_fused.cuh) whenever the graphs can be cut into shared-memory tiles of
@@ -442,6 +444,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       GK_CUDA(cudaMemcpyAsync(h->wlf_buf.p, hp, ((size_t)n_tiles + G + 2) * 4, cudaMemcpyHostToDevice, h->stream));
       GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
       GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
+      GK_CUDA(cudaFuncSetAttribute(wl_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF2_SMEM));
     }
   }
   // feature block: the multi-kernel path fills one open-addressing sub-table per level, the fused
@@ -461,7 +464,66 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     GK_TRY(init_scalars(h, h->n_labels0));
     FeatStats fst;
     GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)std::max(nb, G) * L, &fst));
-    if (fused) {
+    const char* e_v1 = getenv("GRAKEL_B200_WL_V1");
+    const bool wl_v2 = fused && !(e_v1 && atoi(e_v1) != 0);
+    h->wl_sparse_ids = false;
+    if (wl_v2) {
+      // wl_fused2.cuh: labels = representative vertex ids (one grid barrier per level), frozen singleton classes
+      if (L > 1) GK_CUDA(cudaMemsetAsync(h->ht_keys.as<unsigned long long>() + h->ht_cap, 0xFF, h->ht_cap * 8, h->stream));
+      int* wb = h->wlf_buf.as<int>();
+      int* d_cta_tile = wb + n_tiles + 1;
+      unsigned* d_barrier = reinterpret_cast<unsigned*>(d_cta_tile + G + 1 + G);
+      GK_CUDA(cudaMemsetAsync(d_barrier, 0, 4, h->stream));
+      GK_TRY(h->wl_single.ensure((size_t)V));
+      GK_CUDA(cudaMemsetAsync(h->wl_single.p, 0, (size_t)V, h->stream));
+      GK_TRY(h->diag_frozen.ensure((size_t)h->N * 8));
+      GK_CUDA(cudaMemsetAsync(h->diag_frozen.p, 0, (size_t)h->N * 8, h->stream));
+      WlFused2Params fp;
+      memset(&fp, 0, sizeof(fp));
+      fp.V = (int)V; fp.L = L; fp.n_labels0 = h->n_labels0;
+      fp.graph_ptr = h->graph_ptr.as<int>();
+      fp.row_ptr = h->row_ptr.as<int>(); fp.col_idx = h->col_idx.as<int>(); fp.vgraph = h->vgraph.as<int>();
+      fp.labels0 = h->labels0.as<int>(); fp.tile_vbeg = wb; fp.cta_tile = d_cta_tile;
+      fp.barrier = d_barrier;
+      fp.labels_all = labels_all; fp.sig_nbr = h->sig_nbr.as<int>(); fp.slot_of = h->slot_of.as<int>();
+      fp.frozen = h->wl_single.as<unsigned char>();
+      fp.table = h->ht_keys.as<unsigned long long>();
+      fp.ht_mask = (unsigned)(h->ht_cap - 1);
+      fp.coo_keys = h->ft_keys.as<unsigned long long>(); fp.coo_cnt = h->ft_cnt.as<unsigned>();
+      fp.seed = seed; fp.st = fst; fp.sc = sc;
+      fp.diag_frozen = h->diag_frozen.as<unsigned long long>();
+      const bool prof = getenv("GRAKEL_B200_PROF") != nullptr;
+      if (prof) {
+        GK_TRY(h->K_stage.ensure((size_t)G * L * 128));
+        GK_CUDA(cudaMemsetAsync(h->K_stage.p, 0, (size_t)G * L * 128, h->stream));
+        fp.prof = h->K_stage.as<long long>();
+      }
+      void* args[] = {&fp};
+      GK_CUDA(cudaLaunchCooperativeKernel((void*)wl_fused2_kernel, dim3(G), dim3(WLF_THREADS), args, WLF2_SMEM, h->stream));
+      LAUNCH_CHECK(h);
+      h->wl_sparse_ids = L > 1;
+      if (prof) {
+        std::vector<long long> pr((size_t)G * L * 16);
+        GK_CUDA(cudaMemcpyAsync(pr.data(), h->K_stage.p, pr.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        GK_CUDA(cudaStreamSynchronize(h->stream));
+        long long t0 = pr[0];
+        for (int b = 0; b < G; ++b) t0 = std::min(t0, pr[(size_t)b * L * 16]);
+        fprintf(stderr, "[wl_fused2 prof] us; per level: avg over CTAs of the phase duration (max)\n");
+        for (int lv = 0; lv < L; ++lv) {
+          double avg[4] = {0}, mxv[4] = {0};
+          long long end_max = 0;
+          for (int b = 0; b < G; ++b) {
+            const long long* q = &pr[((size_t)b * L + lv) * 16];
+            end_max = std::max(end_max, q[6] - t0);
+            if (lv == 0) { avg[3] += (double)(q[6] - q[0]) / G; mxv[3] = std::max(mxv[3], (double)(q[6] - q[0])); continue; }
+            const double d[4] = {(double)(q[1] - q[0]), (double)(q[2] - q[1]), (double)(q[3] - q[2]), (double)(q[6] - q[3])};
+            for (int k = 0; k < 4; ++k) { avg[k] += d[k] / G; mxv[k] = std::max(mxv[k], d[k]); }
+          }
+          fprintf(stderr, "  level %d: A %.1f (%.1f) wait %.1f (%.1f) B+emit %.1f (%.1f) clear+flush %.1f (%.1f) | level done at %.1f us\n", lv,
+                  avg[0] / 1e3, mxv[0] / 1e3, avg[1] / 1e3, mxv[1] / 1e3, avg[2] / 1e3, mxv[2] / 1e3, avg[3] / 1e3, mxv[3] / 1e3, end_max / 1e3);
+        }
+      }
+    } else if (fused) {
       // one persistent cooperative kernel for all levels; it appends (graph, column, count) entries
       // to ft_keys / ft_cnt used as a compact COO list
       if (L > 1) GK_CUDA(cudaMemsetAsync(h->ht_keys.as<unsigned long long>() + h->ht_cap, 0xFF, h->ht_cap * 8, h->stream));
@@ -592,6 +654,10 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     stats->n_levels = L;
     for (int i = 0; i < L; ++i) stats->level_dims[i] = hs->level_dims[i];
     stats->n_columns = h->n_columns;
+    if (h->wl_sparse_ids) {  // the column space is sparse (n_labels0 + (L-1) V wide); report the number of classes
+      stats->n_columns = 0;
+      for (int i = 0; i < L; ++i) stats->n_columns += hs->level_dims[i];
+    }
     stats->hash_retries = retries;
     stats->kernel_launches = h->launches - launches0;
     stats->ms_features = ev_ms(h->tev[2], h->tev[3]);
@@ -635,8 +701,13 @@ int gk_wl_oa_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       h->oa_keys.as<unsigned long long>(), h->oa_cnt.as<unsigned>(), cur, h->oa_colcnt.as<unsigned>(),
       h->diag_u64.as<unsigned long long>(), h->scalars.as<DevScalars>());
   LAUNCH_CHECK(h);
+  if (h->wl_sparse_ids) {  // frozen vertices wrote no entries: their (level) units of self similarity are kept aside
+    add_u64<<<cdiv(h->N, 256), 256, 0, h->stream>>>((int)h->N, h->diag_frozen.as<unsigned long long>(), h->diag_u64.as<unsigned long long>());
+    LAUNCH_CHECK(h);
+  }
   h->n_part = 1;
-  oa_finish<<<1, 1, 0, h->stream>>>(cur, h->part_max.as<unsigned>(), h->part_new.as<unsigned>());
+  oa_finish<<<1, 1, 0, h->stream>>>(cur, h->part_max.as<unsigned>(), h->part_new.as<unsigned>(), h->scalars.as<DevScalars>(),
+                                    h->wl_sparse_ids ? 1 : 0);
   LAUNCH_CHECK(h);
   GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, cur, sizeof(OaCursors), cudaMemcpyDeviceToHost, h->stream));
   DevScalars* hs;
@@ -658,11 +729,34 @@ int gk_wl_oa_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   return GK_OK;
 }
 
+// dense first-occurrence ids of level `level` (>= 1) of a wl_fused2 run into `dst` (device, V ints)
+static int wl_densify(gk_handle* h, int level, int* dst) {
+  const int V = (int)h->V;
+  const int nb = cdiv(V, DENS_THREADS);
+  GK_TRY(h->block_sums.ensure((size_t)nb * 4));
+  GK_TRY(h->flags.ensure((size_t)V * 4));
+  const int* lab = h->labels_all.as<int>() + (size_t)level * V;
+  wl_dens_count<<<nb, DENS_THREADS, 0, h->stream>>>(V, lab, h->block_sums.as<int>());
+  LAUNCH_CHECK(h);
+  wl_dens_scan<<<1, DENS_THREADS, 0, h->stream>>>(nb, h->block_sums.as<int>());
+  LAUNCH_CHECK(h);
+  wl_dens_rank<<<nb, DENS_THREADS, 0, h->stream>>>(V, lab, h->block_sums.as<int>(), h->flags.as<int>());
+  LAUNCH_CHECK(h);
+  wl_dens_apply<<<cdiv(V, 256), 256, 0, h->stream>>>(V, lab, h->flags.as<int>(), dst);
+  LAUNCH_CHECK(h);
+  return GK_OK;
+}
+
 int gk_wl_labels(gk_handle* h, int32_t level, int32_t* out) {
   if (!h || !out) return fail(GK_ERR_ARG, "gk_wl_labels: null argument");
   if (h->feature_kind != 1 || level < 0 || level >= h->n_levels) return fail(GK_ERR_STATE, "gk_wl_labels: no such level");
   GK_CUDA(cudaSetDevice(h->dev));
-  GK_CUDA(cudaMemcpyAsync(out, h->labels_all.as<int>() + (size_t)level * h->V, h->V * 4, cudaMemcpyDeviceToHost, h->stream));
+  const int* src = h->labels_all.as<int>() + (size_t)level * h->V;
+  if (h->wl_sparse_ids && level >= 1) {
+    GK_TRY(wl_densify(h, level, h->slot_of.as<int>()));
+    src = h->slot_of.as<int>();
+  }
+  GK_CUDA(cudaMemcpyAsync(out, src, h->V * 4, cudaMemcpyDeviceToHost, h->stream));
   GK_CUDA(cudaStreamSynchronize(h->stream));
   return GK_OK;
 }
@@ -687,6 +781,10 @@ static int sp_features_impl(gk_handle* h, int32_t flags, int32_t wl_iter, gk_sta
     if (!with_labels) return fail(GK_ERR_ARG, "gk_wl_sp_features: the base kernel needs vertex labels");
     gk_stats wst;
     GK_TRY(gk_wl_features(h, wl_iter, &wst));
+    if (h->wl_sparse_ids) {  // the base kernel's counters are indexed by dense label ids
+      for (int lv = 1; lv <= wl_iter; ++lv) GK_TRY(wl_densify(h, lv, h->labels_all.as<int>() + (size_t)lv * h->V));
+      h->wl_sparse_ids = false;
+    }
     n_pass = wl_iter + 1;
     level_base.assign(n_pass + 1, 0);
     for (int l = 0; l < n_pass; ++l) level_base[l + 1] = level_base[l] + wst.level_dims[l];

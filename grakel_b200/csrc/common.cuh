@@ -100,7 +100,7 @@ struct DevScalars {
   unsigned long long max_count;          // largest count
   unsigned long long max_diag;           // largest self similarity
   long long n_dense;                     // D_c
-  unsigned long long sp_coo;             // (unused slot)
+  unsigned long long sp_coo;             // wl_fused2: self-similarity units of frozen vertices (= sum of diag_frozen)
   unsigned int sp_dict_size;             // SP: number of distinct (lu,lv,d) keys
   unsigned int sp_nonint;                // SP: a non-integer / out-of-range distance was met
 };
@@ -138,7 +138,9 @@ struct gk_handle {
   size_t ht_cap = 0;
   gk::DevBuf flags, block_sums;
   gk::DevBuf wlf_buf;  // fused WL kernel: [cta_vbeg (G+1) | cta_count (G) | barrier]
-  gk::DevBuf wl_single;  // fused WL kernel, singleton shortcut: one byte per vertex
+  gk::DevBuf wl_single;  // fused WL kernels: one byte per vertex (singleton class / frozen)
+  gk::DevBuf diag_frozen;  // fused WL kernel v2: frozen vertices' share of the self similarities (u64 per graph)
+  bool wl_sparse_ids = false;  // labels of levels >= 1 are representative vertex ids (wl_fused2), not dense ranks
   gk::DevBuf scalars;  // gk::DevScalars
   gk::PinBuf h_scalars;
 

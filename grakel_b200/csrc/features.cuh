@@ -258,6 +258,11 @@ tail_pairs(long long n_tail_cols, const int2* __restrict__ tail_desc, const int2
   }
 }
 
+__global__ void __launch_bounds__(256) add_u64(int n, const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
 // normalisation pass when a tail exists: K_ij / sqrt(d_i d_j)  (+ nan_to_num)
 template <typename OutT>
 __global__ void __launch_bounds__(256)

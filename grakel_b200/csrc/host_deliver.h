@@ -25,19 +25,50 @@ namespace {
 class HostPool {
  public:
   explicit HostPool(int n) : stop_(false), gen_(0), pending_(0) {
-    // Workers stay on the NUMA node of the thread that creates the pool (the one that also allocates
-    // and touches the pinned staging buffers): remote-socket workers made the widening slower with
-    // every added thread on the 2-socket GPU hosts.
-    std::vector<int> cpus = local_node_cpus();
+    // Workers stay on the NUMA node of the thread that creates the pool (the one that also allocates and touches
+    // the pinned staging buffers; remote-socket workers made the widening slower with every added thread on the
+    // 2-socket GPU hosts), one worker per PHYSICAL core -- two workers on hyper-thread siblings turn into the
+    // stragglers every band waits for -- and not on the caller's core, which spins in cudaEventSynchronize.
+    std::vector<int> cpus = pick_cores(local_node_cpus());
     for (int i = 0; i < n; ++i) {
       th_.emplace_back([this, i] { run(i); });
       if (!cpus.empty()) {
         cpu_set_t set;
         CPU_ZERO(&set);
-        for (int c : cpus) CPU_SET(c, &set);
+        if ((int)cpus.size() >= n) CPU_SET(cpus[i], &set);
+        else for (int c : cpus) CPU_SET(c, &set);
         pthread_setaffinity_np(th_.back().native_handle(), sizeof(set), &set);
       }
     }
+  }
+  static int read_int(const char* fmt, int cpu) {
+    char path[160];
+    snprintf(path, sizeof(path), fmt, cpu);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int v = -1;
+    if (fscanf(f, "%d", &v) != 1) v = -1;
+    fclose(f);
+    return v;
+  }
+  // one logical CPU per physical core of `list`, the caller's core excluded (empty list / no topology: unchanged)
+  static std::vector<int> pick_cores(const std::vector<int>& list) {
+    if (list.empty() || getenv("GRAKEL_B200_HOST_NO_PIN")) return list;
+    const int me = sched_getcpu();
+    const int my_core = me >= 0 ? read_int("/sys/devices/system/cpu/cpu%d/topology/core_id", me) : -1;
+    const int my_pkg = me >= 0 ? read_int("/sys/devices/system/cpu/cpu%d/topology/physical_package_id", me) : -1;
+    std::vector<std::pair<int, int>> seen;
+    std::vector<int> out;
+    for (int c : list) {
+      const int core = read_int("/sys/devices/system/cpu/cpu%d/topology/core_id", c);
+      const int pkg = read_int("/sys/devices/system/cpu/cpu%d/topology/physical_package_id", c);
+      if (core < 0) return list;
+      if (core == my_core && pkg == my_pkg) continue;
+      if (std::find(seen.begin(), seen.end(), std::make_pair(pkg, core)) != seen.end()) continue;
+      seen.emplace_back(pkg, core);
+      out.push_back(c);
+    }
+    return out.empty() ? list : out;
   }
   static std::vector<int> local_node_cpus() {
     std::vector<int> out;
@@ -117,7 +148,7 @@ class HostPool {
 
 HostPool& host_pool() {
   static HostPool pool([] {
-    int n = std::min(24, (int)std::thread::hardware_concurrency() / 2);
+    int n = std::min(12, (int)std::thread::hardware_concurrency() / 4);
     if (const char* e = getenv("GRAKEL_B200_HOST_THREADS")) n = atoi(e);
     return std::max(1, std::min(n, 128));
   }());
@@ -256,7 +287,6 @@ static int deliver_rows(Copier& cp, const float* d_src, long long d_ld, long lon
   if (!stage) return GK_ERR_CUDA;
   const long long n_bands = (rows + band_rows - 1) / band_rows;
   HostPool& pool = host_pool();
-  const int nt = pool.size();
   std::atomic<long long> ready(0);
   std::vector<std::atomic<int>> done(n_bands);
   for (auto& d : done) d.store(0);
@@ -267,15 +297,21 @@ static int deliver_rows(Copier& cp, const float* d_src, long long d_ld, long lon
       return fail(GK_ERR_CUDA, "deliver_rows: D2H copy could not be queued");
     return GK_OK;
   };
-  const std::function<void(int)> work = [&](int w) {
-    for (long long c = 0; c < n_bands; ++c) {
+  // tasks: runs of 8 rows, handed out through one atomic counter (a delayed worker holds back 8 rows, not 1/nt of a band)
+  const long long tasks_per_band = (band_rows + 7) / 8;
+  std::atomic<long long> next(0);
+  const std::function<void(int)> work = [&](int) {
+    for (;;) {
+      const long long t = next.fetch_add(1, std::memory_order_relaxed);
+      const long long c = t / tasks_per_band;
+      if (c >= n_bands) return;
       while (ready.load(std::memory_order_acquire) <= c) {
         if (ready.load(std::memory_order_relaxed) < 0) return;  // aborted
         _mm_pause();
       }
       const long long r0 = c * band_rows, nr = std::min(band_rows, rows - r0);
       const float* src = reinterpret_cast<const float*>(stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes);
-      const long long a = nr * w / nt, b = nr * (w + 1) / nt;  // one contiguous run of rows per worker
+      const long long a = (t - c * tasks_per_band) * 8, b = std::min(nr, a + 8);
       for (long long r = a; r < b; ++r) {
         if (drow) widen_row_norm(src + r * cols, dst + (r0 + r) * ld, cols, drow[r0 + r], dcol, nan_to_num);
         else widen_row(src + r * cols, dst + (r0 + r) * ld, cols);
@@ -291,7 +327,7 @@ static int deliver_rows(Copier& cp, const float* d_src, long long d_ld, long lon
     if (!cp.wait((int)(c % DELIVER_SLOTS))) { rc = fail(GK_ERR_CUDA, "deliver_rows: D2H copy failed"); break; }
     ready.store(c + 1, std::memory_order_release);
     if (c >= 1 && c - 1 + DELIVER_SLOTS < n_bands) {  // slot of band c-1 is free once every worker has left it
-      while (done[c - 1].load(std::memory_order_acquire) < nt) _mm_pause();
+      while (done[c - 1].load(std::memory_order_acquire) < (int)tasks_per_band) _mm_pause();
       rc = enqueue(c - 1 + DELIVER_SLOTS);
       if (rc != GK_OK) break;
     }
@@ -324,7 +360,6 @@ static int deliver_tri(Copier& cp, const float* d_src, long long d_ld, long long
   char* stage = cp.stage(slot_bytes * DELIVER_SLOTS);
   if (!stage) return GK_ERR_CUDA;
   HostPool& pool = host_pool();
-  const int nt = pool.size();
   std::atomic<long long> ready(0);
   std::vector<std::atomic<int>> done(n_bands);
   for (auto& d : done) d.store(0);
@@ -335,29 +370,27 @@ static int deliver_tri(Copier& cp, const float* d_src, long long d_ld, long long
       return fail(GK_ERR_CUDA, "deliver_tri: D2H copy could not be queued");
     return GK_OK;
   };
-  const std::function<void(int)> work = [&](int wk) {
-    for (long long c = 0; c < n_bands; ++c) {
+  // tasks: 64-column strips of a band (straight part + its mirrored block), handed out through one atomic counter
+  std::vector<long long> task0(n_bands + 1, 0);
+  for (long long c = 0; c < n_bands; ++c) task0[c + 1] = task0[c] + (n - start[c] + 63) / 64;
+  std::atomic<long long> next(0);
+  const std::function<void(int)> work = [&](int) {
+    long long c = 0;
+    for (;;) {
+      const long long t = next.fetch_add(1, std::memory_order_relaxed);
+      if (t >= task0[n_bands]) return;
+      while (t >= task0[c + 1]) ++c;
       while (ready.load(std::memory_order_acquire) <= c) {
         if (ready.load(std::memory_order_relaxed) < 0) return;
         _mm_pause();
       }
       const long long r0 = start[c], r1 = start[c + 1], nr = r1 - r0, w = n - r0;
       const float* src = reinterpret_cast<const float*>(stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes);
-      // this worker's columns of the band (relative to r0), in units of 16 so that ranges start on 128-byte lines
-      const long long units = (w + 15) / 16;
-      const long long ca = std::min(w, units * wk / nt * 16), cb = std::min(w, units * (wk + 1) / nt * 16);
-      if (cb > ca) {
-        for (long long r = 0; r < nr; ++r) widen_row(src + r * w + ca, dst + (r0 + r) * ld + r0 + ca, cb - ca);
-        // mirrored part: band columns >= nr are rows r1.. of the destination, columns r0..r1
-        const long long ma = std::max(ca, nr);
-        if (cb > ma) {
-          // 64-column pieces keep the 8 x 8 blocks' source lines in L1 between the passes over the band's rows
-          for (long long j = ma; j < cb; j += 64) {
-            const long long nb = std::min<long long>(64, cb - j);
-            transpose_widen(src + j, w, nr, nb, dst + (r0 + j) * ld + r0, ld);
-          }
-        }
-      }
+      const long long ca = (t - task0[c]) * 64, cb = std::min(w, ca + 64);  // columns of the band, relative to r0
+      for (long long r = 0; r < nr; ++r) widen_row(src + r * w + ca, dst + (r0 + r) * ld + r0 + ca, cb - ca);
+      // mirrored part: band columns >= nr are rows r1.. of the destination, columns r0..r1
+      const long long ma = std::max(ca, nr);
+      if (cb > ma) transpose_widen(src + ma, w, nr, cb - ma, dst + (r0 + ma) * ld + r0, ld);
       done[c].fetch_add(1, std::memory_order_release);
     }
   };
@@ -369,7 +402,7 @@ static int deliver_tri(Copier& cp, const float* d_src, long long d_ld, long long
     if (!cp.wait((int)(c % DELIVER_SLOTS))) { rc = fail(GK_ERR_CUDA, "deliver_tri: D2H copy failed"); break; }
     ready.store(c + 1, std::memory_order_release);
     if (c >= 1 && c - 1 + DELIVER_SLOTS < n_bands) {
-      while (done[c - 1].load(std::memory_order_acquire) < nt) _mm_pause();
+      while (done[c - 1].load(std::memory_order_acquire) < (int)(task0[c] - task0[c - 1])) _mm_pause();
       rc = enqueue(c - 1 + DELIVER_SLOTS);
       if (rc != GK_OK) break;
     }

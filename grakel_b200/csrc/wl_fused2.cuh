@@ -1,0 +1,535 @@
+// All WL levels in ONE persistent cooperative kernel, second generation (weisfeiler_lehman.py:199-258 +
+// vertex_histogram.py:107-122 for every level).  Same tile / shared-memory organisation and the same exact
+// hash-proposes / signature-verifies dedup as wl_fused.cuh; what changed is what a level has to do:
+//
+//   * The compressed label of a class is the id of its REPRESENTATIVE vertex (the smallest vertex of the class),
+//     not a dense rank.  The reference's ids never leave the estimator ("bit-exact integer labels" =
+//     identical label partition), and K only needs distinct columns per class.  So the second half of a level
+//     -- CTA-local ranks, the scan of the CTA counts, the rank gather -- and with it the SECOND grid barrier
+//     disappear: a level is   [A] signatures + insert | grid barrier | [B] representative, verification,
+//     labels, feature entries.   Level l >= 1 owns the column range [n_labels0 + (l-1) V, n_labels0 + l V).
+//     Dense first-occurrence ids (gk_wl_labels, the WL-SP base kernel) are produced on demand by wl_densify.
+//   * A vertex whose class has a single member in the whole data set is FROZEN: its label (= its own id) never
+//     changes again, it needs no signature, insert or verification at deeper levels, and its feature column
+//     occurs in one graph only, i.e. it contributes 1 to its graph's self similarity per remaining level and
+//     nothing else.  That contribution is added once, when the vertex freezes, and no feature entry is ever
+//     written for it.  At BASELINE config 2, 93 % of the vertices freeze at level 2 and 96 % by level 3: levels
+//     3..5 touch 4 % of the data.
+//   * Three signature tables rotate (level l uses table l mod 3; the table of level l+2 is cleared in [B] of
+//     level l), which is what makes the single barrier sufficient: a CTA still clearing can never meet a CTA
+//     already inserting.
+//   * A CTA that owns one tile keeps its CSR slice, labels and frozen flags resident in shared memory across
+//     levels.
+//
+// Exactness is unchanged: every non-frozen vertex's full signature (own label, degree, sorted neighbour labels)
+// is compared with its representative's; a mismatch raises the collision flag and the host retries with a new seed.
+#pragma once
+#include "common.cuh"
+#include "wl.cuh"
+#include "wl_fused.cuh"
+
+namespace gk {
+
+struct WlFused2Params {
+  int V, L;
+  int n_labels0;
+  const int* graph_ptr;
+  const int* row_ptr;
+  const int* col_idx;
+  const int* vgraph;
+  const int* labels0;
+  const int* tile_vbeg;  // [n_tiles + 1] first vertex of each tile (whole graphs)
+  const int* cta_tile;   // [grid + 1] first tile of each CTA
+  int* labels_all;       // [L * V]; level 0: the packed dense ids, level >= 1: representative vertex ids
+  int* sig_nbr;          // [E] sorted neighbour labels of the current level (non-frozen vertices)
+  int* slot_of;          // [V] hash slot of the vertex's signature at the current level
+  unsigned char* frozen; // [V] zeroed by the host
+  unsigned long long* table;  // 3 x (ht_mask + 1) packed {31-bit tag | single | representative}; table 1 cleared by the host
+  unsigned ht_mask;
+  unsigned long long* coo_keys;  // feature entries: graph << 32 | column; fixed region of nv slots per (tile, level)
+  unsigned* coo_cnt;
+  unsigned* barrier;  // zeroed by the host before the launch
+  unsigned long long seed;
+  FeatStats st;
+  unsigned long long* diag_frozen;  // [N] zeroed by the host: the frozen vertices' share of st.diag (WL-OA re-adds it)
+  DevScalars* sc;     // level_dims[1..] zeroed by the host, level_base[0], [1] set
+  long long* prof;    // optional [grid][L][16] globaltimer stamps (GRAKEL_B200_PROF), else NULL
+};
+
+// Feature entries of one tile from the labels in lab_s: a non-frozen vertex i emits (graph, base + label, count)
+// iff it is the first vertex of its graph carrying that label; frozen vertices (unique labels) emit nothing.
+// Fixed COO region per (tile, level), unused slots hold EMPTY64; per-column graph counts go through a shared-memory
+// aggregation table first (a column shared by every graph costs one global atomic per tile).
+__device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int nv, const int* lab_s, const unsigned char* frz_s,
+                                          unsigned* agg, long long base, size_t coo_off, int* s_warp, unsigned& mx, unsigned& n_new) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int s = tid; s < WLF_AGG * 2; s += WLF_THREADS) agg[s] = (s & 1) ? 0u : 0xFFFFFFFFu;  // {column, graphs}
+  int g[WLF_VPT], l[WLF_VPT];
+  unsigned cnt[WLF_VPT];
+  bool emit[WLF_VPT];
+  int n_emit = 0;
+#pragma unroll
+  for (int k = 0; k < WLF_VPT; ++k) {
+    const int i = tid + k * WLF_THREADS;
+    g[k] = -1; l[k] = 0; cnt[k] = 0; emit[k] = false;
+    if (i < nv && !frz_s[i]) {
+      g[k] = p.vgraph[v0 + i];
+      const int gs = p.graph_ptr[g[k]] - v0, ge = p.graph_ptr[g[k] + 1] - v0;
+      l[k] = lab_s[i];
+      bool first = true;
+      for (int u = gs; u < ge; ++u) {
+        const bool same = lab_s[u] == l[k];
+        cnt[k] += same ? 1u : 0u;
+        first = first && !(same && u < i);
+      }
+      emit[k] = first;
+      n_emit += first ? 1 : 0;
+    }
+  }
+  int total;
+  int ex = wlf_block_scan(n_emit, &total, s_warp);  // also orders the agg initialisation before its use
+  for (int i = total + tid; i < nv; i += WLF_THREADS) p.coo_keys[coo_off + i] = EMPTY64;  // unused rest of the fixed region
+#pragma unroll
+  for (int k = 0; k < WLF_VPT; ++k) {
+    if (emit[k]) {
+      const unsigned col = (unsigned)(base + l[k]);
+      p.coo_keys[coo_off + ex] = ((unsigned long long)(unsigned)g[k] << 32) | col;
+      p.coo_cnt[coo_off + ex] = cnt[k];
+      ++ex;
+      mx = max(mx, cnt[k]);
+      n_new += 1u;
+      unsigned slot = (col * 0x9E3779B1u >> 12) & (WLF_AGG - 1);
+      while (true) {
+        unsigned prev = agg[2 * slot];
+        if (prev == 0xFFFFFFFFu) prev = atomicCAS(&agg[2 * slot], 0xFFFFFFFFu, col);
+        if (prev == 0xFFFFFFFFu || prev == col) { atomicAdd(&agg[2 * slot + 1], 1u); break; }
+        slot = (slot + 1) & (WLF_AGG - 1);
+      }
+    }
+    // exact self similarity: sum of squared counts per graph (runs of equal g inside the warp)
+    unsigned long long val = emit[k] ? (unsigned long long)cnt[k] * cnt[k] : 0ULL;
+    const int gg = g[k];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_down_sync(0xffffffffu, val, d);
+      const int gy = __shfl_down_sync(0xffffffffu, gg, d);
+      if (lane + d < 32 && gy == gg) val += y;
+    }
+    const int gprev = __shfl_up_sync(0xffffffffu, gg, 1);
+    if (gg >= 0 && (lane == 0 || gprev != gg) && val) atomicAdd(&p.st.diag[gg], val);
+  }
+  __syncthreads();
+  for (int s = tid; s < WLF_AGG; s += WLF_THREADS) {
+    const unsigned col = agg[2 * s];
+    if (col != 0xFFFFFFFFu) atomicAdd(&p.st.colcnt[col], agg[2 * s + 1]);
+  }
+  __syncthreads();  // agg is reused by the next tile / overwritten by the next level's signatures
+}
+
+constexpr int WLF2_SMEM = WLF_SMEM + WLF_TILE_V /*frz_s*/;
+
+__global__ void __launch_bounds__(WLF_THREADS, 1)
+wl_fused2_kernel(WlFused2Params p) {
+  extern __shared__ __align__(16) unsigned char wlf_smem[];
+  int* rp_s = reinterpret_cast<int*>(wlf_smem);
+  unsigned long long* key_s = reinterpret_cast<unsigned long long*>(rp_s + (WLF_TILE_V + 2));
+  int* lab_s = reinterpret_cast<int*>(key_s + WLF_TILE_V);
+  int* sig_s = lab_s + WLF_TILE_V;
+  unsigned* agg = reinterpret_cast<unsigned*>(sig_s);  // emit phase only
+  unsigned short* col_s = reinterpret_cast<unsigned short*>(sig_s + WLF_TILE_E);
+  unsigned char* frz_s = reinterpret_cast<unsigned char*>(col_s + WLF_TILE_E);
+  __shared__ int s_warp[32];
+  __shared__ unsigned s_red[128];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int t_beg = p.cta_tile[b], t_end = p.cta_tile[b + 1];
+  const bool resident = (t_end - t_beg) == 1;  // one tile: CSR slice, labels, frozen flags stay in shared memory
+  const int V = p.V;
+  const size_t ht_cap = (size_t)p.ht_mask + 1;
+  unsigned n_sync = 0;
+  unsigned mx = 0, n_new = 0, n_rep = 0, n_fz = 0;  // n_fz: self-similarity units of vertices frozen at this level
+  WLF_STAMP(0, 0);
+
+  // publish the per-CTA partials of a level (max count, created entries) and add the CTA's class count
+  auto flush_partials = [&](int level) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      n_new += __shfl_xor_sync(0xffffffffu, n_new, d);
+      n_rep += __shfl_xor_sync(0xffffffffu, n_rep, d);
+      n_fz += __shfl_xor_sync(0xffffffffu, n_fz, d);
+    }
+    if (lane == 0) { s_red[wid] = mx; s_red[32 + wid] = n_new; s_red[64 + wid] = n_rep; s_red[96 + wid] = n_fz; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned m = 0, n = 0, r = 0, z = 0;
+      for (int w = 0; w < 32; ++w) { m = max(m, s_red[w]); n += s_red[32 + w]; r += s_red[64 + w]; z += s_red[96 + w]; }
+      if (z) atomicAdd(&p.sc->sp_coo, (unsigned long long)z);  // total of diag_frozen (WL-OA's entry count)
+      p.st.part_max[(size_t)level * G + b] = m;
+      p.st.part_new[(size_t)level * G + b] = n;
+      if (level > 0 && r) atomicAdd((unsigned long long*)&p.sc->level_dims[level], (unsigned long long)r);
+    }
+    mx = 0; n_new = 0; n_rep = 0; n_fz = 0;
+    __syncthreads();
+  };
+
+  // ---- level 0: labels as given (dense ids); nothing is frozen yet
+  for (int t = t_beg; t < t_end; ++t) {
+    const int v0 = p.tile_vbeg[t], nv = p.tile_vbeg[t + 1] - v0;
+    __syncthreads();
+    for (int i = tid; i < nv; i += WLF_THREADS) {
+      const int x = p.labels0[v0 + i];
+      lab_s[i] = x;
+      p.labels_all[v0 + i] = x;
+      frz_s[i] = 0;
+    }
+    if (resident) {  // stage the CSR slice once
+      const int e0 = p.row_ptr[v0], ne = p.row_ptr[v0 + nv] - e0;
+      for (int i = tid; i <= nv; i += WLF_THREADS) rp_s[i] = p.row_ptr[v0 + i] - e0;
+      for (int k = tid; k < ne; k += WLF_THREADS) col_s[k] = (unsigned short)(p.col_idx[e0 + k] - v0);
+    }
+    __syncthreads();
+    wlf2_emit(p, v0, nv, lab_s, frz_s, agg, 0, (size_t)v0, s_warp, mx, n_new);
+  }
+  if (p.L > 2) {  // table of level 2 (first touched after the barrier of level 1)
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    uint4* hk = reinterpret_cast<uint4*>(p.table + 2 * ht_cap);
+    for (size_t i = (size_t)b * WLF_THREADS + tid; i < ht_cap / 2; i += (size_t)G * WLF_THREADS) hk[i] = ones;
+  }
+  if (b == 0 && tid == 0)
+    for (int lv = 1; lv < p.L; ++lv) p.sc->level_base[lv + 1] = (long long)p.n_labels0 + (long long)lv * V;
+  flush_partials(0);
+  WLF_STAMP(0, 6);
+
+  for (int lv = 1; lv < p.L; ++lv) {
+    const int* lab_in = p.labels_all + (size_t)(lv - 1) * V;
+    int* lab_out = p.labels_all + (size_t)lv * V;
+    unsigned long long* tab = p.table + (size_t)(lv % 3) * ht_cap;
+    const long long level_base = (long long)p.n_labels0 + (long long)(lv - 1) * V;
+
+    // ---------------- [A] signatures + insert (non-frozen vertices)
+    WLF_STAMP(lv, 0);
+    for (int t = t_beg; t < t_end; ++t) {
+      const int v0 = p.tile_vbeg[t], nv = p.tile_vbeg[t + 1] - v0;
+      const int e0 = p.row_ptr[v0], ne = p.row_ptr[v0 + nv] - e0;
+      if (!resident) {
+        __syncthreads();  // previous tile's shared memory is no longer read
+        for (int i = tid; i <= nv; i += WLF_THREADS) rp_s[i] = p.row_ptr[v0 + i] - e0;
+        for (int k = tid; k < ne; k += WLF_THREADS) col_s[k] = (unsigned short)(p.col_idx[e0 + k] - v0);
+        for (int i = tid; i < nv; i += WLF_THREADS) { lab_s[i] = lab_in[v0 + i]; frz_s[i] = p.frozen[v0 + i]; }
+        __syncthreads();
+      }
+      WLF_STAMP(lv, 8);
+      // [A1] one thread per vertex of degree <= 8: 19-comparator network in registers
+      for (int i = tid; i < nv; i += WLF_THREADS) {
+        const int beg = rp_s[i];
+        const int deg = rp_s[i + 1] - beg;
+        if (deg > 8 || frz_s[i]) continue;
+        int x0, x1, x2, x3, x4, x5, x6, x7;
+        x0 = 0 < deg ? lab_s[col_s[beg + 0]] : 0x7fffffff;
+        x1 = 1 < deg ? lab_s[col_s[beg + 1]] : 0x7fffffff;
+        x2 = 2 < deg ? lab_s[col_s[beg + 2]] : 0x7fffffff;
+        x3 = 3 < deg ? lab_s[col_s[beg + 3]] : 0x7fffffff;
+        x4 = 4 < deg ? lab_s[col_s[beg + 4]] : 0x7fffffff;
+        x5 = 5 < deg ? lab_s[col_s[beg + 5]] : 0x7fffffff;
+        x6 = 6 < deg ? lab_s[col_s[beg + 6]] : 0x7fffffff;
+        x7 = 7 < deg ? lab_s[col_s[beg + 7]] : 0x7fffffff;
+        GK_CSWAP(x0, x1) GK_CSWAP(x2, x3) GK_CSWAP(x4, x5) GK_CSWAP(x6, x7)
+        GK_CSWAP(x0, x2) GK_CSWAP(x1, x3) GK_CSWAP(x4, x6) GK_CSWAP(x5, x7)
+        GK_CSWAP(x1, x2) GK_CSWAP(x5, x6) GK_CSWAP(x0, x4) GK_CSWAP(x3, x7)
+        GK_CSWAP(x1, x5) GK_CSWAP(x2, x6)
+        GK_CSWAP(x1, x4) GK_CSWAP(x3, x6)
+        GK_CSWAP(x2, x4) GK_CSWAP(x3, x5)
+        GK_CSWAP(x3, x4)
+        const int xs[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+        unsigned ha = 0x243F6A88u, hc = 0x85A308D3u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < deg) {
+            sig_s[beg + j] = xs[j];
+            wlf_seq_step(ha, hc, xs[j]);
+          }
+        }
+        key_s[i] = wlf_finish(ha, hc, lab_s[i], deg, p.seed);
+      }
+      // [A2] higher degrees: one warp per vertex (shuffle bitonic <= 32, in-segment bitonic above)
+      for (int i0 = wid * 32; i0 < nv; i0 += WLF_THREADS) {
+        const int iv = i0 + lane;
+        const bool big = iv < nv && (rp_s[iv + 1] - rp_s[iv]) > 8 && !frz_s[iv];
+        unsigned m = __ballot_sync(0xffffffffu, big);
+        while (m) {
+          const int i = i0 + __ffs(m) - 1;
+          m &= m - 1;
+          const int beg = rp_s[i], deg = rp_s[i + 1] - beg;
+          int* seg = sig_s + beg;
+          unsigned ha = 0, hc = 0;
+          if (deg <= 32) {
+            int x = lane < deg ? lab_s[col_s[beg + lane]] : 0x7fffffff;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+              for (int j = k >> 1; j > 0; j >>= 1) {
+                const int y = __shfl_xor_sync(0xffffffffu, x, j);
+                const bool up = (lane & k) == 0;
+                const bool lower = (lane & j) == 0;
+                x = (lower == up) ? min(x, y) : max(x, y);
+              }
+            }
+            if (lane < deg) {
+              seg[lane] = x;
+              wlf_pos_term(ha, hc, x, lane, p.seed);
+            }
+          } else {
+            for (int j = lane; j < deg; j += 32) seg[j] = lab_s[col_s[beg + j]];
+            __syncwarp();
+            int n2 = 1;
+            while (n2 < deg) n2 <<= 1;
+            for (int k = 2; k <= n2; k <<= 1) {
+              for (int j = lane; j < deg; j += 32) {
+                const int q = j ^ (k - 1);
+                if (q > j && q < deg) {
+                  const int a = seg[j], c = seg[q];
+                  if (a > c) { seg[j] = c; seg[q] = a; }
+                }
+              }
+              __syncwarp();
+              for (int s = k >> 2; s > 0; s >>= 1) {
+                for (int j = lane; j < deg; j += 32) {
+                  const int q = j ^ s;
+                  if (q > j && q < deg) {
+                    const int a = seg[j], c = seg[q];
+                    if (a > c) { seg[j] = c; seg[q] = a; }
+                  }
+                }
+                __syncwarp();
+              }
+            }
+            for (int j = lane; j < deg; j += 32) wlf_pos_term(ha, hc, seg[j], j, p.seed);
+          }
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) {
+            ha += __shfl_xor_sync(0xffffffffu, ha, s);
+            hc += __shfl_xor_sync(0xffffffffu, hc, s);
+          }
+          if (lane == 0) key_s[i] = wlf_finish(ha, hc, lab_s[i], deg, p.seed);
+        }
+      }
+      __syncthreads();
+      WLF_STAMP(lv, 10);
+      // [A3] insert every non-frozen vertex of the tile; the (<= 4) probes of a thread are issued together
+      {
+        unsigned long long key[WLF_VPT], w[WLF_VPT];
+        unsigned slot[WLF_VPT];
+        bool act[WLF_VPT], ins[WLF_VPT];
+#pragma unroll
+        for (int k = 0; k < WLF_VPT; ++k) {
+          const int i = tid + k * WLF_THREADS;
+          act[k] = i < nv && !frz_s[i];
+          ins[k] = act[k];
+          key[k] = act[k] ? key_s[i] : 0ULL;
+          slot[k] = (unsigned)((key[k] & 0xFFFFFFFFULL) * 0x9E3779B1ULL >> 8) & p.ht_mask;
+        }
+        bool any = true;
+        while (any) {
+          // CAS first (no read-before-CAS): a new signature costs ONE L2 round trip; an existing one gets the
+          // slot's word back from the failed CAS
+#pragma unroll
+          for (int k = 0; k < WLF_VPT; ++k) {
+            const unsigned long long mine = (key[k] & 0xFFFFFFFE00000000ULL) | (1ULL << 32) | (unsigned)(v0 + tid + k * WLF_THREADS);
+            w[k] = act[k] ? atomicCAS(&tab[slot[k]], EMPTY64, mine) : 0ULL;
+          }
+          any = false;
+#pragma unroll
+          for (int k = 0; k < WLF_VPT; ++k) {
+            if (!act[k]) continue;
+            const int v = v0 + tid + k * WLF_THREADS;
+            if (w[k] == EMPTY64) { act[k] = false; continue; }  // the CAS installed our word (single bit set)
+            if ((w[k] >> 33) == (key[k] >> 33)) {
+              const unsigned rep = (unsigned)w[k];
+              // a second member: clear the single bit and keep the smaller representative in one atomicMin
+              if (((w[k] >> 32) & 1ULL) || rep > (unsigned)v)
+                atomicMin(&tab[slot[k]], (key[k] & 0xFFFFFFFE00000000ULL) | (unsigned)min(rep, (unsigned)v));
+              act[k] = false;
+              continue;
+            }
+            slot[k] = (slot[k] + 1) & p.ht_mask;
+            any = true;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < WLF_VPT; ++k) {
+          const int i = tid + k * WLF_THREADS;
+          if (ins[k]) p.slot_of[v0 + i] = (int)slot[k];
+        }
+        // sorted neighbour labels of the inserted vertices to global memory: other CTAs verify against them
+#pragma unroll
+        for (int k = 0; k < WLF_VPT; ++k) {
+          const int i = tid + k * WLF_THREADS;
+          if (ins[k]) {
+            const int beg = rp_s[i], end = rp_s[i + 1];
+            for (int j = beg; j < end; ++j) p.sig_nbr[e0 + j] = sig_s[j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    WLF_STAMP(lv, 1);
+    wlf_grid_sync(p.barrier, (++n_sync) * (unsigned)G);
+    WLF_STAMP(lv, 2);
+
+    // ---------------- [B] representative, verification, new labels, freezing, feature entries
+    for (int t = t_beg; t < t_end; ++t) {
+      const int v0 = p.tile_vbeg[t], nv = p.tile_vbeg[t + 1] - v0;
+      if (!resident) {
+        __syncthreads();
+        for (int i = tid; i < nv; i += WLF_THREADS) { lab_s[i] = lab_in[v0 + i]; frz_s[i] = p.frozen[v0 + i]; }
+        __syncthreads();
+      }
+      int r[WLF_VPT];
+      bool act[WLF_VPT], sgl[WLF_VPT];
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        act[k] = i < nv && !frz_s[i];
+        r[k] = act[k] ? p.slot_of[v0 + i] : 0;
+      }
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        sgl[k] = false;
+        if (act[k]) {
+          const unsigned long long word = __ldcg(&tab[r[k]]);
+          r[k] = (int)(unsigned)word;
+          sgl[k] = ((word >> 32) & 1ULL) && r[k] == v0 + i;
+        }
+      }
+      // verification against the representative: CSR row and label of both sides first, then the sorted labels
+      int bv[WLF_VPT], dv[WLF_VPT], br[WLF_VPT], dr[WLF_VPT], lo[WLF_VPT], lr[WLF_VPT];
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        bv[k] = dv[k] = br[k] = dr[k] = lo[k] = lr[k] = 0;
+        if (act[k] && r[k] != v0 + i) {
+          bv[k] = p.row_ptr[v0 + i]; dv[k] = p.row_ptr[v0 + i + 1] - bv[k];
+          br[k] = p.row_ptr[r[k]]; dr[k] = p.row_ptr[r[k] + 1] - br[k];
+          lo[k] = lab_s[i]; lr[k] = __ldcg(&lab_in[r[k]]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        const int v = v0 + i;
+        unsigned long long fz = 0ULL;  // self-similarity contribution of a vertex that freezes now
+        int gg = -1;
+        if (act[k]) {
+          if (r[k] != v) {
+            bool same = (dv[k] == dr[k]) && (lo[k] == lr[k]);
+            if (same && dv[k] <= 8) {
+              int a[8], c[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                a[j] = j < dv[k] ? p.sig_nbr[bv[k] + j] : 0;
+                c[j] = j < dv[k] ? __ldcg(&p.sig_nbr[br[k] + j]) : 0;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) same = same && (a[j] == c[j]);
+            } else {
+              for (int j = 0; same && j < dv[k]; ++j) same = p.sig_nbr[bv[k] + j] == __ldcg(&p.sig_nbr[br[k] + j]);
+            }
+            if (!same) atomicOr(&p.sc->collision, 1u);
+          } else {
+            n_rep += 1u;
+          }
+          if (sgl[k]) {  // a class of one vertex: frozen from this level on, one diagonal unit per remaining level
+            fz = (unsigned long long)(p.L - lv);
+            gg = p.vgraph[v];
+            n_new += (unsigned)(p.L - lv);
+            n_fz += (unsigned)(p.L - lv);
+            mx = max(mx, 1u);
+          }
+        } else if (i < nv) {
+          n_rep += 1u;  // a frozen vertex is a class of its own at every level
+        }
+        // per-graph aggregation of the frozen contributions (runs of equal graph inside the warp)
+        unsigned long long val = fz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned long long y = __shfl_down_sync(0xffffffffu, val, d);
+          const int gy = __shfl_down_sync(0xffffffffu, gg, d);
+          if (lane + d < 32 && gy == gg) val += y;
+        }
+        const int gprev = __shfl_up_sync(0xffffffffu, gg, 1);
+        if (gg >= 0 && (lane == 0 || gprev != gg) && val) {
+          atomicAdd(&p.st.diag[gg], val);
+          atomicAdd(&p.diag_frozen[gg], val);
+        }
+      }
+      __syncthreads();  // every thread has read the old labels / flags of the tile it needs
+#pragma unroll
+      for (int k = 0; k < WLF_VPT; ++k) {
+        const int i = tid + k * WLF_THREADS;
+        if (act[k]) {
+          lab_s[i] = r[k];
+          if (sgl[k]) { frz_s[i] = 1; p.frozen[v0 + i] = 1; }
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < nv; i += WLF_THREADS) lab_out[v0 + i] = lab_s[i];
+      wlf2_emit(p, v0, nv, lab_s, frz_s, agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
+    }
+    WLF_STAMP(lv, 3);
+    if (lv + 2 < p.L) {  // clear the table level lv+2 inserts into (last read in [B] of level lv-1, which every CTA has left)
+      const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      uint4* hk = reinterpret_cast<uint4*>(p.table + (size_t)((lv + 2) % 3) * ht_cap);
+      for (size_t i = (size_t)b * WLF_THREADS + tid; i < ht_cap / 2; i += (size_t)G * WLF_THREADS) hk[i] = ones;
+    }
+    flush_partials(lv);  // ends with __syncthreads
+    WLF_STAMP(lv, 6);
+  }
+}
+
+// ---- dense first-occurrence ids of one level >= 1 on demand (gk_wl_labels, WL-SP): representatives are the
+// vertices with lab[v] == v; their rank in vertex order is the id the reference-order-free parity tests use.
+constexpr int DENS_THREADS = 1024;
+__global__ void __launch_bounds__(DENS_THREADS)
+wl_dens_count(int V, const int* __restrict__ lab, int* __restrict__ block_sums) {
+  __shared__ int s_warp[32];
+  const int v = blockIdx.x * DENS_THREADS + threadIdx.x;
+  const int f = (v < V && lab[v] == v) ? 1 : 0;
+  int total;
+  wlf_block_scan(f, &total, s_warp);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(DENS_THREADS)
+wl_dens_scan(int nb, int* block_sums) {  // one block: exclusive scan in place
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nb; i0 += DENS_THREADS) {
+    const int i = i0 + threadIdx.x;
+    const int x = i < nb ? block_sums[i] : 0;
+    int total;
+    const int ex = wlf_block_scan(x, &total, s_warp);
+    if (i < nb) block_sums[i] = s_carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(DENS_THREADS)
+wl_dens_rank(int V, const int* __restrict__ lab, const int* __restrict__ block_sums, int* __restrict__ rank) {
+  __shared__ int s_warp[32];
+  const int v = blockIdx.x * DENS_THREADS + threadIdx.x;
+  const int f = (v < V && lab[v] == v) ? 1 : 0;
+  int total;
+  const int ex = wlf_block_scan(f, &total, s_warp);
+  if (f) rank[v] = block_sums[blockIdx.x] + ex;
+}
+__global__ void __launch_bounds__(256)
+wl_dens_apply(int V, const int* __restrict__ lab, const int* __restrict__ rank, int* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V) out[v] = rank[lab[v]];
+}
+
+}  // namespace gk

@@ -136,9 +136,11 @@ oa_expand(size_t cap, const unsigned long long* __restrict__ keys, const unsigne
 }
 
 // per-CTA partials of the feature kernels, as diag_finish folds them: one "CTA", largest count 1
-__global__ void oa_finish(const OaCursors* cur, unsigned* part_max, unsigned* part_new) {
-  part_max[0] = cur->n_entries ? 1u : 0u;
-  part_new[0] = (unsigned)cur->n_entries;
+__global__ void oa_finish(const OaCursors* cur, unsigned* part_max, unsigned* part_new, const DevScalars* sc, int add_frozen) {
+  // frozen vertices of wl_fused2 wrote no count entries; each of their (vertex, level) units is one unary entry
+  const unsigned long long n = cur->n_entries + (add_frozen ? sc->sp_coo : 0ULL);
+  part_max[0] = n ? 1u : 0u;
+  part_new[0] = (unsigned)n;
 }
 
 }  // namespace gk
