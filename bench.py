@@ -259,6 +259,68 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_config4(eng, n4, rank, world, local, dist, torch, _lib, steps):
+    """BASELINE config 4: WL-subtree (h=5) Gram of n4 graphs, row-tiled over the ranks (GK_DIST tiles, mirrored halves
+    over NVLink) and assembled on EVERY rank by the in-place all-gather of gk_gram(GK_DIST_GATHER).  Returns rank 0's
+    report; parity = prefix of the assembled matrix against a single-GPU run, checksum equal on all ranks."""
+    gp, rp, ci, lab = pack_workload(n4)
+    eng.pack(gp, rp, ci, lab)
+    rb, re_ = eng.comm_rows(n4)
+    ts, t_feat, t_gemm, t_tail = [], [], [], []
+    for it in range(2 + steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        eng.event_record(2)
+        s = eng.wl_features(H)
+        eng.gram(n4, out=False, dtype=np.float32, row_range=(rb, re_), stats=s, want_diag=False, gather=True)
+        eng.event_record(3)
+        ms = eng.event_elapsed(2, 3)
+        if it >= 2:
+            ts.append(ms); t_feat.append(s.ms_features); t_gemm.append(s.ms_panel + s.ms_gemm); t_tail.append(s.ms_tail)
+    tt = torch.tensor([float(np.mean(ts))], device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ptr, rows, cols, ld, _ = eng.result_device()
+
+    class _View:  # zero-copy torch view of the library-owned fp32 result
+        __cuda_array_interface__ = {"data": (ptr, False), "shape": (rows, ld), "typestr": "<f4", "version": 3}
+    Kd = torch.as_tensor(_View(), device="cuda")[:, :cols]
+    cs = 0.0
+    for r0 in range(0, rows, 4096):  # fp64 checksum in row chunks
+        cs += float(Kd[r0:r0 + 4096].double().sum().item())
+    Kfull = Kd[: min(2048, n4), : min(2048, n4)].cpu().numpy()
+    cst = torch.tensor([cs], device="cuda", dtype=torch.float64)
+    lo, hi = cst.clone(), cst.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok_prefix = None
+    if rank == 0:
+        p1 = min(2048, n4)
+        e1 = _lib.Engine(local)
+        e1.pack(*pack_workload(p1))
+        s1 = e1.wl_features(H)
+        K1, _, _ = e1.gram(p1, dtype=np.float32, stats=s1, want_diag=False)
+        ok_prefix = bool(np.array_equal(Kfull[:p1, :p1], K1))
+        del e1
+    ms = float(tt.item())
+    from grakel_b200.dist import TILE, rows_per_rank
+    per = rows_per_rank(n4, world, TILE)
+    gather_bytes_in = (world - 1) * per * ld * 4
+    t_other = float(np.mean(t_feat)) + float(np.mean(t_gemm))
+    t_gather = float(np.mean(t_tail))  # barrier + tail + all-gather (tev[7] -> end of the device work)
+    return {"workload": f"config4: {n4} ER graphs (avg {NBAR} nodes, 7 labels, seed {SEED}), WL-subtree h={H}, K on every rank",
+            "n_gpus": world, "ms_per_step": ms, "pairs_per_s": n4 * n4 / (ms * 1e-3),
+            "ms_relabel_replicated": float(np.mean(t_feat)), "ms_columns_panel_gemm": float(np.mean(t_gemm)),
+            "ms_barrier_tail_allgather": t_gather,
+            "allgather_bytes_in_per_rank": int(gather_bytes_in),
+            "allgather_GBps_in_per_rank": gather_bytes_in / (t_gather * 1e-3) / 1e9 if t_gather > 0 else None,
+            "nvlink5_peak_GBps_per_direction": 900.0,
+            "result_bytes_per_rank": int(world * per * ld * 4),
+            "checksum": cs, "checksum_equal_on_all_ranks": bool(lo.item() == hi.item()),
+            "prefix_equals_single_gpu": ok_prefix,
+            "note": "the all-gather moves (G-1)/G of a 4 N^2-byte matrix INTO every GPU: at NVLink-5 rates that is longer than the "
+                    "whole compute, so the step is bandwidth-bound by construction; compute is what hides behind it, not the reverse"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,8 +358,13 @@ def main():
     n = int(round(args.graphs * np.sqrt(world)))
     gp, rp, ci, lab = pack_workload(n)
     V, E = int(gp[-1]), int(rp[-1])
-    from grakel_b200.dist import row_block
-    rb, re_ = row_block(n, rank, world)
+    if world > 1:
+        # C-ABI communicator (gk_comm_init): NCCL id broadcast over torch.distributed, everything else in the library
+        from grakel_b200.dist import comm_init
+        comm_init(eng)
+        rb, re_ = eng.comm_rows(n)
+    else:
+        rb, re_ = 0, n
 
     def barrier():
         if world > 1:
@@ -311,7 +378,7 @@ def main():
     def step():
         s = eng.wl_features(H)
         eng.gram(n, out=False, dtype=np.float32, row_range=(rb, re_) if world > 1 else None, stats=s,
-                 want_diag=False)
+                 want_diag=False, dist=world > 1)
         return s
 
     for _ in range(args.warmup):
@@ -350,7 +417,7 @@ def main():
                 return eng.wl_fit_transform_raw(gp_p, rp_p, ci_p, lab_p, H, Kh)
             eng.pack(gp_p, rp_p, ci_p, lab_p)
             s = eng.wl_features(H)
-            eng.gram(n, out=Kh, dtype=np.float64, row_range=(rb, re_), stats=s, want_diag=False)
+            eng.gram(n, out=Kh, dtype=np.float64, row_range=(rb, re_), stats=s, want_diag=False, dist=True)
             return s
 
         for _ in range(2):
@@ -375,11 +442,36 @@ def main():
         tb = {}
         t0 = time.perf_counter(); eng.pack(gp_p, rp_p, ci_p, lab_p); tb["pack_csr(host scans + H2D)"] = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter(); s_ = eng.wl_features(H); tb["wl_features"] = (time.perf_counter() - t0) * 1e3
-        t0 = time.perf_counter(); eng.gram(n, out=Kh, dtype=np.float64, row_range=(rb, re_) if world > 1 else None, stats=s_, want_diag=False)
+        t0 = time.perf_counter(); eng.gram(n, out=Kh, dtype=np.float64, row_range=(rb, re_) if world > 1 else None, stats=s_, want_diag=False, dist=world > 1)
         tb["gram + D2H"] = (time.perf_counter() - t0) * 1e3
         e2e["host_wall_ms"] = tb
         if rank == 0 and world == 1 and n == N_GRAPHS:
             assert float(Kh.sum()) == 22925628586.0, "K checksum differs from the reference golden"
+
+    # ------------------------------------------------ multi-GPU: parity of the tiled result, BASELINE config 4
+    dist_check, config4 = None, None
+    if world > 1:
+        # every rank's row block against rows of a single-GPU run of a prefix (an entry depends on its two graphs only)
+        eng.gram(n, out=False, dtype=np.float32, row_range=(rb, re_), stats=st, want_diag=False, dist=True)
+        p1 = min(1536, n)
+        ok = True
+        if rb < p1:
+            blk = np.empty((min(re_, p1) - rb, n), dtype=np.float32)
+            full = np.empty((re_ - rb, n), dtype=np.float32)
+            eng.fetch(full)
+            blk[:] = full[: blk.shape[0]]
+            e1 = _lib.Engine(local)
+            e1.pack(*pack_workload(p1))
+            s1 = e1.wl_features(H)
+            K1, _, _ = e1.gram(p1, dtype=np.float32, stats=s1, want_diag=False)
+            ok = bool(np.array_equal(blk[:, :p1], K1[rb:rb + blk.shape[0]]))
+            del e1
+        okt = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        dist_check = {"row_blocks_equal_single_gpu_prefix": bool(okt.item() == 1), "prefix": p1}
+        n4 = int(os.environ.get("GRAKEL_B200_CONFIG4_GRAPHS", "50000" if world == 8 else "0"))
+        if n4 > 0:
+            config4 = run_config4(eng, n4, rank, world, local, dist, torch, _lib, max(3, min(args.steps, 5)))
 
     # ------------------------------------------------ end to end through the Python API (SURVEY 8d T_e2e)
     e2e_api = None
@@ -434,8 +526,8 @@ def main():
     peak_tf, peak_hbm, peak_src = peaks()
     Dc = int(st.n_dense_columns)
     g_ms = float(np.mean(gemm_ms))
-    tiles_full = world > 1
-    flops = (2.0 * (re_ - rb) * n * Dc) if tiles_full else (float(n) * (n + 1) * Dc)
+    # multi-GPU: the SYRK tiles are shared between the ranks (each computed once); rank 0's share = its tile count
+    flops = (2.0 * 256 * 256 * Dc * int(st.gemm_tiles)) if world > 1 else (float(n) * (n + 1) * Dc)
     achieved = flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     line = {
         "metric": "graph-pairs/sec, N x N WL-subtree (h=5) Gram", "value": value, "unit": "pairs/s",
@@ -444,12 +536,17 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"config2: {n} ER graphs (avg {NBAR} nodes, 7 labels, seed {SEED}), WL-subtree h={H}",
                    "vertices": V, "directed_edges": E, "feature_columns": int(st.n_columns), "nnz": int(st.n_entries),
-                   "dense_columns_Dc": Dc, "parallelism": f"rows of K tiled over {world} GPU(s), CSR replicated",
+                   "dense_columns_Dc": Dc,
+                   "parallelism": (f"rows of K tiled over {world} GPUs (gk_comm_init / GK_DIST): SYRK tiles shared, mirrored halves "
+                                   f"stored into the owner's row block over NVLink by the GEMM epilogue; CSR + relabel replicated")
+                   if world > 1 else "1 GPU",
                    "l2": "per-step working set (panel %.0f MB + K %.0f MB) exceeds the 126 MB L2" %
                          (n * ((Dc + 63) // 64 * 64) * 2 / 1e6, (re_ - rb if world > 1 else n) * n * 4 / 1e6)},
         "clocks": clk.summary(),
         "e2e": e2e,
         "e2e_api": e2e_api,
+        "dist_check": dist_check,
+        "config4": config4,
         "gpu_launches": launches,
         "roofline": {"kernel": GEMM_KERNEL, "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

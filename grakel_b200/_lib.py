@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libgrakel_b200.so")
 
 GK_F32, GK_F64 = 0, 1
 GK_NORMALIZE, GK_NAN_TO_NUM, GK_GRAM_SIMT, GK_OUT_DEVICE, GK_FULL_TILES, GK_DENSE_ALL = 1, 2, 4, 8, 16, 32
+GK_DIST, GK_DIST_GATHER = 64, 128
 GK_SP_WITH_LABELS, GK_SP_KEEP_DIST = 1, 2
 GK_ERR_RANGE, GK_ERR_UNSUPPORTED = -4, -5
 
@@ -78,6 +79,13 @@ _SYMBOLS = {
     "gk_tu_pack": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gk_tu_fill": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gk_tu_close": (C.c_int, [_P]),
+    "gk_comm_unique_id": (C.c_int, [_P]),
+    "gk_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "gk_comm_destroy": (C.c_int, [_P]),
+    "gk_comm_rows": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gk_result_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int32)]),
+    "gk_selftest_dist_tiles": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "gk_host_alloc": (C.c_int, [C.c_int64, C.POINTER(_P)]),
     "gk_host_free": (C.c_int, [_P, C.c_int64]),
     "gk_selftest_deliver": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, _P, _P, C.c_int32, _P]),
@@ -233,7 +241,7 @@ class Engine:
 
     def gram(self, n_graphs, n_fit=None, normalize=False, nan_to_num=False, out=None, dtype=np.float64,
              row_range=None, simt=False, full_tiles=False, stats=None, want_diag=True, device_ptr=None, ld=0,
-             dense_all=False):
+             dense_all=False, dist=False, gather=False):
         """Returns (K, xdiag, ydiag).  K is a fresh C-order numpy array unless
         `out` (host array) or `device_ptr` (raw device pointer) is given."""
         n_fit = n_graphs if n_fit is None else int(n_fit)
@@ -244,6 +252,7 @@ class Engine:
         code = GK_F64 if dt == np.float64 else GK_F32
         flags = (GK_NORMALIZE if normalize else 0) | (GK_NAN_TO_NUM if nan_to_num else 0)
         flags |= (GK_GRAM_SIMT if simt else 0) | (GK_FULL_TILES if full_tiles else 0) | (GK_DENSE_ALL if dense_all else 0)
+        flags |= (GK_DIST if dist else 0) | (GK_DIST_GATHER if gather else 0)
         K = None
         kptr = None
         if device_ptr is not None:
@@ -264,6 +273,37 @@ class Engine:
             self._check(self.lib.gk_gram(self.h, n_fit, flags, rb, re_, kptr, code, int(ld), _ptr(xd), _ptr(yd),
                                          C.byref(st)))
         return K, xd, yd
+
+    # ---- multi-GPU (one process per GPU; collective calls)
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id created by one rank; hand it to every rank (torch.distributed, MPI, a file ...)."""
+        buf = C.create_string_buffer(128)
+        lib = load_library()
+        if lib.gk_comm_unique_id(buf) != 0:
+            raise GrakelB200Error("gk_comm_unique_id: " + lib.gk_last_error().decode())
+        return bytes(buf.raw)
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.gk_comm_init(self.h, int(nranks), int(rank), buf))
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def comm_rows(self, n_rows):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.gk_comm_rows(self.h, int(n_rows), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def result_device(self):
+        """(device pointer, rows, cols, ld, dtype code) of the library-owned result of the last gram()."""
+        p, r, c, ld, dt = _P(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        self._check(self.lib.gk_result_device(self.h, C.byref(p), C.byref(r), C.byref(c), C.byref(ld), C.byref(dt)))
+        return p.value, r.value, c.value, ld.value, dt.value
+
+    def fetch(self, out):
+        code = GK_F64 if out.dtype == np.float64 else GK_F32
+        self._check(self.lib.gk_fetch(self.h, _ptr(out), code, out.shape[1]))
+        return out
 
     def wl_labels(self, level, n_vertices):
         out = np.empty(n_vertices, dtype=np.int32)

@@ -6,6 +6,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <atomic>
 #include <thread>
 
 #include <immintrin.h>
@@ -25,6 +26,7 @@
 #include "wl_fused2.cuh"
 #include "wl_oa.cuh"
 #include "tu_reader.h"
+#include "comm.h"
 
 namespace gk {
 thread_local std::string g_last_error;
@@ -165,6 +167,77 @@ int gk_create(int device_ordinal, gk_handle** out) {
   return GK_OK;
 }
 
+// --------------------------------------------------------------------------- multi-GPU (comm.h)
+int gk_comm_unique_id(void* out128) {
+  if (!out128) return fail(GK_ERR_ARG, "gk_comm_unique_id: null argument");
+  NcclApi* api = nccl_api();
+  if (!api->lib || !api->error.empty()) return fail(GK_ERR_UNSUPPORTED, "gk_comm_unique_id: " + api->error);
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  GK_NCCL(api, api->GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  return GK_OK;
+}
+
+int gk_comm_destroy(gk_handle* h) {
+  if (!h || !h->comm) return GK_OK;
+  Comm* c = reinterpret_cast<Comm*>(h->comm);
+  cudaSetDevice(h->dev);
+  cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < c->nranks; ++r)
+    if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+  if (c->d_token) cudaFree(c->d_token);
+  if (c->d_handles) cudaFree(c->d_handles);
+  NcclApi* api = nccl_api();
+  if (c->comm && api->CommDestroy) api->CommDestroy(c->comm);
+  delete c;
+  h->comm = nullptr;
+  return GK_OK;
+}
+
+int gk_comm_init(gk_handle* h, int32_t nranks, int32_t rank, const void* unique_id128) {
+  if (!h || !unique_id128) return fail(GK_ERR_ARG, "gk_comm_init: null argument");
+  if (nranks < 1 || nranks > DIST_MAX_RANKS || rank < 0 || rank >= nranks) return fail(GK_ERR_ARG, "gk_comm_init: 1..8 ranks");
+  if (h->comm) return fail(GK_ERR_STATE, "gk_comm_init: the handle already has a communicator");
+  NcclApi* api = nccl_api();
+  if (!api->lib || !api->error.empty()) return fail(GK_ERR_UNSUPPORTED, "gk_comm_init: " + api->error);
+  GK_CUDA(cudaSetDevice(h->dev));
+  Comm* c = new Comm();
+  c->nranks = nranks; c->rank = rank;
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  ncclResult_t r = api->CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) { delete c; return fail(GK_ERR_CUDA, std::string("ncclCommInitRank: ") + api->GetErrorString(r)); }
+  if (cudaMalloc(&c->d_token, 256) != cudaSuccess || cudaMalloc(&c->d_handles, (size_t)(nranks + 1) * 64) != cudaSuccess) {
+    delete c;
+    return fail(GK_ERR_CUDA, "gk_comm_init: cudaMalloc failed");
+  }
+  cudaMemset(c->d_token, 0, 256);
+  h->comm = c;
+  return GK_OK;
+}
+
+int gk_comm_rows(gk_handle* h, int64_t n_rows, int64_t* row_begin, int64_t* row_end) {
+  if (!h || !row_begin || !row_end || n_rows < 0) return fail(GK_ERR_ARG, "gk_comm_rows: bad arguments");
+  Comm* c = reinterpret_cast<Comm*>(h->comm);
+  const int nranks = c ? c->nranks : 1, rank = c ? c->rank : 0;
+  const long long per = dist_rows_per_rank(n_rows, nranks);
+  *row_begin = std::min<long long>(n_rows, rank * per);
+  *row_end = std::min<long long>(n_rows, (rank + 1) * per);
+  return GK_OK;
+}
+
+// Host-only: the tile list of one rank (tests of the partition; no device, no communicator needed)
+int gk_selftest_dist_tiles(int64_t n_rows, int32_t nranks, int32_t rank, int32_t* tiles_xy, int64_t cap, int64_t* n_tiles) {
+  if (!n_tiles || nranks < 1 || nranks > DIST_MAX_RANKS || rank < 0 || rank >= nranks) return fail(GK_ERR_ARG, "gk_selftest_dist_tiles: bad arguments");
+  std::vector<int2> t;
+  dist_tiles(n_rows, nranks, rank, t);
+  *n_tiles = (int64_t)t.size();
+  if (tiles_xy)
+    for (size_t i = 0; i < t.size() && (int64_t)i < cap; ++i) { tiles_xy[2 * i] = t[i].x; tiles_xy[2 * i + 1] = t[i].y; }
+  return GK_OK;
+}
+
 int gk_destroy(gk_handle* h) {
   if (!h) return GK_OK;
   cudaSetDevice(h->dev);
@@ -190,6 +263,7 @@ int gk_destroy(gk_handle* h) {
   cudaEventDestroy(h->ev_fork);
   cudaEventDestroy(h->ev_join);
   for (auto& e : h->ev_stage) cudaEventDestroy(e);
+  gk_comm_destroy(h);
   drop_extra(h);
   delete h;
   return GK_OK;
@@ -510,7 +584,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
         for (int b = 0; b < G; ++b) t0 = std::min(t0, pr[(size_t)b * L * 16]);
         fprintf(stderr, "[wl_fused2 prof] us; per level: avg over CTAs of the phase duration (max)\n");
         for (int lv = 0; lv < L; ++lv) {
-          double avg[4] = {0}, mxv[4] = {0};
+          double avg[4] = {0}, mxv[4] = {0}, sub[5] = {0};
           long long end_max = 0;
           for (int b = 0; b < G; ++b) {
             const long long* q = &pr[((size_t)b * L + lv) * 16];
@@ -518,9 +592,12 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
             if (lv == 0) { avg[3] += (double)(q[6] - q[0]) / G; mxv[3] = std::max(mxv[3], (double)(q[6] - q[0])); continue; }
             const double d[4] = {(double)(q[1] - q[0]), (double)(q[2] - q[1]), (double)(q[3] - q[2]), (double)(q[6] - q[3])};
             for (int k = 0; k < 4; ++k) { avg[k] += d[k] / G; mxv[k] = std::max(mxv[k], d[k]); }
+            sub[0] += (double)(q[10] - q[0]) / G; sub[1] += (double)(q[1] - q[10]) / G;   // A: signatures | insert + copy-out
+            sub[2] += (double)(q[4] - q[2]) / G; sub[3] += (double)(q[5] - q[4]) / G; sub[4] += (double)(q[3] - q[5]) / G;  // B: verify | labels | emit
           }
-          fprintf(stderr, "  level %d: A %.1f (%.1f) wait %.1f (%.1f) B+emit %.1f (%.1f) clear+flush %.1f (%.1f) | level done at %.1f us\n", lv,
-                  avg[0] / 1e3, mxv[0] / 1e3, avg[1] / 1e3, mxv[1] / 1e3, avg[2] / 1e3, mxv[2] / 1e3, avg[3] / 1e3, mxv[3] / 1e3, end_max / 1e3);
+          fprintf(stderr, "  level %d: A %.1f (%.1f) wait %.1f (%.1f) B+emit %.1f (%.1f) clear+flush %.1f (%.1f) | A = sig %.1f + insert %.1f | B = verify %.1f + labels %.1f + emit %.1f | level done at %.1f us\n", lv,
+                  avg[0] / 1e3, mxv[0] / 1e3, avg[1] / 1e3, mxv[1] / 1e3, avg[2] / 1e3, mxv[2] / 1e3, avg[3] / 1e3, mxv[3] / 1e3,
+                  sub[0] / 1e3, sub[1] / 1e3, sub[2] / 1e3, sub[3] / 1e3, sub[4] / 1e3, end_max / 1e3);
         }
       }
     } else if (fused) {
@@ -1269,6 +1346,44 @@ static void build_tiles(std::vector<int2>& tiles, int a0, int a1, int b0, int b1
   }
 }
 
+// ---- multi-GPU helpers (collective: every rank of the communicator calls them in the same order)
+static int comm_barrier(gk_handle* h) {
+  Comm* c = reinterpret_cast<Comm*>(h->comm);
+  NcclApi* api = nccl_api();
+  GK_NCCL(api, api->AllReduce(c->d_token, c->d_token, 1, ncclInt32, ncclSum, c->comm, h->stream));
+  return GK_OK;
+}
+
+// Make h->K (>= bytes, the same request on every rank) visible to the peers: CUDA IPC handles travel through one
+// ncclAllGather; mappings are renewed only when the buffer had to grow (the same call on every rank).
+static int comm_share_K(gk_handle* h, size_t bytes) {
+  Comm* c = reinterpret_cast<Comm*>(h->comm);
+  NcclApi* api = nccl_api();
+  if (c->exported && c->exported == h->K.p && h->K.cap >= bytes) return GK_OK;
+  // peers unmap the old buffer before anybody frees it
+  for (int r = 0; r < c->nranks; ++r)
+    if (r != c->rank && c->peer_base[r]) { cudaIpcCloseMemHandle(c->peer_base[r]); c->peer_base[r] = nullptr; }
+  GK_TRY(comm_barrier(h));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  GK_TRY(h->K.ensure(bytes));
+  cudaIpcMemHandle_t mine;
+  GK_CUDA(cudaIpcGetMemHandle(&mine, h->K.p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  unsigned char* d_mine = c->d_handles + (size_t)c->nranks * 64;
+  GK_CUDA(cudaMemcpyAsync(d_mine, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+  GK_NCCL(api, api->AllGather(d_mine, c->d_handles, 64, ncclChar, c->comm, h->stream));
+  std::vector<cudaIpcMemHandle_t> all(c->nranks);
+  GK_CUDA(cudaMemcpyAsync(all.data(), c->d_handles, (size_t)c->nranks * 64, cudaMemcpyDeviceToHost, h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < c->nranks; ++r) {
+    if (r == c->rank) { c->peer_base[r] = h->K.p; continue; }
+    GK_CUDA(cudaIpcOpenMemHandle(&c->peer_base[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+  }
+  c->exported = h->K.p;
+  c->exported_cap = h->K.cap;
+  return GK_OK;
+}
+
 extern "C" {
 
 int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64_t row_end, void* K_out,
@@ -1417,6 +1532,24 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   const int32_t dev_dtype = widen_on_host ? GK_F32 : out_dtype;
   const size_t dev_esz = dev_dtype == GK_F64 ? 8 : 4;
 
+  // multi-GPU row tiling (GK_DIST, collective): SYRK tiles shared between the ranks, mirrored halves stored into the
+  // owner's row block over NVLink.  Needs the tensor path and fp32 device output; otherwise every rank computes its
+  // row block with full tiles (the decision depends on replicated data only, so all ranks take the same branch).
+  Comm* comm = reinterpret_cast<Comm*>(h->comm);
+  const bool dist_req = (flags & (GK_DIST | GK_DIST_GATHER)) != 0;
+  if (dist_req) {
+    if (!comm) return fail(GK_ERR_STATE, "gk_gram: GK_DIST without gk_comm_init");
+    if (!square || d_row_map) return fail(GK_ERR_UNSUPPORTED, "gk_gram: GK_DIST needs the square fit_transform case without a row map");
+    if (flags & GK_OUT_DEVICE) return fail(GK_ERR_UNSUPPORTED, "gk_gram: GK_DIST results are library-owned (gk_result_device / gk_fetch / host K_out)");
+    int64_t rb = 0, re = 0;
+    GK_TRY(gk_comm_rows(h, N, &rb, &re));
+    if (row_begin != rb || row_end != re) return fail(GK_ERR_ARG, "gk_gram: GK_DIST row range must be the one gk_comm_rows returns");
+  }
+  const bool dist = dist_req && path == 1 && dev_dtype == GK_F32 && !normalize;
+  const bool gather = dist && (flags & GK_DIST_GATHER);
+  const long long dist_per = dist_req ? dist_rows_per_rank(N, comm->nranks) : 0;
+
+
   // ---- output buffer
   void* d_out = nullptr;
   if (flags & GK_OUT_DEVICE) {
@@ -1426,8 +1559,15 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     // library-owned K: rows padded to a multiple of 8 elements so that every row is 32-byte aligned
     // (TMA / 256-bit stores in the GEMM epilogue for any n_fit, e.g. 14 142 graphs on 2 GPUs)
     h->K_ld = (k_cols + 7) / 8 * 8;
-    GK_TRY(h->K.ensure((size_t)std::max<int64_t>(k_rows, 1) * h->K_ld * dev_esz));
-    d_out = h->K.p;
+    if (dist_req) {
+      // the same request on every rank: a block of dist_per rows (all comm->nranks of them for the gathered result)
+      const size_t blk = (size_t)dist_per * h->K_ld * dev_esz;
+      GK_TRY(comm_share_K(h, (flags & GK_DIST_GATHER) ? blk * comm->nranks : blk));
+      d_out = (flags & GK_DIST_GATHER) ? (void*)(h->K.as<char>() + (size_t)comm->rank * blk) : h->K.p;
+    } else {
+      GK_TRY(h->K.ensure((size_t)std::max<int64_t>(k_rows, 1) * h->K_ld * dev_esz));
+      d_out = h->K.p;
+    }
     h->K_rows = k_rows; h->K_cols = k_cols; h->K_dtype = dev_dtype;
   }
   const long long d_ld = (flags & GK_OUT_DEVICE) ? ld : h->K_ld;
@@ -1436,7 +1576,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   const int a0 = (int)((square ? 0 : n_fit) + row_begin), a1 = (int)((square ? 0 : n_fit) + row_end);
   const int b0 = 0, b1 = (int)n_fit;
   const bool full_square = square && row_begin == 0 && row_end == N;
-  const bool mirror = full_square && !(flags & GK_FULL_TILES);
+  const bool mirror = (full_square && !(flags & GK_FULL_TILES)) || dist;
   const bool has_tail = path != 2 && n_tail_cols > 0;
   const bool norm_in_epilogue = normalize && !has_tail && !host_norm;
 
@@ -1450,6 +1590,14 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   p.nan_to_num = (flags & GK_NAN_TO_NUM) ? 1 : 0;
   p.vec_ok = (((uintptr_t)d_out) % 32 == 0 && (d_ld * (long long)dev_esz) % 32 == 0) ? 1 : 0;
   p.diag = h->diag_f64.as<double>();
+  if (dist) {
+    const size_t blk = (size_t)dist_per * d_ld * 4;
+    for (int r = 0; r < comm->nranks; ++r)
+      p.peer[r] = (flags & GK_DIST_GATHER) ? (void*)((char*)comm->peer_base[r] + (size_t)r * blk) : comm->peer_base[r];
+    p.n_peers = comm->nranks;
+    p.peer_rows = (int)dist_per;
+  }
+  if (dist_req) GK_TRY(comm_barrier(h));  // nobody still reads the block a peer is about to overwrite
 
   GK_CUDA(cudaEventRecord(h->tev[5], h->stream));
   int64_t n_tiles = 0;
@@ -1477,7 +1625,12 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       const bool cta2 = !(e_cta2 && atoi(e_cta2) == 0) && dev_dtype == GK_F32 && !norm_in_epilogue &&
                         ((uintptr_t)d_out) % 16 == 0 && (d_ld * 4) % 16 == 0 && !getenv("GRAKEL_B200_NO_TMA_STORE");
       std::vector<int2> tiles;
-      build_tiles(tiles, a0, a1, b0, b1, mirror, cta2 ? BM2 : BM);
+      if (dist) {
+        if (!cta2) return fail(GK_ERR_UNSUPPORTED, "gk_gram: GK_DIST needs the CTA-pair kernel (GRAKEL_B200_CTA2=0 is set?)");
+        dist_tiles(N, comm->nranks, comm->rank, tiles);
+      } else {
+        build_tiles(tiles, a0, a1, b0, b1, mirror, cta2 ? BM2 : BM);
+      }
       n_tiles = (int64_t)tiles.size();
       GK_TRY(h->h_tiles.ensure(tiles.size() * sizeof(int2)));
       memcpy(h->h_tiles.p, tiles.data(), tiles.size() * sizeof(int2));
@@ -1492,7 +1645,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
           !getenv("GRAKEL_B200_NO_TMA_STORE")) {
         GK_TRY(make_out_map(&tmC, d_out, k_cols, k_rows, d_ld));
         p.tma_store = 1;
-        if (p.mirror) {  // full square: the mirrored half goes through the same tensor map
+        if (p.mirror && !dist) {  // full square: the mirrored half goes through the same tensor map
           const char* e = getenv("GRAKEL_B200_MIRROR_TMA");
           if (!e || atoi(e) != 0) p.mirror = 2;
         }
@@ -1508,7 +1661,8 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
         p.prof = h->K_stage.as<long long>();
       }
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
-      if (cta2) gram_tc2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM, h->stream>>>(tmA, tmC, p);
+      if (n_tiles == 0) { /* a trailing rank without rows */ }
+      else if (cta2) gram_tc2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM, h->stream>>>(tmA, tmC, p);
       else if (dev_dtype == GK_F64) { if (norm_in_epilogue) launch_tc<double, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<double, false>(h, tmA, tmB, tmC, p, grid); }
       else { if (norm_in_epilogue) launch_tc<float, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<float, false>(h, tmA, tmB, tmC, p, grid); }
       LAUNCH_CHECK(h);
@@ -1540,6 +1694,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       LAUNCH_CHECK(h);
     }
     GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
+    if (dist_req) GK_TRY(comm_barrier(h));  // the peers' mirrored stores into this block precede the tail's atomics
     if (has_tail) {
       const int grid = cdiv(n_tail_cols * 32, 256);
       if (dev_dtype == GK_F64)
@@ -1564,6 +1719,16 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   } else {
     GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
     GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
+    if (dist_req) GK_TRY(comm_barrier(h));
+  }
+  if (dist_req && (flags & GK_DIST_GATHER)) {
+    // BASELINE config 4: every rank ends up with the full matrix -- one in-place all-gather of the finished row
+    // blocks (NCCL over NVLink / NVSwitch); the library-owned result is reached through gk_result_device / gk_fetch
+    NcclApi* api = nccl_api();
+    const size_t cnt = (size_t)dist_per * d_ld;
+    GK_CUDA(cudaEventRecord(h->ev[12], h->stream));
+    GK_NCCL(api, api->AllGather(d_out, h->K.p, cnt, dev_dtype == GK_F64 ? ncclFloat64 : ncclFloat32, comm->comm, h->stream));
+    h->K_rows = N;
   }
   GK_CUDA(cudaEventRecord(h->ev[13], h->stream));
   const int64_t launches_gram = h->launches - launches0;
@@ -1631,6 +1796,17 @@ int gk_set_row_map(gk_handle* h, int64_t n_rows, const int32_t* row_of_graph) {
   GK_CUDA(cudaMemcpyAsync(h->row_map.p, row_of_graph, h->N * 4, cudaMemcpyHostToDevice, h->stream));
   GK_CUDA(cudaStreamSynchronize(h->stream));
   h->n_rows = n_rows;
+  return GK_OK;
+}
+
+int gk_result_device(gk_handle* h, void** ptr, int64_t* rows, int64_t* cols, int64_t* ld, int32_t* dtype) {
+  if (!h || !ptr) return fail(GK_ERR_ARG, "gk_result_device: null argument");
+  if (!h->K.p || h->K_rows <= 0) return fail(GK_ERR_STATE, "gk_result_device: no device-resident result");
+  *ptr = h->K.p;
+  if (rows) *rows = h->K_rows;
+  if (cols) *cols = h->K_cols;
+  if (ld) *ld = h->K_ld;
+  if (dtype) *dtype = h->K_dtype;
   return GK_OK;
 }
 

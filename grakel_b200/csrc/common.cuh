@@ -189,4 +189,5 @@ struct gk_handle {
   gk::PinBuf h_stage;  // pinned staging ring of the result delivery
   gk::PinBuf h_diag;   // self similarities on the host (normalisation during the widening)
   int64_t launches = 0;
+  void* comm = nullptr;  // gk::Comm (comm.h) after gk_comm_init
 };

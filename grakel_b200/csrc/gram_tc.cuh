@@ -48,6 +48,12 @@ struct GramParams {
   const double* diag;  // self similarity per graph (fp64, exact integers)
   long long* prof;     // optional [gridDim.x][8] cycle counters (GRAKEL_B200_PROF), else NULL
   int tma_store;       // fp32 output through a TMA store of smem-staged 32x32 blocks (tmC valid)
+  // multi-GPU row tiling (gk_comm_init): the mirrored half of a tile belongs to the rank that owns K rows
+  // [tile.y, tile.y + 256) and is stored straight into THAT rank's row block over NVLink (peer-mapped memory);
+  // peer[r] = first row of rank r's block, peer_rows (a multiple of 256) rows per rank.  n_peers = 0: one GPU.
+  void* peer[8];
+  int n_peers;
+  int peer_rows;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -168,6 +174,10 @@ __device__ __forceinline__ void epi_tma_store_tile(const GramParams& p, const CU
   float dself = 0.f;
   if (diag_tile && row_ok) dself = (float)p.diag[arow];
   OutT* mptr = out + (long long)tile.y * p.ld + arow;
+  if (p.n_peers) {  // the mirrored block lives in its owner's row block (this rank's own for tiles of its diagonal block)
+    const int owner = tile.y / p.peer_rows;
+    mptr = reinterpret_cast<OutT*>(p.peer[owner]) + (long long)(tile.y - owner * p.peer_rows) * p.ld + arow;
+  }
   const long long ld = p.ld;
   const bool rows_in = arow0 < p.a_row_end;  // warp-uniform: any row of this warp's block inside
 #pragma unroll 1

@@ -61,9 +61,9 @@ struct WlFused2Params {
 // Fixed COO region per (tile, level), unused slots hold EMPTY64; per-column graph counts go through a shared-memory
 // aggregation table first (a column shared by every graph costs one global atomic per tile).
 __device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int nv, const int* lab_s, const unsigned char* frz_s,
+                                          const int* gid_s, const unsigned short* gbeg_s, const unsigned short* gend_s,
                                           unsigned* agg, long long base, size_t coo_off, int* s_warp, unsigned& mx, unsigned& n_new) {
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int s = tid; s < WLF_AGG * 2; s += WLF_THREADS) agg[s] = (s & 1) ? 0u : 0xFFFFFFFFu;  // {column, graphs}
   int g[WLF_VPT], l[WLF_VPT];
   unsigned cnt[WLF_VPT];
   bool emit[WLF_VPT];
@@ -71,10 +71,10 @@ __device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int n
 #pragma unroll
   for (int k = 0; k < WLF_VPT; ++k) {
     const int i = tid + k * WLF_THREADS;
-    g[k] = -1; l[k] = 0; cnt[k] = 0; emit[k] = false;
+    g[k] = i < nv ? gid_s[i] : -1;  // every vertex of the tile, frozen or not: graphs stay contiguous lane runs
+    l[k] = 0; cnt[k] = 0; emit[k] = false;
     if (i < nv && !frz_s[i]) {
-      g[k] = p.vgraph[v0 + i];
-      const int gs = p.graph_ptr[g[k]] - v0, ge = p.graph_ptr[g[k] + 1] - v0;
+      const int gs = gbeg_s[i], ge = gend_s[i];
       l[k] = lab_s[i];
       bool first = true;
       for (int u = gs; u < ge; ++u) {
@@ -87,7 +87,14 @@ __device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int n
     }
   }
   int total;
-  int ex = wlf_block_scan(n_emit, &total, s_warp);  // also orders the agg initialisation before its use
+  int ex = wlf_block_scan(n_emit, &total, s_warp);
+  // few entries (deep levels, where most vertices are frozen): straight to the global column counters; otherwise
+  // aggregate per tile in shared memory first (a column shared by every graph costs one global atomic per tile)
+  const bool use_agg = total > 256;
+  if (use_agg) {
+    for (int s = tid; s < WLF_AGG * 2; s += WLF_THREADS) agg[s] = (s & 1) ? 0u : 0xFFFFFFFFu;  // {column, graphs}
+    __syncthreads();
+  }
   for (int i = total + tid; i < nv; i += WLF_THREADS) p.coo_keys[coo_off + i] = EMPTY64;  // unused rest of the fixed region
 #pragma unroll
   for (int k = 0; k < WLF_VPT; ++k) {
@@ -98,12 +105,16 @@ __device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int n
       ++ex;
       mx = max(mx, cnt[k]);
       n_new += 1u;
-      unsigned slot = (col * 0x9E3779B1u >> 12) & (WLF_AGG - 1);
-      while (true) {
-        unsigned prev = agg[2 * slot];
-        if (prev == 0xFFFFFFFFu) prev = atomicCAS(&agg[2 * slot], 0xFFFFFFFFu, col);
-        if (prev == 0xFFFFFFFFu || prev == col) { atomicAdd(&agg[2 * slot + 1], 1u); break; }
-        slot = (slot + 1) & (WLF_AGG - 1);
+      if (use_agg) {
+        unsigned slot = (col * 0x9E3779B1u >> 12) & (WLF_AGG - 1);
+        while (true) {
+          unsigned prev = agg[2 * slot];
+          if (prev == 0xFFFFFFFFu) prev = atomicCAS(&agg[2 * slot], 0xFFFFFFFFu, col);
+          if (prev == 0xFFFFFFFFu || prev == col) { atomicAdd(&agg[2 * slot + 1], 1u); break; }
+          slot = (slot + 1) & (WLF_AGG - 1);
+        }
+      } else {
+        atomicAdd(&p.st.colcnt[col], 1u);
       }
     }
     // exact self similarity: sum of squared counts per graph (runs of equal g inside the warp)
@@ -118,15 +129,17 @@ __device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int n
     const int gprev = __shfl_up_sync(0xffffffffu, gg, 1);
     if (gg >= 0 && (lane == 0 || gprev != gg) && val) atomicAdd(&p.st.diag[gg], val);
   }
-  __syncthreads();
-  for (int s = tid; s < WLF_AGG; s += WLF_THREADS) {
-    const unsigned col = agg[2 * s];
-    if (col != 0xFFFFFFFFu) atomicAdd(&p.st.colcnt[col], agg[2 * s + 1]);
+  if (use_agg) {
+    __syncthreads();
+    for (int s = tid; s < WLF_AGG; s += WLF_THREADS) {
+      const unsigned col = agg[2 * s];
+      if (col != 0xFFFFFFFFu) atomicAdd(&p.st.colcnt[col], agg[2 * s + 1]);
+    }
   }
   __syncthreads();  // agg is reused by the next tile / overwritten by the next level's signatures
 }
 
-constexpr int WLF2_SMEM = WLF_SMEM + WLF_TILE_V /*frz_s*/;
+constexpr int WLF2_SMEM = WLF_SMEM + WLF_TILE_V /*frz_s*/ + WLF_TILE_V * 4 /*gid_s*/ + WLF_TILE_V * 4 /*gbeg_s, gend_s*/;
 
 __global__ void __launch_bounds__(WLF_THREADS, 1)
 wl_fused2_kernel(WlFused2Params p) {
@@ -138,6 +151,9 @@ wl_fused2_kernel(WlFused2Params p) {
   unsigned* agg = reinterpret_cast<unsigned*>(sig_s);  // emit phase only
   unsigned short* col_s = reinterpret_cast<unsigned short*>(sig_s + WLF_TILE_E);
   unsigned char* frz_s = reinterpret_cast<unsigned char*>(col_s + WLF_TILE_E);
+  int* gid_s = reinterpret_cast<int*>(frz_s + WLF_TILE_V);  // graph of every tile vertex
+  unsigned short* gbeg_s = reinterpret_cast<unsigned short*>(gid_s + WLF_TILE_V);  // its graph's vertex range, tile-local
+  unsigned short* gend_s = gbeg_s + WLF_TILE_V;
   __shared__ int s_warp[32];
   __shared__ unsigned s_red[128];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -173,6 +189,15 @@ wl_fused2_kernel(WlFused2Params p) {
     __syncthreads();
   };
 
+  auto stage_graphs = [&](int v0, int nv) {
+    for (int i = tid; i < nv; i += WLF_THREADS) {
+      const int g = p.vgraph[v0 + i];
+      gid_s[i] = g;
+      gbeg_s[i] = (unsigned short)(p.graph_ptr[g] - v0);
+      gend_s[i] = (unsigned short)(p.graph_ptr[g + 1] - v0);
+    }
+  };
+
   // ---- level 0: labels as given (dense ids); nothing is frozen yet
   for (int t = t_beg; t < t_end; ++t) {
     const int v0 = p.tile_vbeg[t], nv = p.tile_vbeg[t + 1] - v0;
@@ -183,13 +208,14 @@ wl_fused2_kernel(WlFused2Params p) {
       p.labels_all[v0 + i] = x;
       frz_s[i] = 0;
     }
+    stage_graphs(v0, nv);
     if (resident) {  // stage the CSR slice once
       const int e0 = p.row_ptr[v0], ne = p.row_ptr[v0 + nv] - e0;
       for (int i = tid; i <= nv; i += WLF_THREADS) rp_s[i] = p.row_ptr[v0 + i] - e0;
       for (int k = tid; k < ne; k += WLF_THREADS) col_s[k] = (unsigned short)(p.col_idx[e0 + k] - v0);
     }
     __syncthreads();
-    wlf2_emit(p, v0, nv, lab_s, frz_s, agg, 0, (size_t)v0, s_warp, mx, n_new);
+    wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, agg, 0, (size_t)v0, s_warp, mx, n_new);
   }
   if (p.L > 2) {  // table of level 2 (first touched after the barrier of level 1)
     const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -383,6 +409,7 @@ wl_fused2_kernel(WlFused2Params p) {
       if (!resident) {
         __syncthreads();
         for (int i = tid; i < nv; i += WLF_THREADS) { lab_s[i] = lab_in[v0 + i]; frz_s[i] = p.frozen[v0 + i]; }
+        stage_graphs(v0, nv);
         __syncthreads();
       }
       int r[WLF_VPT];
@@ -420,7 +447,7 @@ wl_fused2_kernel(WlFused2Params p) {
         const int i = tid + k * WLF_THREADS;
         const int v = v0 + i;
         unsigned long long fz = 0ULL;  // self-similarity contribution of a vertex that freezes now
-        int gg = -1;
+        const int gg = i < nv ? gid_s[i] : -1;  // every vertex: graphs stay contiguous lane runs
         if (act[k]) {
           if (r[k] != v) {
             bool same = (dv[k] == dr[k]) && (lo[k] == lr[k]);
@@ -442,7 +469,6 @@ wl_fused2_kernel(WlFused2Params p) {
           }
           if (sgl[k]) {  // a class of one vertex: frozen from this level on, one diagonal unit per remaining level
             fz = (unsigned long long)(p.L - lv);
-            gg = p.vgraph[v];
             n_new += (unsigned)(p.L - lv);
             n_fz += (unsigned)(p.L - lv);
             mx = max(mx, 1u);
@@ -464,6 +490,7 @@ wl_fused2_kernel(WlFused2Params p) {
           atomicAdd(&p.diag_frozen[gg], val);
         }
       }
+      WLF_STAMP(lv, 4);
       __syncthreads();  // every thread has read the old labels / flags of the tile it needs
 #pragma unroll
       for (int k = 0; k < WLF_VPT; ++k) {
@@ -475,7 +502,8 @@ wl_fused2_kernel(WlFused2Params p) {
       }
       __syncthreads();
       for (int i = tid; i < nv; i += WLF_THREADS) lab_out[v0 + i] = lab_s[i];
-      wlf2_emit(p, v0, nv, lab_s, frz_s, agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
+      WLF_STAMP(lv, 5);
+      wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
     }
     WLF_STAMP(lv, 3);
     if (lv + 2 < p.L) {  // clear the table level lv+2 inserts into (last read in [B] of level lv-1, which every CTA has left)

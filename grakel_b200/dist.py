@@ -11,10 +11,42 @@ from __future__ import annotations
 import numpy as np
 
 
-def row_block(n_rows: int, rank: int, world: int):
-    """Contiguous block of rows owned by `rank` (ceil split; trailing ranks may be empty)."""
+TILE = 256  # row blocks of the tiled Gram are multiples of the CTA-pair tile (csrc/comm.h DIST_ALIGN)
+
+
+def rows_per_rank(n_rows: int, world: int, align: int = 1):
     per = (n_rows + world - 1) // world
+    return (per + align - 1) // align * align
+
+
+def row_block(n_rows: int, rank: int, world: int, align: int = 1):
+    """Contiguous block of rows owned by `rank` (ceil split, optionally rounded up to `align` rows per rank;
+    trailing ranks may own fewer rows or none).  align=TILE is gk_comm_rows' partition."""
+    per = rows_per_rank(n_rows, world, align)
     return min(n_rows, rank * per), min(n_rows, (rank + 1) * per)
+
+
+def dist_tiles(n_rows: int, rank: int, world: int):
+    """The {row, column} tiles gk_gram(GK_DIST) makes `rank` compute (host-only query of the C library)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load_library()
+    n = C.c_int64()
+    if lib.gk_selftest_dist_tiles(n_rows, world, rank, None, 0, C.byref(n)) != 0:
+        raise ValueError(lib.gk_last_error().decode())
+    out = np.empty((n.value, 2), dtype=np.int32)
+    lib.gk_selftest_dist_tiles(n_rows, world, rank, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
+    return out
+
+
+def comm_init(engine, group=None):
+    """Collective: create the engine's communicator (gk_comm_init) with the NCCL id broadcast over torch.distributed."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.comm_init(world, rank, box[0])
+    return rank, world
 
 
 def all_gather_rows(k_local, n_rows: int, group=None):

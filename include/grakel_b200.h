@@ -160,6 +160,30 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
  * n_rows <= 0 restores the identity. */
 int gk_set_row_map(gk_handle* h, int64_t n_rows, const int32_t* row_of_graph);
 
+/* ---- multi-GPU: one process per GPU, one handle per process (the N x N output tiled over GPUs,
+ * a final all-gather over NVLink only when the whole matrix must live on every device).
+ * Every rank packs the same block and runs the same feature call (the relabel prologue is replicated: the whole
+ * graph set is a few tens of MB); gk_gram with GK_DIST then computes the rank's row block [gk_comm_rows) of K.
+ * The SYRK tiles are shared between the ranks -- each off-diagonal 256 x 256 tile is computed once, by one of
+ * the two ranks that own its rows / columns -- and the GEMM epilogue stores the mirrored half straight into the
+ * owning rank's row block through peer-mapped memory (CUDA IPC over NVLink), so the exchange overlaps the MMA
+ * tile by tile and no rank recomputes what another one has.  NCCL carries the bootstrap, the handle exchange,
+ * the two barriers of a call and, with GK_DIST_GATHER, the in-place all-gather of the finished row blocks
+ * (BASELINE config 4: the full fp32 K on every rank, library-owned: gk_result_device / gk_fetch).
+ * gk_comm_unique_id: rank 0 creates the 128-byte NCCL id, the application hands it to every rank (any channel).
+ * All of these are collective: every rank calls them in the same order with the same sizes. */
+#define GK_DIST 64          /* gk_gram flag: row block of this rank, tiles shared with the peers */
+#define GK_DIST_GATHER 128  /* gk_gram flag: GK_DIST + all-gather, the full K stays on every device */
+int gk_comm_unique_id(void* out128);
+int gk_comm_init(gk_handle* h, int32_t nranks, int32_t rank, const void* unique_id128);
+int gk_comm_destroy(gk_handle* h);
+/* the row block of this rank: ceil(n_rows / nranks) rounded up to 256 rows per rank (identity without a communicator) */
+int gk_comm_rows(gk_handle* h, int64_t n_rows, int64_t* row_begin, int64_t* row_end);
+/* library-owned device result of the last gk_gram (valid until the next call on the handle) */
+int gk_result_device(gk_handle* h, void** ptr, int64_t* rows, int64_t* cols, int64_t* ld, int32_t* dtype);
+/* host-only (tests): the {row, column} tile list gk_gram(GK_DIST) gives rank `rank` of `nranks` */
+int gk_selftest_dist_tiles(int64_t n_rows, int32_t nranks, int32_t rank, int32_t* tiles_xy, int64_t cap, int64_t* n_tiles);
+
 /* Copy rows of the device-resident K of the last gk_gram to the host. */
 int gk_fetch(gk_handle* h, void* K_out, int32_t out_dtype, int64_t ld);
 

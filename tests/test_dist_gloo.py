@@ -51,6 +51,36 @@ def test_row_blocks_cover_everything():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
 
 
+@pytest.mark.parametrize("n,world", [(1, 2), (255, 2), (256, 2), (1000, 3), (3000, 4), (10000, 8), (14142, 2), (28284, 8)])
+def test_dist_tiles_cover_every_block_exactly_once(n, world):
+    """gk_gram(GK_DIST): every rank computes the upper triangle of its diagonal block plus its parity share of the
+    rectangles it shares with the other ranks; the direct block of a tile lands in the computing rank's rows, the
+    mirrored block in the owner of the tile's columns.  Together they must write every 256 x 256 block of K
+    exactly once (diagonal tiles: once), and the load must be balanced."""
+    from grakel_b200.dist import TILE, dist_tiles, row_block, rows_per_rank
+    per = rows_per_rank(n, world, TILE)
+    nt = (n + TILE - 1) // TILE
+    written = np.zeros((nt, nt), dtype=np.int32)
+    loads = []
+    for r in range(world):
+        rb, re_ = row_block(n, r, world, TILE)
+        t = dist_tiles(n, r, world)
+        loads.append(len(t))
+        for x, y in t.tolist():
+            assert x % TILE == 0 and y % TILE == 0 and rb <= x < re_ and y < n
+            ti, tj = x // TILE, y // TILE
+            written[ti, tj] += 1
+            if ti != tj:
+                written[tj, ti] += 1  # the mirrored half, stored into the owner of rows [y, y + 256)
+                owner = y // per
+                orb, ore = row_block(n, owner, world, TILE)
+                assert orb <= y < ore
+    assert np.all(written == 1), "a block of K is written twice or never"
+    busy = [l for l in loads if l]
+    if n >= 3000:
+        assert max(busy) <= 1.35 * (sum(loads) / world) + 2
+
+
 def test_gloo_world2_row_tiling_and_gather():
     world = 2
     port = 29500 + (os.getpid() % 2000)
