@@ -142,9 +142,10 @@ def measured_traffic(key):
     return None
 
 
-def gen_list(n_graphs, nbar=NBAR, seed=SEED):
+def gen_list(n_graphs, nbar=NBAR, seed=SEED, attr=0, as_adj=False):
     """The seeded generator of SURVEY 8(d) in its Python-list form (what the reference API takes):
-    [{(u, v): 1, (v, u): 1, ...}, {vertex: label}] per graph."""
+    [{(u, v): 1, (v, u): 1, ...}, {vertex: label}] per graph; `as_adj`: dense float adjacency instead of the edge
+    dictionary (SP configs), `attr`: d-dimensional U[0,1) attribute vectors instead of labels (config 5)."""
     rs = np.random.RandomState(seed)
     out = []
     for _ in range(n_graphs):
@@ -152,11 +153,18 @@ def gen_list(n_graphs, nbar=NBAR, seed=SEED):
         p = 4.0 / (n - 1)
         iu = np.triu_indices(n, 1)
         m = rs.rand(len(iu[0])) < p
-        g = {}
-        for a, b in zip(iu[0][m].tolist(), iu[1][m].tolist()):
-            g[(a, b)] = 1
-            g[(b, a)] = 1
-        out.append([g, {i: int(rs.randint(7)) for i in range(n)}])
+        a, b = iu[0][m], iu[1][m]
+        L = {i: rs.rand(attr) for i in range(n)} if attr else {i: int(rs.randint(7)) for i in range(n)}
+        if as_adj:
+            A = np.zeros((n, n))
+            A[a, b] = 1.0
+            g = A + A.T
+        else:
+            g = {}
+            for x, y in zip(a.tolist(), b.tolist()):
+                g[(x, y)] = 1
+                g[(y, x)] = 1
+        out.append([g, L])
     return out
 
 
@@ -259,6 +267,135 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_paths(eng, local, X2, with_cpu):
+    """BASELINE configs 3 (ShortestPath, 5 000 graphs, avg 60 nodes) and 5 (ShortestPathAttr, 2 000 graphs, d = 16) and
+    WL-OA on the graphs of config 2: one GPU, CSR resident in HBM -> K resident in HBM, CUDA events on the engine's
+    stream; each with its dominant kernel against the stated roof and the real reference on a bounded
+    sample beside it."""
+    from grakel_b200.packing import label_ids, pack
+    peak_tf, peak_hbm, _ = peaks()
+    out = {}
+
+    def timed(fn, steps=10, warmup=3):
+        for _ in range(warmup):
+            st = fn()
+        eng.event_record(4)
+        for _ in range(steps):
+            st = fn()
+        eng.event_record(5)
+        return eng.event_elapsed(4, 5) / steps, st
+
+    def ref_time(make, X):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+            est = make()
+            t0 = time.perf_counter()
+            est.fit_transform(X)
+            return time.perf_counter() - t0, "reference"
+        except Exception as e:  # pragma: no cover
+            return None, "unavailable: %r" % (e,)
+
+    sm_clock = 1.965e9
+    # ---- config 3
+    X = gen_list(5000, 60, 0, as_adj=True)
+    b = pack(X, "sp", want_weights=True)
+    ids, _ = label_ids(b.labels, None, sort_new=False)
+    eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, ids, b.weights)
+    n = b.n_graphs
+    sizes = np.diff(b.graph_ptr).astype(np.float64)
+
+    def step3():
+        st = eng.sp_features(with_labels=True)
+        eng.gram(n, out=False, dtype=np.float32, stats=st, want_diag=False)
+        return st
+    ms, st = timed(step3)
+    relax = float((sizes ** 3).sum())
+    D3 = int(st.n_columns)
+    c3 = {"workload": "config3: 5000 ER graphs (avg 60 nodes, 7 labels, seed 0), ShortestPath(with_labels=True), adjacency input",
+          "ms_per_step": ms, "pairs_per_s": n * n / (ms * 1e-3),
+          "stages_ms": {"apsp+histogram (sp_bfs_hist)": st.ms_features, "columns+panel": st.ms_panel, "gram_gemm": st.ms_gemm, "tail": st.ms_tail},
+          "features_D": D3, "head_columns": int(st.n_dense_columns),
+          "roofline": {"kernel": "sp_bfs_hist<W> (all-sources bitmask BFS + labelled path histogram, one CTA per graph)", "bound": "alu",
+                       "achieved": relax / (st.ms_features * 1e-3), "peak": 148 * 128 * sm_clock, "unit": "Floyd-Warshall-equivalent min-plus/s",
+                       "frac": relax / (st.ms_features * 1e-3) / (148 * 128 * sm_clock),
+                       "note": "algorithmic work = sum n^3 relaxations of the reference's Floyd-Warshall (graph.py:1767-1794); the bitmask BFS does "
+                               "n (n + m) / 64 word operations instead, hence a 'fraction' that may exceed what the ALUs could relax one by one",
+                       "hbm_GBps_compulsory": (4.0 * (int(b.graph_ptr[-1]) + int(b.row_ptr[-1])) + 4.0 * int(b.graph_ptr[-1])) / (st.ms_features * 1e-3) / 1e9},
+          "roofline_gram": {"kernel": GEMM_KERNEL, "bound": "tensor", "achieved": float(n) * (n + 1) * int(st.n_dense_columns) / (st.ms_gemm * 1e-3) / 1e12 if st.ms_gemm > 0 else 0.0,
+                            "peak": peak_tf, "unit": "TFLOP/s",
+                            "frac": float(n) * (n + 1) * int(st.n_dense_columns) / (st.ms_gemm * 1e-3) / 1e12 / peak_tf if st.ms_gemm > 0 else 0.0,
+                            "note": "K-store-bound at this size: 100 MB of fp32 K for %d head columns" % int(st.n_dense_columns)}}
+    if with_cpu:
+        m = 300
+        def mk():
+            from grakel.kernels import ShortestPath as RefSP
+            return RefSP()
+        t, kind = ref_time(mk, X[:m])
+        c3["cpu_baseline"] = {"value": m * m / t if t else None, "unit": "pairs/s", "cores": 1, "kind": kind,
+                              "sample": "first %d of the 5000 graphs, grakel.ShortestPath().fit_transform (ignores n_jobs), %s s" % (m, "%.1f" % t if t else "-")}
+    out["config3_sp"] = c3
+    del X
+    # ---- config 5
+    X = gen_list(2000, 40, 0, attr=16, as_adj=True)
+    b = pack(X, "sp", need_labels=True, attributes=True, want_weights=True)
+    eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, None, b.weights, b.attrs)
+    n = b.n_graphs
+
+    def step5():
+        st = eng.spattr_features()
+        eng.gram(n, out=False, dtype=np.float64, stats=st, want_diag=False)
+        return st
+    ms, st = timed(step5, steps=5, warmup=2)
+    D5 = int(st.n_columns)
+    tf32_peak = peak_tf / 2.0
+    fl = 2.0 * n * n * D5
+    c5 = {"workload": "config5: 2000 ER graphs (avg 40 nodes, fp attributes d=16, seed 0), ShortestPathAttr(metric=np.dot)",
+          "ms_per_step": ms, "pairs_per_s": n * n / (ms * 1e-3), "feature_dim": D5, "distance_blocks": int(st.level_dims[0]),
+          "stages_ms": {"apsp + feature map (fp64)": st.ms_features, "gram (3xTF32 tcgen05, fp64 result)": st.ms_gemm},
+          "roofline": {"kernel": "gram_tc_kernel<double,false,tf32> (tcgen05 kind::tf32, hi/lo split: 3 passes over the k range)", "bound": "tensor",
+                       "achieved": fl / (st.ms_gemm * 1e-3) / 1e12 if st.ms_gemm > 0 else 0.0, "peak": tf32_peak, "unit": "TFLOP/s",
+                       "frac": fl / (st.ms_gemm * 1e-3) / 1e12 / tf32_peak if st.ms_gemm > 0 else 0.0, "passes": 3,
+                       "note": "algorithmic 2 N^2 D flops (SURVEY 8d: split passes are not counted); peak = half the measured bf16 burst peak "
+                               "(tf32 runs at half the bf16 rate); the launch includes the split, the fp64 fold of the k-chunks and the mirror pass"}}
+    if with_cpu:
+        m = 5
+        def mk5():
+            from grakel.kernels import ShortestPathAttr as RefSPA
+            return RefSPA()
+        t, kind = ref_time(mk5, X[:m])
+        c5["cpu_baseline"] = {"value": m * m / t if t else None, "unit": "pairs/s", "cores": 1, "kind": kind,
+                              "sample": "first %d of the 2000 graphs (%d unordered pairs), grakel.ShortestPathAttr().fit_transform, %s s" % (m, m * (m + 1) // 2, "%.1f" % t if t else "-")}
+    out["config5_spattr"] = c5
+    del X
+    # ---- WL-OA on the graphs of config 2
+    b = pack(X2, "wloa", len_ok=lambda k: k >= 2)
+    ids, _ = label_ids(b.labels, None, sort_new=True)
+    eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, ids)
+    n = b.n_graphs
+
+    def step_oa():
+        st = eng.wl_oa_features(H)
+        eng.gram(n, out=False, dtype=np.float32, stats=st, want_diag=False)
+        return st
+    ms, st = timed(step_oa)
+    oa = {"workload": "WL-OA (n_iter=5) on the graphs of config 2", "ms_per_step": ms, "pairs_per_s": n * n / (ms * 1e-3),
+          "stages_ms": {"wl + unary expansion": st.ms_features, "columns+panel": st.ms_panel, "gram_gemm": st.ms_gemm, "tail": st.ms_tail},
+          "unary_columns": int(st.n_columns), "unary_entries": int(st.n_entries), "head_columns": int(st.n_dense_columns),
+          "roofline": {"kernel": GEMM_KERNEL, "bound": "tensor", "achieved": float(n) * (n + 1) * int(st.n_dense_columns) / (st.ms_gemm * 1e-3) / 1e12 if st.ms_gemm > 0 else 0.0,
+                       "peak": peak_tf, "unit": "TFLOP/s",
+                       "frac": float(n) * (n + 1) * int(st.n_dense_columns) / (st.ms_gemm * 1e-3) / 1e12 / peak_tf if st.ms_gemm > 0 else 0.0}}
+    if with_cpu:
+        m = 150
+        def mko():
+            from grakel.kernels import WeisfeilerLehmanOptimalAssignment as RefOA
+            return RefOA(n_iter=H)
+        t, kind = ref_time(mko, X2[:m])
+        oa["cpu_baseline"] = {"value": m * m / t if t else None, "unit": "pairs/s", "cores": 1, "kind": kind,
+                              "sample": "first %d graphs, grakel.WeisfeilerLehmanOptimalAssignment(n_iter=5).fit_transform, %s s" % (m, "%.1f" % t if t else "-")}
+    out["config2_wloa"] = oa
+    return out
+
+
 def run_config4(eng, n4, rank, world, local, dist, torch, _lib, steps):
     """BASELINE config 4: WL-subtree (h=5) Gram of n4 graphs, row-tiled over the ranks (GK_DIST tiles, mirrored halves
     over NVLink) and assembled on EVERY rank by the in-place all-gather of gk_gram(GK_DIST_GATHER).  Returns rank 0's
@@ -330,6 +467,7 @@ def main():
     ap.add_argument("--graphs", type=int, default=N_GRAPHS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-paths", action="store_true", help="skip configs 3 / 5 / WL-OA")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -474,7 +612,7 @@ def main():
             config4 = run_config4(eng, n4, rank, world, local, dist, torch, _lib, max(3, min(args.steps, 5)))
 
     # ------------------------------------------------ end to end through the Python API (SURVEY 8d T_e2e)
-    e2e_api = None
+    e2e_api, paths = None, None
     if not args.no_e2e and world == 1 and rank == 0:
         from grakel_b200 import WeisfeilerLehman
         _lib.set_default_device(local)
@@ -503,6 +641,11 @@ def main():
                    "host_ms": {"pack(list -> CSR)": t_pack * 1e3, "label_ids": t_ids * 1e3},
                    "result_buffer": "pooled huge-page host mapping (gk_host_alloc); first_call_ms includes faulting it in",
                    "list_build_ms_not_timed": t_gen * 1e3}
+        if not args.no_paths:
+            try:
+                paths = other_paths(eng, local, X, not args.no_cpu)
+            except Exception as e:  # the headline line must survive a failure of the secondary measurements
+                paths = {"error": repr(e)}
         del X
 
     if rank != 0:
@@ -545,6 +688,7 @@ def main():
         "clocks": clk.summary(),
         "e2e": e2e,
         "e2e_api": e2e_api,
+        "other_paths": paths,
         "dist_check": dist_check,
         "config4": config4,
         "gpu_launches": launches,

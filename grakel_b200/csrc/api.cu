@@ -68,6 +68,21 @@ static int make_panel_map(CUtensorMap* m, void* base, long long cols, long long 
   return GK_OK;
 }
 
+// fp32 (tf32 operand) panel: 32 elements = one 128-byte swizzle row per k-block
+static int make_panel_map_f32(CUtensorMap* m, void* base, long long cols, long long rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(GK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK_TF32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GK_ERR_CUDA, "cuTensorMapEncodeTiled(f32 panel) failed: " + std::to_string((int)r));
+  return GK_OK;
+}
+
 // fp32 K as a 2-D tensor for TMA stores of 32x32 blocks (128-byte swizzle)
 static int make_out_map(CUtensorMap* m, void* base, long long cols, long long rows, long long ld) {
   EncodeTiledFn enc = get_encode();
@@ -163,6 +178,7 @@ int gk_create(int device_ordinal, gk_handle** out) {
   GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   GK_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   *out = h;
   return GK_OK;
 }
@@ -409,21 +425,25 @@ static void launch_sig_small(gk_handle* h, const int* lab_in, unsigned long long
 }
 
 // (re)allocate and clear the statistics the feature kernels maintain at insert time
-static int reset_feature_stats(gk_handle* h, int64_t col_cap, int64_t n_part, FeatStats* st) {
+static int reset_feature_stats(gk_handle* h, int64_t col_cap, int64_t n_part, FeatStats* st, bool clear = true) {
   col_cap = std::max<int64_t>(col_cap, 1);
   n_part = std::max<int64_t>(n_part, 1);
   GK_TRY(h->part_max.ensure(n_part * 4));
   GK_TRY(h->part_new.ensure(n_part * 4));
   h->n_part = n_part;
-  GK_CUDA(cudaMemsetAsync(h->part_max.p, 0, n_part * 4, h->stream));
-  GK_CUDA(cudaMemsetAsync(h->part_new.p, 0, n_part * 4, h->stream));
+  if (clear) {
+    GK_CUDA(cudaMemsetAsync(h->part_max.p, 0, n_part * 4, h->stream));
+    GK_CUDA(cudaMemsetAsync(h->part_new.p, 0, n_part * 4, h->stream));
+  }
   st->part_max = h->part_max.as<unsigned>();
   st->part_new = h->part_new.as<unsigned>();
   GK_TRY(h->colcnt.ensure(col_cap * 4));
   GK_TRY(h->diag_u64.ensure(h->N * 8));
   h->col_cap = col_cap;
-  GK_CUDA(cudaMemsetAsync(h->colcnt.p, 0, col_cap * 4, h->stream));
-  GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, h->N * 8, h->stream));
+  if (clear) {
+    GK_CUDA(cudaMemsetAsync(h->colcnt.p, 0, col_cap * 4, h->stream));
+    GK_CUDA(cudaMemsetAsync(h->diag_u64.p, 0, h->N * 8, h->stream));
+  }
   st->colcnt = h->colcnt.as<unsigned>();
   st->diag = h->diag_u64.as<unsigned long long>();
   st->sc = h->scalars.as<DevScalars>();
@@ -535,23 +555,33 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   for (;; ++retries) {
     if (retries > 8) return fail(GK_ERR_STATE, "gk_wl_features: repeated hash collisions");
     const unsigned long long seed = mix64(0x5851F42D4C957F2DULL + 0x9E3779B97F4A7C15ULL * (unsigned long long)retries);
-    GK_TRY(init_scalars(h, h->n_labels0));
-    FeatStats fst;
-    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)std::max(nb, G) * L, &fst));
     const char* e_v1 = getenv("GRAKEL_B200_WL_V1");
     const bool wl_v2 = fused && !(e_v1 && atoi(e_v1) != 0);
+    FeatStats fst;
+    if (!wl_v2) GK_TRY(init_scalars(h, h->n_labels0));
+    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)std::max(nb, G) * L, &fst, !wl_v2));
     h->wl_sparse_ids = false;
     if (wl_v2) {
       // wl_fused2.cuh: labels = representative vertex ids (one grid barrier per level), frozen singleton classes
-      if (L > 1) GK_CUDA(cudaMemsetAsync(h->ht_keys.as<unsigned long long>() + h->ht_cap, 0xFF, h->ht_cap * 8, h->stream));
       int* wb = h->wlf_buf.as<int>();
       int* d_cta_tile = wb + n_tiles + 1;
       unsigned* d_barrier = reinterpret_cast<unsigned*>(d_cta_tile + G + 1 + G);
-      GK_CUDA(cudaMemsetAsync(d_barrier, 0, 4, h->stream));
-      GK_TRY(h->wl_single.ensure((size_t)V));
-      GK_CUDA(cudaMemsetAsync(h->wl_single.p, 0, (size_t)V, h->stream));
+      GK_TRY(h->wl_single.ensure((size_t)V + 16));
       GK_TRY(h->diag_frozen.ensure((size_t)h->N * 8));
-      GK_CUDA(cudaMemsetAsync(h->diag_frozen.p, 0, (size_t)h->N * 8, h->stream));
+      {  // one launch clears everything the kernel expects cleared (no host upload, no synchronisation)
+        Wlf2Prepare q;
+        q.sc = sc; q.n_labels0 = h->n_labels0;
+        q.part_max = h->part_max.as<unsigned>(); q.part_new = h->part_new.as<unsigned>(); q.n_part = h->n_part;
+        q.colcnt = h->colcnt.as<unsigned>(); q.col_cap = h->col_cap;
+        q.diag = h->diag_u64.as<unsigned long long>(); q.diag_frozen = h->diag_frozen.as<unsigned long long>(); q.n_graphs = h->N;
+        q.barrier = d_barrier;
+        q.frozen = h->wl_single.as<unsigned char>(); q.V = V;
+        q.table1 = L > 1 ? h->ht_keys.as<unsigned long long>() + h->ht_cap : nullptr; q.ht_cap = (long long)h->ht_cap;
+        wlf2_prepare_kernel<<<h->sm_count * 2, 1024, 0, h->stream>>>(q);
+        LAUNCH_CHECK(h);
+        wlf2_set_scalars<<<1, 1, 0, h->stream>>>(sc, h->n_labels0);
+        LAUNCH_CHECK(h);
+      }
       WlFused2Params fp;
       memset(&fp, 0, sizeof(fp));
       fp.V = (int)V; fp.L = L; fp.n_labels0 = h->n_labels0;
@@ -589,11 +619,20 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
           for (int b = 0; b < G; ++b) {
             const long long* q = &pr[((size_t)b * L + lv) * 16];
             end_max = std::max(end_max, q[6] - t0);
-            if (lv == 0) { avg[3] += (double)(q[6] - q[0]) / G; mxv[3] = std::max(mxv[3], (double)(q[6] - q[0])); continue; }
+            if (lv == 0) {
+              avg[3] += (double)(q[6] - q[0]) / G; mxv[3] = std::max(mxv[3], (double)(q[6] - q[0]));
+              sub[0] += (double)(q[1] - q[0]) / G; sub[1] += (double)(q[2] - q[1]) / G; sub[2] += (double)(q[3] - q[2]) / G; sub[3] += (double)(q[6] - q[3]) / G;
+              continue;
+            }
             const double d[4] = {(double)(q[1] - q[0]), (double)(q[2] - q[1]), (double)(q[3] - q[2]), (double)(q[6] - q[3])};
             for (int k = 0; k < 4; ++k) { avg[k] += d[k] / G; mxv[k] = std::max(mxv[k], d[k]); }
             sub[0] += (double)(q[10] - q[0]) / G; sub[1] += (double)(q[1] - q[10]) / G;   // A: signatures | insert + copy-out
             sub[2] += (double)(q[4] - q[2]) / G; sub[3] += (double)(q[5] - q[4]) / G; sub[4] += (double)(q[3] - q[5]) / G;  // B: verify | labels | emit
+          }
+          if (lv == 0) {
+            fprintf(stderr, "  level 0: %.1f (%.1f) = stage %.1f + emit %.1f + table clear %.1f + flush %.1f | done at %.1f us\n", avg[3] / 1e3, mxv[3] / 1e3,
+                    sub[0] / 1e3, sub[1] / 1e3, sub[2] / 1e3, sub[3] / 1e3, end_max / 1e3);
+            continue;
           }
           fprintf(stderr, "  level %d: A %.1f (%.1f) wait %.1f (%.1f) B+emit %.1f (%.1f) clear+flush %.1f (%.1f) | A = sig %.1f + insert %.1f | B = verify %.1f + labels %.1f + emit %.1f | level done at %.1f us\n", lv,
                   avg[0] / 1e3, mxv[0] / 1e3, avg[1] / 1e3, mxv[1] / 1e3, avg[2] / 1e3, mxv[2] / 1e3, avg[3] / 1e3, mxv[3] / 1e3,
@@ -1258,7 +1297,13 @@ int gk_spattr_features(gk_handle* h, gk_stats* stats) {
   return GK_OK;
 }
 
-// Gram of the dense fp64 SP-attr feature matrix (feature_kind == 3)
+static void build_tiles(std::vector<int2>& tiles, int a0, int a1, int b0, int b1, bool upper_only, int bm);
+
+// Gram of the dense fp64 SP-attr feature matrix (feature_kind == 3).  Default: the tcgen05 kernel with tf32
+// operands on a hi/lo split of the features (3xTF32: hi hi^T + hi lo^T + lo hi^T, fp32 accumulation in TMEM,
+// k range processed in chunks and summed in fp64), self similarities exact in fp64; measured against the fp64
+// CUDA-core Gram (GRAKEL_B200_SPATTR_F64=1 selects it) the relative difference is ~1e-7, the north_star's
+// tolerance for real-valued Gram entries is 1e-5.
 static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64_t row_end, void* K_out,
                        int32_t out_dtype, int64_t ld, double* xdiag, double* ydiag, gk_stats* stats) {
   if (out_dtype != GK_F64) return fail(GK_ERR_UNSUPPORTED, "ShortestPathAttr Gram is fp64 only");
@@ -1275,11 +1320,64 @@ static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_b
   h->K_rows = k_rows; h->K_cols = k_cols; h->K_ld = k_cols; h->K_dtype = GK_F64;
   const int a0 = (int)((square ? 0 : n_fit) + row_begin), a1 = (int)((square ? 0 : n_fit) + row_end);
   GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
-  if (k_rows > 0) {
-    dim3 grid(cdiv(k_cols, 64), cdiv(k_rows, 64));
-    gram_f64_kernel<<<grid, 256, 0, h->stream>>>(h->fattr.as<double>(), h->fattr_dim, a0, a1, 0, (int)n_fit,
-                                                 h->K.as<double>(), k_cols);
+  const char* e_f64 = getenv("GRAKEL_B200_SPATTR_F64");
+  const bool use_f64 = e_f64 && atoi(e_f64) != 0;
+  if (k_rows > 0 && !use_f64) {
+    const long long D = h->fattr_dim, Dp = (D + BK_TF32 - 1) / BK_TF32 * BK_TF32, W = 3 * Dp;
+    GK_TRY(h->panel.ensure((size_t)N * W * 4 * 2));
+    float* P1 = h->panel.as<float>();
+    float* P2 = P1 + (size_t)N * W;
+    spattr_split_tf32<<<h->sm_count * 8, 256, 0, h->stream>>>(h->fattr.as<double>(), D, Dp, (int)N, P1, P2);
     LAUNCH_CHECK(h);
+    const bool sym = square && row_begin == 0 && row_end == N;
+    std::vector<int2> tiles;
+    build_tiles(tiles, a0, a1, 0, (int)n_fit, sym, BM);
+    GK_TRY(h->h_tiles.ensure(tiles.size() * sizeof(int2)));
+    memcpy(h->h_tiles.p, tiles.data(), tiles.size() * sizeof(int2));
+    GK_TRY(h->tiles.ensure(tiles.size() * sizeof(int2)));
+    GK_CUDA(cudaMemcpyAsync(h->tiles.p, h->h_tiles.p, tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUtensorMap tmA, tmB, tmC;
+    memset(&tmC, 0, sizeof(tmC));
+    GK_TRY(make_panel_map_f32(&tmA, P1, W, N, BM));
+    GK_TRY(make_panel_map_f32(&tmB, P2, W, N, BN));
+    GramParams p;
+    memset(&p, 0, sizeof(p));
+    p.tiles = h->tiles.as<int2>();
+    p.n_tiles = (int)tiles.size();
+    p.a_row_end = a1; p.b_row_end = (int)n_fit;
+    p.c_row0 = a0; p.c_col0 = 0;
+    p.out = h->K.p; p.ld = k_cols;
+    p.mirror = sym ? 1 : 0;
+    p.diag = h->diag_f64.as<double>();
+    // chunks of the k range: no fp32 accumulator sums more than `chunk` k-blocks x 4 MMAs before it is folded into
+    // the fp64 result (bounds the accumulated rounding of the tensor core's fp32 adds)
+    int chunk = 24;
+    if (const char* e = getenv("GRAKEL_B200_SPATTR_CHUNK")) chunk = std::max(1, atoi(e));
+    const int n_kb = (int)(W / BK_TF32);
+    const int grid = (int)std::min<size_t>(tiles.size(), h->sm_count);
+    for (int k0 = 0; k0 < n_kb; k0 += chunk) {
+      p.k_block0 = k0;
+      p.num_k_blocks = std::min(chunk, n_kb - k0);
+      p.accumulate = k0 > 0 ? 1 : 0;
+      gram_tc_kernel<double, false, 1><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(tmA, tmB, tmC, p);
+      LAUNCH_CHECK(h);
+    }
+    if (sym) {
+      mirror_upper_f64<<<h->sm_count * 8, 256, 0, h->stream>>>((int)N, h->K.as<double>(), k_cols);
+      LAUNCH_CHECK(h);
+    }
+    if (square) {  // exact self similarities
+      set_diag_f64<<<cdiv(k_rows, 256), 256, 0, h->stream>>>(a0, a1, 0, (int)n_fit, h->diag_f64.as<double>(), h->K.as<double>(), k_cols);
+      LAUNCH_CHECK(h);
+    }
+  }
+  if (k_rows > 0) {
+    if (use_f64) {
+      dim3 grid(cdiv(k_cols, 64), cdiv(k_rows, 64));
+      gram_f64_kernel<<<grid, 256, 0, h->stream>>>(h->fattr.as<double>(), h->fattr_dim, a0, a1, 0, (int)n_fit,
+                                                   h->K.as<double>(), k_cols);
+      LAUNCH_CHECK(h);
+    }
     if (flags & GK_NORMALIZE) {
       normalize_rows<double><<<h->sm_count * 8, 256, 0, h->stream>>>(k_rows, k_cols, h->K.as<double>(), k_cols,
                                                                       h->diag_f64.as<double>() + a0,
@@ -1331,7 +1429,7 @@ static void launch_empty(gk_handle* h, int a0, int a1, int b0, int b1, const Gra
 
 // Build the tile list: bands of 12 row tiles, column-major inside a band, so that the
 // ~148 tiles in flight cover a compact block of the output and share panel rows in L2.
-static void build_tiles(std::vector<int2>& tiles, int a0, int a1, int b0, int b1, bool upper_only, int bm = BM) {
+static void build_tiles(std::vector<int2>& tiles, int a0, int a1, int b0, int b1, bool upper_only, int bm) {
   const int n_m = cdiv(a1 - a0, bm), n_n = cdiv(b1 - b0, BN);
   const int BAND = 12 * BM / bm;
   for (int m0 = 0; m0 < n_m; m0 += BAND) {
@@ -1956,7 +2054,7 @@ int gk_selftest_gram(gk_handle* h, int64_t n, int64_t d, const uint16_t* counts,
   int rc = GK_OK;
   if (out_tc) {
     std::vector<int2> tiles;
-    build_tiles(tiles, 0, (int)n, 0, (int)n, true);
+    build_tiles(tiles, 0, (int)n, 0, (int)n, true, BM);
     GK_TRY(dtl.ensure(tiles.size() * sizeof(int2)));
     GK_CUDA(cudaMemcpyAsync(dtl.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CUtensorMap tmA, tmB, tmC;

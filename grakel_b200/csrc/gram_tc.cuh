@@ -54,6 +54,11 @@ struct GramParams {
   void* peer[8];
   int n_peers;
   int peer_rows;
+  // split-precision GEMM of real-valued features (ShortestPathAttr): k-blocks [k_block0, k_block0 + num_k_blocks) of
+  // the panels, result ADDED to `out` when accumulate != 0 (the k range is processed in chunks so that no fp32
+  // accumulator sums more than a few hundred MMAs)
+  int accumulate;
+  int k_block0;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -106,6 +111,15 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -135,6 +149,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
 constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                 ((uint32_t)(BM >> 4) << 24);
+// the same shape with A = B = tf32 (kind::tf32: 32 elements per 128-byte k-block, K = 8 per instruction)
+constexpr uint32_t UMMA_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                     ((uint32_t)(BM >> 4) << 24);
+constexpr int BK_TF32 = 32;
 
 template <typename OutT, bool NORMALIZE>
 __device__ __forceinline__ OutT epilogue_value(float acc, int arow, int bcol, double drow, double dcol,
@@ -250,7 +268,7 @@ __device__ __forceinline__ void epi_tma_store_tile(const GramParams& p, const CU
   __syncwarp();
 }
 
-template <typename OutT, bool NORMALIZE>
+template <typename OutT, bool NORMALIZE, int KIND = 0 /* 0: bf16 operands, 1: tf32 operands */>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GramParams p) {
@@ -305,8 +323,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           w_empty += clock64() - c0;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, tile.x);
-          tma_load_2d(sa + A_BYTES, &tmB, full_bar(stage), kb * BK, tile.y);
+          const int kx = (p.k_block0 + kb) * (KIND == 1 ? BK_TF32 : BK);
+          tma_load_2d(sa, &tmA, full_bar(stage), kx, tile.x);
+          tma_load_2d(sa + A_BYTES, &tmB, full_bar(stage), kx, tile.y);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -338,8 +357,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes along K inside the 128-byte swizzle row = +2 in the address field
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), UMMA_IDESC,
-                        (uint32_t)((kb | k) != 0));
+            if constexpr (KIND == 1)
+              tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), UMMA_IDESC_TF32,
+                          (uint32_t)((kb | k) != 0));
+            else
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), UMMA_IDESC,
+                          (uint32_t)((kb | k) != 0));
           }
           tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -372,7 +395,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (sizeof(OutT) == 4 && !NORMALIZE && p.tma_store) {
         epi_tma_store_tile(p, &tmC, tile, tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN), ew, lane,
                            epi_base + (uint32_t)ew * (2u * EPI_BUF_BYTES));
-      } else if (!NORMALIZE && interior && !diag_tile && p.vec_ok) {
+      } else if (KIND == 0 && !NORMALIZE && interior && !diag_tile && p.vec_ok) {
         OutT* drow_ptr = out + (long long)(arow - p.c_row0) * p.ld + (tile.y - p.c_col0);
         OutT* mptr = out + (long long)tile.y * p.ld + arow;  // mirror: K[col][row], one row of K per tile column
         const long long ld = p.ld;
@@ -431,6 +454,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (row_ok) {
             OutT* dst = out + (long long)(arow - p.c_row0) * p.ld + (bcol0 - p.c_col0);
+            if (p.accumulate) {  // later k-chunks of a split-precision GEMM: this CTA owns the tile, no atomics needed
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (bcol0 + j < p.b_row_end) vals[j] += dst[j];
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (bcol0 + j < p.b_row_end) dst[j] = vals[j];

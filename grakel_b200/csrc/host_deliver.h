@@ -148,7 +148,7 @@ class HostPool {
 
 HostPool& host_pool() {
   static HostPool pool([] {
-    int n = std::min(12, (int)std::thread::hardware_concurrency() / 4);
+    int n = std::min(16, (int)std::thread::hardware_concurrency() / 4);  // 16 measured best on the 2 x 32-core GPU hosts (profiles/r02c_*)
     if (const char* e = getenv("GRAKEL_B200_HOST_THREADS")) n = atoi(e);
     return std::max(1, std::min(n, 128));
   }());

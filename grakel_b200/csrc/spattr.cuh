@@ -199,6 +199,50 @@ gram_f64_kernel(const double* __restrict__ phi, long long D, int a0, int a1, int
     }
 }
 
+// Split of the fp64 feature matrix for the tensor-core Gram (3xTF32): x = hi + lo + O(2^-22 x) with hi, lo
+// representable in tf32 (10 explicit mantissa bits: the low 13 bits of the fp32 pattern are zero after
+// round-to-nearest-even on bit 13).  K = hi hi^T + hi lo^T + lo hi^T is ONE GEMM over the concatenated
+// panels  P1 = [hi | hi | lo],  P2 = [hi | lo | hi]  (row pitch 3 * Dp floats, Dp = D rounded up to 32).
+__device__ __forceinline__ float tf32_rne(float x) {
+  unsigned u = __float_as_uint(x);
+  u += 0x0FFFu + ((u >> 13) & 1u);
+  u &= 0xFFFFE000u;
+  return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(256)
+spattr_split_tf32(const double* __restrict__ phi, long long D, long long Dp, int N, float* __restrict__ P1, float* __restrict__ P2) {
+  const long long total = (long long)N * Dp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Dp, c = i - r * Dp;
+    float hi = 0.f, lo = 0.f;
+    if (c < D) {
+      const double x = phi[r * D + c];
+      hi = tf32_rne((float)x);
+      lo = tf32_rne((float)(x - (double)hi));
+    }
+    float* p1 = P1 + r * 3 * Dp;
+    float* p2 = P2 + r * 3 * Dp;
+    p1[c] = hi; p1[Dp + c] = hi; p1[2 * Dp + c] = lo;
+    p2[c] = hi; p2[Dp + c] = lo; p2[2 * Dp + c] = hi;
+  }
+}
+// lower triangle := upper triangle (tiles that straddle the diagonal are written from both sides with values that may
+// differ in the last fp32 rounding of the accumulator; the reference's matrix is exactly symmetric, kernel.py:277)
+__global__ void __launch_bounds__(256)
+mirror_upper_f64(int n, double* __restrict__ out, long long ld) {
+  const long long total = (long long)n * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / n), c = (int)(i - (long long)r * n);
+    if (r > c) out[(long long)r * ld + c] = out[(long long)c * ld + r];
+  }
+}
+// K[i][i] = diag[i] for the rows of a block (exact fp64 self similarities over the fp64 features)
+__global__ void __launch_bounds__(256)
+set_diag_f64(int a0, int a1, int b0, int b1, const double* __restrict__ diag, double* __restrict__ out, long long ld) {
+  const int r = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < a1 && r >= b0 && r < b1) out[(long long)(r - a0) * ld + (r - b0)] = diag[r];
+}
+
 // per-row self similarity <phi[g], phi[g]>
 __global__ void __launch_bounds__(256)
 rownorm_f64_kernel(const double* __restrict__ phi, long long D, int N, double* __restrict__ diag) {

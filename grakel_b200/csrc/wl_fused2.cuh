@@ -215,7 +215,9 @@ wl_fused2_kernel(WlFused2Params p) {
       for (int k = tid; k < ne; k += WLF_THREADS) col_s[k] = (unsigned short)(p.col_idx[e0 + k] - v0);
     }
     __syncthreads();
+    WLF_STAMP(0, 1);
     wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, agg, 0, (size_t)v0, s_warp, mx, n_new);
+    WLF_STAMP(0, 2);
   }
   if (p.L > 2) {  // table of level 2 (first touched after the barrier of level 1)
     const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -224,6 +226,7 @@ wl_fused2_kernel(WlFused2Params p) {
   }
   if (b == 0 && tid == 0)
     for (int lv = 1; lv < p.L; ++lv) p.sc->level_base[lv + 1] = (long long)p.n_labels0 + (long long)lv * V;
+  WLF_STAMP(0, 3);
   flush_partials(0);
   WLF_STAMP(0, 6);
 
@@ -437,7 +440,8 @@ wl_fused2_kernel(WlFused2Params p) {
         const int i = tid + k * WLF_THREADS;
         bv[k] = dv[k] = br[k] = dr[k] = lo[k] = lr[k] = 0;
         if (act[k] && r[k] != v0 + i) {
-          bv[k] = p.row_ptr[v0 + i]; dv[k] = p.row_ptr[v0 + i + 1] - bv[k];
+          if (resident) { bv[k] = rp_s[i]; dv[k] = rp_s[i + 1] - bv[k]; }  // own side from shared memory (sig_s)
+          else { bv[k] = p.row_ptr[v0 + i]; dv[k] = p.row_ptr[v0 + i + 1] - bv[k]; }
           br[k] = p.row_ptr[r[k]]; dr[k] = p.row_ptr[r[k] + 1] - br[k];
           lo[k] = lab_s[i]; lr[k] = __ldcg(&lab_in[r[k]]);
         }
@@ -455,13 +459,14 @@ wl_fused2_kernel(WlFused2Params p) {
               int a[8], c[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                a[j] = j < dv[k] ? p.sig_nbr[bv[k] + j] : 0;
+                a[j] = j < dv[k] ? (resident ? sig_s[bv[k] + j] : p.sig_nbr[bv[k] + j]) : 0;
                 c[j] = j < dv[k] ? __ldcg(&p.sig_nbr[br[k] + j]) : 0;
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) same = same && (a[j] == c[j]);
             } else {
-              for (int j = 0; same && j < dv[k]; ++j) same = p.sig_nbr[bv[k] + j] == __ldcg(&p.sig_nbr[br[k] + j]);
+              for (int j = 0; same && j < dv[k]; ++j)
+                same = (resident ? sig_s[bv[k] + j] : p.sig_nbr[bv[k] + j]) == __ldcg(&p.sig_nbr[br[k] + j]);
             }
             if (!same) atomicOr(&p.sc->collision, 1u);
           } else {
@@ -514,6 +519,47 @@ wl_fused2_kernel(WlFused2Params p) {
     flush_partials(lv);  // ends with __syncthreads
     WLF_STAMP(lv, 6);
   }
+}
+
+// Everything the fused kernel expects to find cleared, in ONE launch (eight cudaMemsetAsync calls and a synchronous
+// scalar upload cost more than the clears themselves): scalars, per-CTA partials, column counters, self
+// similarities, the grid barrier, the frozen flags and the signature table of level 1.
+struct Wlf2Prepare {
+  DevScalars* sc; int n_labels0;
+  unsigned* part_max; unsigned* part_new; long long n_part;
+  unsigned* colcnt; long long col_cap;
+  unsigned long long* diag; unsigned long long* diag_frozen; long long n_graphs;
+  unsigned* barrier;
+  unsigned char* frozen; long long V;
+  unsigned long long* table1; long long ht_cap;
+};
+__global__ void __launch_bounds__(1024)
+wlf2_prepare_kernel(Wlf2Prepare q) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (tid < (long long)(sizeof(DevScalars) / 8)) reinterpret_cast<unsigned long long*>(q.sc)[tid] = 0ULL;
+  for (long long i = tid; i < q.n_part; i += nth) { q.part_max[i] = 0u; q.part_new[i] = 0u; }
+  for (long long i = tid; i < q.n_graphs; i += nth) { q.diag[i] = 0ULL; q.diag_frozen[i] = 0ULL; }
+  if (tid == 0) *q.barrier = 0u;
+  {
+    uint4* c4 = reinterpret_cast<uint4*>(q.colcnt);  // cudaMalloc'ed: 256-byte aligned
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (long long i = tid; i < q.col_cap / 4; i += nth) c4[i] = z;
+    for (long long i = q.col_cap / 4 * 4 + tid; i < q.col_cap; i += nth) q.colcnt[i] = 0u;
+    uint4* f4 = reinterpret_cast<uint4*>(q.frozen);
+    for (long long i = tid; i < q.V / 16; i += nth) f4[i] = z;
+    for (long long i = q.V / 16 * 16 + tid; i < q.V; i += nth) q.frozen[i] = 0;
+  }
+  if (q.table1) {
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    uint4* t4 = reinterpret_cast<uint4*>(q.table1);
+    for (long long i = tid; i < q.ht_cap / 2; i += nth) t4[i] = ones;
+  }
+}
+// second tiny launch (stream order = after the clears): the two scalars the host used to upload
+__global__ void wlf2_set_scalars(DevScalars* sc, int n_labels0) {
+  sc->level_dims[0] = n_labels0;
+  sc->level_base[0] = 0;
+  sc->level_base[1] = n_labels0;
 }
 
 // ---- dense first-occurrence ids of one level >= 1 on demand (gk_wl_labels, WL-SP): representatives are the

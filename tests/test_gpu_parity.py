@@ -306,20 +306,26 @@ def test_wl_fused_and_multikernel_paths_agree(fused, monkeypatch, eng):
 
 
 def test_fp32_transport_with_host_widening_is_exact(monkeypatch):
-    """GRAKEL_B200_WIDEN=1: K crosses PCIe as fp32 and is widened to float64 by the library's host
-    threads (chunked, double-buffered) -- must be bit-identical to the fp64 transport, also for row
-    counts that are not a multiple of the chunk or of the worker count."""
+    """Default delivery: K crosses PCIe as fp32 -- the upper triangle only for the square case -- and is widened,
+    mirrored (and normalised in fp64) by the library's host threads (host_deliver.h); it must be bit-identical to
+    the plain fp64 transport of a device-side fp64 result (GRAKEL_B200_WIDEN=0), also for sizes that are not a
+    multiple of the band, the strip or the 8 x 8 transpose block, for transform (rectangular) and normalised results."""
     k = _k()
-    for n, nbar in ((257, 10), (1031, 8)):
+    for n, nbar in ((257, 10), (1031, 8), (2500, 6)):
         X = gen(n, nbar, 9)
-        monkeypatch.delenv("GRAKEL_B200_WIDEN", raising=False)
+        monkeypatch.setenv("GRAKEL_B200_WIDEN", "0")
         K0 = k.WeisfeilerLehman(n_iter=2).fit_transform(X)
-        monkeypatch.setenv("GRAKEL_B200_WIDEN", "1")
+        Kn0 = k.WeisfeilerLehman(n_iter=2, normalize=True).fit_transform(X)
+        monkeypatch.delenv("GRAKEL_B200_WIDEN", raising=False)
         K1 = k.WeisfeilerLehman(n_iter=2).fit_transform(X)
-        assert K1.dtype == np.float64
+        assert K1.dtype == np.float64 and K1.flags.c_contiguous
         _same(K1, K0)
+        _same(k.WeisfeilerLehman(n_iter=2, normalize=True).fit_transform(X), Kn0)
         Kt = k.WeisfeilerLehman(n_iter=2).fit(X[:-5]).transform(X[-5:])
         _same(Kt, K0[-5:, :-5])
+        monkeypatch.setenv("GRAKEL_B200_NO_TRI", "1")  # all rows as fp32 instead of the triangle
+        _same(k.WeisfeilerLehman(n_iter=2).fit_transform(X), K0)
+        monkeypatch.delenv("GRAKEL_B200_NO_TRI", raising=False)
 
 
 # --------------------------------------------------------------- SP
@@ -361,26 +367,49 @@ def test_config3_small_and_large_graph_path():
 
 
 # --------------------------------------------------------------- SP-attr
-def test_shortest_path_attr_matches_reference_loop():
-    """Golden from the real reference's 4-deep loop (shortest_path.py:151-162) on tiny graphs,
-    then the oracle's feature-map form on a config-5 shaped subset (tolerance 1e-5 relative as
-    BASELINE.json states; the device path is fp64 end to end)."""
+@pytest.mark.parametrize("mode", ["tf32x3", "fp64"])
+def test_shortest_path_attr_matches_reference_loop(mode, monkeypatch):
+    """Golden from the real reference's 4-deep loop (shortest_path.py:151-162) on tiny graphs, then the oracle's
+    feature-map form on a config-5 shaped subset and SURVEY 8c's real-reference K[0,:5] of config 5.
+
+    Default path: tcgen05 kind::tf32 GEMM on a hi/lo split of the fp64 features (3 passes, fp32 accumulation folded
+    into fp64 every few hundred MMAs); tolerance 1e-5 relative, the north_star's bound for real-valued Gram entries
+    (observed ~1e-7).  GRAKEL_B200_SPATTR_F64=1: the fp64 CUDA-core Gram, 1e-9.  Self similarities (the diagonal
+    and what normalisation divides by) are exact fp64 in both."""
     from oracle.gk_oracle import SPAttrOracle
+    tol = 1e-9 if mode == "fp64" else 1e-5
+    if mode == "fp64":
+        monkeypatch.setenv("GRAKEL_B200_SPATTR_F64", "1")
+    else:
+        monkeypatch.delenv("GRAKEL_B200_SPATTR_F64", raising=False)
     k = _k()
     d = gio.load(os.path.join(G, "spattr.json.gz"))
     X, Y = gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"])
     est = k.ShortestPathAttr()
-    np.testing.assert_allclose(est.fit_transform(X), np.asarray(d["K"]), rtol=1e-9)
-    np.testing.assert_allclose(est.transform(Y), np.asarray(d["Kt"]), rtol=1e-9)
+    K = est.fit_transform(X)
+    np.testing.assert_allclose(K, np.asarray(d["K"]), rtol=tol)
+    assert np.array_equal(K, K.T)
+    np.testing.assert_allclose(np.diagonal(K), np.diagonal(np.asarray(d["K"])), rtol=1e-12)
+    np.testing.assert_allclose(est.transform(Y), np.asarray(d["Kt"]), rtol=tol)
     est = k.ShortestPathAttr(normalize=True)
-    np.testing.assert_allclose(est.fit_transform(X), np.asarray(d["Kn"]), rtol=1e-9)
-    np.testing.assert_allclose(est.transform(Y), np.asarray(d["Ktn"]), rtol=1e-9)
+    np.testing.assert_allclose(est.fit_transform(X), np.asarray(d["Kn"]), rtol=tol)
+    np.testing.assert_allclose(est.transform(Y), np.asarray(d["Ktn"]), rtol=tol)
     Xc = gen(24, 40, 0, attr=16, as_adj=True)  # first graphs of BASELINE config 5
     Ko = SPAttrOracle().fit_transform(Xc)
     Kd = k.GraphKernel(kernel={"name": "shortest_path", "as_attributes": True}).fit_transform(Xc)
-    np.testing.assert_allclose(Kd, Ko, rtol=1e-5)
+    np.testing.assert_allclose(Kd, Ko, rtol=tol)
     np.testing.assert_allclose(Kd[0, :5], [837683.171027, 2683836.635183, 1663520.495733, 1549141.171651, 2537314.325017],
-                               rtol=1e-9)  # SURVEY.md 8c: real-reference K[0,:5] of config 5
+                               rtol=max(tol, 1e-9))  # SURVEY.md 8c: real-reference K[0,:5] of config 5
+    if mode == "tf32x3":  # the observed error, not just the bound: a regression to plain tf32 (1e-3) or bf16 would show
+        err = float(np.max(np.abs(Kd - Ko) / np.abs(Ko)))
+        assert err < 2e-6, err
+        # a few hundred graphs: several row tiles, k-chunk folding, mirrored tiles, against the fp64 device Gram
+        Xm = gen(300, 30, 3, attr=16, as_adj=True)
+        K32 = k.ShortestPathAttr().fit_transform(Xm)
+        monkeypatch.setenv("GRAKEL_B200_SPATTR_F64", "1")
+        K64 = k.ShortestPathAttr().fit_transform(Xm)
+        assert np.array_equal(K32, K32.T)
+        np.testing.assert_allclose(K32, K64, rtol=2e-6)
     with pytest.raises(NotImplementedError):
         k.ShortestPathAttr(metric=lambda a, b: float(np.dot(a, b))).fit_transform(Xc[:2])
 
