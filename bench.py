@@ -168,6 +168,25 @@ def gen_list(n_graphs, nbar=NBAR, seed=SEED, attr=0, as_adj=False):
     return out
 
 
+def bind_to_gpu_node(torch, local):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off (what `numactl --cpunodebind` would do): host
+    buffers the bench allocates (pinned CSR / K) then live next to the GPU's PCIe root.  Returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def host_info():
     info = {"logical_cores": os.cpu_count()}
     try:
@@ -486,6 +505,8 @@ def main():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa_node = bind_to_gpu_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from grakel_b200 import _lib
@@ -558,12 +579,15 @@ def main():
             eng.gram(n, out=Kh, dtype=np.float64, row_range=(rb, re_), stats=s, want_diag=False, dist=True)
             return s
 
-        for _ in range(2):
+        for _ in range(4):
             e2e_step()
         barrier()
         t0 = time.perf_counter()
+        per_step = []
         for _ in range(args.steps):
+            t1 = time.perf_counter()
             es = e2e_step()
+            per_step.append((time.perf_counter() - t1) * 1e3)
         barrier()
         e2e_t = torch.tensor([(time.perf_counter() - t0) / args.steps], device="cuda")
         if world > 1:
@@ -571,6 +595,7 @@ def main():
         e2e = {"value": n * n / float(e2e_t.item()), "unit": "pairs/s",
                "h2d_bytes_per_step": int(gp.nbytes + rp.nbytes + ci.nbytes + lab.nbytes),
                "d2h_bytes_per_step": int(kr * n * 8), "ms_per_step": float(e2e_t.item()) * 1e3,
+               "ms_per_step_min_median_max": [float(np.min(per_step)), float(np.median(per_step)), float(np.max(per_step))],
                "api": "gk_wl_fit_transform (C-ABI), pinned host CSR in, pinned float64 K out (fp32 upper triangle over "
                       "PCIe, widened + mirrored by host threads)",
                "pcie_d2h_bytes_per_step": int(n * (n + 1) // 2 * 4) if world == 1 else int(kr * n * 4),
@@ -683,6 +708,7 @@ def main():
                    "parallelism": (f"rows of K tiled over {world} GPUs (gk_comm_init / GK_DIST): SYRK tiles shared, mirrored halves "
                                    f"stored into the owner's row block over NVLink by the GEMM epilogue; CSR + relabel replicated")
                    if world > 1 else "1 GPU",
+                   "host_numa_node": numa_node,
                    "l2": "per-step working set (panel %.0f MB + K %.0f MB) exceeds the 126 MB L2" %
                          (n * ((Dc + 63) // 64 * 64) * 2 / 1e6, (re_ - rb if world > 1 else n) * n * 4 / 1e6)},
         "clocks": clk.summary(),
@@ -717,6 +743,7 @@ def main():
         "dense_gemm_mode": dense,
     }
     if not args.no_cpu and world == 1:
+        os.sched_setaffinity(0, all_cpus)  # the CPU leg may use every core of the box
         line["cpu_baseline"] = cpu_baseline_obj(cpu_arm(steps=1, budget_s=12.0), n)
     print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libgrakel_b200.so")
 GK_F32, GK_F64 = 0, 1
 GK_NORMALIZE, GK_NAN_TO_NUM, GK_GRAM_SIMT, GK_OUT_DEVICE, GK_FULL_TILES, GK_DENSE_ALL = 1, 2, 4, 8, 16, 32
 GK_DIST, GK_DIST_GATHER = 64, 128
-GK_SP_WITH_LABELS, GK_SP_KEEP_DIST = 1, 2
+GK_SP_WITH_LABELS, GK_SP_KEEP_DIST, GK_SP_DIJKSTRA_ORDER = 1, 2, 4
 GK_ERR_RANGE, GK_ERR_UNSUPPORTED = -4, -5
 
 
@@ -57,7 +57,7 @@ _SYMBOLS = {
     "gk_pack_csr": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32]),
     "gk_wl_features": (C.c_int, [_P, C.c_int32, C.POINTER(GkStats)]),
     "gk_sp_features": (C.c_int, [_P, C.c_int32, C.POINTER(GkStats)]),
-    "gk_spattr_features": (C.c_int, [_P, C.POINTER(GkStats)]),
+    "gk_spattr_features": (C.c_int, [_P, C.c_int32, C.POINTER(GkStats)]),
     "gk_wl_sp_features": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(GkStats)]),
     "gk_wl_oa_features": (C.c_int, [_P, C.c_int32, C.POINTER(GkStats)]),
     "gk_gram": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int32, C.c_int64, _P, _P,
@@ -219,24 +219,25 @@ class Engine:
             self._check(self.lib.gk_wl_oa_features(self.h, int(n_iter), C.byref(st)))
         return st
 
-    def sp_features(self, with_labels=True, keep_dist=False):
+    def sp_features(self, with_labels=True, keep_dist=False, dijkstra_order=False):
         st = GkStats()
         flags = (GK_SP_WITH_LABELS if with_labels else 0) | (GK_SP_KEEP_DIST if keep_dist else 0)
+        flags |= GK_SP_DIJKSTRA_ORDER if dijkstra_order else 0
         with self._lock:
             self._check(self.lib.gk_sp_features(self.h, flags, C.byref(st)))
         return st
 
-    def wl_sp_features(self, n_iter, keep_dist=False):
+    def wl_sp_features(self, n_iter, keep_dist=False, dijkstra_order=True):
         st = GkStats()
-        flags = GK_SP_WITH_LABELS | (GK_SP_KEEP_DIST if keep_dist else 0)
+        flags = GK_SP_WITH_LABELS | (GK_SP_KEEP_DIST if keep_dist else 0) | (GK_SP_DIJKSTRA_ORDER if dijkstra_order else 0)
         with self._lock:
             self._check(self.lib.gk_wl_sp_features(self.h, int(n_iter), flags, C.byref(st)))
         return st
 
-    def spattr_features(self):
+    def spattr_features(self, dijkstra_order=False):
         st = GkStats()
         with self._lock:
-            self._check(self.lib.gk_spattr_features(self.h, C.byref(st)))
+            self._check(self.lib.gk_spattr_features(self.h, GK_SP_DIJKSTRA_ORDER if dijkstra_order else 0, C.byref(st)))
         return st
 
     def gram(self, n_graphs, n_fit=None, normalize=False, nan_to_num=False, out=None, dtype=np.float64,

@@ -1025,17 +1025,22 @@ static int sp_features_impl(gk_handle* h, int32_t flags, int32_t wl_iter, gk_sta
       pa.dict_mask = (unsigned)(dkey_cap - 1);
       pa.keep = nullptr;
       const size_t smem_a = max_small_nn * 8 + 16;
+      // path sums in the reference's order: Floyd-Warshall (adjacency input) or Dijkstra (edge dictionaries)
+      const bool dj = flags & GK_SP_DIJKSTRA_ORDER;
       GK_CUDA(cudaFuncSetAttribute(spattr_apsp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_a, 16)));
+      GK_CUDA(cudaFuncSetAttribute(sp_dijkstra_order_apsp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_a, 16)));
       if (!small.empty()) {
         pa.glist = lists.as<int>();
         pa.dist_in_global = 0;
-        spattr_apsp<double><<<(int)small.size(), SP_THREADS, smem_a, h->stream>>>(pa);
+        if (dj) sp_dijkstra_order_apsp<<<(int)small.size(), SP_THREADS, smem_a, h->stream>>>(pa);
+        else spattr_apsp<double><<<(int)small.size(), SP_THREADS, smem_a, h->stream>>>(pa);
         LAUNCH_CHECK(h);
       }
       if (!big.empty()) {
         pa.glist = lists.as<int>() + small.size();
         pa.dist_in_global = 1;
-        spattr_apsp<double><<<(int)big.size(), SP_THREADS, 16, h->stream>>>(pa);
+        if (dj) sp_dijkstra_order_apsp<<<(int)big.size(), SP_THREADS, 16, h->stream>>>(pa);
+        else spattr_apsp<double><<<(int)big.size(), SP_THREADS, 16, h->stream>>>(pa);
         LAUNCH_CHECK(h);
       }
       SpParams pb = p;
@@ -1159,7 +1164,7 @@ int gk_sp_distances(gk_handle* h, int64_t g, double* out) {
   return GK_OK;
 }
 
-int gk_spattr_features(gk_handle* h, gk_stats* stats) {
+int gk_spattr_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   if (!h) return fail(GK_ERR_ARG, "null handle");
   if (h->N <= 0) return fail(GK_ERR_STATE, "gk_spattr_features: no graphs packed");
   if (!h->attrs.p || h->attr_dim <= 0) return fail(GK_ERR_ARG, "gk_spattr_features: node attributes are required");
@@ -1216,12 +1221,15 @@ int gk_spattr_features(gk_handle* h, gk_stats* stats) {
   p.dict_mask = (unsigned)(dict_cap - 1);
   p.sc = h->scalars.as<DevScalars>();
   const size_t smem_small = max_small_nn * esz + 16;
+  const bool dj = !use_u16 && (flags & GK_SP_DIJKSTRA_ORDER);  // real-valued weights: path sums in Dijkstra's order
   if (use_u16) GK_CUDA(cudaFuncSetAttribute(spattr_apsp<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+  else if (dj) GK_CUDA(cudaFuncSetAttribute(sp_dijkstra_order_apsp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
   else GK_CUDA(cudaFuncSetAttribute(spattr_apsp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
   if (!small.empty()) {
     p.glist = h->large_list.as<int>();
     p.dist_in_global = 0;
     if (use_u16) spattr_apsp<unsigned short><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
+    else if (dj) sp_dijkstra_order_apsp<<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
     else spattr_apsp<double><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
     LAUNCH_CHECK(h);
   }
@@ -1229,6 +1237,7 @@ int gk_spattr_features(gk_handle* h, gk_stats* stats) {
     p.glist = h->large_list.as<int>() + small.size();
     p.dist_in_global = 1;
     if (use_u16) spattr_apsp<unsigned short><<<(int)big.size(), SP_THREADS, 16, h->stream>>>(p);
+    else if (dj) sp_dijkstra_order_apsp<<<(int)big.size(), SP_THREADS, 16, h->stream>>>(p);
     else spattr_apsp<double><<<(int)big.size(), SP_THREADS, 16, h->stream>>>(p);
     LAUNCH_CHECK(h);
   }

@@ -70,10 +70,49 @@ class HostPool {
     }
     return out.empty() ? list : out;
   }
+  // NUMA node the current CUDA device hangs off (its PCIe root), -1 if unknown
+  static int gpu_numa_node() {
+    int dev = 0;
+    char bus[32] = {0};
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) return -1;
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+  }
+  static std::vector<int> node_cpus(int node) {
+    std::vector<int> list;
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return list;
+    char buf[4096] = {0};
+    if (fgets(buf, sizeof(buf), f)) {
+      for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; ++c) list.push_back(c); }
+        else if (sscanf(tok, "%d", &a) == 1) list.push_back(a);
+      }
+    }
+    fclose(f);
+    return list;
+  }
+  // CPUs of the node the GPU is attached to (its DMA lands in that node's memory without crossing the socket
+  // interconnect); failing that, of the node the calling thread runs on
   static std::vector<int> local_node_cpus() {
     std::vector<int> out;
     if (const char* e = getenv("GRAKEL_B200_HOST_ANY_NODE"))
       if (atoi(e) != 0) return out;
+    const int gnode = gpu_numa_node();
+    if (gnode >= 0) {
+      out = node_cpus(gnode);
+      if (!out.empty()) return out;
+    }
     const int cpu = sched_getcpu();
     if (cpu < 0) return out;
     for (int node = 0; node < 64; ++node) {
@@ -257,7 +296,22 @@ constexpr int DELIVER_SLOTS = 4;
 // host-only self test of the band / transpose logic (gk_selftest_deliver), another host matrix
 struct DeviceCopier {
   gk_handle* h;
-  char* stage(size_t bytes) { return h->h_stage.ensure(bytes) == GK_OK ? h->h_stage.as<char>() : nullptr; }
+  // pinned staging ring, allocated (and thereby first touched) while the calling thread sits on the GPU's NUMA node
+  char* stage(size_t bytes) {
+    if (bytes <= h->h_stage.cap) return h->h_stage.as<char>();
+    cpu_set_t old_set, node_set;
+    bool moved = false;
+    std::vector<int> cpus = HostPool::local_node_cpus();
+    if (!cpus.empty() && pthread_getaffinity_np(pthread_self(), sizeof(old_set), &old_set) == 0) {
+      CPU_ZERO(&node_set);
+      for (int c : cpus) CPU_SET(c, &node_set);
+      moved = pthread_setaffinity_np(pthread_self(), sizeof(node_set), &node_set) == 0;
+    }
+    const int rc = h->h_stage.ensure(bytes);
+    if (rc == GK_OK) memset(h->h_stage.p, 0, 4096);
+    if (moved) pthread_setaffinity_np(pthread_self(), sizeof(old_set), &old_set);
+    return rc == GK_OK ? h->h_stage.as<char>() : nullptr;
+  }
   bool copy(int slot, void* dst, size_t dpitch, const float* src, size_t spitch, size_t width, size_t height) {
     if (cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return false;
     return cudaEventRecord(h->ev_stage[slot], h->stream) == cudaSuccess;

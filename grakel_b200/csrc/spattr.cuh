@@ -68,6 +68,64 @@ spattr_apsp(SpParams p) {
   }
 }
 
+// Dijkstra semantics for real-valued weights (graph.py:1712-1764, tools.py:14-83).  The reference's Dijkstra sums a
+// path left to right, dist[v] = fl(dist[u] + w(u, v)) with u the predecessor, where Floyd-Warshall adds two partial
+// paths, so the two differ in the last bit on real weights -- and feature keys compare distances by exact float
+// equality (shortest_path.py:472, 511).  With non-negative weights and monotone rounding, Dijkstra's result from a
+// source s is the LEAST fixed point of  d[v] = min over edges (u, v) of fl(d[u] + w(u, v)),  d[s] = 0  (every walk's
+// left-associated sum bounds it from above by induction, and it is attained), independent of the heap's tie
+// breaking.  A chaotic Bellman-Ford iteration reaches the same fixed point: all sources of a graph at once, one CTA
+// per graph, relaxations as 64-bit atomicMin on the bit patterns (order-preserving for non-negative doubles).
+__global__ void __launch_bounds__(SP_THREADS)
+sp_dijkstra_order_apsp(SpParams p) {
+  extern __shared__ __align__(16) unsigned char sp_smem[];
+  const int g = p.glist ? p.glist[blockIdx.x] : blockIdx.x;
+  const int v0 = p.graph_ptr[g];
+  const int n = p.graph_ptr[g + 1] - v0;
+  if (n <= 0) return;
+  double* gout = reinterpret_cast<double*>(p.gdist) + p.goff[g];
+  unsigned long long* dist = reinterpret_cast<unsigned long long*>(p.dist_in_global ? (void*)gout : (void*)sp_smem);
+  const int tid = threadIdx.x;
+  const long long nn = (long long)n * n;
+  const unsigned long long INF = 0x7ff0000000000000ULL;
+  for (long long i = tid; i < nn; i += SP_THREADS) dist[i] = (i / n == i % n) ? 0ULL : INF;
+  __shared__ int changed;
+  if (tid == 0) changed = 1;
+  __syncthreads();
+  for (int round = 0; round < n + 1; ++round) {
+    if (!changed) break;  // uniform: read after the barrier below
+    __syncthreads();
+    if (tid == 0) changed = 0;
+    __syncthreads();
+    // (source s, vertex u) pairs: relax the out-edges of u for source s
+    for (long long i = tid; i < nn; i += SP_THREADS) {
+      const int sidx = (int)(i / n), u = (int)(i - (long long)sidx * n);
+      const unsigned long long du_bits = dist[i];
+      if (du_bits >= INF) continue;
+      const double du = __longlong_as_double((long long)du_bits);
+      const int b = p.row_ptr[v0 + u], e = p.row_ptr[v0 + u + 1];
+      for (int k = b; k < e; ++k) {
+        const int w = p.col_idx[k] - v0;
+        const double cand = du + (p.weights ? p.weights[k] : 1.0);
+        const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
+        unsigned long long* dst = &dist[(long long)sidx * n + w];
+        if (cb < *dst) {
+          const unsigned long long old = atomicMin(dst, cb);
+          if (cb < old) changed = 1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (long long i = tid; i < nn; i += SP_THREADS) {
+    const unsigned long long d = dist[i];
+    if (!p.dist_in_global) gout[i] = __longlong_as_double((long long)d);
+    const int u = (int)(i / n), w = (int)(i - (long long)u * n);
+    if (u == w || d >= INF) continue;
+    sp_dict_slot(p.dict_keys, p.dict_mask, d, p.sc);  // exact-equality key = the bit pattern
+  }
+}
+
 // Real-valued edge weights: histogram of (l(u), l(v), id(d(u,v))) from distance matrices kept
 // in global memory, where id() is the slot of the distance's bit pattern in the global distance
 // dictionary filled by spattr_apsp<double> (exact float equality, shortest_path.py:472, 511).

@@ -201,6 +201,25 @@ class VertexHistogram(Kernel):
 
 
 # ------------------------------------------------------------------------------
+def _path_sum_order(block, algorithm_type):
+    """Which of the reference's two shortest-path algorithms defines the path sums of a block with real-valued
+    weights: "auto" runs Floyd-Warshall on adjacency input and Dijkstra on edge dictionaries (shortest_path.py:244-252,
+    graph.py:652-656), and the two round differently.  Returns True for Dijkstra's order.  Integer-valued
+    weights give the same distances either way."""
+    if block.weights is None or not np.any(block.weights != np.rint(block.weights)):
+        return False
+    if algorithm_type == "floyd_warshall":
+        return False
+    if algorithm_type == "dijkstra":
+        return True
+    if block.all_adjacency:
+        return False
+    if getattr(block, "any_adjacency", False):
+        raise NotImplementedError("real-valued edge weights with adjacency and dictionary inputs mixed in one call: the "
+                                  "reference would use a different algorithm per graph; pass algorithm_type explicitly")
+    return True
+
+
 def _edge_label_values(X):
     """Edge-label values per element, with the element checks of EdgeHistogram.parse_input
     (edge_histogram.py:76-103): elements must have exactly three members (graph, node labels,
@@ -347,10 +366,7 @@ class WeisfeilerLehman(Kernel):
         if base is ShortestPath:
             # the base kernel receives the edge DICTIONARY of every graph (weisfeiler_lehman.py:188, 218):
             # Dijkstra semantics whatever the input spelling; labels are the WL vertex set
-            block = pack(X, "wl", len_ok=len_ok, want_weights=True)
-            if block.weights is not None and np.any(block.weights != np.rint(block.weights)):
-                raise NotImplementedError("non-integer edge weights are supported with Floyd-Warshall semantics only")
-            return block
+            return pack(X, "wl", len_ok=len_ok, want_weights=True)
         return pack(X, "wl", len_ok=len_ok)
 
     def parse_input(self, X):
@@ -407,7 +423,7 @@ class WeisfeilerLehman(Kernel):
 
     def _device_features(self, eng):
         if self._base_graph_kernel is ShortestPath:
-            return eng.wl_sp_features(self._n_iter - 1)
+            return eng.wl_sp_features(self._n_iter - 1, dijkstra_order=True)  # the base kernel gets edge dictionaries
         return eng.wl_features(self._n_iter - 1)
 
 
@@ -538,14 +554,14 @@ class ShortestPath(Kernel):
             block = pack(X, "sp", need_labels=wl, len_ok=lambda n: n in (2, 3) or (n == 1 and not wl),
                          want_weights=True, fw_zero_is_absent=self.algorithm_type == "floyd_warshall",
                          type_error_msg="each element of X must have at least one and at most 3 elements\n")
-        if block.weights is not None and np.any(block.weights != np.rint(block.weights)):
-            # Feature keys compare path lengths by exact float equality (shortest_path.py:472, 511), and the
-            # reference's own Dijkstra and Floyd-Warshall disagree in the last bit on real weights.  The device
-            # runs the k-ordered fp64 Floyd-Warshall, so only that semantics is reproduced bit for bit.
-            fw = self.algorithm_type == "floyd_warshall" or (self.algorithm_type == "auto" and block.all_adjacency)
-            if not fw:
-                raise NotImplementedError("non-integer edge weights are supported with Floyd-Warshall semantics only "
-                                          "(adjacency input or algorithm_type='floyd_warshall')")
+        # real-valued weights: feature keys compare path lengths by exact float equality (shortest_path.py:472, 511)
+        # and the reference's Dijkstra and Floyd-Warshall round differently; the device reproduces whichever the
+        # reference would run (k-ordered fp64 Floyd-Warshall, or the Dijkstra-order fixed point of sp_dijkstra_order_apsp)
+        dj = _path_sum_order(block, self.algorithm_type)
+        if self._method_calling in (1, 2):
+            self._dijkstra_order = dj
+        elif dj != getattr(self, "_dijkstra_order", dj) and block.weights is not None:
+            self._dijkstra_order = self._dijkstra_order or dj
         if self._method_calling in (1, 2):
             self._nx = block.n_graphs
             if wl:
@@ -588,7 +604,7 @@ class ShortestPath(Kernel):
         return np.reshape(out, (-1, 1))
 
     def _device_features(self, eng):
-        return eng.sp_features(with_labels=bool(self.with_labels))
+        return eng.sp_features(with_labels=bool(self.with_labels), dijkstra_order=bool(getattr(self, "_dijkstra_order", False)))
 
 
 class ShortestPathAttr(Kernel):
@@ -623,6 +639,7 @@ class ShortestPathAttr(Kernel):
                      fw_zero_is_absent=self.algorithm_type == "floyd_warshall", attributes=True,
                      type_error_msg="each element of X must be either a graph or an iterable with at least 2 and at "
                                     "most 3 elements\n")
+        self._dijkstra_order = _path_sum_order(block, self.algorithm_type) or getattr(self, "_dijkstra_order", False)
         return Fitted(block, None, {})
 
     def fit_transform(self, X, y=None):
@@ -649,4 +666,4 @@ class ShortestPathAttr(Kernel):
         return K
 
     def _device_features(self, eng):
-        return eng.spattr_features()
+        return eng.spattr_features(dijkstra_order=bool(getattr(self, "_dijkstra_order", False)))

@@ -132,6 +132,7 @@ class Block:
         self.labels = labels  # list of Python objects (len V) or None
         self.attrs = attrs
         self.all_adjacency = all_adjacency  # every graph came as an adjacency matrix ("auto" -> Floyd-Warshall)
+        self.any_adjacency = all_adjacency  # ... or at least one did (pack() refines this for mixed lists)
         self.n_graphs = len(self.graph_ptr) - 1
         self.mode = None  # vertex-set rule the block was packed with: 'wl' | 'sp' | 'wloa' (pack / datasets.read_tu)
 
@@ -159,6 +160,7 @@ class Block:
             lab = list(a.labels) + list(b.labels)
         at = None if a.attrs is None or b.attrs is None else np.concatenate([a.attrs, b.attrs])
         out = Block(gp, rp, ci, w, lab, at, a.all_adjacency and b.all_adjacency)
+        out.any_adjacency = a.any_adjacency or b.any_adjacency
         out.mode = a.mode if a.mode == b.mode else None
         return out
 
@@ -302,6 +304,7 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
     deg_total = 0
     any_weight = False
     all_adjacency = True
+    any_adjacency = False
     for idx, g, L in iter_elements(X, len_ok, type_error_msg):
         base = graph_ptr[-1]
         fast = None
@@ -326,6 +329,7 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
                              "valid input types for graph type object.")
         base = graph_ptr[-1]
         if kind == "adjacency":
+            any_adjacency = True
             A = _adjacency_array(g)
             n = A.shape[0]
             ii, jj = np.nonzero(A > 0)  # graph.py:963 / 1198
@@ -431,6 +435,7 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
     if graph_ptr[-1] >= 2 ** 31 or len(col_idx) >= 2 ** 31:
         raise ValueError("graph block exceeds int32 indexing")
     out = Block(np.asarray(graph_ptr), row_ptr, col_idx, weights, labels, attrs, all_adjacency)
+    out.any_adjacency = any_adjacency
     out.mode = mode
     return out
 

@@ -76,6 +76,8 @@ typedef struct gk_handle gk_handle;
 /* gk_sp_features flags */
 #define GK_SP_WITH_LABELS 1
 #define GK_SP_KEEP_DIST 2    /* keep fp64 APSP matrices for gk_sp_distances (tests) */
+#define GK_SP_DIJKSTRA_ORDER 4 /* real-valued weights: path sums associate as in dijkstra (graph.py:1712-1764), not as in
+                                floyd_warshall (:1767-1794); integer-valued distances are the same either way */
 
 /* error codes */
 #define GK_OK 0
@@ -128,7 +130,7 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
 /* Build the sparse feature block of the packed graphs on the device. */
 int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats);
 int gk_sp_features(gk_handle* h, int32_t flags, gk_stats* stats);
-int gk_spattr_features(gk_handle* h, gk_stats* stats);
+int gk_spattr_features(gk_handle* h, int32_t flags /* GK_SP_DIJKSTRA_ORDER or 0 */, gk_stats* stats);
 /* WeisfeilerLehman(base_graph_kernel=ShortestPath), weisfeiler_lehman.py:260-270 over
  * shortest_path.py:370-410: n_iter WL rounds, then the labelled shortest-path histogram of every
  * level in one feature block (level-unique label ids => disjoint columns), so that one gk_gram
