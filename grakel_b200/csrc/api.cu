@@ -265,7 +265,7 @@ int gk_destroy(gk_handle* h) {
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
                         &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt, &h->wl_single,
-                        &h->diag_frozen};
+                        &h->diag_frozen, &h->sp_lists};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
@@ -332,6 +332,7 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
   }
   h->N = N; h->V = V; h->E = E;
   h->has_weights = weights != nullptr;
+  h->has_labels = labels != nullptr;
   h->attr_dim = attrs ? attr_dim : 0;
   h->max_graph_size = max_n;
   h->features_ready = false;
@@ -467,7 +468,7 @@ extern "C" {
 int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   if (!h) return fail(GK_ERR_ARG, "null handle");
   if (h->N <= 0) return fail(GK_ERR_STATE, "gk_wl_features: no graphs packed");
-  if (!h->labels0.p || h->V == 0) return fail(GK_ERR_ARG, "gk_wl_features: vertex labels are required");
+  if (!h->has_labels || h->V == 0) return fail(GK_ERR_ARG, "gk_wl_features: vertex labels are required");
   if (n_iter < 0 || n_iter + 1 >= MAX_LEVELS) return fail(GK_ERR_ARG, "gk_wl_features: n_iter out of range");
   GK_CUDA(cudaSetDevice(h->dev));
   const int64_t V = h->V, E = h->E;
@@ -889,7 +890,7 @@ static int sp_features_impl(gk_handle* h, int32_t flags, int32_t wl_iter, gk_sta
   if (h->N <= 0) return fail(GK_ERR_STATE, "gk_sp_features: no graphs packed");
   GK_CUDA(cudaSetDevice(h->dev));
   const bool with_labels = flags & GK_SP_WITH_LABELS;
-  if (with_labels && !h->labels0.p) return fail(GK_ERR_ARG, "gk_sp_features: vertex labels are required");
+  if (with_labels && !h->has_labels) return fail(GK_ERR_ARG, "gk_sp_features: vertex labels are required");
   std::vector<long long> level_base(1, 0);  // first label id of each pass
   int n_pass = 1;
   long long n_labels_total = h->n_labels0;
@@ -944,7 +945,7 @@ static int sp_features_impl(gk_handle* h, int32_t flags, int32_t wl_iter, gk_sta
   const size_t smem_big = SP_LOCAL_SLOTS * 12 + 16;
 
   // device buffers
-  gk::DevBuf& lists = h->large_list;  // reuse: [small list | big list]
+  gk::DevBuf& lists = h->sp_lists;  // [small list | big list | BFS classes]
   GK_TRY(lists.ensure((size_t)N * 4 + 16));
   std::vector<int> order(small);
   order.insert(order.end(), big.begin(), big.end());
@@ -1195,8 +1196,8 @@ int gk_spattr_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   ex->sp_goff[N] = off_all;
   std::vector<int> order(small);
   order.insert(order.end(), big.begin(), big.end());
-  GK_TRY(h->large_list.ensure((size_t)N * 4 + 16));
-  GK_CUDA(cudaMemcpyAsync(h->large_list.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  GK_TRY(h->sp_lists.ensure((size_t)N * 4 + 16));
+  GK_CUDA(cudaMemcpyAsync(h->sp_lists.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
   GK_TRY(h->sp_graph_off.ensure((size_t)(N + 1) * 8));
   GK_CUDA(cudaMemcpyAsync(h->sp_graph_off.p, ex->sp_goff.data(), (N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
   GK_TRY(h->sp_dist.ensure((size_t)std::max<long long>(off_all, 1) * esz));
@@ -1226,7 +1227,7 @@ int gk_spattr_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   else if (dj) GK_CUDA(cudaFuncSetAttribute(sp_dijkstra_order_apsp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
   else GK_CUDA(cudaFuncSetAttribute(spattr_apsp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
   if (!small.empty()) {
-    p.glist = h->large_list.as<int>();
+    p.glist = h->sp_lists.as<int>();
     p.dist_in_global = 0;
     if (use_u16) spattr_apsp<unsigned short><<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
     else if (dj) sp_dijkstra_order_apsp<<<(int)small.size(), SP_THREADS, smem_small, h->stream>>>(p);
@@ -1234,7 +1235,7 @@ int gk_spattr_features(gk_handle* h, int32_t flags, gk_stats* stats) {
     LAUNCH_CHECK(h);
   }
   if (!big.empty()) {
-    p.glist = h->large_list.as<int>() + small.size();
+    p.glist = h->sp_lists.as<int>() + small.size();
     p.dist_in_global = 1;
     if (use_u16) spattr_apsp<unsigned short><<<(int)big.size(), SP_THREADS, 16, h->stream>>>(p);
     else if (dj) sp_dijkstra_order_apsp<<<(int)big.size(), SP_THREADS, 16, h->stream>>>(p);
@@ -1356,21 +1357,21 @@ static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_b
     p.a_row_end = a1; p.b_row_end = (int)n_fit;
     p.c_row0 = a0; p.c_col0 = 0;
     p.out = h->K.p; p.ld = k_cols;
-    p.mirror = sym ? 1 : 0;
+    p.mirror = 0;  // the symmetric case mirrors the upper triangle once, after all chunks (mirror_upper_f64)
     p.diag = h->diag_f64.as<double>();
-    // chunks of the k range: no fp32 accumulator sums more than `chunk` k-blocks x 4 MMAs before it is folded into
-    // the fp64 result (bounds the accumulated rounding of the tensor core's fp32 adds)
-    int chunk = 24;
+    // The tensor core's fp32 accumulate truncates (measured: -1.8e-5 relative for 960 sequential MMAs on all-positive
+    // data, profiles/r02e_spattr_err.txt), so no accumulator sums more than `chunk` k-blocks x 4 MMAs: the kernel
+    // folds every chunk of a tile into the fp64 result itself (double-buffered TMEM accumulators: the MMAs of chunk
+    // c+1 run while the epilogue adds chunk c).
+    int chunk = 8;
     if (const char* e = getenv("GRAKEL_B200_SPATTR_CHUNK")) chunk = std::max(1, atoi(e));
-    const int n_kb = (int)(W / BK_TF32);
+    p.k_block0 = 0;
+    p.num_k_blocks = (int)(W / BK_TF32);
+    p.k_chunk = chunk;
+    p.accumulate = 0;
     const int grid = (int)std::min<size_t>(tiles.size(), h->sm_count);
-    for (int k0 = 0; k0 < n_kb; k0 += chunk) {
-      p.k_block0 = k0;
-      p.num_k_blocks = std::min(chunk, n_kb - k0);
-      p.accumulate = k0 > 0 ? 1 : 0;
-      gram_tc_kernel<double, false, 1><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(tmA, tmB, tmC, p);
-      LAUNCH_CHECK(h);
-    }
+    gram_tc_kernel<double, false, 1><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(tmA, tmB, tmC, p);
+    LAUNCH_CHECK(h);
     if (sym) {
       mirror_upper_f64<<<h->sm_count * 8, 256, 0, h->stream>>>((int)N, h->K.as<double>(), k_cols);
       LAUNCH_CHECK(h);

@@ -125,6 +125,8 @@ struct gk_handle {
   int32_t attr_dim = 0;
   int32_t max_degree = 0, max_graph_size = 0;
   gk::DevBuf graph_ptr, row_ptr, col_idx, labels0, weights, attrs, vgraph;
+  bool has_labels = false;  // the current block was packed with vertex labels (labels0 may hold an older block's)
+  gk::DevBuf sp_lists;      // graph lists of the shortest-path launches (kept apart from large_list: gk_wl_features reads that)
   gk::DevBuf large_list;  // vertices with degree > group width
   int64_t n_large = 0;
   int group_width = 32;

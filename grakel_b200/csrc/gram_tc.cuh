@@ -59,6 +59,7 @@ struct GramParams {
   // accumulator sums more than a few hundred MMAs)
   int accumulate;
   int k_block0;
+  int k_chunk;         // k-blocks per accumulator (0 = all): the kernel folds every chunk of a tile into `out` itself
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -338,7 +339,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int it = 0;
       long long w_tempty = 0, w_full = 0;
       const long long t_start = clock64();
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int kc = p.k_chunk > 0 ? p.k_chunk : p.num_k_blocks;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+      for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += kc, ++it) {  // one accumulator per (tile, k-chunk)
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         long long c0 = clock64();
@@ -346,7 +349,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         w_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int kb1 = min(p.num_k_blocks, kb0 + kc);
+        for (int kb = kb0; kb < kb1; ++kb) {
           c0 = clock64();
           mbar_wait(full_bar(stage), phase);
           w_full += clock64() - c0;
@@ -359,10 +363,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // +32 bytes along K inside the 128-byte swizzle row = +2 in the address field
             if constexpr (KIND == 1)
               tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), UMMA_IDESC_TF32,
-                          (uint32_t)((kb | k) != 0));
+                          (uint32_t)(((kb - kb0) | k) != 0));
             else
               tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), UMMA_IDESC,
-                          (uint32_t)((kb | k) != 0));
+                          (uint32_t)(((kb - kb0) | k) != 0));
           }
           tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -377,10 +381,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     OutT* __restrict__ out = reinterpret_cast<OutT*>(p.out);
     int it = 0;
     long long w_tfull = 0, t_work = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+    const int kc_e = p.k_chunk > 0 ? p.k_chunk : p.num_k_blocks;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+    for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += kc_e, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const int2 tile = p.tiles[t];
+      const bool acc_out = p.accumulate || kb0 > 0;  // later chunks of the tile add to what the earlier ones stored
       const long long c_w = clock64();
       mbar_wait(tfull_bar(as), aphase);
       const long long c_s = clock64();
@@ -454,7 +461,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (row_ok) {
             OutT* dst = out + (long long)(arow - p.c_row0) * p.ld + (bcol0 - p.c_col0);
-            if (p.accumulate) {  // later k-chunks of a split-precision GEMM: this CTA owns the tile, no atomics needed
+            if (acc_out) {  // later k-chunks of a split-precision GEMM: this CTA owns the tile, no atomics needed
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (bcol0 + j < p.b_row_end) vals[j] += dst[j];

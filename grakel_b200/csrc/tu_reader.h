@@ -298,6 +298,14 @@ inline int pack(gk_tu* t, int32_t mode, std::string* err) {
   } else {
     for (int64_t i = 0; i < n; ++i)
       for (uint32_t x = start[i]; x < start[i] + deg[i]; ++x) { keep[i] = 1; keep[rv[x]] = 1; }
+    // a vertex of an edge without a label (e.g. degree labels and a node that is only ever an edge target):
+    // read_data leaves it unlabelled and ShortestPath raises KeyError on it -- no silent label 0 here
+    if (!label.empty())
+      for (int64_t i = 0; i < n; ++i)
+        if (keep[i] && !labelled[i]) {
+          *err = "node " + std::to_string(i + 1) + " occurs in an edge but has no label (the reference raises KeyError)";
+          return GK_ERR_ARG;
+        }
   }
   // vertices grouped by graph, node order inside a graph (stable counting sort)
   t->graph_ptr.assign(t->n_graphs + 1, 0);

@@ -19,10 +19,7 @@
 //     level l), which is what makes the single barrier sufficient: a CTA still clearing can never meet a CTA
 //     already inserting.
 //   * A CTA that owns one tile keeps its CSR slice, labels and frozen flags resident in shared memory across
-//     levels, and dedups its signatures LOCALLY first: only the smallest vertex of each distinct 64-bit key of the
-//     tile goes to the global table and verifies against the global representative; the other vertices verify
-//     against that local representative in shared memory.  At level 1 of config 2 (31 115 classes for 399 901
-//     vertices) that removes most of the global atomics and ~140 MB of L2 sector traffic of the verification.
+//     levels.
 //
 // Exactness is unchanged: every non-frozen vertex's full signature (own label, degree, sorted neighbour labels)
 // is compared with its representative's; a mismatch raises the collision flag and the host retries with a new seed.
@@ -142,6 +139,12 @@ __device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int n
   __syncthreads();  // agg is reused by the next tile / overwritten by the next level's signatures
 }
 
+// CTA-local signature dedup before the global table (resident tiles).  Measured on B200 at config 2
+// (profiles/r02e_wl_prof_local_dedup.txt vs profiles/r02d_wl_prof.txt): level 1 (31 115 classes for 399 901 vertices) gains 6 us (verification 22 -> 18 us:
+// a tile of ~2 700 vertices still holds ~1 500 distinct keys), every other level loses 2-8 us to the shared-memory
+// table (initialisation, probing at load 0.66, two more block barriers): 218 us against 205 us for all levels.
+// Kept behind this switch as a measured negative result; the code is compiled out.
+constexpr bool WLF2_LOCAL_DEDUP = false;
 constexpr int WLF2_LTAB = 4096;  // per-tile signature table (resident tiles): >= WLF_TILE_V slots
 static_assert(WLF2_LTAB >= WLF_TILE_V, "every vertex of a tile must find a slot");
 constexpr int WLF2_SMEM = WLF_SMEM + WLF_TILE_V /*frz_s*/ + WLF_TILE_V * 4 /*gid_s*/ + WLF_TILE_V * 4 /*gbeg_s, gend_s*/ +
@@ -368,7 +371,7 @@ wl_fused2_kernel(WlFused2Params p) {
           key[k] = act[k] ? key_s[i] : 0ULL;
           lone[k] = true;
         }
-        if (resident) {
+        if (WLF2_LOCAL_DEDUP && resident) {
           // CTA-local dedup: slot -> smallest vertex of the tile with this key; later vertices of the key mark it "multi"
           for (int s2 = tid; s2 < WLF2_LTAB; s2 += WLF_THREADS) ltab[s2] = 0xFFFFFFFFu;
           for (int s2 = tid; s2 < WLF2_LTAB / 32; s2 += WLF_THREADS) lmulti[s2] = 0u;
@@ -480,7 +483,7 @@ wl_fused2_kernel(WlFused2Params p) {
         act[k] = i < nv && !frz_s[i];
         fol[k] = false;
         lrep[k] = i;
-        if (act[k] && resident) {
+        if (WLF2_LOCAL_DEDUP && act[k] && resident) {
           lrep[k] = (int)ltab[lslot[i]];
           if (lrep[k] != i) { fol[k] = true; act[k] = false; }
         }
@@ -567,7 +570,7 @@ wl_fused2_kernel(WlFused2Params p) {
       }
       WLF_STAMP(lv, 4);
       __syncthreads();  // every thread has read the old labels / flags of the tile it needs
-      if (resident) {  // followers take the label of their local representative (key_s is free after [A]: new labels)
+      if (WLF2_LOCAL_DEDUP && resident) {  // followers take the label of their local representative (key_s is free after [A]: new labels)
         int* newlab = reinterpret_cast<int*>(key_s);
 #pragma unroll
         for (int k = 0; k < WLF_VPT; ++k)

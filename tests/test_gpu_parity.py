@@ -4,6 +4,7 @@ integer-valued matrices; normalised matrices within 1e-5 relative (in practice
 they are bit-identical too, the epilogue uses the reference's fp64 formula)."""
 import os
 import pickle
+import sys
 
 import numpy as np
 import pytest
@@ -78,16 +79,37 @@ def test_fit_then_transform_with_unseen_labels(tag):
     _run_case(gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"]), d["out"])
 
 
-def test_real_weights_floyd_warshall_semantics():
-    """Real-valued weights: path lengths are compared by exact float equality, so the device must
-    reproduce the reference's fp64 k-ordered Floyd-Warshall bit for bit (adjacency input / forced
-    FW); the Dijkstra flavour differs in the last bit inside the reference itself and is refused."""
+def test_real_weights_both_path_sum_orders():
+    """Real-valued weights: path lengths are compared by exact float equality (shortest_path.py:472, 511) and the
+    reference's two algorithms associate the sums differently, so the device reproduces each bit for bit:
+    the fp64 k-ordered Floyd-Warshall (adjacency input / forced FW) and Dijkstra's left-to-right sums (edge
+    dictionaries / forced dijkstra: the least fixed point of d[v] = min fl(d[u] + w), sp_dijkstra_order_apsp)."""
     d = gio.load(os.path.join(G, "fit_transform.json.gz"))["realw"]
     X, Y = gio.dec_dataset(d["X"]), gio.dec_dataset(d["Y"])
-    out = {k: v for k, v in d["out"].items() if "dijkstra" not in k}
-    _run_case(X, Y, out)
-    with pytest.raises(NotImplementedError):
-        _k().ShortestPath(algorithm_type="dijkstra").fit_transform(X)
+    _run_case(X, Y, d["out"])
+
+
+def test_dijkstra_order_goldens_from_the_reference():
+    """tests/golden/make_golden_dijkstra.py: edge dictionaries with weights from {0.1, 0.2, 0.3, 0.7, 1.1} -- path
+    lengths coincide only when the sums associate as in the reference -- through ShortestPath (auto -> dijkstra),
+    its Floyd-Warshall twin (different matrix), WL over ShortestPath and ShortestPathAttr(algorithm_type="dijkstra")."""
+    sys.path.insert(0, G)
+    from make_golden_dijkstra import gen_real
+    k = _k()
+    ref = np.load(os.path.join(G, "dijkstra_real.npz"))
+    X = gen_real(40, 12, 21)
+    fit, new = X[:30], X[30:]
+    for tag, wl in (("lab", True), ("nolab", False)):
+        e = k.ShortestPath(with_labels=wl)
+        _same(e.fit_transform(fit), ref[f"dj_{tag}_K"])
+        _same(e.transform(new), ref[f"dj_{tag}_Kt"])
+        _same(k.ShortestPath(with_labels=wl, algorithm_type="floyd_warshall").fit_transform(fit), ref[f"fw_{tag}_K"])
+    _same(k.ShortestPath(normalize=True).fit_transform(fit), ref["dj_norm_K"])
+    w = k.WeisfeilerLehman(n_iter=2, base_graph_kernel=k.ShortestPath)
+    _same(w.fit_transform(fit), ref["wlsp_K"])
+    _same(w.transform(new), ref["wlsp_Kt"])
+    A = gen_real(7, 8, 5, attr=3)
+    np.testing.assert_allclose(k.ShortestPathAttr(algorithm_type="dijkstra").fit_transform(A), ref["attr_dj_K"], rtol=1e-5)
 
 
 def test_mutag_goldens():
