@@ -339,7 +339,8 @@ class Engine:
         return a, b
 
     def selftest_deliver(self, src, mode=0, diag=None, nan_to_num=False):
-        """Host-only: fp32 matrix -> float64 through the delivery code of gk_gram (no device work)."""
+        """Host-only: fp32 matrix -> float64 through the delivery code of gk_gram (no device work).  mode 0: upper
+        triangle as fp32, 1: all rows, 2: all rows + normalisation, 3: upper triangle band-packed as u16."""
         src = np.ascontiguousarray(src, dtype=np.float32)
         rows, cols = src.shape
         dst = np.full((rows, cols), np.nan)

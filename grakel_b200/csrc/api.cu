@@ -1363,11 +1363,14 @@ static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_b
     // data, profiles/r02e_spattr_err.txt), so no accumulator sums more than `chunk` k-blocks x 4 MMAs: the kernel
     // folds every chunk of a tile into the fp64 result itself (double-buffered TMEM accumulators: the MMAs of chunk
     // c+1 run while the epilogue adds chunk c).
-    int chunk = 8;
+    // Only the hi x hi third of the k range needs short chunks: the two cross thirds are 2^-11 of the sum, their
+    // accumulated truncation is 2^-11 of the bound and they go through one accumulator.
+    int chunk = 16;
     if (const char* e = getenv("GRAKEL_B200_SPATTR_CHUNK")) chunk = std::max(1, atoi(e));
     p.k_block0 = 0;
     p.num_k_blocks = (int)(W / BK_TF32);
     p.k_chunk = chunk;
+    p.k_split = (int)(Dp / BK_TF32);
     p.accumulate = 0;
     const int grid = (int)std::min<size_t>(tiles.size(), h->sm_count);
     gram_tc_kernel<double, false, 1><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(tmA, tmB, tmC, p);
@@ -1855,7 +1858,25 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
         GK_TRY(deliver_rows(cp, d_k, d_ld, k_rows, k_cols, dst, ld, h->h_diag.as<double>() + a0, h->h_diag.as<double>() + b0,
                             p.nan_to_num));
       } else if (full_square && !getenv("GRAKEL_B200_NO_TRI")) {
-        GK_TRY(deliver_tri(cp, d_k, d_ld, k_rows, dst, ld));
+        // entries are bounded by the largest self similarity: below 2^16 they travel as two bytes (an eighth of the
+        // float64 bytes over PCIe); the triangle is packed band by band on the device first
+        if (max_diag < 65536 && !getenv("GRAKEL_B200_NO_U16")) {
+          const std::vector<long long> start = tri_bands(k_rows);
+          const int nb = (int)start.size() - 1;
+          std::vector<long long> tab(start);
+          long long off = 0;
+          for (int c = 0; c < nb; ++c) { tab.push_back(off); off += (start[c + 1] - start[c]) * (k_rows - start[c]); }
+          GK_TRY(h->K_stage.ensure((size_t)off * 2 + tab.size() * 8 + 64));
+          GK_TRY(h->h_tiles.ensure(tab.size() * 8));
+          memcpy(h->h_tiles.p, tab.data(), tab.size() * 8);
+          long long* d_tab = reinterpret_cast<long long*>(h->K_stage.as<char>() + (((size_t)off * 2 + 63) / 64 * 64));
+          GK_CUDA(cudaMemcpyAsync(d_tab, h->h_tiles.p, tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
+          pack_tri_u16<<<h->sm_count * 8, 256, 0, h->stream>>>(d_k, d_ld, k_rows, d_tab, d_tab + nb + 1, nb, h->K_stage.as<unsigned short>());
+          LAUNCH_CHECK(h);
+          GK_TRY(deliver_tri<uint16_t>(cp, h->K_stage.as<uint16_t>(), 0, k_rows, dst, ld));
+        } else {
+          GK_TRY(deliver_tri<float>(cp, d_k, d_ld, k_rows, dst, ld));
+        }
       } else {
         GK_TRY(deliver_rows(cp, d_k, d_ld, k_rows, k_cols, dst, ld, nullptr, nullptr, 0));
       }

@@ -263,6 +263,25 @@ __global__ void __launch_bounds__(256) add_u64(int n, const unsigned long long* 
   if (i < n) dst[i] += src[i];
 }
 
+// Upper triangle of an fp32 matrix of integers < 65 536 -> band-packed u16 (host_deliver.h tri_bands): band c holds
+// rows [start[c], start[c+1]) x columns [start[c], n) contiguously at element offset off[c].  One CTA per (band, row).
+__global__ void __launch_bounds__(256)
+pack_tri_u16(const float* __restrict__ K, long long ld, long long n, const long long* __restrict__ start, const long long* __restrict__ off,
+             int n_bands, unsigned short* __restrict__ out) {
+  for (long long row = blockIdx.x; row < n; row += gridDim.x) {
+    int c = 0;  // band of this row (bands are few: linear search from a proportional guess)
+    {
+      int lo = 0, hi = n_bands - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (start[mid] <= row) lo = mid; else hi = mid - 1; }
+      c = lo;
+    }
+    const long long r0 = start[c], w = n - r0;
+    const float* src = K + row * ld + r0;
+    unsigned short* dst = out + off[c] + (row - r0) * w;
+    for (long long j = threadIdx.x; j < w; j += blockDim.x) dst[j] = (unsigned short)src[j];
+  }
+}
+
 // normalisation pass when a tail exists: K_ij / sqrt(d_i d_j)  (+ nan_to_num)
 template <typename OutT>
 __global__ void __launch_bounds__(256)

@@ -60,6 +60,7 @@ struct GramParams {
   int accumulate;
   int k_block0;
   int k_chunk;         // k-blocks per accumulator (0 = all): the kernel folds every chunk of a tile into `out` itself
+  int k_split;         // chunking applies to k-blocks [0, k_split); the rest is ONE chunk (0 = chunk everything)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -339,9 +340,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int it = 0;
       long long w_tempty = 0, w_full = 0;
       const long long t_start = clock64();
-      const int kc = p.k_chunk > 0 ? p.k_chunk : p.num_k_blocks;
+      const int kc_base = p.k_chunk > 0 ? p.k_chunk : p.num_k_blocks;
+      const int ksplit = p.k_split > 0 ? p.k_split : p.num_k_blocks;
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
-      for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += kc, ++it) {  // one accumulator per (tile, k-chunk)
+      for (int kb0 = 0, kc = 0; kb0 < p.num_k_blocks; kb0 += kc, ++it) {  // one accumulator per (tile, k-chunk)
+        kc = kb0 < ksplit ? min(kc_base, ksplit - kb0) : p.num_k_blocks - kb0;
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         long long c0 = clock64();
@@ -381,9 +384,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     OutT* __restrict__ out = reinterpret_cast<OutT*>(p.out);
     int it = 0;
     long long w_tfull = 0, t_work = 0;
-    const int kc_e = p.k_chunk > 0 ? p.k_chunk : p.num_k_blocks;
+    const int kc_base = p.k_chunk > 0 ? p.k_chunk : p.num_k_blocks;
+    const int ksplit = p.k_split > 0 ? p.k_split : p.num_k_blocks;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
-    for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += kc_e, ++it) {
+    for (int kb0 = 0, kc_e = 0; kb0 < p.num_k_blocks; kb0 += kc_e, ++it) {
+      kc_e = kb0 < ksplit ? min(kc_base, ksplit - kb0) : p.num_k_blocks - kb0;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const int2 tile = p.tiles[t];
@@ -461,6 +466,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (row_ok) {
             OutT* dst = out + (long long)(arow - p.c_row0) * p.ld + (bcol0 - p.c_col0);
+            if constexpr (sizeof(OutT) == 8) {
+              if (!p.mirror && bcol0 + 32 <= p.b_row_end && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                // full block of a split-precision GEMM: 16-byte loads / stores of the running fp64 sums
+                double2* d2 = reinterpret_cast<double2*>(dst);
+                if (acc_out) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { const double2 o = d2[j]; vals[2 * j] += o.x; vals[2 * j + 1] += o.y; }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) d2[j] = make_double2(vals[2 * j], vals[2 * j + 1]);
+                continue;
+              }
+            }
             if (acc_out) {  // later k-chunks of a split-precision GEMM: this CTA owns the tile, no atomics needed
 #pragma unroll
               for (int j = 0; j < 32; ++j)

@@ -290,6 +290,80 @@ inline void transpose_widen(const float* __restrict__ src, long long pitch, long
     for (long long a = 0; a < na; ++a) dst[b * ld + a] = (double)src[a * pitch + b];
 }
 
+// ---- the same two primitives for u16 sources (matrices whose entries are integers < 65 536 travel as 2 bytes)
+__attribute__((target("avx2"))) inline void widen_row_u16_avx2(const uint16_t* __restrict__ src, double* __restrict__ dst, long long n) {
+  long long j = 0;
+  for (; j < n && (reinterpret_cast<uintptr_t>(dst + j) & 31); ++j) dst[j] = (double)src[j];
+  for (; j + 8 <= n; j += 8) {
+    const __m256i v = _mm256_cvtepu16_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i*>(src + j)));
+    _mm256_stream_pd(dst + j, _mm256_cvtepi32_pd(_mm256_castsi256_si128(v)));
+    _mm256_stream_pd(dst + j + 4, _mm256_cvtepi32_pd(_mm256_extracti128_si256(v, 1)));
+  }
+  for (; j < n; ++j) dst[j] = (double)src[j];
+}
+inline void widen_row(const uint16_t* __restrict__ src, double* __restrict__ dst, long long n) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) return widen_row_u16_avx2(src, dst, n);
+  for (long long j = 0; j < n; ++j) dst[j] = (double)src[j];
+}
+__attribute__((target("avx2"))) inline void transpose_widen_u16_avx2(const uint16_t* __restrict__ src, long long pitch, long long na,
+                                                                     long long nb, double* __restrict__ dst, long long ld) {
+  long long b = 0;
+  for (; b + 8 <= nb; b += 8) {
+    long long a = 0;
+    for (; a + 8 <= na; a += 8) {
+      const uint16_t* s = src + a * pitch + b;
+      __m128i r[8];
+      for (int k = 0; k < 8; ++k) r[k] = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k * pitch));
+      // 8 x 8 transpose of 16-bit lanes
+      const __m128i t0 = _mm_unpacklo_epi16(r[0], r[1]), t1 = _mm_unpackhi_epi16(r[0], r[1]), t2 = _mm_unpacklo_epi16(r[2], r[3]),
+                    t3 = _mm_unpackhi_epi16(r[2], r[3]), t4 = _mm_unpacklo_epi16(r[4], r[5]), t5 = _mm_unpackhi_epi16(r[4], r[5]),
+                    t6 = _mm_unpacklo_epi16(r[6], r[7]), t7 = _mm_unpackhi_epi16(r[6], r[7]);
+      const __m128i u0 = _mm_unpacklo_epi32(t0, t2), u1 = _mm_unpackhi_epi32(t0, t2), u2 = _mm_unpacklo_epi32(t1, t3),
+                    u3 = _mm_unpackhi_epi32(t1, t3), u4 = _mm_unpacklo_epi32(t4, t6), u5 = _mm_unpackhi_epi32(t4, t6),
+                    u6 = _mm_unpacklo_epi32(t5, t7), u7 = _mm_unpackhi_epi32(t5, t7);
+      __m128i c[8];
+      c[0] = _mm_unpacklo_epi64(u0, u4); c[1] = _mm_unpackhi_epi64(u0, u4); c[2] = _mm_unpacklo_epi64(u1, u5);
+      c[3] = _mm_unpackhi_epi64(u1, u5); c[4] = _mm_unpacklo_epi64(u2, u6); c[5] = _mm_unpackhi_epi64(u2, u6);
+      c[6] = _mm_unpacklo_epi64(u3, u7); c[7] = _mm_unpackhi_epi64(u3, u7);
+      for (int k = 0; k < 8; ++k) {
+        double* d = dst + (b + k) * ld + a;
+        const __m256i v = _mm256_cvtepu16_epi32(c[k]);
+        const __m256d lo = _mm256_cvtepi32_pd(_mm256_castsi256_si128(v)), hi = _mm256_cvtepi32_pd(_mm256_extracti128_si256(v, 1));
+        if ((reinterpret_cast<uintptr_t>(d) & 31) == 0) { _mm256_stream_pd(d, lo); _mm256_stream_pd(d + 4, hi); }
+        else { _mm256_storeu_pd(d, lo); _mm256_storeu_pd(d + 4, hi); }
+      }
+    }
+    for (; a < na; ++a)
+      for (int k = 0; k < 8; ++k) dst[(b + k) * ld + a] = (double)src[a * pitch + b + k];
+  }
+  for (; b < nb; ++b)
+    for (long long a = 0; a < na; ++a) dst[b * ld + a] = (double)src[a * pitch + b];
+}
+inline void transpose_widen(const uint16_t* __restrict__ src, long long pitch, long long na, long long nb, double* __restrict__ dst,
+                            long long ld) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) return transpose_widen_u16_avx2(src, pitch, na, nb, dst, ld);
+  for (long long b = 0; b < nb; ++b)
+    for (long long a = 0; a < na; ++a) dst[b * ld + a] = (double)src[a * pitch + b];
+}
+
+// Row bands of the upper triangle, of about `area` elements each: rows [start[c], start[c+1]), columns [start[c], n);
+// row counts are multiples of 8.  Shared by the host delivery and the device-side u16 packer.
+inline std::vector<long long> tri_bands(long long n) {
+  long long area = 2LL << 20;
+  if (const char* e = getenv("GRAKEL_B200_BAND_MB")) area = std::max(1, atoi(e)) * (1LL << 18);
+  std::vector<long long> start;
+  for (long long r = 0; r < n;) {
+    start.push_back(r);
+    long long nr = std::max<long long>(8, area / (n - r) / 8 * 8);
+    if (r + nr + 8 > n) nr = n - r;  // no sliver at the end
+    r += nr;
+  }
+  start.push_back(n);
+  return start;
+}
+
 constexpr int DELIVER_SLOTS = 4;
 
 // where the bands come from: the device (cudaMemcpy2DAsync + one event per staging slot) or, for the
@@ -312,7 +386,7 @@ struct DeviceCopier {
     if (moved) pthread_setaffinity_np(pthread_self(), sizeof(old_set), &old_set);
     return rc == GK_OK ? h->h_stage.as<char>() : nullptr;
   }
-  bool copy(int slot, void* dst, size_t dpitch, const float* src, size_t spitch, size_t width, size_t height) {
+  bool copy(int slot, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
     if (cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return false;
     return cudaEventRecord(h->ev_stage[slot], h->stream) == cudaSuccess;
   }
@@ -321,7 +395,7 @@ struct DeviceCopier {
 struct HostCopier {
   std::vector<char> buf;
   char* stage(size_t bytes) { buf.resize(bytes); return buf.data(); }
-  bool copy(int, void* dst, size_t dpitch, const float* src, size_t spitch, size_t width, size_t height) {
+  bool copy(int, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
     for (size_t r = 0; r < height; ++r) memcpy((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
     return true;
   }
@@ -393,23 +467,16 @@ static int deliver_rows(Copier& cp, const float* d_src, long long d_ld, long lon
 }
 
 // Symmetric n x n fp32 device matrix -> full float64 host matrix; only the upper triangle is copied.
-template <class Copier>
-static int deliver_tri(Copier& cp, const float* d_src, long long d_ld, long long n, double* dst, long long ld) {
-  // bands of about `area` elements: rows [r0, r1), columns [r0, n); row counts are multiples of 8
-  long long area = 2LL << 20;  // 8 MB of fp32 per band
-  if (const char* e = getenv("GRAKEL_B200_BAND_MB")) area = std::max(1, atoi(e)) * (1LL << 18);
-  std::vector<long long> start;
-  for (long long r = 0; r < n;) {
-    start.push_back(r);
-    long long nr = std::max<long long>(8, area / (n - r) / 8 * 8);
-    if (r + nr + 8 > n) nr = n - r;  // no sliver at the end
-    r += nr;
-  }
-  start.push_back(n);
+// T = float: `d_src` is the n x n matrix itself (pitch d_ld elements).  T = uint16_t: `d_src` is the band-packed upper
+// triangle produced by pack_tri_u16 (band c at element offset sum_{b<c} rows_b * width_b, pitch = its own width).
+template <class T, class Copier>
+static int deliver_tri(Copier& cp, const T* d_src, long long d_ld, long long n, double* dst, long long ld) {
+  const bool packed = sizeof(T) == 2;
+  const std::vector<long long> start = tri_bands(n);
   const long long n_bands = (long long)start.size() - 1;
   size_t slot_bytes = 0;
   for (long long c = 0; c < n_bands; ++c)
-    slot_bytes = std::max(slot_bytes, (size_t)(start[c + 1] - start[c]) * (size_t)(n - start[c]) * 4);
+    slot_bytes = std::max(slot_bytes, (size_t)(start[c + 1] - start[c]) * (size_t)(n - start[c]) * sizeof(T));
   slot_bytes = (slot_bytes + 255) / 256 * 256;
   char* stage = cp.stage(slot_bytes * DELIVER_SLOTS);
   if (!stage) return GK_ERR_CUDA;
@@ -417,10 +484,14 @@ static int deliver_tri(Copier& cp, const float* d_src, long long d_ld, long long
   std::atomic<long long> ready(0);
   std::vector<std::atomic<int>> done(n_bands);
   for (auto& d : done) d.store(0);
+  std::vector<long long> packed_off(n_bands + 1, 0);
+  for (long long c = 0; c < n_bands; ++c) packed_off[c + 1] = packed_off[c] + (start[c + 1] - start[c]) * (n - start[c]);
   auto enqueue = [&](long long c) -> int {
     const long long r0 = start[c], nr = start[c + 1] - r0, w = n - r0;
-    if (!cp.copy((int)(c % DELIVER_SLOTS), stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes, (size_t)w * 4, d_src + r0 * d_ld + r0,
-                 (size_t)d_ld * 4, (size_t)w * 4, (size_t)nr))
+    const T* src = packed ? d_src + packed_off[c] : d_src + r0 * d_ld + r0;
+    const size_t spitch = (size_t)(packed ? w : d_ld) * sizeof(T);
+    if (!cp.copy((int)(c % DELIVER_SLOTS), stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes, (size_t)w * sizeof(T), src, spitch,
+                 (size_t)w * sizeof(T), (size_t)nr))
       return fail(GK_ERR_CUDA, "deliver_tri: D2H copy could not be queued");
     return GK_OK;
   };
@@ -439,7 +510,7 @@ static int deliver_tri(Copier& cp, const float* d_src, long long d_ld, long long
         _mm_pause();
       }
       const long long r0 = start[c], r1 = start[c + 1], nr = r1 - r0, w = n - r0;
-      const float* src = reinterpret_cast<const float*>(stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes);
+      const T* src = reinterpret_cast<const T*>(stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes);
       const long long ca = (t - task0[c]) * 64, cb = std::min(w, ca + 64);  // columns of the band, relative to r0
       for (long long r = 0; r < nr; ++r) widen_row(src + r * w + ca, dst + (r0 + r) * ld + r0 + ca, cb - ca);
       // mirrored part: band columns >= nr are rows r1.. of the destination, columns r0..r1
@@ -492,9 +563,16 @@ int gk_selftest_deliver(int32_t mode, int64_t rows, int64_t cols, const float* s
                         double* dst) {
   if (!src || !dst || rows <= 0 || cols <= 0) return fail(GK_ERR_ARG, "gk_selftest_deliver: bad arguments");
   HostCopier cp;
-  if (mode == 0) {
-    if (rows != cols) return fail(GK_ERR_ARG, "gk_selftest_deliver: mode 0 needs a square matrix");
-    return deliver_tri(cp, src, cols, rows, dst, cols);
+  if (mode == 0 || mode == 3) {
+    if (rows != cols) return fail(GK_ERR_ARG, "gk_selftest_deliver: modes 0 and 3 need a square matrix");
+    if (mode == 0) return deliver_tri<float>(cp, src, cols, rows, dst, cols);
+    // mode 3: what pack_tri_u16 does on the device, on the host -- then the u16 delivery
+    const std::vector<long long> start = tri_bands(rows);
+    std::vector<uint16_t> packed;
+    for (size_t c = 0; c + 1 < start.size(); ++c)
+      for (long long r = start[c]; r < start[c + 1]; ++r)
+        for (long long j = start[c]; j < cols; ++j) packed.push_back((uint16_t)src[r * cols + j]);
+    return deliver_tri<uint16_t>(cp, packed.data(), 0, rows, dst, cols);
   }
   return deliver_rows(cp, src, cols, rows, cols, dst, cols, mode == 2 ? diag : nullptr, mode == 2 ? diag : nullptr, nan_to_num);
 }

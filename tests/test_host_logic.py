@@ -339,6 +339,8 @@ def test_host_delivery_bands_widen_and_mirror():
         A = np.triu(A) + np.triu(A, 1).T
         assert np.array_equal(deliver(A, 0), A.astype(np.float64)), n
         assert np.array_equal(deliver(A, 1), A.astype(np.float64)), n
+        A16 = np.floor(A / 256.0).astype(np.float32)  # integers < 2^16: the two-byte transport
+        assert np.array_equal(deliver(A16, 3), A16.astype(np.float64)), n
         d = rs.randint(0, 50, size=n).astype(np.float64)
         with np.errstate(all="ignore"):
             ref = A.astype(np.float64) / np.sqrt(np.outer(d, d))  # kernel.py:198-203

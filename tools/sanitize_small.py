@@ -1,0 +1,37 @@
+"""Small end-to-end calls of every device path for compute-sanitizer (memcheck / racecheck): WL (fused persistent
+kernel, cooperative launch, grid barrier, CAS tables), head/tail Gram (tcgen05 + TMA + atomics), SP (bitmask BFS,
+Floyd-Warshall, Dijkstra order), SP-attr (tf32 GEMM), WL-OA, transform (rectangular)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from bench import gen_list  # noqa: E402
+from grakel_b200 import (ShortestPath, ShortestPathAttr, WeisfeilerLehman,  # noqa: E402
+                         WeisfeilerLehmanOptimalAssignment)
+from make_golden_dijkstra import gen_real  # noqa: E402
+
+X = gen_list(300, 14, 3)
+K = WeisfeilerLehman(n_iter=3).fit_transform(X)
+Kn = WeisfeilerLehman(n_iter=3, normalize=True).fit(X[:250]).transform(X[250:])
+print("WL", K.shape, float(K.sum()), Kn.shape)
+os.environ["GRAKEL_B200_FORCE_T"] = "4"
+K2 = WeisfeilerLehman(n_iter=3).fit_transform(X)
+assert np.array_equal(K, K2)
+del os.environ["GRAKEL_B200_FORCE_T"]
+Ko = WeisfeilerLehmanOptimalAssignment(n_iter=2).fit_transform(X[:120])
+print("WL-OA", Ko.shape, float(Ko.sum()))
+A = gen_list(120, 16, 4, as_adj=True)
+Ks = ShortestPath().fit_transform(A)
+print("SP", Ks.shape, float(Ks.sum()))
+R = gen_real(40, 10, 2)
+Kr = ShortestPath().fit_transform(R)
+Kf = ShortestPath(algorithm_type="floyd_warshall").fit_transform(R)
+print("SP real", float(Kr.sum()), float(Kf.sum()))
+At = gen_list(60, 12, 5, attr=4, as_adj=True)
+Ka = ShortestPathAttr().fit_transform(At)
+print("SP-attr", Ka.shape, float(Ka.sum()))
+print("sanitize_small ok")
