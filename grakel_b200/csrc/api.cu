@@ -272,6 +272,7 @@ int gk_destroy(gk_handle* h) {
   h->h_tiles.release();
   h->h_stage.release();
   h->h_diag.release();
+  h->h_bands.release();
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->tev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -498,8 +499,10 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     HandleExtra* ex = extra_of(h);
     std::vector<int> tv, ct(G + 1, 0);
     bool ok = false;
-    for (int per = std::max<int64_t>(1, std::max((V + (int64_t)G * WLF_TILE_V - 1) / ((int64_t)G * WLF_TILE_V),
-                                                 (E + (int64_t)G * WLF_TILE_E - 1) / ((int64_t)G * WLF_TILE_E)));
+    int64_t per0 = std::max<int64_t>(1, std::max((V + (int64_t)G * WLF_TILE_V - 1) / ((int64_t)G * WLF_TILE_V),
+                                                  (E + (int64_t)G * WLF_TILE_E - 1) / ((int64_t)G * WLF_TILE_E)));
+    if (const char* e = getenv("GRAKEL_B200_WL_TILES_PER_CTA")) per0 = std::max<int64_t>(per0, atoi(e));  // tests: multi-tile CTAs on small inputs
+    for (int per = (int)per0;
          per <= 4096 && !ok; per *= 2) {
       // G * per tiles of whole graphs, balanced by vertex count
       const int T = G * per;
@@ -1365,7 +1368,7 @@ static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_b
     // c+1 run while the epilogue adds chunk c).
     // Only the hi x hi third of the k range needs short chunks: the two cross thirds are 2^-11 of the sum, their
     // accumulated truncation is 2^-11 of the bound and they go through one accumulator.
-    int chunk = 16;
+    int chunk = 8;
     if (const char* e = getenv("GRAKEL_B200_SPATTR_CHUNK")) chunk = std::max(1, atoi(e));
     p.k_block0 = 0;
     p.num_k_blocks = (int)(W / BK_TF32);
@@ -1867,10 +1870,10 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
           long long off = 0;
           for (int c = 0; c < nb; ++c) { tab.push_back(off); off += (start[c + 1] - start[c]) * (k_rows - start[c]); }
           GK_TRY(h->K_stage.ensure((size_t)off * 2 + tab.size() * 8 + 64));
-          GK_TRY(h->h_tiles.ensure(tab.size() * 8));
-          memcpy(h->h_tiles.p, tab.data(), tab.size() * 8);
+          GK_TRY(h->h_bands.ensure(tab.size() * 8));
+          memcpy(h->h_bands.p, tab.data(), tab.size() * 8);
           long long* d_tab = reinterpret_cast<long long*>(h->K_stage.as<char>() + (((size_t)off * 2 + 63) / 64 * 64));
-          GK_CUDA(cudaMemcpyAsync(d_tab, h->h_tiles.p, tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
+          GK_CUDA(cudaMemcpyAsync(d_tab, h->h_bands.p, tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
           pack_tri_u16<<<h->sm_count * 8, 256, 0, h->stream>>>(d_k, d_ld, k_rows, d_tab, d_tab + nb + 1, nb, h->K_stage.as<unsigned short>());
           LAUNCH_CHECK(h);
           GK_TRY(deliver_tri<uint16_t>(cp, h->K_stage.as<uint16_t>(), 0, k_rows, dst, ld));

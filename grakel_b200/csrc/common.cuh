@@ -183,6 +183,7 @@ struct gk_handle {
   // ---- GEMM
   gk::DevBuf tiles;  // int2 list
   gk::PinBuf h_tiles;
+  gk::PinBuf h_bands;  // band table of the u16 result transport (its own buffer: h_tiles may still feed an async copy)
   gk::DevBuf K;      // device-resident result of the last gk_gram
   int64_t K_rows = 0, K_cols = 0, K_ld = 0;  // K_ld: row pitch in elements (>= K_cols)
   int K_dtype = GK_F32;

@@ -296,12 +296,18 @@ def test_high_degree_and_empty_edge_graphs():
         _same(k.ShortestPath().fit_transform(X[:4]), SPOracle().fit_transform(X[:4]))
 
 
-@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("fused", ["0", "1", "1-multitile", "v1"])
 def test_wl_fused_and_multikernel_paths_agree(fused, monkeypatch, eng):
     """The persistent cooperative WL kernel (wl_fused.cuh) and the per-level kernels (wl.cuh)
     must produce the same labels (first-occurrence ids), level sizes and Gram matrix -- on a
     sparse set (thread-per-vertex signatures), on a set with hubs of degree > 32 (warp path)
     and on a block smaller than the grid (empty CTA ranges)."""
+    if fused == "1-multitile":  # several tiles per CTA: shared memory is re-staged per tile and level (large inputs)
+        monkeypatch.setenv("GRAKEL_B200_WL_TILES_PER_CTA", "3")
+        fused = "1"
+    if fused == "v1":  # the first-generation fused kernel (dense ranks, two barriers per level)
+        monkeypatch.setenv("GRAKEL_B200_WL_V1", "1")
+        fused = "1"
     monkeypatch.setenv("GRAKEL_B200_WL_FUSED", fused)
     k = _k()
     rs = np.random.RandomState(11)
@@ -424,14 +430,14 @@ def test_shortest_path_attr_matches_reference_loop(mode, monkeypatch):
                                rtol=max(tol, 1e-9))  # real-reference K[0,:5] of config 5
     if mode == "tf32x3":  # the observed error, not just the bound: a regression to plain tf32 (1e-3) or bf16 would show
         err = float(np.max(np.abs(Kd - Ko) / np.abs(Ko)))
-        assert err < 2e-6, err
+        assert err < 3e-6, err
         # a few hundred graphs: several row tiles, k-chunk folding, mirrored tiles, against the fp64 device Gram
         Xm = gen(300, 30, 3, attr=16, as_adj=True)
         K32 = k.ShortestPathAttr().fit_transform(Xm)
         monkeypatch.setenv("GRAKEL_B200_SPATTR_F64", "1")
         K64 = k.ShortestPathAttr().fit_transform(Xm)
         assert np.array_equal(K32, K32.T)
-        np.testing.assert_allclose(K32, K64, rtol=2e-6)
+        np.testing.assert_allclose(K32, K64, rtol=3e-6)
     with pytest.raises(NotImplementedError):
         k.ShortestPathAttr(metric=lambda a, b: float(np.dot(a, b))).fit_transform(Xc[:2])
 
