@@ -61,39 +61,31 @@ struct WlFused2Params {
 // Fixed COO region per (tile, level), unused slots hold EMPTY64; per-column graph counts go through a shared-memory
 // aggregation table first (a column shared by every graph costs one global atomic per tile).
 // Per-vertex label multiplicity inside its graph, and whether the vertex is the first of its graph with that label:
-// cf_s[i] = count | (first ? 0x8000 : 0).  One WARP per graph: the labels of up to 128 vertices sit in the lanes'
-// registers, __match_any_sync counts inside a 32-vertex chunk, 32 rotations compare two chunks -- ~50 warp
-// instructions for a 40-vertex graph where the per-vertex scan (each vertex reads its whole graph) needed ~1 600, and
-// warps with a single non-frozen vertex no longer drag 31 idle lanes through a 40-iteration loop (the scan was the
-// whole cost of the feature phase: 10 / 16 / 7.5 / 5.7 us at levels 0 / 1 / 2 / >= 3, profiles/r02d_wl_prof.txt).
-__device__ __forceinline__ void wlf2_count(const WlFused2Params& p, int v0, int nv, const int* lab_s, const int* gid_s,
-                                           unsigned short* cf_s) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (nv <= 0) return;
-  const int g_first = gid_s[0], g_last = gid_s[nv - 1];
-  for (int g = g_first + wid; g <= g_last; g += WLF_THREADS / 32) {
-    const int gs = p.graph_ptr[g] - v0, ge = p.graph_ptr[g + 1] - v0;  // a tile holds whole graphs
-    const int n = ge - gs;
-    if (n <= 128) {
-      for (int a = 0; a * 32 < n; ++a) {  // warp-uniform trip count
-        const int ia = a * 32 + lane;
-        const int xa = ia < n ? lab_s[gs + ia] : -2 - lane;  // labels are >= 0: padding lanes match nothing
-        const unsigned m = __match_any_sync(0xffffffffu, xa);
-        int cnt = __popc(m);
-        bool first = (__ffs(m) - 1) == lane;
-        for (int b = 0; b * 32 < n; ++b) {
-          if (b == a) continue;
-          for (int r = 0; r < 32; ++r) {  // the other chunk, rotated: conflict-free shared-memory reads
-            const int j = b * 32 + ((lane + r) & 31);
-            const int y = j < n ? lab_s[gs + j] : -1;
-            if (y == xa) { ++cnt; if (b < a) first = false; }
-          }
-        }
-        if (ia < n) cf_s[gs + ia] = (unsigned short)(cnt | (first ? 0x8000 : 0));
-      }
-    } else {  // a large graph: every lane scans the graph for its vertices
-      for (int i = gs + lane; i < ge; i += 32) {
-        const int l = lab_s[i];
+// cf_s[i] = count | (first ? 0x8000 : 0) for the non-frozen vertices.
+//   dense tiles (levels 0-2: most vertices still active): every vertex scans its graph -- lanes of a warp are
+//     consecutive vertices of (mostly) one graph, so the scan is warp-uniform: ~n iterations per 32 vertices;
+//   sparse tiles (deep levels: a few per cent active): that scan would still run in almost every warp (one active
+//     lane is enough), 5.7 us for ~100 active vertices (profiles/r02d_wl_prof.txt).  Instead the active vertices are
+//     compacted and each one is handled by a whole warp whose lanes scan the graph in parallel (ballot + popc).
+// (A warp-per-graph variant with rotating chunk compares was measured slower at every level: profiles/r02h_wl_prof.txt.)
+__device__ __forceinline__ void wlf2_count(const WlFused2Params& p, int nv, const int* lab_s, const unsigned char* frz_s,
+                                           const unsigned short* gbeg_s, const unsigned short* gend_s, unsigned short* cf_s,
+                                           unsigned short* list_s, int* s_warp) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int mine = 0;
+#pragma unroll
+  for (int k = 0; k < WLF_VPT; ++k) {
+    const int i = tid + k * WLF_THREADS;
+    mine += (i < nv && !frz_s[i]) ? 1 : 0;
+  }
+  int n_act;
+  const int ex0 = wlf_block_scan(mine, &n_act, s_warp);
+  if (4 * n_act > nv) {
+#pragma unroll
+    for (int k = 0; k < WLF_VPT; ++k) {
+      const int i = tid + k * WLF_THREADS;
+      if (i < nv && !frz_s[i]) {
+        const int gs = gbeg_s[i], ge = gend_s[i], l = lab_s[i];
         int cnt = 0;
         bool first = true;
         for (int u = gs; u < ge; ++u) {
@@ -104,14 +96,37 @@ __device__ __forceinline__ void wlf2_count(const WlFused2Params& p, int v0, int 
         cf_s[i] = (unsigned short)(cnt | (first ? 0x8000 : 0));
       }
     }
+  } else {
+    int ex = ex0;
+#pragma unroll
+    for (int k = 0; k < WLF_VPT; ++k) {
+      const int i = tid + k * WLF_THREADS;
+      if (i < nv && !frz_s[i]) list_s[ex++] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int a = wid; a < n_act; a += WLF_THREADS / 32) {
+      const int i = list_s[a];
+      const int gs = gbeg_s[i], ge = gend_s[i], l = lab_s[i];
+      int cnt = 0;
+      bool earlier = false;
+      for (int u0 = gs; u0 < ge; u0 += 32) {
+        const int u = u0 + lane;
+        const bool same = u < ge && lab_s[u] == l;
+        const unsigned m = __ballot_sync(0xffffffffu, same);
+        cnt += __popc(m);
+        earlier = earlier || (__ballot_sync(0xffffffffu, same && u < i) != 0u);
+      }
+      if (lane == 0) cf_s[i] = (unsigned short)(cnt | (earlier ? 0 : 0x8000));
+    }
   }
 }
 
 __device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int nv, const int* lab_s, const unsigned char* frz_s,
-                                          const int* gid_s, unsigned short* cf_s,
+                                          const int* gid_s, const unsigned short* gbeg_s, const unsigned short* gend_s,
+                                          unsigned short* cf_s, unsigned short* list_s,
                                           unsigned* agg, long long base, size_t coo_off, int* s_warp, unsigned& mx, unsigned& n_new) {
   const int tid = threadIdx.x, lane = tid & 31;
-  wlf2_count(p, v0, nv, lab_s, gid_s, cf_s);
+  wlf2_count(p, nv, lab_s, frz_s, gbeg_s, gend_s, cf_s, list_s, s_warp);
   __syncthreads();
   int g[WLF_VPT], l[WLF_VPT];
   unsigned cnt[WLF_VPT];
@@ -274,7 +289,7 @@ wl_fused2_kernel(WlFused2Params p) {
     }
     __syncthreads();
     WLF_STAMP(0, 1);
-    wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, reinterpret_cast<unsigned short*>(key_s), agg, 0, (size_t)v0, s_warp, mx, n_new);
+    wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, reinterpret_cast<unsigned short*>(key_s), lslot, agg, 0, (size_t)v0, s_warp, mx, n_new);
     WLF_STAMP(0, 2);
   }
   if (p.L > 2) {  // table of level 2 (first touched after the barrier of level 1)
@@ -636,7 +651,7 @@ wl_fused2_kernel(WlFused2Params p) {
       __syncthreads();
       for (int i = tid; i < nv; i += WLF_THREADS) lab_out[v0 + i] = lab_s[i];
       WLF_STAMP(lv, 5);
-      wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, reinterpret_cast<unsigned short*>(key_s), agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
+      wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, reinterpret_cast<unsigned short*>(key_s), lslot, agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
     }
     WLF_STAMP(lv, 3);
     if (lv + 2 < p.L) {  // clear the table level lv+2 inserts into (last read in [B] of level lv-1, which every CTA has left)
