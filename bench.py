@@ -559,8 +559,13 @@ def main():
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
     t_ms = torch.tensor([dev_ms], device="cuda")
+    stages_per_rank = None
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        mine = {"rank": rank, "ms_per_step": dev_ms / args.steps, "wl_features": float(np.mean(feat_ms)), "columns+panel(+barrier)": float(np.mean(panel_ms)),
+                "gram_gemm": float(np.mean(gemm_ms)), "barrier+tail": float(np.mean(tail_ms)), "tiles": int(st.gemm_tiles)}
+        stages_per_rank = [None] * world
+        dist.all_gather_object(stages_per_rank, mine)
     ms_step = float(t_ms.item()) / args.steps
     value = n * n / (ms_step * 1e-3)
 
@@ -675,6 +680,7 @@ def main():
 
     if rank != 0:
         if world > 1:
+            eng.close()  # collective: peers unmap each other's blocks before anybody frees them
             dist.destroy_process_group()
         return
 
@@ -715,6 +721,7 @@ def main():
         "e2e": e2e,
         "e2e_api": e2e_api,
         "other_paths": paths,
+        "stages_ms_per_rank": stages_per_rank,
         "dist_check": dist_check,
         "config4": config4,
         "gpu_launches": launches,
@@ -747,6 +754,7 @@ def main():
         line["cpu_baseline"] = cpu_baseline_obj(cpu_arm(steps=1, budget_s=12.0), n)
     print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
+        eng.close()
         dist.destroy_process_group()
 
 

@@ -174,11 +174,15 @@ class Engine:
         self.h = h
         self._lock = threading.RLock()
 
+    def close(self):
+        """Destroy the handle now (collective when a communicator exists: every rank calls it)."""
+        if getattr(self, "h", None):
+            self.lib.gk_destroy(self.h)
+            self.h = None
+
     def __del__(self):
         try:
-            if getattr(self, "h", None):
-                self.lib.gk_destroy(self.h)
-                self.h = None
+            self.close()
         except Exception:
             pass
 

@@ -201,7 +201,12 @@ int gk_comm_destroy(gk_handle* h) {
   cudaSetDevice(h->dev);
   cudaStreamSynchronize(h->stream);
   for (int r = 0; r < c->nranks; ++r)
-    if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    if (r != c->rank && c->peer_base[r]) { cudaIpcCloseMemHandle(c->peer_base[r]); c->peer_base[r] = nullptr; }
+  // collective: nobody frees an exported block (gk_destroy does, right after this) before every peer has unmapped it
+  if (c->comm && c->nranks > 1 && nccl_api()->AllReduce) {
+    nccl_api()->AllReduce(c->d_token, c->d_token, 1, ncclInt32, ncclSum, c->comm, h->stream);
+    cudaStreamSynchronize(h->stream);
+  }
   if (c->d_token) cudaFree(c->d_token);
   if (c->d_handles) cudaFree(c->d_handles);
   NcclApi* api = nccl_api();
@@ -479,7 +484,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   const int64_t launches0 = h->launches;
 
   GK_TRY(h->labels_all.ensure((size_t)L * V * 4));
-  GK_TRY(h->sig_nbr.ensure(std::max<int64_t>(E, 1) * 4));
+  GK_TRY(h->sig_nbr.ensure(std::max<int64_t>(E, 1) * 4 * 2));  // wl_fused2 double-buffers the rows by level parity
   GK_TRY(h->slot_of.ensure(V * 4));
   GK_TRY(h->flags.ensure(V * 4));
   const int nb = cdiv(V, 256);
@@ -557,7 +562,9 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   int retries = 0;
   GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
   for (;; ++retries) {
-    if (retries > 8) return fail(GK_ERR_STATE, "gk_wl_features: repeated hash collisions");
+    if (retries > 8)
+      return fail(GK_ERR_STATE, "gk_wl_features: repeated hash collisions (level mask 0x" +
+                                    [&] { char b[16]; snprintf(b, sizeof(b), "%x", h->h_scalars.as<DevScalars>()->collision); return std::string(b); }() + ")");
     const unsigned long long seed = mix64(0x5851F42D4C957F2DULL + 0x9E3779B97F4A7C15ULL * (unsigned long long)retries);
     const char* e_v1 = getenv("GRAKEL_B200_WL_V1");
     const bool wl_v2 = fused && !(e_v1 && atoi(e_v1) != 0);
@@ -594,12 +601,14 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       fp.labels0 = h->labels0.as<int>(); fp.tile_vbeg = wb; fp.cta_tile = d_cta_tile;
       fp.barrier = d_barrier;
       fp.labels_all = labels_all; fp.sig_nbr = h->sig_nbr.as<int>(); fp.slot_of = h->slot_of.as<int>();
+      fp.E = std::max<int64_t>(E, 1);
       fp.frozen = h->wl_single.as<unsigned char>();
       fp.table = h->ht_keys.as<unsigned long long>();
       fp.ht_mask = (unsigned)(h->ht_cap - 1);
       fp.coo_keys = h->ft_keys.as<unsigned long long>(); fp.coo_cnt = h->ft_cnt.as<unsigned>();
       fp.seed = seed; fp.st = fst; fp.sc = sc;
       fp.diag_frozen = h->diag_frozen.as<unsigned long long>();
+      if (const char* e = getenv("GRAKEL_B200_WL_DBG")) fp.dbg = atoi(e);
       const bool prof = getenv("GRAKEL_B200_PROF") != nullptr;
       if (prof) {
         GK_TRY(h->K_stage.ensure((size_t)G * L * 128));

@@ -16,8 +16,9 @@
 //     written for it.  At BASELINE config 2, 93 % of the vertices freeze at level 2 and 96 % by level 3: levels
 //     3..5 touch 4 % of the data.
 //   * Three signature tables rotate (level l uses table l mod 3; the table of level l+2 is cleared in [B] of
-//     level l), which is what makes the single barrier sufficient: a CTA still clearing can never meet a CTA
-//     already inserting.
+//     level l) and the verification rows are double-buffered by level parity, which is what makes the single
+//     barrier sufficient: a CTA that is already in [A] of level l+1 never touches what a CTA still in [B] of
+//     level l reads (a CTA cannot be two levels ahead: the barrier of l+1 waits for everybody's [B] of l).
 //   * A CTA that owns one tile keeps its CSR slice, labels and frozen flags resident in shared memory across
 //     levels.
 //
@@ -41,7 +42,10 @@ struct WlFused2Params {
   const int* tile_vbeg;  // [n_tiles + 1] first vertex of each tile (whole graphs)
   const int* cta_tile;   // [grid + 1] first tile of each CTA
   int* labels_all;       // [L * V]; level 0: the packed dense ids, level >= 1: representative vertex ids
-  int* sig_nbr;          // [E] sorted neighbour labels of the current level (non-frozen vertices)
+  int* sig_nbr;          // [2][E] sorted neighbour labels of the non-frozen vertices, double-buffered by level parity:
+                         // with one barrier per level a fast CTA writes the rows of level l+1 while a slow one still
+                         // verifies against the rows of level l
+  long long E;
   int* slot_of;          // [V] hash slot of the vertex's signature at the current level
   unsigned char* frozen; // [V] zeroed by the host
   unsigned long long* table;  // 3 x (ht_mask + 1) packed {31-bit tag | single | representative}; table 1 cleared by the host
@@ -54,6 +58,7 @@ struct WlFused2Params {
   unsigned long long* diag_frozen;  // [N] zeroed by the host: the frozen vertices' share of st.diag (WL-OA re-adds it)
   DevScalars* sc;     // level_dims[1..] zeroed by the host, level_base[0], [1] set
   long long* prof;    // optional [grid][L][16] globaltimer stamps (GRAKEL_B200_PROF), else NULL
+  int dbg;            // GRAKEL_B200_WL_DBG: 1 = no bulk copy-out, 2 = L2 loads for the own row, 4 = print the first mismatch
 };
 
 // Feature entries of one tile from the labels in lab_s: a non-frozen vertex i emits (graph, base + label, count)
@@ -308,6 +313,7 @@ wl_fused2_kernel(WlFused2Params p) {
     int* lab_out = p.labels_all + (size_t)lv * V;
     unsigned long long* tab = p.table + (size_t)(lv % 3) * ht_cap;
     const long long level_base = (long long)p.n_labels0 + (long long)(lv - 1) * V;
+    int* sig_g = p.sig_nbr + (size_t)(lv & 1) * (size_t)p.E;  // this level's rows
 
     // ---------------- [A] signatures + insert (non-frozen vertices)
     WLF_STAMP(lv, 0);
@@ -506,15 +512,15 @@ wl_fused2_kernel(WlFused2Params p) {
         int n_ins = 0;
 #pragma unroll
         for (int k = 0; k < WLF_VPT; ++k) n_ins += __syncthreads_count(ins[k] ? 1 : 0);
-        if (2 * n_ins >= nv) {
-          for (int j = tid; j < ne; j += WLF_THREADS) p.sig_nbr[e0 + j] = sig_s[j];
+        if (2 * n_ins >= nv && !(p.dbg & 1)) {
+          for (int j = tid; j < ne; j += WLF_THREADS) sig_g[e0 + j] = sig_s[j];
         } else {
 #pragma unroll
           for (int k = 0; k < WLF_VPT; ++k) {
             const int i = tid + k * WLF_THREADS;
             if (ins[k]) {
               const int beg = rp_s[i], end = rp_s[i + 1];
-              for (int j = beg; j < end; ++j) p.sig_nbr[e0 + j] = sig_s[j];
+              for (int j = beg; j < end; ++j) sig_g[e0 + j] = sig_s[j];
             }
           }
         }
@@ -591,16 +597,21 @@ wl_fused2_kernel(WlFused2Params p) {
               int a[8], c[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                a[j] = j < dv[k] ? (resident ? sig_s[bv[k] + j] : p.sig_nbr[bv[k] + j]) : 0;
-                c[j] = j < dv[k] ? __ldcg(&p.sig_nbr[br[k] + j]) : 0;
+                a[j] = j < dv[k] ? (resident ? sig_s[bv[k] + j] : ((p.dbg & 2) ? __ldcg(&sig_g[bv[k] + j]) : sig_g[bv[k] + j])) : 0;
+                c[j] = j < dv[k] ? __ldcg(&sig_g[br[k] + j]) : 0;
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) same = same && (a[j] == c[j]);
             } else {
               for (int j = 0; same && j < dv[k]; ++j)
-                same = (resident ? sig_s[bv[k] + j] : p.sig_nbr[bv[k] + j]) == __ldcg(&p.sig_nbr[br[k] + j]);
+                same = (resident ? sig_s[bv[k] + j] : sig_g[bv[k] + j]) == __ldcg(&sig_g[br[k] + j]);
             }
-            if (!same) atomicOr(&p.sc->collision, 1u);
+            if (!same) {
+              const unsigned before = atomicOr(&p.sc->collision, 1u << min(lv, 30));  // bit = level (error message / retry)
+              if ((p.dbg & 4) && before == 0u)
+                printf("[wl_fused2] mismatch level %d cta %d tile %d v %d rep %d deg %d/%d own label %d/%d resident %d first nbr %d/%d\n", lv, b, t, v,
+                       r[k], dv[k], dr[k], lo[k], lr[k], (int)resident, dv[k] ? sig_g[p.row_ptr[v]] : -1, dr[k] ? sig_g[br[k]] : -1);
+            }
           } else {
             n_rep += 1u;
           }

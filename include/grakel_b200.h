@@ -178,7 +178,7 @@ int gk_set_row_map(gk_handle* h, int64_t n_rows, const int32_t* row_of_graph);
 #define GK_DIST_GATHER 128  /* gk_gram flag: GK_DIST + all-gather, the full K stays on every device */
 int gk_comm_unique_id(void* out128);
 int gk_comm_init(gk_handle* h, int32_t nranks, int32_t rank, const void* unique_id128);
-int gk_comm_destroy(gk_handle* h);
+int gk_comm_destroy(gk_handle* h);  /* collective; gk_destroy calls it */
 /* the row block of this rank: ceil(n_rows / nranks) rounded up to 256 rows per rank (identity without a communicator) */
 int gk_comm_rows(gk_handle* h, int64_t n_rows, int64_t* row_begin, int64_t* row_end);
 /* library-owned device result of the last gk_gram (valid until the next call on the handle) */
