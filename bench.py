@@ -129,11 +129,22 @@ def peaks():
     return 1683.9, 6582.5, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_sha1():
+    """sha1 over the sources of the Gram GEMM kernels: profiles/traffic.json is only valid for the kernel it was captured from."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("gram_tc.cuh", "gram_tc2.cuh"):
+        h.update(open(os.path.join(ROOT, "grakel_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
 def measured_traffic(key):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-    (profiles/traffic.json), or None."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/traffic.json),
+    or None -- also None when the GEMM sources changed since the capture (the file carries their sha1)."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if d.get("gemm_source_sha1") != kernel_source_sha1():
+            return None
         for k, v in d.items():
             if isinstance(v, dict) and key in k:
                 return v["dram_read_bytes"] + v["dram_write_bytes"]
@@ -678,10 +689,18 @@ def main():
                 paths = {"error": repr(e)}
         del X
 
+    def leave():
+        """Multi-rank exit: every rank has finished its device work (barrier), rank 0 has printed; the process then ends
+        without tearing down two NCCL communicators, IPC mappings and the CUDA context in interpreter-finalisation order
+        (one exit-time SIGSEGV in ~5 runs of the 2-GPU job otherwise; gk_comm_destroy / Engine.close remain the API)."""
+        barrier()
+        real_stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     if rank != 0:
         if world > 1:
-            eng.close()  # collective: peers unmap each other's blocks before anybody frees them
-            dist.destroy_process_group()
+            leave()
         return
 
     # the tensor-bound configuration of the same GEMM kernel (every shared column dense), for the
@@ -738,7 +757,7 @@ def main():
         # the other large kernel of a step, against the HBM roof with SURVEY 8(d)'s algorithmic bytes: K1 relabel
         # (12V + 4E + 4) + K2 compaction 16V per iteration, K3 histogram 4V + 8 nnz_i per level.  It is bound by
         # dependent L2 operations and two grid barriers per level, not by bytes -- the fraction says so.
-        "roofline_relabel": (lambda b, ms: {"kernel": "wl_fused_kernel (all WL levels, one persistent launch)", "bound": "hbm",
+        "roofline_relabel": (lambda b, ms: {"kernel": "wl_fused2_kernel (all WL levels, one persistent cooperative launch, one grid barrier per level)", "bound": "hbm",
                                             "algorithmic_bytes": b, "ms_per_launch": ms, "achieved": b / (ms * 1e-3) / 1e9,
                                             "peak": peak_hbm, "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / peak_hbm,
                                             "share_of_step": ms / ms_step})(
@@ -754,8 +773,7 @@ def main():
         line["cpu_baseline"] = cpu_baseline_obj(cpu_arm(steps=1, budget_s=12.0), n)
     print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
-        eng.close()
-        dist.destroy_process_group()
+        leave()
 
 
 if __name__ == "__main__":

@@ -43,7 +43,7 @@ def main():
         jobs.append(wl)
     if "sp" in what:
         from grakel_b200.packing import label_ids, pack
-        from oracle.gk_oracle import gen  # workload generator only
+        from bench import gen_list as gen  # workload generator
         b = pack(gen(5000, 60, 0, as_adj=True), "sp", want_weights=True)
         ids, _ = label_ids(b.labels, None, sort_new=False)
 
@@ -54,7 +54,7 @@ def main():
         jobs.append(sp)
     if "spattr" in what:
         from grakel_b200.packing import pack
-        from oracle.gk_oracle import gen
+        from bench import gen_list as gen
         b5 = pack(gen(2000, 40, 0, attr=16, as_adj=True), "sp", need_labels=True, attributes=True, want_weights=True)
 
         def spattr():
@@ -64,7 +64,7 @@ def main():
         jobs.append(spattr)
     if "wloa" in what:
         from grakel_b200.packing import label_ids, pack
-        from oracle.gk_oracle import gen  # workload generator only
+        from bench import gen_list as gen  # workload generator
         bo = pack(gen(10000, 40, 0), "wloa", len_ok=lambda k: k >= 2)
         ido, _ = label_ids(bo.labels, None, sort_new=True)
 
