@@ -1764,6 +1764,8 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       GK_TRY(h->tiles.ensure(tiles.size() * sizeof(int2)));
       GK_CUDA(cudaMemcpyAsync(h->tiles.p, h->h_tiles.p, tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
       CUtensorMap tmA, tmB, tmC;
+      PeerMaps peer_maps;
+      memset(&peer_maps, 0, sizeof(peer_maps));
       GK_TRY(make_panel_map(&tmA, h->panel.p, h->Dc_pad, N, BM));
       GK_TRY(make_panel_map(&tmB, h->panel.p, h->Dc_pad, N, BN));
       memset(&tmC, 0, sizeof(tmC));
@@ -1775,6 +1777,16 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
         if (p.mirror && !dist) {  // full square: the mirrored half goes through the same tensor map
           const char* e = getenv("GRAKEL_B200_MIRROR_TMA");
           if (!e || atoi(e) != 0) p.mirror = 2;
+        }
+        if (dist) {  // mirrored blocks as bulk TMA stores into the owners' row blocks (else 32 row stores of 128 B per block)
+          const char* e = getenv("GRAKEL_B200_DIST_TMA");
+          if (e && atoi(e) != 0) {
+            for (int r = 0; r < comm->nranks; ++r) {
+              const long long r_rows = std::min<long long>(N, (long long)(r + 1) * dist_per) - std::min<long long>(N, (long long)r * dist_per);
+              if (r_rows > 0) GK_TRY(make_out_map(&peer_maps.m[r], p.peer[r], k_cols, r_rows, d_ld));
+            }
+            p.mirror = 2;
+          }
         }
       }
       p.tiles = h->tiles.as<int2>();
@@ -1789,7 +1801,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       }
       GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
       if (n_tiles == 0) { /* a trailing rank without rows */ }
-      else if (cta2) gram_tc2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM, h->stream>>>(tmA, tmC, p);
+      else if (cta2) gram_tc2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM, h->stream>>>(tmA, tmC, p, peer_maps);
       else if (dev_dtype == GK_F64) { if (norm_in_epilogue) launch_tc<double, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<double, false>(h, tmA, tmB, tmC, p, grid); }
       else { if (norm_in_epilogue) launch_tc<float, true>(h, tmA, tmB, tmC, p, grid); else launch_tc<float, false>(h, tmA, tmB, tmC, p, grid); }
       LAUNCH_CHECK(h);

@@ -177,8 +177,14 @@ __device__ __forceinline__ OutT epilogue_value(float acc, int arow, int bcol, do
 // Epilogue of one 128 x 256 accumulator for fp32, un-normalised output through TMA stores (shared by the
 // one-CTA and the CTA-pair kernel).  `tile` = {first A row of THIS CTA's 128 rows, first B row}; `acc` = TMEM
 // address of the accumulator's first column in this warp's lane quarter; `my_buf` = the warp's two staging tiles.
+// tensor maps of the peers' row blocks (multi-GPU, mirrored blocks through TMA: GRAKEL_B200_DIST_TMA)
+struct PeerMaps {
+  CUtensorMap m[8];
+};
+
 __device__ __forceinline__ void epi_tma_store_tile(const GramParams& p, const CUtensorMap* tmC_ptr, int2 tile,
-                                                   uint32_t acc, int ew, int lane, uint32_t my_buf) {
+                                                   uint32_t acc, int ew, int lane, uint32_t my_buf,
+                                                   const CUtensorMap* peer_maps = nullptr) {
   using OutT = float;
   const CUtensorMap& tmC = *tmC_ptr;
   OutT* __restrict__ out = reinterpret_cast<OutT*>(p.out);
@@ -248,7 +254,12 @@ __device__ __forceinline__ void epi_tma_store_tile(const GramParams& p, const CU
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&tmC, mbuf, arow0 - p.c_col0, bcol0 - p.c_row0);
+        if (p.n_peers && peer_maps) {  // the block belongs to the rank that owns K rows [bcol0, bcol0 + 32): one bulk store over NVLink
+          const int owner = tile.y / p.peer_rows;
+          tma_store_2d(&peer_maps[owner], mbuf, arow0, bcol0 - owner * p.peer_rows);
+        } else {
+          tma_store_2d(&tmC, mbuf, arow0 - p.c_col0, bcol0 - p.c_row0);
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     } else if (p.mirror && row_ok) {

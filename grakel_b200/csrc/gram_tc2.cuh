@@ -73,7 +73,8 @@ __device__ __forceinline__ void tc2_mma_bf16(uint32_t d_tmem, uint64_t adesc, ui
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gram_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, GramParams p) {
+gram_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, GramParams p,
+                const __grid_constant__ PeerMaps pm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
@@ -170,7 +171,8 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tile.x += (int)rank * BM;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      epi_tma_store_tile(p, &tmC, tile, tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN), ew, lane, my_buf);
+      epi_tma_store_tile(p, &tmC, tile, tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN), ew, lane, my_buf,
+                         p.mirror == 2 && p.n_peers ? pm.m : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0));

@@ -17,3 +17,6 @@ print('N=1 ms/step', d['ms_per_step'], d['stages_ms'], 'traffic', d['roofline'][
 print('e2e', d['e2e']['ms_per_step'], d['e2e']['ms_per_step_min_median_max'], 'api', d['e2e_api']['ms_per_step'], d['e2e_api']['min_ms'])
 print(json.dumps(d['cpu_baseline'])[:400])
 PY
+echo "== 28284 graphs, V2 vs V1 relabel"
+timeout 600 python bench.py --graphs 28284 --steps 5 --warmup 3 --no-cpu --no-e2e --no-paths 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('V2', d['ms_per_step'], d['stages_ms'])"
+GRAKEL_B200_WL_V1=1 timeout 600 python bench.py --graphs 28284 --steps 5 --warmup 3 --no-cpu --no-e2e --no-paths 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('V1', d['ms_per_step'], d['stages_ms'])"
