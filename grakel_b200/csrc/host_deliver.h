@@ -30,12 +30,16 @@ class HostPool {
     // 2-socket GPU hosts), one worker per PHYSICAL core -- two workers on hyper-thread siblings turn into the
     // stragglers every band waits for -- and not on the caller's core, which spins in cudaEventSynchronize.
     std::vector<int> cpus = pick_cores(local_node_cpus());
+    // several processes on one host (one per GPU): each takes its own slice of the node's cores
+    int local_rank = 0;
+    if (const char* e = getenv("LOCAL_RANK")) local_rank = std::max(0, atoi(e));
+    const int first = cpus.empty() ? 0 : (int)(((long long)local_rank * n) % (long long)cpus.size());
     for (int i = 0; i < n; ++i) {
       th_.emplace_back([this, i] { run(i); });
       if (!cpus.empty()) {
         cpu_set_t set;
         CPU_ZERO(&set);
-        if ((int)cpus.size() >= n) CPU_SET(cpus[i], &set);
+        if ((int)cpus.size() >= n) CPU_SET(cpus[(first + i) % (int)cpus.size()], &set);
         else for (int c : cpus) CPU_SET(c, &set);
         pthread_setaffinity_np(th_.back().native_handle(), sizeof(set), &set);
       }
@@ -188,6 +192,12 @@ class HostPool {
 HostPool& host_pool() {
   static HostPool pool([] {
     int n = std::min(16, (int)std::thread::hardware_concurrency() / 4);  // 16 measured best on the 2 x 32-core GPU hosts (profiles/r02c_*)
+    // one process per GPU (torchrun sets LOCAL_WORLD_SIZE): the processes share the host's cores -- eight pools of 16
+    // spinning workers on 64 cores took 687 ms for a delivery that takes 9 ms with the cores to itself (profiles/r02q_bench8.json)
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+      const int lws = atoi(e);
+      if (lws > 1) n = std::max(2, std::min(n, (int)std::thread::hardware_concurrency() / 2 / lws - 1));
+    }
     if (const char* e = getenv("GRAKEL_B200_HOST_THREADS")) n = atoi(e);
     return std::max(1, std::min(n, 128));
   }());
@@ -433,9 +443,9 @@ static int deliver_rows(Copier& cp, const float* d_src, long long d_ld, long lon
       const long long t = next.fetch_add(1, std::memory_order_relaxed);
       const long long c = t / tasks_per_band;
       if (c >= n_bands) return;
-      while (ready.load(std::memory_order_acquire) <= c) {
+      for (unsigned spins = 0; ready.load(std::memory_order_acquire) <= c; ++spins) {
         if (ready.load(std::memory_order_relaxed) < 0) return;  // aborted
-        _mm_pause();
+        if ((spins & 1023u) == 1023u) sched_yield(); else _mm_pause();
       }
       const long long r0 = c * band_rows, nr = std::min(band_rows, rows - r0);
       const float* src = reinterpret_cast<const float*>(stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes);
@@ -505,9 +515,9 @@ static int deliver_tri(Copier& cp, const T* d_src, long long d_ld, long long n, 
       const long long t = next.fetch_add(1, std::memory_order_relaxed);
       if (t >= task0[n_bands]) return;
       while (t >= task0[c + 1]) ++c;
-      while (ready.load(std::memory_order_acquire) <= c) {
+      for (unsigned spins = 0; ready.load(std::memory_order_acquire) <= c; ++spins) {
         if (ready.load(std::memory_order_relaxed) < 0) return;
-        _mm_pause();
+        if ((spins & 1023u) == 1023u) sched_yield(); else _mm_pause();
       }
       const long long r0 = start[c], r1 = start[c + 1], nr = r1 - r0, w = n - r0;
       const T* src = reinterpret_cast<const T*>(stage + (size_t)(c % DELIVER_SLOTS) * slot_bytes);

@@ -65,17 +65,20 @@ struct WlFused2Params {
 // iff it is the first vertex of its graph carrying that label; frozen vertices (unique labels) emit nothing.
 // Fixed COO region per (tile, level), unused slots hold EMPTY64; per-column graph counts go through a shared-memory
 // aggregation table first (a column shared by every graph costs one global atomic per tile).
-// Per-vertex label multiplicity inside its graph, and whether the vertex is the first of its graph with that label:
-// cf_s[i] = count | (first ? 0x8000 : 0) for the non-frozen vertices.
-//   dense tiles (levels 0-2: most vertices still active): every vertex scans its graph -- lanes of a warp are
-//     consecutive vertices of (mostly) one graph, so the scan is warp-uniform: ~n iterations per 32 vertices;
-//   sparse tiles (deep levels: a few per cent active): that scan would still run in almost every warp (one active
-//     lane is enough), 5.7 us for ~100 active vertices (profiles/r02d_wl_prof.txt).  Instead the active vertices are
-//     compacted and each one is handled by a whole warp whose lanes scan the graph in parallel (ballot + popc).
+// Per-vertex label multiplicity inside its graph and ONE emitting vertex per (graph, label):
+// cf_s[i] = count | (emitter ? 0x8000 : 0) for the non-frozen vertices.
+//   dense tiles (levels 0-2: most vertices still active): a shared-memory hash table keyed by (graph, label) -- the
+//     slot word is {count : 16 | tile index of the vertex that installed it : 16}, the key is compared through that
+//     vertex -- so every vertex costs one probe sequence and one atomic instead of a scan of its whole graph
+//     (the scan was 10 / 17 / 5.5 us at levels 0 / 1 / 2, profiles/r02d_wl_prof.txt);
+//   sparse tiles (deep levels: a few per cent active): the active vertices are compacted and each one is handled by a
+//     whole warp whose lanes scan the graph in parallel (ballot + popc).
 // (A warp-per-graph variant with rotating chunk compares was measured slower at every level: profiles/r02h_wl_prof.txt.)
+constexpr int WLF2_CT = 8192;  // slots of the (graph, label) table: >= 2 x WLF_TILE_V
+static_assert(WLF2_CT >= 2 * WLF_TILE_V && WLF2_CT * 4 <= WLF_TILE_V * 8, "the table lives in the key_s region");
 __device__ __forceinline__ void wlf2_count(const WlFused2Params& p, int nv, const int* lab_s, const unsigned char* frz_s,
-                                           const unsigned short* gbeg_s, const unsigned short* gend_s, unsigned short* cf_s,
-                                           unsigned short* list_s, int* s_warp) {
+                                           const int* gid_s, const unsigned short* gbeg_s, const unsigned short* gend_s,
+                                           unsigned short* cf_s, unsigned* ct, unsigned short* list_s, int* s_warp) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int mine = 0;
 #pragma unroll
@@ -86,20 +89,35 @@ __device__ __forceinline__ void wlf2_count(const WlFused2Params& p, int nv, cons
   int n_act;
   const int ex0 = wlf_block_scan(mine, &n_act, s_warp);
   if (4 * n_act > nv) {
+    for (int s2 = tid; s2 < WLF2_CT; s2 += WLF_THREADS) ct[s2] = 0xFFFFFFFFu;
+    __syncthreads();
+    unsigned slot[WLF_VPT];
+    bool inst[WLF_VPT];
 #pragma unroll
     for (int k = 0; k < WLF_VPT; ++k) {
       const int i = tid + k * WLF_THREADS;
+      inst[k] = false;
+      slot[k] = 0;
       if (i < nv && !frz_s[i]) {
-        const int gs = gbeg_s[i], ge = gend_s[i], l = lab_s[i];
-        int cnt = 0;
-        bool first = true;
-        for (int u = gs; u < ge; ++u) {
-          const bool same = lab_s[u] == l;
-          cnt += same ? 1 : 0;
-          first = first && !(same && u < i);
+        const int l = lab_s[i], g = gid_s[i];
+        unsigned h = (((unsigned)l * 0x9E3779B1u) ^ ((unsigned)g * 0x85EBCA77u)) >> 15 & (WLF2_CT - 1);
+        while (true) {
+          unsigned w = ct[h];
+          if (w == 0xFFFFFFFFu) {
+            w = atomicCAS(&ct[h], 0xFFFFFFFFu, (1u << 16) | (unsigned)i);
+            if (w == 0xFFFFFFFFu) { inst[k] = true; slot[k] = h; break; }
+          }
+          const unsigned o = w & 0xFFFFu;
+          if (lab_s[o] == l && gid_s[o] == g) { atomicAdd(&ct[h], 1u << 16); break; }
+          h = (h + 1) & (WLF2_CT - 1);
         }
-        cf_s[i] = (unsigned short)(cnt | (first ? 0x8000 : 0));
       }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WLF_VPT; ++k) {
+      const int i = tid + k * WLF_THREADS;
+      if (i < nv && !frz_s[i]) cf_s[i] = inst[k] ? (unsigned short)((ct[slot[k]] >> 16) | 0x8000u) : (unsigned short)0;
     }
   } else {
     int ex = ex0;
@@ -128,10 +146,10 @@ __device__ __forceinline__ void wlf2_count(const WlFused2Params& p, int nv, cons
 
 __device__ __forceinline__ void wlf2_emit(const WlFused2Params& p, int v0, int nv, const int* lab_s, const unsigned char* frz_s,
                                           const int* gid_s, const unsigned short* gbeg_s, const unsigned short* gend_s,
-                                          unsigned short* cf_s, unsigned short* list_s,
+                                          unsigned short* cf_s, unsigned* ct, unsigned short* list_s,
                                           unsigned* agg, long long base, size_t coo_off, int* s_warp, unsigned& mx, unsigned& n_new) {
   const int tid = threadIdx.x, lane = tid & 31;
-  wlf2_count(p, nv, lab_s, frz_s, gbeg_s, gend_s, cf_s, list_s, s_warp);
+  wlf2_count(p, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, cf_s, ct, list_s, s_warp);
   __syncthreads();
   int g[WLF_VPT], l[WLF_VPT];
   unsigned cnt[WLF_VPT];
@@ -294,7 +312,7 @@ wl_fused2_kernel(WlFused2Params p) {
     }
     __syncthreads();
     WLF_STAMP(0, 1);
-    wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, reinterpret_cast<unsigned short*>(key_s), lslot, agg, 0, (size_t)v0, s_warp, mx, n_new);
+    wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, lslot, reinterpret_cast<unsigned*>(key_s), reinterpret_cast<unsigned short*>(ltab), agg, 0, (size_t)v0, s_warp, mx, n_new);
     WLF_STAMP(0, 2);
   }
   if (p.L > 2) {  // table of level 2 (first touched after the barrier of level 1)
@@ -662,7 +680,7 @@ wl_fused2_kernel(WlFused2Params p) {
       __syncthreads();
       for (int i = tid; i < nv; i += WLF_THREADS) lab_out[v0 + i] = lab_s[i];
       WLF_STAMP(lv, 5);
-      wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, reinterpret_cast<unsigned short*>(key_s), lslot, agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
+      wlf2_emit(p, v0, nv, lab_s, frz_s, gid_s, gbeg_s, gend_s, lslot, reinterpret_cast<unsigned*>(key_s), reinterpret_cast<unsigned short*>(ltab), agg, level_base, (size_t)lv * V + v0, s_warp, mx, n_new);
     }
     WLF_STAMP(lv, 3);
     if (lv + 2 < p.L) {  // clear the table level lv+2 inserts into (last read in [B] of level lv-1, which every CTA has left)
