@@ -1672,7 +1672,10 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     GK_TRY(gk_comm_rows(h, N, &rb, &re));
     if (row_begin != rb || row_end != re) return fail(GK_ERR_ARG, "gk_gram: GK_DIST row range must be the one gk_comm_rows returns");
   }
-  const bool dist = dist_req && path == 1 && dev_dtype == GK_F32 && !normalize;
+  // GRAKEL_B200_DIST_SHARE=0: no tile sharing -- every rank computes its row block with full tiles (twice the SYRK
+  // flops, no peer stores, no barriers): the round-1 scheme, kept for A/B measurements
+  const char* e_share = getenv("GRAKEL_B200_DIST_SHARE");
+  const bool dist = dist_req && path == 1 && dev_dtype == GK_F32 && !normalize && !(e_share && atoi(e_share) == 0);
   const bool gather = dist && (flags & GK_DIST_GATHER);
   const long long dist_per = dist_req ? dist_rows_per_rank(N, comm->nranks) : 0;
 
@@ -1724,7 +1727,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     p.n_peers = comm->nranks;
     p.peer_rows = (int)dist_per;
   }
-  if (dist_req) GK_TRY(comm_barrier(h));  // nobody still reads the block a peer is about to overwrite
+  if (dist) GK_TRY(comm_barrier(h));  // nobody still reads the block a peer is about to overwrite
 
   GK_CUDA(cudaEventRecord(h->tev[5], h->stream));
   int64_t n_tiles = 0;
@@ -1833,7 +1836,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       LAUNCH_CHECK(h);
     }
     GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
-    if (dist_req) GK_TRY(comm_barrier(h));  // the peers' mirrored stores into this block precede the tail's atomics
+    if (dist) GK_TRY(comm_barrier(h));  // the peers' mirrored stores into this block precede the tail's atomics
     if (has_tail) {
       const int grid = cdiv(n_tail_cols * 32, 256);
       if (dev_dtype == GK_F64)
@@ -1858,7 +1861,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   } else {
     GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
     GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
-    if (dist_req) GK_TRY(comm_barrier(h));
+    if (dist) GK_TRY(comm_barrier(h));
   }
   if (dist_req && (flags & GK_DIST_GATHER)) {
     // BASELINE config 4: every rank ends up with the full matrix -- one in-place all-gather of the finished row
