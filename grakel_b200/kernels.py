@@ -285,6 +285,63 @@ class EdgeHistogram(Kernel):
 
 
 # ------------------------------------------------------------------------------
+class _LevelDictionaries(dict):
+    """`_inv_labels` of a fitted WL estimator (weisfeiler_lehman.py:208-257): level 0 is built on the host by `fit`;
+    the dictionaries of the levels >= 1 -- credential string -> compressed label, in the reference's own numbering --
+    are exported from the device relabelling the first time one of them is asked for."""
+
+    def __init__(self, level0, owner):
+        super().__init__({0: level0})
+        self._owner = owner
+
+    def __missing__(self, level):
+        owner = self._owner
+        if owner is None or type(level) is not int or not 0 < level < owner._n_iter:
+            raise KeyError(level)
+        self.update(owner._export_level_dictionaries())
+        return dict.__getitem__(self, level)
+
+    def __reduce__(self):  # pickles as what has been materialised plus the owner
+        return (_restore_level_dictionaries, (dict(self), self._owner))
+
+
+def _restore_level_dictionaries(content, owner):
+    d = _LevelDictionaries(content.get(0), owner)
+    d.update(content)
+    return d
+
+
+def wl_reference_dictionaries(row_ptr, col_idx, level0_ids, n_level0, classes):
+    """The reference's per-level label dictionaries from the device partition.
+
+    `classes[i]` (i >= 1) holds one class id per vertex (any numbering; `gk_wl_labels`).  The reference names a
+    class by the string  str(own label) + "," + str(sorted neighbour labels)  over the labels of level i-1, sorts the
+    distinct strings and numbers them on from where the previous level stopped (weisfeiler_lehman.py:223-246).
+    One string per CLASS is built here (from the class's first vertex), not one per vertex.
+    Returns ({level: {credential: label}}, [reference label of every vertex, per level])."""
+    prev = np.asarray(level0_ids, dtype=np.int64)
+    count = int(n_level0)
+    out, labels = {}, [prev]
+    for i in range(1, len(classes)):
+        uniq, first, inv = np.unique(np.asarray(classes[i]), return_index=True, return_inverse=True)
+        creds = []
+        for v in first.tolist():
+            nb = prev[col_idx[row_ptr[v]:row_ptr[v + 1]]]
+            creds.append(str(int(prev[v])) + "," + str(sorted(nb.tolist())))
+        if len(set(creds)) != len(creds):
+            raise RuntimeError("two classes of level %d share a signature: the device partition is not the "
+                               "reference's" % i)
+        order = sorted(range(len(creds)), key=creds.__getitem__)
+        new_id = np.empty(len(uniq), dtype=np.int64)
+        new_id[order] = count + np.arange(len(uniq), dtype=np.int64)
+        out[i] = {creds[k]: count + r for r, k in enumerate(order)}
+        prev = new_id[inv.reshape(-1)]
+        labels.append(prev)
+        count += len(uniq)
+    return out, labels
+
+
+# ------------------------------------------------------------------------------
 class WeisfeilerLehman(Kernel):
     """Weisfeiler-Lehman subtree kernel (weisfeiler_lehman.py:23-555).
 
@@ -378,7 +435,7 @@ class WeisfeilerLehman(Kernel):
             block = self._pack_for_base(X, lambda n: n >= 2)  # weisfeiler_lehman.py:152
             self._nx = block.n_graphs
             ids, dictionary = label_ids(block.labels, None, sort_new=True)  # :199-206
-            self._inv_labels = {0: dictionary}
+            self._inv_labels = _LevelDictionaries(dictionary, self)
             return Fitted(block, ids, dictionary)
         if self._method_calling != 3:
             raise ValueError("method call must be called either from fit or fit-transform")
@@ -425,6 +482,20 @@ class WeisfeilerLehman(Kernel):
         if self._base_graph_kernel is ShortestPath:
             return eng.wl_sp_features(self._n_iter - 1, dijkstra_order=True)  # the base kernel gets edge dictionaries
         return eng.wl_features(self._n_iter - 1)
+
+    def _export_level_dictionaries(self):
+        """`_inv_labels[i]` for i >= 1 (weisfeiler_lehman.py:257): the fitted graphs are relabelled on the device, the
+        per-level classes come back through `gk_wl_labels`, and the host names every class the way the reference
+        does.  Also keeps `wl_labels_`: the reference's compressed label of every packed vertex, per level."""
+        check_is_fitted(self, ["X", "_nx"])
+        block, ids = self.X.block, self.X.ids
+        with _lib.engine(getattr(self, "device_", None)) as eng:
+            eng.pack(block.graph_ptr, block.row_ptr, block.col_idx, ids, None, None)
+            eng.wl_features(self._n_iter - 1)
+            classes = [ids] + [eng.wl_labels(lv, block.n_vertices) for lv in range(1, self._n_iter)]
+        out, self.wl_labels_ = wl_reference_dictionaries(np.asarray(block.row_ptr), np.asarray(block.col_idx), ids,
+                                                         len(self.X.dictionary), classes)
+        return out
 
 
 # ------------------------------------------------------------------------------

@@ -476,3 +476,28 @@ def test_config3_full_size_properties():
     assert float(K.sum()) == big["sum"] and float(np.trace(K)) == big["trace"] and float(K.max()) == big["max"]
     assert np.array_equal(K[rows["rows"]], rows["K_rows"].astype(np.float64))
     assert np.array_equal(K, K.T)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["er60", "er25_deep"])
+def test_exported_level_dictionaries_equal_the_references(name):
+    """`WeisfeilerLehman._inv_labels[i]` for every level (weisfeiler_lehman.py:208-257): device relabel ->
+    gk_wl_labels -> the reference's credential strings and numbering, against the real reference's dictionaries
+    (tests/golden/make_golden_invlabels.py).  Asking for a level does not disturb the fitted state."""
+    import gzip
+    import json
+    with gzip.open(os.path.join(G, "inv_labels.json.gz"), "rt") as f:
+        case = json.load(f)[name]
+    c = case["params"]
+    X = gen(c["N"], c["nbar"], c["seed"], nl=c["nl"])
+    k = _k()
+    wl = k.WeisfeilerLehman(n_iter=c["n_iter"])
+    K = wl.fit_transform(X)
+    for i, pairs in case["levels"].items():
+        want = {(key if int(i) else int(key)): v for key, v in pairs}
+        assert wl._inv_labels[int(i)] == want, f"level {i}"
+    assert len(wl.wl_labels_) == c["n_iter"] + 1
+    Kt = wl.transform(X[:5])
+    _same(Kt, K[:5])
+    w2 = pickle.loads(pickle.dumps(wl))
+    assert sorted(w2._inv_labels) == list(range(c["n_iter"] + 1))

@@ -417,3 +417,50 @@ def test_fast_edge_dict_path_equals_the_general_packer(mode, monkeypatch):
     for weird in ([[{(0.0, 1.0): 1}, {0.0: 1, 1.0: 2}]], [[{(0, 1): "x"}, {0: 1, 1: 2}]], [[[(0, 1)], {0: 1, 1: 2}]],
                   [[{(0, 2 ** 70): 1}, {0: 1, 2 ** 70: 2}]], [[{}, {0: 1}]], [[{(0, 1, 2): 1}, {0: 1, 1: 2}]]):
         assert cmod.pack_edge_dicts(weird, 0 if mode == "wl" else 1, 1) is None
+
+
+def _golden_inv_labels(name):
+    """(generator parameters, {level: dictionary}) of one case of tests/golden/inv_labels.json.gz."""
+    import gzip
+    import json
+    with gzip.open(os.path.join(G, "inv_labels.json.gz"), "rt") as f:
+        case = json.load(f)[name]
+    return case["params"], {int(i): {(k if int(i) else int(k)): v for k, v in pairs}
+                            for i, pairs in case["levels"].items()}
+
+
+@pytest.mark.parametrize("name", ["er60", "er25_deep"])
+def test_level_dictionaries_from_a_partition_are_the_references(name):
+    """`_inv_labels[i]`, i >= 1 (weisfeiler_lehman.py:223-257): the host half of the export -- class arrays (here the
+    oracle's; on the device gk_wl_labels) -> credential strings in the reference's numbering -- against the
+    dictionaries the real reference built (tests/golden/make_golden_invlabels.py)."""
+    from grakel_b200.kernels import wl_reference_dictionaries
+    from oracle.gk_oracle import WLOracle, gen, wl_partitions
+    c, want = _golden_inv_labels(name)
+    X = gen(c["N"], c["nbar"], c["seed"], nl=c["nl"])
+    block = pack(X, "wl", len_ok=lambda n: n >= 2)
+    ids, d0 = label_ids(block.labels, None, sort_new=True)
+    assert d0 == want[0]
+    _, levels = WLOracle(n_iter=c["n_iter"]).fit_transform(X, return_levels=True)
+    parts = wl_partitions(levels)
+    got, labels = wl_reference_dictionaries(np.asarray(block.row_ptr), np.asarray(block.col_idx), ids, len(d0), parts)
+    assert sorted(got) == list(range(1, c["n_iter"] + 1))
+    for i in got:
+        assert got[i] == want[i], f"level {i}"
+    assert len(labels) == c["n_iter"] + 1 and all(len(l) == block.n_vertices for l in labels)
+
+
+def test_level_dictionaries_are_lazy_and_pickle(monkeypatch):
+    X = gio.dec_dataset(gio.load(os.path.join(G, "spellings.json.gz"))["cases"]["dict_tuple"]["X"])
+    wl = WeisfeilerLehman(n_iter=2).fit(X)
+    calls = []
+    monkeypatch.setattr(WeisfeilerLehman, "_export_level_dictionaries",
+                        lambda self: calls.append(1) or {1: {"a": 7}, 2: {"b": 9}})
+    assert list(wl._inv_labels) == [0] and not calls
+    w2 = pickle.loads(pickle.dumps(wl))
+    assert list(w2._inv_labels) == [0] and w2._inv_labels._owner is w2
+    assert wl._inv_labels[2] == {"b": 9} and wl._inv_labels[1] == {"a": 7} and len(calls) == 1
+    with pytest.raises(KeyError):
+        wl._inv_labels[3]
+    with pytest.raises(KeyError):
+        wl._inv_labels["x"]
