@@ -120,6 +120,17 @@ struct HandleExtra {
   std::vector<int> graph_ptr;
   std::vector<int> graph_eptr;  // first edge of each graph (row_ptr[graph_ptr[g]])
   std::vector<long long> sp_goff;
+  // fused WL kernel: the tile partition of the packed block (device copy in wlf_buf) is kept between calls
+  bool wl_tiles_valid = false;
+  bool wl_tiles_fused = false;
+  int wl_n_tiles = 0;
+  long long wl_tiles_key = -1;  // GRAKEL_B200_WL_TILES_PER_CTA the partition was built with
+  // Gram prologue run by gk_wl_features (pro_serial): what gk_gram would otherwise read back after a synchronisation
+  ColStats pro_hist;
+  long long pro_max_count = 0, pro_max_diag = 0, pro_n_entries = 0;
+  // GEMM tile list on the device (h->tiles): rebuilt and uploaded only when its key changes
+  long long tiles_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  long long tiles_n = 0;
 };
 static std::vector<std::pair<gk_handle*, HandleExtra*>> g_extra;
 static HandleExtra* extra_of(gk_handle* h) {
@@ -179,6 +190,9 @@ int gk_create(int device_ordinal, gk_handle** out) {
   GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   GK_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
   GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(wl_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF2_SMEM));
   *out = h;
   return GK_OK;
 }
@@ -341,10 +355,11 @@ int gk_pack_csr(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const 
   h->has_labels = labels != nullptr;
   h->attr_dim = attrs ? attr_dim : 0;
   h->max_graph_size = max_n;
-  h->features_ready = false;
+  h->features_ready = false; h->feat_serial++;
   h->feature_kind = 0;
   h->n_rows = 0;  // a new block starts without a row map
   HandleExtra* ex = extra_of(h);
+  ex->wl_tiles_valid = false;
   ex->graph_ptr.assign(graph_ptr, graph_ptr + N + 1);
   ex->graph_eptr.resize(N + 1);
   for (int64_t g = 0; g <= N; ++g) ex->graph_eptr[g] = V ? row_ptr[graph_ptr[g]] : 0;
@@ -480,7 +495,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   const int64_t V = h->V, E = h->E;
   const int L = n_iter + 1;
   h->n_levels = L;
-  h->features_ready = false;
+  h->features_ready = false; h->feat_serial++;
   const int64_t launches0 = h->launches;
 
   GK_TRY(h->labels_all.ensure((size_t)L * V * 4));
@@ -504,7 +519,13 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   if (const char* e = getenv("GRAKEL_B200_WL_FUSED")) fused = atoi(e) != 0;
   const int G = std::min(h->sm_count, 1024);
   int n_tiles = 0;
-  if (fused) {
+  long long tiles_env = 0;
+  if (const char* e = getenv("GRAKEL_B200_WL_TILES_PER_CTA")) tiles_env = atoi(e);
+  if (fused && extra_of(h)->wl_tiles_valid && extra_of(h)->wl_tiles_key == tiles_env) {
+    // same packed block as the last call: the partition is still in wlf_buf (the kernels only touch its barrier word)
+    fused = extra_of(h)->wl_tiles_fused;
+    n_tiles = extra_of(h)->wl_n_tiles;
+  } else if (fused) {
     HandleExtra* ex = extra_of(h);
     std::vector<int> tv, ct(G + 1, 0);
     bool ok = false;
@@ -549,10 +570,8 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       memcpy(hp, tv.data(), (size_t)(n_tiles + 1) * 4);
       memcpy(hp + n_tiles + 1, ct.data(), (size_t)(G + 1) * 4);
       GK_CUDA(cudaMemcpyAsync(h->wlf_buf.p, hp, ((size_t)n_tiles + G + 2) * 4, cudaMemcpyHostToDevice, h->stream));
-      GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
-      GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
-      GK_CUDA(cudaFuncSetAttribute(wl_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF2_SMEM));
     }
+    ex->wl_tiles_valid = true; ex->wl_tiles_fused = fused; ex->wl_n_tiles = n_tiles; ex->wl_tiles_key = tiles_env;
   }
   // feature block: the multi-kernel path fills one open-addressing sub-table per level, the fused
   // kernel appends at most V entries per level to the same arrays used as a COO list
@@ -564,8 +583,10 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   DevScalars* sc = h->scalars.as<DevScalars>();
   int* labels_all = h->labels_all.as<int>();
   int retries = 0;
+  bool pro_enqueued = false, used_v2 = false;
   GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
   for (;; ++retries) {
+    pro_enqueued = false;
     if (retries > 8)
       return fail(GK_ERR_STATE, "gk_wl_features: repeated hash collisions (level mask 0x" +
                                     [&] { char b[16]; snprintf(b, sizeof(b), "%x", h->h_scalars.as<DevScalars>()->collision); return std::string(b); }() + ")");
@@ -576,6 +597,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     if (!wl_v2) GK_TRY(init_scalars(h, h->n_labels0));
     GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)std::max(nb, G) * L, &fst, !wl_v2));
     h->wl_sparse_ids = false;
+    used_v2 = wl_v2;
     if (wl_v2) {
       // wl_fused2.cuh: labels = representative vertex ids (one grid barrier per level), frozen singleton classes
       int* wb = h->wlf_buf.as<int>();
@@ -593,8 +615,6 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
         q.frozen = h->wl_single.as<unsigned char>(); q.V = V;
         q.table1 = L > 1 ? h->ht_keys.as<unsigned long long>() + h->ht_cap : nullptr; q.ht_cap = (long long)h->ht_cap;
         wlf2_prepare_kernel<<<h->sm_count * 2, 1024, 0, h->stream>>>(q);
-        LAUNCH_CHECK(h);
-        wlf2_set_scalars<<<1, 1, 0, h->stream>>>(sc, h->n_labels0);
         LAUNCH_CHECK(h);
       }
       WlFused2Params fp;
@@ -623,6 +643,26 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       GK_CUDA(cudaLaunchCooperativeKernel((void*)wl_fused2_kernel, dim3(G), dim3(WLF_THREADS), args, WLF2_SMEM, h->stream));
       LAUNCH_CHECK(h);
       h->wl_sparse_ids = L > 1;
+      GK_CUDA(cudaEventRecord(h->tev[3], h->stream));  // end of the feature stage
+      if (!prof && !getenv("GRAKEL_B200_NO_PROLOGUE")) {
+        // Gram prologue of the square (fit_transform) case, enqueued BEFORE this call's one host synchronisation:
+        // self similarities + per-CTA partials (diag_finish) and the column histogram (col_hist).  gk_gram then
+        // finds everything its host-side decisions need (threshold T, D_c, exactness bounds) already on the host
+        // and launches without a synchronisation of its own (pro_serial).
+        const int64_t D = (int64_t)h->n_labels0 + V * (int64_t)(L - 1);
+        GK_TRY(h->diag_f64.ensure(h->N * 8));
+        GK_TRY(h->colstats.ensure(sizeof(ColStats)));
+        GK_TRY(h->h_colstats.ensure(sizeof(ColStats)));
+        diag_finish<<<cdiv(h->N, 256), 256, 0, h->stream>>>((int)h->N, h->diag_u64.as<unsigned long long>(), h->diag_f64.as<double>(),
+                                                            (int)h->n_part, h->part_max.as<unsigned>(), h->part_new.as<unsigned>(), sc);
+        LAUNCH_CHECK(h);
+        GK_CUDA(cudaMemsetAsync(h->colstats.p, 0, sizeof(ColStats), h->stream));
+        col_hist<<<cdiv(std::max<int64_t>(D, 1), 256), 256, 0, h->stream>>>(std::max<int64_t>(D, 1), 1, (int)h->N, h->colcnt.as<unsigned>(),
+                                                                          nullptr, nullptr, h->colstats.as<ColStats>());
+        LAUNCH_CHECK(h);
+        GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, h->colstats.p, sizeof(ColStats), cudaMemcpyDeviceToHost, h->stream));
+        pro_enqueued = true;
+      }
       if (prof) {
         std::vector<long long> pr((size_t)G * L * 16);
         GK_CUDA(cudaMemcpyAsync(pr.data(), h->K_stage.p, pr.size() * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -775,12 +815,20 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
     if (hs->ft_overflow) return fail(GK_ERR_STATE, "gk_wl_features: feature table overflow");
     if (!hs->collision) break;
   }
-  GK_CUDA(cudaEventRecord(h->tev[3], h->stream));
-  GK_CUDA(cudaEventSynchronize(h->tev[3]));
+  if (!used_v2) {  // (wl_fused2 recorded the end of its stage right after the kernel; read_scalars synchronised)
+    GK_CUDA(cudaEventRecord(h->tev[3], h->stream));
+    GK_CUDA(cudaEventSynchronize(h->tev[3]));
+  }
   DevScalars* hs = h->h_scalars.as<DevScalars>();
   h->n_columns = hs->level_base[L];
-  h->features_ready = true;
+  h->features_ready = true; h->feat_serial++;
   h->feature_kind = 1;
+  if (pro_enqueued) {
+    HandleExtra* ex = extra_of(h);
+    ex->pro_hist = *h->h_colstats.as<ColStats>();
+    ex->pro_max_count = (long long)hs->max_count; ex->pro_max_diag = (long long)hs->max_diag; ex->pro_n_entries = (long long)hs->n_entries;
+    h->pro_serial = h->feat_serial;
+  }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     stats->n_graphs = h->N; stats->n_vertices = V; stats->n_edges = E;
@@ -804,7 +852,7 @@ int gk_wl_oa_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   gk_stats local;
   gk_stats* st = stats ? stats : &local;
   GK_TRY(gk_wl_features(h, n_iter, st));
-  h->features_ready = false;
+  h->features_ready = false; h->feat_serial++;
   const int64_t launches0 = h->launches;
   const int64_t D = std::max<int64_t>(h->n_columns, 1);
   const size_t out_cap = std::max<size_t>((size_t)h->V * (size_t)h->n_levels, 1);  // one entry per (vertex, level)
@@ -855,7 +903,7 @@ int gk_wl_oa_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   h->ft_cap = out_cap;
   h->col_cap = (int64_t)out_cap + 1;
   h->n_columns = (int64_t)hc.n_cols;
-  h->features_ready = true;
+  h->features_ready = true; h->feat_serial++;
   st->n_columns = h->n_columns;
   st->kernel_launches += h->launches - launches0;
   st->ms_features = ev_ms(h->tev[2], h->tev[3]);
@@ -929,7 +977,7 @@ static int sp_features_impl(gk_handle* h, int32_t flags, int32_t wl_iter, gk_sta
   HandleExtra* ex = extra_of(h);
   const int64_t N = h->N;
   const int64_t launches0 = h->launches;
-  h->features_ready = false;
+  h->features_ready = false; h->feat_serial++;
   h->sp_flags = flags;
 
   // plan: graphs whose distance matrix fits the shared-memory budget vs the rest
@@ -1148,7 +1196,7 @@ static int sp_features_impl(gk_handle* h, int32_t flags, int32_t wl_iter, gk_sta
   GK_CUDA(cudaEventSynchronize(h->tev[3]));
   DevScalars* hs = h->h_scalars.as<DevScalars>();
   h->n_columns = (int64_t)dict_cap;  // column id = dictionary slot
-  h->features_ready = true;
+  h->features_ready = true; h->feat_serial++;
   h->feature_kind = 2;
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -1193,7 +1241,7 @@ int gk_spattr_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   const size_t esz = use_u16 ? 2 : 8;
   HandleExtra* ex = extra_of(h);
   const int64_t launches0 = h->launches;
-  h->features_ready = false;
+  h->features_ready = false; h->feat_serial++;
   if ((size_t)h->max_graph_size * h->max_graph_size * 2 + (size_t)h->max_graph_size * da * 8 + (size_t)dd * 8 > 200 * 1024)
     return fail(GK_ERR_UNSUPPORTED, "gk_spattr_features: graph too large for the shared-memory feature kernel");
 
@@ -1308,7 +1356,7 @@ int gk_spattr_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   GK_CUDA(cudaEventRecord(h->tev[3], h->stream));
   GK_CUDA(cudaStreamSynchronize(h->stream));  // host vectors above are sources of async copies
   h->n_columns = Dfeat;
-  h->features_ready = true;
+  h->features_ready = true; h->feat_serial++;
   h->feature_kind = 3;
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -1549,7 +1597,9 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   GK_TRY(h->colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->h_colstats.ensure(sizeof(ColStats)));
   GK_TRY(h->diag_f64.ensure(N * 8));
-  GK_CUDA(cudaMemsetAsync(&sc->n_entries, 0, sizeof(unsigned long long) * 3 + sizeof(long long), h->stream));
+  HandleExtra* hx = extra_of(h);
+  const bool pro = square && !d_row_map && h->pro_serial == h->feat_serial && D <= h->col_cap;  // prologue already on the host
+  if (!pro) GK_CUDA(cudaMemsetAsync(&sc->n_entries, 0, sizeof(unsigned long long) * 3 + sizeof(long long), h->stream));
   const unsigned long long* d_diag_u64 = h->diag_u64.as<unsigned long long>();
   if (d_row_map) {
     GK_TRY(h->diag_rows.ensure(N * 8));
@@ -1558,10 +1608,12 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
     LAUNCH_CHECK(h);
     d_diag_u64 = h->diag_rows.as<unsigned long long>();
   }
-  diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, d_diag_u64,
-                                                   h->diag_f64.as<double>(), (int)h->n_part,
-                                                   h->part_max.as<unsigned>(), h->part_new.as<unsigned>(), sc);
-  LAUNCH_CHECK(h);
+  if (!pro) {
+    diag_finish<<<cdiv(N, 256), 256, 0, h->stream>>>((int)N, d_diag_u64,
+                                                     h->diag_f64.as<double>(), (int)h->n_part,
+                                                     h->part_max.as<unsigned>(), h->part_new.as<unsigned>(), sc);
+    LAUNCH_CHECK(h);
+  }
   if (!square) {  // which columns occur on both the X and the Y side
     GK_TRY(h->colmin.ensure(D * 4));
     GK_TRY(h->colmax.ensure(D * 4));
@@ -1583,14 +1635,20 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   ColStats* cs = h->colstats.as<ColStats>();
   ColStats hc;
   DevScalars* hs = nullptr;
-  GK_CUDA(cudaMemsetAsync(cs, 0, sizeof(ColStats), h->stream));
-  col_hist<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, (int)n_fit, h->colcnt.as<unsigned>(), h->colmin.as<int>(),
-                                       h->colmax.as<int>(), cs);
-  LAUNCH_CHECK(h);
-  GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, cs, sizeof(ColStats), cudaMemcpyDeviceToHost, h->stream));
-  GK_TRY(read_scalars(h, &hs));  // the one host synchronisation of gk_gram
-  hc = *h->h_colstats.as<ColStats>();
-  const int64_t max_count = (int64_t)hs->max_count, max_diag = (int64_t)hs->max_diag, n_entries = (int64_t)hs->n_entries;
+  int64_t max_count, max_diag, n_entries;
+  if (pro) {  // gk_wl_features ran diag_finish + col_hist and brought the results back with its own synchronisation
+    hc = hx->pro_hist;
+    max_count = hx->pro_max_count; max_diag = hx->pro_max_diag; n_entries = hx->pro_n_entries;
+  } else {
+    GK_CUDA(cudaMemsetAsync(cs, 0, sizeof(ColStats), h->stream));
+    col_hist<<<nbc, 256, 0, h->stream>>>(D, square ? 1 : 0, (int)n_fit, h->colcnt.as<unsigned>(), h->colmin.as<int>(),
+                                         h->colmax.as<int>(), cs);
+    LAUNCH_CHECK(h);
+    GK_CUDA(cudaMemcpyAsync(h->h_colstats.p, cs, sizeof(ColStats), cudaMemcpyDeviceToHost, h->stream));
+    GK_TRY(read_scalars(h, &hs));  // the one host synchronisation of gk_gram
+    hc = *h->h_colstats.as<ColStats>();
+    max_count = (int64_t)hs->max_count; max_diag = (int64_t)hs->max_diag; n_entries = (int64_t)hs->n_entries;
+  }
   // ---- choose the Gram path and the head/tail threshold (host side, from the histogram)
   int path = 1;
   if ((flags & GK_GRAM_SIMT) || max_count > 256 || max_diag >= (1LL << 24)) { path = 2; force_T = 1; }
@@ -1754,18 +1812,22 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
       const char* e_cta2 = getenv("GRAKEL_B200_CTA2");
       const bool cta2 = !(e_cta2 && atoi(e_cta2) == 0) && dev_dtype == GK_F32 && !norm_in_epilogue &&
                         ((uintptr_t)d_out) % 16 == 0 && (d_ld * 4) % 16 == 0 && !getenv("GRAKEL_B200_NO_TMA_STORE");
-      std::vector<int2> tiles;
-      if (dist) {
-        if (!cta2) return fail(GK_ERR_UNSUPPORTED, "gk_gram: GK_DIST needs the CTA-pair kernel (GRAKEL_B200_CTA2=0 is set?)");
-        dist_tiles(N, comm->nranks, comm->rank, tiles);
-      } else {
-        build_tiles(tiles, a0, a1, b0, b1, mirror, cta2 ? BM2 : BM);
+      if (dist && !cta2) return fail(GK_ERR_UNSUPPORTED, "gk_gram: GK_DIST needs the CTA-pair kernel (GRAKEL_B200_CTA2=0 is set?)");
+      // the tile list depends on the shape of the request only: built and uploaded when that changes
+      const long long tkey[8] = {dist ? 1 : 0, dist ? (long long)N : a0, dist ? comm->nranks : a1, dist ? comm->rank : b0, b1,
+                                 mirror ? 1 : 0, cta2 ? BM2 : BM, 0};
+      if (memcmp(tkey, hx->tiles_key, sizeof(tkey)) != 0 || !h->tiles.p) {
+        std::vector<int2> tiles;
+        if (dist) dist_tiles(N, comm->nranks, comm->rank, tiles);
+        else build_tiles(tiles, a0, a1, b0, b1, mirror, cta2 ? BM2 : BM);
+        GK_TRY(h->h_tiles.ensure(tiles.size() * sizeof(int2) + 16));
+        memcpy(h->h_tiles.p, tiles.data(), tiles.size() * sizeof(int2));
+        GK_TRY(h->tiles.ensure(tiles.size() * sizeof(int2) + 16));
+        GK_CUDA(cudaMemcpyAsync(h->tiles.p, h->h_tiles.p, tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+        memcpy(hx->tiles_key, tkey, sizeof(tkey));
+        hx->tiles_n = (long long)tiles.size();
       }
-      n_tiles = (int64_t)tiles.size();
-      GK_TRY(h->h_tiles.ensure(tiles.size() * sizeof(int2)));
-      memcpy(h->h_tiles.p, tiles.data(), tiles.size() * sizeof(int2));
-      GK_TRY(h->tiles.ensure(tiles.size() * sizeof(int2)));
-      GK_CUDA(cudaMemcpyAsync(h->tiles.p, h->h_tiles.p, tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+      n_tiles = hx->tiles_n;
       CUtensorMap tmA, tmB, tmC;
       PeerMaps peer_maps;
       memset(&peer_maps, 0, sizeof(peer_maps));

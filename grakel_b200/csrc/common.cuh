@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 
+#include <cstddef>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -105,6 +106,8 @@ struct DevScalars {
   unsigned int sp_nonint;                // SP: a non-integer / out-of-range distance was met
 };
 
+static_assert(sizeof(DevScalars) % 8 == 0, "cleared as 64-bit words");
+
 }  // namespace gk
 
 // The opaque handle of the C-ABI.
@@ -151,6 +154,10 @@ struct gk_handle {
   size_t ft_cap = 0;
   int64_t n_columns = 0;
   bool features_ready = false;
+  int64_t feat_serial = 0;   // bumped whenever the feature block changes state
+  int64_t pro_serial = -1;   // feat_serial for which gk_wl_features already ran the Gram prologue (square case):
+                             // self similarities finished, column histogram on the host -- gk_gram then needs no
+                             // host synchronisation before its launches
   int feature_kind = 0;  // 1 = WL, 2 = SP, 3 = SP-attr (dense fp32 features)
 
   gk::DevBuf oa_keys, oa_cnt, oa_colcnt;  // WL-OA: unary-expanded block, swapped with ft_keys / ft_cnt / colcnt

@@ -708,7 +708,12 @@ struct Wlf2Prepare {
 __global__ void __launch_bounds__(1024)
 wlf2_prepare_kernel(Wlf2Prepare q) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  if (tid < (long long)(sizeof(DevScalars) / 8)) reinterpret_cast<unsigned long long*>(q.sc)[tid] = 0ULL;
+  // scalars: all zero except level_dims[0] = level_base[1] = n_labels0 (what the host used to upload)
+  if (tid < (long long)(sizeof(DevScalars) / 8)) {
+    const bool is_n0 = tid == (long long)(offsetof(DevScalars, level_dims) / 8) ||
+                       tid == (long long)(offsetof(DevScalars, level_base) / 8 + 1);
+    reinterpret_cast<unsigned long long*>(q.sc)[tid] = is_n0 ? (unsigned long long)q.n_labels0 : 0ULL;
+  }
   for (long long i = tid; i < q.n_part; i += nth) { q.part_max[i] = 0u; q.part_new[i] = 0u; }
   for (long long i = tid; i < q.n_graphs; i += nth) { q.diag[i] = 0ULL; q.diag_frozen[i] = 0ULL; }
   if (tid == 0) *q.barrier = 0u;
@@ -727,13 +732,6 @@ wlf2_prepare_kernel(Wlf2Prepare q) {
     for (long long i = tid; i < q.ht_cap / 2; i += nth) t4[i] = ones;
   }
 }
-// second tiny launch (stream order = after the clears): the two scalars the host used to upload
-__global__ void wlf2_set_scalars(DevScalars* sc, int n_labels0) {
-  sc->level_dims[0] = n_labels0;
-  sc->level_base[0] = 0;
-  sc->level_base[1] = n_labels0;
-}
-
 // ---- dense first-occurrence ids of one level >= 1 on demand (gk_wl_labels, WL-SP): representatives are the
 // vertices with lab[v] == v; their rank in vertex order is the id the reference-order-free parity tests use.
 constexpr int DENS_THREADS = 1024;
