@@ -192,7 +192,8 @@ int gk_create(int device_ordinal, gk_handle** out) {
   GK_CUDA(cudaFuncSetAttribute(gram_tc_kernel<double, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
   GK_CUDA(cudaFuncSetAttribute(wl_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF_SMEM));
-  GK_CUDA(cudaFuncSetAttribute(wl_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF2_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(wl_fused2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF2_SMEM));
+  GK_CUDA(cudaFuncSetAttribute(wl_fused2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WLF2_SMEM));
   *out = h;
   return GK_OK;
 }
@@ -284,7 +285,7 @@ int gk_destroy(gk_handle* h) {
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
                         &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt, &h->wl_single,
-                        &h->diag_frozen, &h->sp_lists};
+                        &h->diag_frozen, &h->sp_lists, &h->wl_payload};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
@@ -626,6 +627,13 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       fp.barrier = d_barrier;
       fp.labels_all = labels_all; fp.sig_nbr = h->sig_nbr.as<int>(); fp.slot_of = h->slot_of.as<int>();
       fp.E = std::max<int64_t>(E, 1);
+      {  // slot payloads (wl_fused2.cuh [A3]/[B]); GRAKEL_B200_WL_PAYLOAD=0: verify against the representative's CSR row
+        const char* e = getenv("GRAKEL_B200_WL_PAYLOAD");
+        if (!(e && atoi(e) == 0)) {
+          GK_TRY(h->wl_payload.ensure(h->ht_cap * 32 * 2));
+          fp.payload = h->wl_payload.as<int>();
+        }
+      }
       fp.frozen = h->wl_single.as<unsigned char>();
       fp.table = h->ht_keys.as<unsigned long long>();
       fp.ht_mask = (unsigned)(h->ht_cap - 1);
@@ -640,7 +648,7 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
         fp.prof = h->K_stage.as<long long>();
       }
       void* args[] = {&fp};
-      GK_CUDA(cudaLaunchCooperativeKernel((void*)wl_fused2_kernel, dim3(G), dim3(WLF_THREADS), args, WLF2_SMEM, h->stream));
+      GK_CUDA(cudaLaunchCooperativeKernel(fp.payload ? (void*)wl_fused2_kernel<true> : (void*)wl_fused2_kernel<false>, dim3(G), dim3(WLF_THREADS), args, WLF2_SMEM, h->stream));
       LAUNCH_CHECK(h);
       h->wl_sparse_ids = L > 1;
       GK_CUDA(cudaEventRecord(h->tev[3], h->stream));  // end of the feature stage

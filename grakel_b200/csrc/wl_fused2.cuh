@@ -46,7 +46,9 @@ struct WlFused2Params {
                          // with one barrier per level a fast CTA writes the rows of level l+1 while a slow one still
                          // verifies against the rows of level l
   long long E;
-  int* slot_of;          // [V] hash slot of the vertex's signature at the current level
+  int* slot_of;          // [V] hash slot of the vertex's signature at the current level (bit 31: the vertex installed the slot)
+  int* payload;          // [2][ht_cap][8] the installing vertex's signature next to its slot, double-buffered by level
+                         // parity like sig_nbr; NULL = verify against the representative's CSR row (first scheme)
   unsigned char* frozen; // [V] zeroed by the host
   unsigned long long* table;  // 3 x (ht_mask + 1) packed {31-bit tag | single | representative}; table 1 cleared by the host
   unsigned ht_mask;
@@ -233,6 +235,10 @@ constexpr int WLF2_SMEM = WLF_SMEM + WLF_TILE_V /*frz_s*/ + WLF_TILE_V * 4 /*gid
                           WLF2_LTAB * 4 /*ltab*/ + WLF2_LTAB / 8 /*lmulti*/ + WLF_TILE_V * 2 /*lslot*/;
 static_assert(WLF2_SMEM <= 232448, "shared memory budget of one CTA");
 
+// PAY: slot payloads (see [A3]) instead of the representative's CSR row as the verification reference.  A template
+// parameter, not a runtime switch: with both schemes live in one instance the kernel spilled 368 bytes per thread
+// at its 64-register budget and every phase slowed down (profiles/r02w_*).
+template <bool PAY>
 __global__ void __launch_bounds__(WLF_THREADS, 1)
 wl_fused2_kernel(WlFused2Params p) {
   extern __shared__ __align__(16) unsigned char wlf_smem[];
@@ -250,6 +256,10 @@ wl_fused2_kernel(WlFused2Params p) {
   unsigned* ltab = reinterpret_cast<unsigned*>(gend_s + WLF_TILE_V);   // slot -> smallest tile vertex with this key
   unsigned* lmulti = ltab + WLF2_LTAB;                                 // bit per slot: the key has more than one vertex in the tile
   unsigned short* lslot = reinterpret_cast<unsigned short*>(lmulti + WLF2_LTAB / 32);  // vertex -> its slot
+  // payload scheme, resident tiles: slot (| installer bit) of every tile vertex from [A] to [B] of a level; the region is
+  // the emit phase's compaction list otherwise, which runs after [B] has consumed the slots
+  unsigned* slot_s = ltab;
+  static_assert(WLF2_LTAB * 4 >= WLF_TILE_V * 4, "slot_s holds one word per tile vertex");
   __shared__ int s_warp[32];
   __shared__ unsigned s_red[128];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -332,6 +342,7 @@ wl_fused2_kernel(WlFused2Params p) {
     unsigned long long* tab = p.table + (size_t)(lv % 3) * ht_cap;
     const long long level_base = (long long)p.n_labels0 + (long long)(lv - 1) * V;
     int* sig_g = p.sig_nbr + (size_t)(lv & 1) * (size_t)p.E;  // this level's rows
+    int* pay = PAY ? p.payload + (size_t)(lv & 1) * ht_cap * 8 : nullptr;  // this level's slot payloads
 
     // ---------------- [A] signatures + insert (non-frozen vertices)
     WLF_STAMP(lv, 0);
@@ -446,13 +457,14 @@ wl_fused2_kernel(WlFused2Params p) {
       {
         unsigned long long key[WLF_VPT], w[WLF_VPT];
         unsigned slot[WLF_VPT];
-        bool act[WLF_VPT], ins[WLF_VPT], lone[WLF_VPT];
+        bool act[WLF_VPT], ins[WLF_VPT], lone[WLF_VPT], won[WLF_VPT];
 #pragma unroll
         for (int k = 0; k < WLF_VPT; ++k) {
           const int i = tid + k * WLF_THREADS;
           act[k] = i < nv && !frz_s[i];
           key[k] = act[k] ? key_s[i] : 0ULL;
           lone[k] = true;
+          won[k] = false;
         }
         if (WLF2_LOCAL_DEDUP && resident) {
           // CTA-local dedup: slot -> smallest vertex of the tile with this key; later vertices of the key mark it "multi"
@@ -507,7 +519,7 @@ wl_fused2_kernel(WlFused2Params p) {
           for (int k = 0; k < WLF_VPT; ++k) {
             if (!act[k]) continue;
             const int v = v0 + tid + k * WLF_THREADS;
-            if (w[k] == EMPTY64) { act[k] = false; continue; }  // the CAS installed our word (single bit set)
+            if (w[k] == EMPTY64) { act[k] = false; won[k] = true; continue; }  // the CAS installed our word (single bit set)
             if ((w[k] >> 33) == (key[k] >> 33)) {
               const unsigned rep = (unsigned)w[k];
               // a second member: clear the single bit and keep the smaller representative in one atomicMin
@@ -520,17 +532,50 @@ wl_fused2_kernel(WlFused2Params p) {
             any = true;
           }
         }
+        if (PAY) {
+          // Verification data travels WITH the slot: the vertex whose CAS installed a slot writes its full signature
+          // {label, degree, first sorted neighbour labels} into the slot's 32-byte payload; every other vertex that
+          // matched the slot's tag compares its own signature with that payload in [B] -- one L2 round trip next to the
+          // table word instead of the chain slot -> representative -> CSR row -> neighbour row.  Sound: all vertices
+          // of a slot that pass carry the installer's signature, i.e. they are one class; any other vertex raises the
+          // collision flag.  Degrees above 6: the payload holds five labels and the installer's row offset, the rest of
+          // the row is compared through sig_nbr (only installers of such degrees write their rows there).
 #pragma unroll
-        for (int k = 0; k < WLF_VPT; ++k) {
-          const int i = tid + k * WLF_THREADS;
-          if (ins[k]) p.slot_of[v0 + i] = (int)slot[k];
+          for (int k = 0; k < WLF_VPT; ++k) {
+            const int i = tid + k * WLF_THREADS;
+            if (!ins[k]) continue;
+            const unsigned sw = slot[k] | (won[k] ? 0x80000000u : 0u);
+            if (resident) slot_s[i] = sw; else p.slot_of[v0 + i] = (int)sw;
+            if (won[k]) {
+              const int beg = rp_s[i], deg = rp_s[i + 1] - beg;
+              int nb[6];
+#pragma unroll
+              for (int j = 0; j < 6; ++j) nb[j] = j < deg ? sig_s[beg + j] : 0x7fffffff;
+              if (deg > 6) nb[5] = e0 + beg;
+              uint4* dst = reinterpret_cast<uint4*>(pay + (size_t)slot[k] * 8);
+              dst[0] = make_uint4((unsigned)lab_s[i], (unsigned)deg, (unsigned)nb[0], (unsigned)nb[1]);
+              dst[1] = make_uint4((unsigned)nb[2], (unsigned)nb[3], (unsigned)nb[4], (unsigned)nb[5]);
+              if (resident && deg > 6)
+                for (int j = 5; j < deg; ++j) sig_g[e0 + beg + j] = sig_s[beg + j];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < WLF_VPT; ++k) {
+            const int i = tid + k * WLF_THREADS;
+            if (ins[k]) p.slot_of[v0 + i] = (int)slot[k];
+          }
         }
         // sorted neighbour labels of the inserted vertices to global memory: other CTAs verify against them.  Most of
         // the tile inserting: one coalesced copy of the whole segment array (stale rows are never read); few: row by row
+        // (payload scheme on a resident tile: nothing -- own rows stay in shared memory, see above)
         int n_ins = 0;
+        if (!(PAY && resident)) {
 #pragma unroll
-        for (int k = 0; k < WLF_VPT; ++k) n_ins += __syncthreads_count(ins[k] ? 1 : 0);
-        if (2 * n_ins >= nv && !(p.dbg & 1)) {
+          for (int k = 0; k < WLF_VPT; ++k) n_ins += __syncthreads_count(ins[k] ? 1 : 0);
+        }
+        if (PAY && resident) {
+        } else if (2 * n_ins >= nv && !(p.dbg & 1)) {
           for (int j = tid; j < ne; j += WLF_THREADS) sig_g[e0 + j] = sig_s[j];
         } else {
 #pragma unroll
@@ -570,14 +615,25 @@ wl_fused2_kernel(WlFused2Params p) {
           lrep[k] = (int)ltab[lslot[i]];
           if (lrep[k] != i) { fol[k] = true; act[k] = false; }
         }
-        r[k] = act[k] ? p.slot_of[v0 + i] : 0;
+        r[k] = act[k] ? ((PAY && resident) ? (int)slot_s[i] : p.slot_of[v0 + i]) : 0;
       }
+      uint4 pl0[WLF_VPT], pl1[WLF_VPT];  // payload scheme: the installer's signature (vertices that did not install)
+      bool chk[WLF_VPT];
 #pragma unroll
       for (int k = 0; k < WLF_VPT; ++k) {
         const int i = tid + k * WLF_THREADS;
         sgl[k] = false;
+        chk[k] = false;
+        pl0[k] = pl1[k] = make_uint4(0u, 0u, 0u, 0u);
         if (act[k]) {
-          const unsigned long long word = __ldcg(&tab[r[k]]);
+          const unsigned sl = (unsigned)r[k] & 0x7fffffffu;
+          if (PAY && !((unsigned)r[k] >> 31)) {
+            chk[k] = true;
+            const uint4* src = reinterpret_cast<const uint4*>(pay + (size_t)sl * 8);
+            pl0[k] = __ldcg(src);
+            pl1[k] = __ldcg(src + 1);
+          }
+          const unsigned long long word = __ldcg(&tab[PAY ? sl : (unsigned)r[k]]);
           r[k] = (int)(unsigned)word;
           sgl[k] = ((word >> 32) & 1ULL) && r[k] == v0 + i;
         }
@@ -588,7 +644,13 @@ wl_fused2_kernel(WlFused2Params p) {
       for (int k = 0; k < WLF_VPT; ++k) {
         const int i = tid + k * WLF_THREADS;
         bv[k] = dv[k] = br[k] = dr[k] = lo[k] = lr[k] = 0;
-        if (act[k] && r[k] != v0 + i) {
+        if (PAY) {
+          if (chk[k]) {
+            if (resident) { bv[k] = rp_s[i]; dv[k] = rp_s[i + 1] - bv[k]; }
+            else { bv[k] = p.row_ptr[v0 + i]; dv[k] = p.row_ptr[v0 + i + 1] - bv[k]; }
+            lo[k] = lab_s[i];
+          }
+        } else if (act[k] && r[k] != v0 + i) {
           if (resident) { bv[k] = rp_s[i]; dv[k] = rp_s[i + 1] - bv[k]; }  // own side from shared memory (sig_s)
           else { bv[k] = p.row_ptr[v0 + i]; dv[k] = p.row_ptr[v0 + i + 1] - bv[k]; }
           br[k] = p.row_ptr[r[k]]; dr[k] = p.row_ptr[r[k] + 1] - br[k];
@@ -608,8 +670,36 @@ wl_fused2_kernel(WlFused2Params p) {
           for (int j = 0; same && j < di; ++j) same = sig_s[bi + j] == sig_s[bl + j];
           if (!same) atomicOr(&p.sc->collision, 1u);
         }
+        if (PAY && chk[k]) {  // compare with the installer's signature in the slot payload
+          const int pn[6] = {(int)pl0[k].z, (int)pl0[k].w, (int)pl1[k].x, (int)pl1[k].y, (int)pl1[k].z, (int)pl1[k].w};
+          const int d = dv[k];
+          bool same = ((int)pl0[k].x == lo[k]) && ((int)pl0[k].y == d);
+          if (same) {
+            const int nd = d > 6 ? 5 : d;
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+              if (j < nd) same = same && ((resident ? sig_s[bv[k] + j] : sig_g[bv[k] + j]) == pn[j]);
+            if (d > 6) {
+              const int off = pn[5] - 0;  // installer's row offset in sig_nbr
+              for (int j = 5; same && j < d; ++j)
+                same = (resident ? sig_s[bv[k] + j] : sig_g[bv[k] + j]) == __ldcg(&sig_g[off + j]);
+            }
+          }
+          if (!same) {
+            const unsigned before = atomicOr(&p.sc->collision, 1u << min(lv, 30));
+#ifdef WLF2_DEBUG_PRINT
+            if ((p.dbg & 4) && before == 0u)
+              printf("[wl_fused2] payload mismatch level %d cta %d tile %d v %d deg %d/%d own label %d/%d resident %d\n", lv, b, t, v, d,
+                     (int)pl0[k].y, lo[k], (int)pl0[k].x, (int)resident);
+#else
+            (void)before;
+#endif
+          }
+        }
         if (act[k]) {
-          if (r[k] != v) {
+          if (PAY) {
+            if (r[k] == v) n_rep += 1u;
+          } else if (r[k] != v) {
             bool same = (dv[k] == dr[k]) && (lo[k] == lr[k]);
             if (same && dv[k] <= 8) {
               int a[8], c[8];
@@ -626,9 +716,13 @@ wl_fused2_kernel(WlFused2Params p) {
             }
             if (!same) {
               const unsigned before = atomicOr(&p.sc->collision, 1u << min(lv, 30));  // bit = level (error message / retry)
+#ifdef WLF2_DEBUG_PRINT
               if ((p.dbg & 4) && before == 0u)
                 printf("[wl_fused2] mismatch level %d cta %d tile %d v %d rep %d deg %d/%d own label %d/%d resident %d first nbr %d/%d\n", lv, b, t, v,
                        r[k], dv[k], dr[k], lo[k], lr[k], (int)resident, dv[k] ? sig_g[p.row_ptr[v]] : -1, dr[k] ? sig_g[br[k]] : -1);
+#else
+              (void)before;
+#endif
             }
           } else {
             n_rep += 1u;
