@@ -546,9 +546,12 @@ def main():
     st = _lib.GkStats()
 
     def step():
+        if world == 1:
+            # one C call for the whole pass (gk_wl_gram): features, column statistics, head/tail decision on the
+            # device, panel, GEMM, tail -- a single host synchronisation at the end
+            return eng.wl_gram(H, out=False, dtype=np.float32)[2]
         s = eng.wl_features(H)
-        eng.gram(n, out=False, dtype=np.float32, row_range=(rb, re_) if world > 1 else None, stats=s,
-                 want_diag=False, dist=world > 1)
+        eng.gram(n, out=False, dtype=np.float32, row_range=(rb, re_), stats=s, want_diag=False, dist=True)
         return s
 
     for _ in range(args.warmup):

@@ -68,6 +68,7 @@ _SYMBOLS = {
     "gk_sp_distances": (C.c_int, [_P, C.c_int64, _P]),
     "gk_wl_fit_transform": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int64,
                                       _P, C.POINTER(GkStats)]),
+    "gk_wl_gram": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int64, _P, C.POINTER(GkStats)]),
     "gk_sp_fit_transform": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32,
                                       C.c_int64, _P, C.POINTER(GkStats)]),
     "gk_event_record": (C.c_int, [_P, C.c_int32]),
@@ -205,6 +206,7 @@ class Engine:
         with self._lock:
             self._check(self.lib.gk_pack_csr(self.h, len(gp) - 1, _ptr(gp), _ptr(rp), _ptr(ci), _ptr(lab), _ptr(w),
                                              _ptr(at), ad))
+            self.n_graphs = len(gp) - 1
 
     def set_row_map(self, n_rows, row_of_graph):
         m = None if row_of_graph is None else _i32(row_of_graph)
@@ -332,6 +334,33 @@ class Engine:
                                                      _ptr(col_idx), _ptr(labels), int(n_iter), flags, _ptr(out), code,
                                                      out.shape[1], None, C.byref(st)))
         return st
+
+    def wl_gram(self, n_iter, out=None, dtype=np.float64, device_ptr=None, ld=0, dense_all=False, want_diag=False,
+                stats=None):
+        """WL features + square Gram of the packed block in ONE C call (gk_wl_gram): the asynchronous pass -- one host
+        synchronisation, head/tail decision on the device -- when it applies, else gk_wl_features + gk_gram.
+        Returns (K, xdiag, stats); `out` / `device_ptr` as in gram()."""
+        n = self.n_graphs
+        dt = np.dtype(dtype)
+        code = GK_F64 if dt == np.float64 else GK_F32
+        flags = GK_DENSE_ALL if dense_all else 0
+        K, kptr = None, None
+        if device_ptr is not None:
+            flags |= GK_OUT_DEVICE
+            kptr = C.c_void_p(int(device_ptr))
+        elif out is not None:
+            if out is not False:
+                K = out
+                assert K.dtype == dt and K.flags.c_contiguous and K.shape == (n, n)
+                kptr = _ptr(K)
+        else:
+            K = host_matrix(n, n, dt)
+            kptr = _ptr(K)
+        xd = np.empty(n, dtype=np.float64) if want_diag else None
+        st = stats if stats is not None else GkStats()
+        with self._lock:
+            self._check(self.lib.gk_wl_gram(self.h, int(n_iter), flags, kptr, code, int(ld), _ptr(xd), C.byref(st)))
+        return K, xd, st
 
     def selftest_gram(self, counts):
         counts = np.ascontiguousarray(counts, dtype=np.uint16)

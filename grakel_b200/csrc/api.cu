@@ -285,10 +285,11 @@ int gk_destroy(gk_handle* h) {
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
                         &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt, &h->wl_single,
-                        &h->diag_frozen, &h->sp_lists, &h->wl_payload};
+                        &h->diag_frozen, &h->sp_lists, &h->wl_payload, &h->gram_dyn};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
+  h->h_dyn.release();
   h->h_tiles.release();
   h->h_stage.release();
   h->h_diag.release();
@@ -485,20 +486,16 @@ static int init_scalars(gk_handle* h, int n_labels0) {
   return GK_OK;
 }
 
-extern "C" {
+// What gk_wl_features decides and allocates before its first launch (shared with the asynchronous pass, gk_wl_gram)
+struct WlPlan {
+  int L = 0, G = 0, nb = 0, n_tiles = 0;
+  bool fused = false;
+  size_t ft_level_cap = 0;
+};
 
-int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
-  if (!h) return fail(GK_ERR_ARG, "null handle");
-  if (h->N <= 0) return fail(GK_ERR_STATE, "gk_wl_features: no graphs packed");
-  if (!h->has_labels || h->V == 0) return fail(GK_ERR_ARG, "gk_wl_features: vertex labels are required");
-  if (n_iter < 0 || n_iter + 1 >= MAX_LEVELS) return fail(GK_ERR_ARG, "gk_wl_features: n_iter out of range");
-  GK_CUDA(cudaSetDevice(h->dev));
+static int wl_setup(gk_handle* h, int n_iter, WlPlan* pl) {
   const int64_t V = h->V, E = h->E;
   const int L = n_iter + 1;
-  h->n_levels = L;
-  h->features_ready = false; h->feat_serial++;
-  const int64_t launches0 = h->launches;
-
   GK_TRY(h->labels_all.ensure((size_t)L * V * 4));
   GK_TRY(h->sig_nbr.ensure(std::max<int64_t>(E, 1) * 4 * 2));  // wl_fused2 double-buffers the rows by level parity
   GK_TRY(h->slot_of.ensure(V * 4));
@@ -580,26 +577,17 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
   if (h->ft_cap > (1ULL << 31)) return fail(GK_ERR_ARG, "gk_wl_features: feature table too large");
   GK_TRY(h->ft_keys.ensure(h->ft_cap * 8));
   GK_TRY(h->ft_cnt.ensure(h->ft_cap * 4));
+  pl->L = L; pl->G = G; pl->nb = nb; pl->n_tiles = n_tiles; pl->fused = fused; pl->ft_level_cap = ft_level_cap;
+  return GK_OK;
+}
 
+// prepare + wl_fused2 on the handle's stream; no synchronisation
+static int wl_launch_v2(gk_handle* h, const WlPlan& pl, unsigned long long seed, const FeatStats& fst, bool prof) {
+  const int64_t V = h->V, E = h->E;
+  const int L = pl.L, G = pl.G, n_tiles = pl.n_tiles;
   DevScalars* sc = h->scalars.as<DevScalars>();
   int* labels_all = h->labels_all.as<int>();
-  int retries = 0;
-  bool pro_enqueued = false, used_v2 = false;
-  GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
-  for (;; ++retries) {
-    pro_enqueued = false;
-    if (retries > 8)
-      return fail(GK_ERR_STATE, "gk_wl_features: repeated hash collisions (level mask 0x" +
-                                    [&] { char b[16]; snprintf(b, sizeof(b), "%x", h->h_scalars.as<DevScalars>()->collision); return std::string(b); }() + ")");
-    const unsigned long long seed = mix64(0x5851F42D4C957F2DULL + 0x9E3779B97F4A7C15ULL * (unsigned long long)retries);
-    const char* e_v1 = getenv("GRAKEL_B200_WL_V1");
-    const bool wl_v2 = fused && !(e_v1 && atoi(e_v1) != 0);
-    FeatStats fst;
-    if (!wl_v2) GK_TRY(init_scalars(h, h->n_labels0));
-    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)std::max(nb, G) * L, &fst, !wl_v2));
-    h->wl_sparse_ids = false;
-    used_v2 = wl_v2;
-    if (wl_v2) {
+  {
       // wl_fused2.cuh: labels = representative vertex ids (one grid barrier per level), frozen singleton classes
       int* wb = h->wlf_buf.as<int>();
       int* d_cta_tile = wb + n_tiles + 1;
@@ -641,7 +629,6 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       fp.seed = seed; fp.st = fst; fp.sc = sc;
       fp.diag_frozen = h->diag_frozen.as<unsigned long long>();
       if (const char* e = getenv("GRAKEL_B200_WL_DBG")) fp.dbg = atoi(e);
-      const bool prof = getenv("GRAKEL_B200_PROF") != nullptr;
       if (prof) {
         GK_TRY(h->K_stage.ensure((size_t)G * L * 128));
         GK_CUDA(cudaMemsetAsync(h->K_stage.p, 0, (size_t)G * L * 128, h->stream));
@@ -650,6 +637,52 @@ int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
       void* args[] = {&fp};
       GK_CUDA(cudaLaunchCooperativeKernel(fp.payload ? (void*)wl_fused2_kernel<true> : (void*)wl_fused2_kernel<false>, dim3(G), dim3(WLF_THREADS), args, WLF2_SMEM, h->stream));
       LAUNCH_CHECK(h);
+  }
+  return GK_OK;
+}
+
+extern "C" {
+
+int gk_wl_features(gk_handle* h, int32_t n_iter, gk_stats* stats) {
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  if (h->N <= 0) return fail(GK_ERR_STATE, "gk_wl_features: no graphs packed");
+  if (!h->has_labels || h->V == 0) return fail(GK_ERR_ARG, "gk_wl_features: vertex labels are required");
+  if (n_iter < 0 || n_iter + 1 >= MAX_LEVELS) return fail(GK_ERR_ARG, "gk_wl_features: n_iter out of range");
+  GK_CUDA(cudaSetDevice(h->dev));
+  const int64_t V = h->V, E = h->E;
+  const int L = n_iter + 1;
+  h->n_levels = L;
+  h->features_ready = false; h->feat_serial++;
+  const int64_t launches0 = h->launches;
+
+  WlPlan pl;
+  GK_TRY(wl_setup(h, n_iter, &pl));
+  const bool fused = pl.fused;
+  const int G = pl.G, nb = pl.nb, n_tiles = pl.n_tiles;
+  const size_t ft_level_cap = pl.ft_level_cap;
+  (void)n_tiles;
+
+  DevScalars* sc = h->scalars.as<DevScalars>();
+  int* labels_all = h->labels_all.as<int>();
+  int retries = 0;
+  bool pro_enqueued = false, used_v2 = false;
+  GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
+  for (;; ++retries) {
+    pro_enqueued = false;
+    if (retries > 8)
+      return fail(GK_ERR_STATE, "gk_wl_features: repeated hash collisions (level mask 0x" +
+                                    [&] { char b[16]; snprintf(b, sizeof(b), "%x", h->h_scalars.as<DevScalars>()->collision); return std::string(b); }() + ")");
+    const unsigned long long seed = mix64(0x5851F42D4C957F2DULL + 0x9E3779B97F4A7C15ULL * (unsigned long long)retries);
+    const char* e_v1 = getenv("GRAKEL_B200_WL_V1");
+    const bool wl_v2 = fused && !(e_v1 && atoi(e_v1) != 0);
+    FeatStats fst;
+    if (!wl_v2) GK_TRY(init_scalars(h, h->n_labels0));
+    GK_TRY(reset_feature_stats(h, (int64_t)h->n_labels0 + V * (int64_t)(L - 1) + 1, (int64_t)std::max(nb, G) * L, &fst, !wl_v2));
+    h->wl_sparse_ids = false;
+    used_v2 = wl_v2;
+    if (wl_v2) {
+      const bool prof = getenv("GRAKEL_B200_PROF") != nullptr;
+      GK_TRY(wl_launch_v2(h, pl, seed, fst, prof));
       h->wl_sparse_ids = L > 1;
       GK_CUDA(cudaEventRecord(h->tev[3], h->stream));  // end of the feature stage
       if (!prof && !getenv("GRAKEL_B200_NO_PROLOGUE")) {
@@ -1227,7 +1260,25 @@ int gk_wl_sp_features(gk_handle* h, int32_t n_iter, int32_t flags, gk_stats* sta
 
 int gk_sp_distances(gk_handle* h, int64_t g, double* out) {
   if (!h || !out) return fail(GK_ERR_ARG, "gk_sp_distances: null argument");
-  if (h->feature_kind != 2 || !(h->sp_flags & GK_SP_KEEP_DIST)) return fail(GK_ERR_STATE, "gk_sp_distances: run gk_sp_features with GK_SP_KEEP_DIST first");
+  if (h->feature_kind == 3 && h->sp_dist_esz) {
+    // after gk_spattr_features: the APSP matrices of every graph are still in sp_dist (u16 with the saturated
+    // value 0x3FFF for "no path", or fp64 with +inf)
+    if (g < 0 || g >= h->N) return fail(GK_ERR_ARG, "gk_sp_distances: bad graph index");
+    HandleExtra* ex = extra_of(h);
+    const long long off = ex->sp_goff[g], cnt = ex->sp_goff[g + 1] - off;
+    GK_CUDA(cudaSetDevice(h->dev));
+    if (h->sp_dist_esz == 8) {
+      GK_CUDA(cudaMemcpyAsync(out, h->sp_dist.as<double>() + off, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+      GK_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+      std::vector<unsigned short> tmp((size_t)cnt);
+      GK_CUDA(cudaMemcpyAsync(tmp.data(), h->sp_dist.as<unsigned short>() + off, cnt * 2, cudaMemcpyDeviceToHost, h->stream));
+      GK_CUDA(cudaStreamSynchronize(h->stream));
+      for (long long i = 0; i < cnt; ++i) out[i] = tmp[i] < 0x3FFF ? (double)tmp[i] : INFINITY;
+    }
+    return GK_OK;
+  }
+  if (h->feature_kind != 2 || !(h->sp_flags & GK_SP_KEEP_DIST)) return fail(GK_ERR_STATE, "gk_sp_distances: run gk_sp_features with GK_SP_KEEP_DIST (or gk_spattr_features) first");
   if (g < 0 || g >= h->N) return fail(GK_ERR_ARG, "gk_sp_distances: bad graph index");
   HandleExtra* ex = extra_of(h);
   const long long off = ex->sp_goff[g], cnt = ex->sp_goff[g + 1] - off;
@@ -1366,6 +1417,7 @@ int gk_spattr_features(gk_handle* h, int32_t flags, gk_stats* stats) {
   h->n_columns = Dfeat;
   h->features_ready = true; h->feat_serial++;
   h->feature_kind = 3;
+  h->sp_dist_esz = (int)esz;
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     stats->n_graphs = N; stats->n_vertices = h->V; stats->n_edges = h->E;
@@ -1495,6 +1547,29 @@ static int gram_spattr(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_b
 // through a ring of pinned staging buffers; host threads widen each band into the destination rows and
 // write the mirrored half (8 x 8 register transposes) while the next bands are on the PCIe bus.
 #include "host_deliver.h"
+
+// Symmetric integer-valued fp32 result -> the caller's float64 host matrix: upper triangle over PCIe in the narrowest
+// exact type (u16 when the largest self similarity is below 2^16, packed band by band on the device first; else fp32),
+// widened and mirrored by the host pool (host_deliver.h).
+static int deliver_square(gk_handle* h, const float* d_k, long long d_ld, int64_t k_rows, double* dst, int64_t ld, int64_t max_diag) {
+  DeviceCopier cp{h};
+  if (max_diag < 65536 && !getenv("GRAKEL_B200_NO_U16")) {
+    const std::vector<long long> start = tri_bands(k_rows);
+    const int nb = (int)start.size() - 1;
+    std::vector<long long> tab(start);
+    long long off = 0;
+    for (int c = 0; c < nb; ++c) { tab.push_back(off); off += (start[c + 1] - start[c]) * (k_rows - start[c]); }
+    GK_TRY(h->K_stage.ensure((size_t)off * 2 + tab.size() * 8 + 64));
+    GK_TRY(h->h_bands.ensure(tab.size() * 8));
+    memcpy(h->h_bands.p, tab.data(), tab.size() * 8);
+    long long* d_tab = reinterpret_cast<long long*>(h->K_stage.as<char>() + (((size_t)off * 2 + 63) / 64 * 64));
+    GK_CUDA(cudaMemcpyAsync(d_tab, h->h_bands.p, tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    pack_tri_u16<<<h->sm_count * 8, 256, 0, h->stream>>>(d_k, d_ld, k_rows, d_tab, d_tab + nb + 1, nb, h->K_stage.as<unsigned short>());
+    LAUNCH_CHECK(h);
+    return deliver_tri<uint16_t>(cp, h->K_stage.as<uint16_t>(), 0, k_rows, dst, ld);
+  }
+  return deliver_tri<float>(cp, d_k, d_ld, k_rows, dst, ld);
+}
 
 template <typename OutT, bool NORM>
 static void launch_tc(gk_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
@@ -1959,25 +2034,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
         GK_TRY(deliver_rows(cp, d_k, d_ld, k_rows, k_cols, dst, ld, h->h_diag.as<double>() + a0, h->h_diag.as<double>() + b0,
                             p.nan_to_num));
       } else if (full_square && !getenv("GRAKEL_B200_NO_TRI")) {
-        // entries are bounded by the largest self similarity: below 2^16 they travel as two bytes (an eighth of the
-        // float64 bytes over PCIe); the triangle is packed band by band on the device first
-        if (max_diag < 65536 && !getenv("GRAKEL_B200_NO_U16")) {
-          const std::vector<long long> start = tri_bands(k_rows);
-          const int nb = (int)start.size() - 1;
-          std::vector<long long> tab(start);
-          long long off = 0;
-          for (int c = 0; c < nb; ++c) { tab.push_back(off); off += (start[c + 1] - start[c]) * (k_rows - start[c]); }
-          GK_TRY(h->K_stage.ensure((size_t)off * 2 + tab.size() * 8 + 64));
-          GK_TRY(h->h_bands.ensure(tab.size() * 8));
-          memcpy(h->h_bands.p, tab.data(), tab.size() * 8);
-          long long* d_tab = reinterpret_cast<long long*>(h->K_stage.as<char>() + (((size_t)off * 2 + 63) / 64 * 64));
-          GK_CUDA(cudaMemcpyAsync(d_tab, h->h_bands.p, tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
-          pack_tri_u16<<<h->sm_count * 8, 256, 0, h->stream>>>(d_k, d_ld, k_rows, d_tab, d_tab + nb + 1, nb, h->K_stage.as<unsigned short>());
-          LAUNCH_CHECK(h);
-          GK_TRY(deliver_tri<uint16_t>(cp, h->K_stage.as<uint16_t>(), 0, k_rows, dst, ld));
-        } else {
-          GK_TRY(deliver_tri<float>(cp, d_k, d_ld, k_rows, dst, ld));
-        }
+        GK_TRY(deliver_square(h, d_k, d_ld, k_rows, dst, ld, max_diag));
       } else {
         GK_TRY(deliver_rows(cp, d_k, d_ld, k_rows, k_cols, dst, ld, nullptr, nullptr, 0));
       }
@@ -2115,6 +2172,243 @@ int gk_tu_close(gk_tu* t) {
 }
 
 // ---------------------------------------------------------------------------
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// The asynchronous WL pass: feature kernels, column statistics, the head/tail decision (gram_choose, ON THE DEVICE),
+// panel, GEMM and tail are enqueued back to back -- the host synchronises once, at the end.  The synchronous route
+// (gk_wl_features + gk_gram) needs the column histogram on the host between the two halves; here the host only sizes
+// things by CAPACITY (the panel's row pitch, the tail buffers: what earlier passes on this handle allocated) and the
+// device reports through GramDyn::bad when a capacity, an exactness bound or the WL hash check fails, in which case
+// the caller repeats the pass through the synchronous route (which also grows the buffers).  Square fit_transform
+// case with an fp32 device result: library-owned, caller's device buffer, or float64 host delivery.
+static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_out, int32_t out_dtype, int64_t ld,
+                         double* xdiag, gk_stats* stats, bool* done) {
+  *done = false;
+  for (const char* name : {"GRAKEL_B200_NO_ASYNC", "GRAKEL_B200_PROF", "GRAKEL_B200_NO_PROLOGUE", "GRAKEL_B200_WL_V1",
+                           "GRAKEL_B200_WL_FUSED", "GRAKEL_B200_CTA2", "GRAKEL_B200_NO_TMA_STORE", "GRAKEL_B200_WIDEN",
+                           "GRAKEL_B200_NO_TRI", "GRAKEL_B200_MIRROR_TMA", "GRAKEL_B200_DEBUG"})
+    if (getenv(name)) return GK_OK;
+  if (flags & ~(GK_OUT_DEVICE | GK_DENSE_ALL)) return GK_OK;
+  if (h->N <= 0 || !h->has_labels || h->V == 0 || n_iter < 0 || n_iter + 1 >= MAX_LEVELS || h->n_rows > 0) return GK_OK;
+  const int64_t N = h->N, V = h->V;
+  const bool dev_out = (flags & GK_OUT_DEVICE) != 0;
+  const bool host_out = K_out && !dev_out;
+  if (host_out && out_dtype != GK_F64) return GK_OK;
+  if (!host_out && out_dtype != GK_F32) return GK_OK;
+  if (dev_out && !K_out) return GK_OK;
+  if (ld > 0 && ld < N) return GK_OK;  // (the synchronous route reports the error)
+  if (dev_out && (((uintptr_t)K_out) % 16 != 0 || ((ld > 0 ? ld : N) * 4) % 16 != 0)) return GK_OK;
+  // capacities left by earlier passes
+  const int64_t S = (int64_t)(h->panel.cap / ((size_t)N * 2)) / BK * BK;
+  if (S < BK || !h->tail_desc.p || !h->tail_cur.p || !h->tail_ent.p) return GK_OK;
+  const long long cap_tail_cols = (long long)std::min(h->tail_desc.cap / sizeof(int2), h->tail_cur.cap / 4);
+  const long long cap_tail_ent = (long long)(h->tail_ent.cap / sizeof(int2));
+  GK_CUDA(cudaSetDevice(h->dev));
+  const int L = n_iter + 1;
+  h->n_levels = L;
+  h->features_ready = false; h->feat_serial++;
+  const int64_t launches0 = h->launches;
+  WlPlan pl;
+  GK_TRY(wl_setup(h, n_iter, &pl));
+  if (!pl.fused) return GK_OK;
+  HandleExtra* hx = extra_of(h);
+  const int64_t D = (int64_t)h->n_labels0 + V * (int64_t)(L - 1);
+  FeatStats fst;
+  GK_TRY(reset_feature_stats(h, D + 1, (int64_t)std::max(pl.nb, pl.G) * L, &fst, false));
+  GK_TRY(h->colstats.ensure(sizeof(ColStats)));
+  if (!h->gram_dyn.p) {
+    GK_TRY(h->gram_dyn.ensure(sizeof(GramDyn)));
+    GK_CUDA(cudaMemsetAsync(h->gram_dyn.p, 0, sizeof(GramDyn), h->stream));  // the block ticket starts at zero
+  }
+  DevScalars* sc = h->scalars.as<DevScalars>();
+  ColStats* cs = h->colstats.as<ColStats>();
+  GramDyn* dyn = h->gram_dyn.as<GramDyn>();
+  // ---- features first: everything else the host has to prepare overlaps the WL kernel
+  GK_CUDA(cudaMemsetAsync(cs, 0, sizeof(ColStats), h->stream));
+  GK_CUDA(cudaEventRecord(h->tev[2], h->stream));
+  const unsigned long long seed = mix64(0x5851F42D4C957F2DULL);
+  GK_TRY(wl_launch_v2(h, pl, seed, fst, false));
+  h->wl_sparse_ids = L > 1;
+  GK_CUDA(cudaEventRecord(h->tev[3], h->stream));
+  // ---- the panel (full row pitch) is zeroed on the side stream while the column statistics run (the WL kernel itself
+  // owns every register file: nothing can share an SM with it)
+  GK_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+  GK_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+  panel_zero_rows<<<h->sm_count * 4, 256, 0, h->stream2>>>(h->panel.as<__nv_bfloat16>(), N, S, (int)(S / 8));
+  LAUNCH_CHECK(h);
+  GK_CUDA(cudaEventRecord(h->ev_stage[0], h->stream2));
+
+  GK_TRY(h->colslot.ensure(std::max<int64_t>(D, 1) * 4));
+  GK_TRY(h->h_dyn.ensure(sizeof(GramDyn)));
+  GK_TRY(h->diag_f64.ensure(N * 8));
+  // output
+  void* d_out;
+  long long d_ld;
+  if (dev_out) {
+    d_out = K_out;
+    d_ld = ld > 0 ? ld : N;
+  } else {
+    h->K_ld = (N + 7) / 8 * 8;
+    GK_TRY(h->K.ensure((size_t)N * h->K_ld * 4));
+    d_out = h->K.p;
+    d_ld = h->K_ld;
+    h->K_rows = N; h->K_cols = N; h->K_dtype = GK_F32;
+  }
+  // tile list (same key as gk_gram's)
+  {
+    const long long tkey[8] = {0, 0, (long long)N, 0, (long long)N, 1, BM2, 0};
+    if (memcmp(tkey, hx->tiles_key, sizeof(tkey)) != 0 || !h->tiles.p) {
+      std::vector<int2> tiles;
+      build_tiles(tiles, 0, (int)N, 0, (int)N, true, BM2);
+      GK_TRY(h->h_tiles.ensure(tiles.size() * sizeof(int2) + 16));
+      memcpy(h->h_tiles.p, tiles.data(), tiles.size() * sizeof(int2));
+      GK_TRY(h->tiles.ensure(tiles.size() * sizeof(int2) + 16));
+      GK_CUDA(cudaMemcpyAsync(h->tiles.p, h->h_tiles.p, tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+      memcpy(hx->tiles_key, tkey, sizeof(tkey));
+      hx->tiles_n = (long long)tiles.size();
+    }
+  }
+  const int64_t n_tiles = hx->tiles_n;
+  CUtensorMap tmA, tmC;
+  PeerMaps peer_maps;
+  memset(&peer_maps, 0, sizeof(peer_maps));
+  GK_TRY(make_panel_map(&tmA, h->panel.p, S, N, BM));
+  GK_TRY(make_out_map(&tmC, d_out, N, N, d_ld));
+  int force_T = (flags & GK_DENSE_ALL) ? 1 : -1;
+  if (force_T < 0) {
+    const char* e = getenv("GRAKEL_B200_FORCE_T");
+    if (e && *e) force_T = std::max(1, atoi(e));
+  }
+  // ---- columns: self similarities, histogram, the decision -- one launch, one copy back
+  GK_CUDA(cudaEventRecord(h->tev[4], h->stream));
+  const int64_t Dn = std::max<int64_t>(D, 1);
+  const int nbc = cdiv(Dn, 256);
+  {
+    ColFusedParams q;
+    q.D = Dn; q.N = (int)N; q.L = L;
+    q.colcnt = h->colcnt.as<unsigned>();
+    q.diag = h->diag_u64.as<unsigned long long>(); q.diag_f64 = h->diag_f64.as<double>();
+    q.n_part = (int)h->n_part; q.part_max = h->part_max.as<unsigned>(); q.part_new = h->part_new.as<unsigned>();
+    q.cs = cs; q.sc = sc; q.dyn = dyn;
+    q.flops_per_col = (double)N * (double)(N + 1); q.rate = 1.5e15; q.t_atomic = 3.5e-11;
+    q.force_T = force_T; q.stride_cap = (int)S; q.bk = BK;
+    q.cap_tail_cols = cap_tail_cols; q.cap_tail_ent = cap_tail_ent;
+    col_stats_fused<<<h->sm_count * 4, 256, 0, h->stream>>>(q);
+    LAUNCH_CHECK(h);
+  }
+  // the copy back travels on the side stream: the main stream goes straight on to the classification
+  GK_CUDA(cudaEventRecord(h->ev_stage[1], h->stream));
+  GK_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_stage[1], 0));
+  GK_CUDA(cudaMemcpyAsync(h->h_dyn.p, dyn, sizeof(GramDyn), cudaMemcpyDeviceToHost, h->stream2));
+  GK_CUDA(cudaEventRecord(h->ev_join, h->stream2));  // the host waits for THIS, not for the GEMM behind it
+  unsigned* col_counters = reinterpret_cast<unsigned*>(cs);  // cleared by the deciding block
+  col_classify<<<nbc, 256, 0, h->stream>>>(Dn, 1, (int)N, h->colcnt.as<unsigned>(), nullptr, nullptr, 1, h->colslot.as<int>(),
+                                           h->tail_desc.as<int2>(), h->tail_cur.as<unsigned>(), col_counters, dyn);
+  LAUNCH_CHECK(h);
+  GK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_stage[0], 0));  // the zeroed panel
+  feat_scatter<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+      h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(), nullptr,
+      h->panel.as<__nv_bfloat16>(), S, h->tail_cur.as<unsigned>(), h->tail_desc.as<int2>(), h->tail_ent.as<int2>());
+  LAUNCH_CHECK(h);
+  // ---- GEMM (k extent read from the device) + tail
+  GramParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_row_end = (int)N; p.b_row_end = (int)N;
+  p.out = d_out; p.ld = d_ld;
+  p.mirror = 2;
+  p.fix_diag = 1;
+  p.vec_ok = (((uintptr_t)d_out) % 32 == 0 && (d_ld * 4) % 32 == 0) ? 1 : 0;
+  p.diag = h->diag_f64.as<double>();
+  p.tma_store = 1;
+  p.tiles = h->tiles.as<int2>();
+  p.n_tiles = (int)n_tiles;
+  p.num_k_blocks = 1;
+  p.nkb_dev = &dyn->num_k_blocks;
+  const int grid = 2 * (int)std::min<int64_t>(n_tiles, h->sm_count / 2);
+  GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
+  gram_tc2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM, h->stream>>>(tmA, tmC, p, peer_maps);
+  LAUNCH_CHECK(h);
+  GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
+  tail_pairs<float><<<h->sm_count * 16, 256, 0, h->stream>>>(0, h->tail_desc.as<int2>(), h->tail_ent.as<int2>(), (int)N, 1, 0, (int)N,
+                                                            (float*)d_out, d_ld, dyn);
+  LAUNCH_CHECK(h);
+  GK_CUDA(cudaEventRecord(h->ev[13], h->stream));
+  const int64_t launches_all = h->launches - launches0;
+
+  // ---- the decision reaches the host while the GEMM runs
+  GK_CUDA(cudaEventSynchronize(h->ev_join));
+  const GramDyn hd = *h->h_dyn.as<GramDyn>();
+  if (hd.bad) {  // repeat through the synchronous route (it reports errors, retries hash seeds, grows buffers)
+    GK_CUDA(cudaStreamSynchronize(h->stream));
+    return GK_OK;
+  }
+  GK_CUDA(cudaEventRecord(h->ev[14], h->stream));
+  if (host_out) GK_TRY(deliver_square(h, reinterpret_cast<const float*>(d_out), d_ld, N, reinterpret_cast<double*>(K_out), ld > 0 ? ld : N,
+                                      (int64_t)hd.max_diag));
+  if (xdiag) GK_CUDA(cudaMemcpyAsync(xdiag, h->diag_f64.p, N * 8, cudaMemcpyDeviceToHost, h->stream));
+  GK_CUDA(cudaEventRecord(h->ev[15], h->stream));
+  GK_CUDA(cudaStreamSynchronize(h->stream));
+  // ---- state as gk_wl_features + gk_gram leave it
+  h->n_columns = hd.n_columns;
+  h->features_ready = true; h->feat_serial++;
+  h->feature_kind = 1;
+  h->Dc = hd.Dc; h->Dc_pad = hd.Dc_pad;
+  hx->pro_hist = hd.hist;
+  hx->pro_max_count = (long long)hd.max_count; hx->pro_max_diag = (long long)hd.max_diag; hx->pro_n_entries = (long long)hd.n_entries;
+  h->pro_serial = h->feat_serial;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_graphs = N; stats->n_vertices = V; stats->n_edges = h->E;
+    stats->n_levels = L;
+    for (int i = 0; i < L; ++i) { stats->level_dims[i] = hd.level_dims[i]; stats->n_columns += hd.level_dims[i]; }
+    if (L == 1) stats->n_columns = h->n_columns;
+    stats->hash_retries = 0;
+    stats->kernel_launches = launches_all;
+    stats->ms_features = ev_ms(h->tev[2], h->tev[3]);
+    stats->n_entries = (int64_t)hd.n_entries;
+    stats->n_dense_columns = hd.Dc;
+    stats->n_tail_columns = hd.n_tail_cols;
+    stats->tail_updates = (int64_t)hd.tail_work;
+    stats->threshold = hd.T;
+    stats->max_count = (int64_t)hd.max_count;
+    stats->max_diag = (int64_t)hd.max_diag;
+    stats->gram_path = 1;
+    stats->gemm_tiles = n_tiles;
+    stats->gemm_launches = 0;
+    stats->ms_panel = ev_ms(h->tev[4], h->tev[6]);
+    stats->ms_gemm = ev_ms(h->tev[6], h->tev[7]);
+    stats->ms_tail = ev_ms(h->tev[7], h->ev[13]);
+    stats->ms_d2h = ev_ms(h->ev[14], h->ev[15]);
+    stats->ms_total = ev_ms(h->tev[2], h->ev[15]);
+  }
+  *done = true;
+  return GK_OK;
+}
+
+extern "C" {
+
+// WL features + square Gram in one call on the packed block (gk_wl_features followed by gk_gram(n_fit = N)): the
+// asynchronous pass above when it applies, else the two synchronous calls.
+int gk_wl_gram(gk_handle* h, int32_t n_iter, int32_t flags, void* K_out, int32_t out_dtype, int64_t ld, double* xdiag,
+               gk_stats* stats) {
+  if (!h) return fail(GK_ERR_ARG, "null handle");
+  if (out_dtype != GK_F32 && out_dtype != GK_F64) return fail(GK_ERR_ARG, "gk_wl_gram: bad out_dtype");
+  bool done = false;
+  GK_TRY(wl_gram_async(h, n_iter, flags, K_out, out_dtype, ld, xdiag, stats, &done));
+  if (done) return GK_OK;
+  gk_stats s1, s2;
+  memset(&s1, 0, sizeof(s1));
+  GK_TRY(gk_wl_features(h, n_iter, &s1));
+  s2 = s1;
+  GK_TRY(gk_gram(h, h->N, flags, 0, -1, K_out, out_dtype, ld, xdiag, nullptr, &s2));
+  if (stats) {
+    *stats = s2;
+    stats->kernel_launches = s1.kernel_launches;
+  }
+  return GK_OK;
+}
+
 int gk_wl_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr, const int32_t* row_ptr,
                         const int32_t* col_idx, const int32_t* labels, int32_t n_iter, int32_t flags, void* K_out,
                         int32_t out_dtype, int64_t ld, double* diag, gk_stats* stats) {
@@ -2122,12 +2416,10 @@ int gk_wl_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr
   memset(&s1, 0, sizeof(s1));
   memset(&s2, 0, sizeof(s2));
   GK_TRY(gk_pack_csr(h, n_graphs, graph_ptr, row_ptr, col_idx, labels, nullptr, nullptr, 0));
-  GK_TRY(gk_wl_features(h, n_iter, &s1));
-  s2 = s1;
-  GK_TRY(gk_gram(h, n_graphs, flags, 0, -1, K_out, out_dtype, ld, diag, nullptr, &s2));
+  GK_TRY(gk_wl_gram(h, n_iter, flags, K_out, out_dtype, ld, diag, &s2));
+  (void)s1;
   if (stats) {
     *stats = s2;
-    stats->kernel_launches = s1.kernel_launches;
     stats->ms_h2d = ev_ms(h->tev[0], h->tev[1]);
   }
   return GK_OK;

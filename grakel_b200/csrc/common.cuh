@@ -169,6 +169,8 @@ struct gk_handle {
   int64_t n_part = 0;
   gk::DevBuf tail_desc, tail_ent, tail_cur;
   gk::PinBuf h_colstats;
+  gk::DevBuf gram_dyn;   // gk::GramDyn: device-side decisions of the asynchronous pass (gk_wl_gram)
+  gk::PinBuf h_dyn;
   gk::DevBuf diag_u64, diag_f64;
   gk::DevBuf row_map, diag_rows;  // gk_set_row_map: packed graph -> row of K (0 rows = identity)
   int64_t n_rows = 0;
@@ -183,6 +185,7 @@ struct gk_handle {
   size_t sp_dict_cap = 0;
   gk::DevBuf sp_graph_off; // per-graph offset into sp_dist (for gk_sp_distances)
   int sp_flags = 0;
+  int sp_dist_esz = 0;     // gk_spattr_features: element size of the matrices it left in sp_dist (2 = u16, 8 = fp64)
 
   // ---- SP-attr dense fp32 feature matrix
   gk::DevBuf fattr;

@@ -36,6 +36,26 @@ struct ColStats {           // device-side, zeroed per gk_gram
   int pad;
 };
 
+// Decisions of one ASYNCHRONOUS pass, taken on the device (gram_choose) so that the host never waits between the
+// feature kernels and the GEMM: the head/tail threshold and everything that follows from it.  `bad` != 0: the pass
+// cannot be finished this way (see the bits) -- the remaining kernels then do no harm and the host repeats the pass
+// through the synchronous route.
+struct GramDyn {
+  int T;             // head/tail threshold
+  int Dc, Dc_pad;    // head columns, padded to the k-block
+  int num_k_blocks;  // Dc_pad / BK, or 1 when bad (the GEMM still runs, its result is discarded)
+  int n_tail_cols, n_tail_ent;
+  int bad;           // 1: counts / self similarities beyond the exact bf16 x fp32 range, 2: no head column,
+                     // 4: panel stride too small, 8: tail buffers too small, 16: WL hash collision, 32: table overflow
+  unsigned ticket;   // blocks of col_stats_fused that have finished (reset by the last one)
+  unsigned long long tail_work;
+  // what the host wants to know afterwards, gathered here so that ONE copy brings it back
+  unsigned long long max_count, max_diag, n_entries;
+  long long n_columns;              // level_base[L]
+  long long level_dims[MAX_LEVELS];
+  ColStats hist;
+};
+
 // rectangular (transform) case only: smallest / largest graph id per column.  In table
 // (hash) order the running extrema converge after O(log m) updates per column, so the
 // L2-read filter removes almost all atomics even for columns present in every graph.
@@ -132,6 +152,149 @@ col_hist(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt
   }
 }
 
+// Column statistics of the asynchronous pass in ONE launch: self similarities + per-CTA partials (diag_finish), the log2
+// histogram of the contributing columns (col_hist, square case), and -- in the block that finishes last -- the
+// host-side choice of gk_gram on the device: threshold T = 2^k minimising head_cols * flops_per_col / rate +
+// tail_updates * t_atomic (one thread per candidate k), the bucket sums that follow from it, the exactness bounds,
+// the capacity checks; everything the host reads afterwards is copied into `dyn`.  The first words of `cs` (the tail
+// counters of col_classify) are cleared on the way out.
+struct ColFusedParams {
+  long long D; int N; int L;
+  const unsigned* colcnt;
+  const unsigned long long* diag; double* diag_f64;
+  int n_part; const unsigned* part_max; const unsigned* part_new;
+  ColStats* cs; DevScalars* sc; GramDyn* dyn;
+  double flops_per_col, rate, t_atomic;
+  int force_T, stride_cap, bk;
+  long long cap_tail_cols, cap_tail_ent;
+};
+__global__ void __launch_bounds__(256)
+col_stats_fused(ColFusedParams q) {
+  __shared__ unsigned long long hc[HIST_BUCKETS], hw[HIST_BUCKETS], he[HIST_BUCKETS];
+  __shared__ double s_cost[HIST_BUCKETS];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  if (tid < HIST_BUCKETS) { hc[tid] = 0; hw[tid] = 0; he[tid] = 0; }
+  __syncthreads();
+  // ---- self similarities and partials (diag_finish); a few hundred fat blocks, grid-stride: every block costs one
+  // ticket and a handful of same-address atomics at the end
+  {
+    const int g0 = blockIdx.x * blockDim.x + tid, gs = gridDim.x * blockDim.x;
+    unsigned long long d = 0;
+    for (int g = g0; g < q.N; g += gs) {
+      const unsigned long long x = q.diag[g];
+      q.diag_f64[g] = (double)x;
+      d = d > x ? d : x;
+    }
+    unsigned mx = 0;
+    unsigned long long nn = 0;
+    for (int i = g0; i < q.n_part; i += gs) { mx = max(mx, q.part_max[i]); nn += q.part_new[i]; }
+#pragma unroll
+    for (int s2 = 16; s2 > 0; s2 >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, d, s2);
+      d = d > o ? d : o;
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s2));
+      nn += __shfl_xor_sync(0xffffffffu, nn, s2);
+    }
+    if ((tid & 31) == 0) {
+      if (d) atomicMax(&q.sc->max_diag, d);
+      if (mx) atomicMax(&q.sc->max_count, (unsigned long long)mx);
+      if (nn) atomicAdd(&q.sc->n_entries, nn);
+    }
+  }
+  // ---- histogram of the contributing columns (col_hist, square)
+  {
+    for (long long c = (long long)blockIdx.x * blockDim.x + tid; c < q.D; c += (long long)gridDim.x * blockDim.x) {
+      const unsigned m = q.colcnt[c];
+      if (m >= 2) {
+        const int b = size_bucket(m);
+        atomicAdd(&hc[b], 1ULL);
+        atomicAdd(&hw[b], (unsigned long long)m * (m - 1));
+        atomicAdd(&he[b], (unsigned long long)m);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < HIST_BUCKETS && hc[tid]) {
+    atomicAdd(&q.cs->hist_cols[tid], hc[tid]);
+    atomicAdd(&q.cs->hist_work[tid], hw[tid]);
+    atomicAdd(&q.cs->hist_entries[tid], he[tid]);
+  }
+  // ---- the last block decides
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&q.dyn->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  volatile ColStats* cs = q.cs;
+  volatile DevScalars* sc = q.sc;
+  GramDyn* dyn = q.dyn;
+  if (tid < HIST_BUCKETS) {
+    hc[tid] = cs->hist_cols[tid]; hw[tid] = cs->hist_work[tid]; he[tid] = cs->hist_entries[tid];
+  }
+  __syncthreads();
+  if (tid < HIST_BUCKETS) {  // candidate k = tid
+    double head_cols = 0, tail_upd = 0;
+    for (int b = 0; b < HIST_BUCKETS; ++b) {
+      if (b > tid) head_cols += (double)hc[b];
+      else tail_upd += (double)hw[b];
+    }
+    s_cost[tid] = head_cols * q.flops_per_col / q.rate + tail_upd * q.t_atomic;
+    dyn->hist.hist_cols[tid] = hc[tid]; dyn->hist.hist_work[tid] = hw[tid]; dyn->hist.hist_entries[tid] = he[tid];
+  }
+  for (int i = tid; i < MAX_LEVELS; i += blockDim.x) dyn->level_dims[i] = sc->level_dims[i];
+  __syncthreads();
+  if (tid == 0) {
+    int T = 1;
+    double best = -1.0;
+    for (int k = 0; k <= HIST_BUCKETS - 2; ++k)
+      if (best < 0 || s_cost[k] < best) { best = s_cost[k]; T = 1 << k; }
+    if (q.force_T >= 1) T = q.force_T;
+    long long Dc = 0, n_tail_cols = 0, n_tail_ent = 0;
+    unsigned long long tail_work = 0;
+    for (int b = 0; b < HIST_BUCKETS; ++b) {
+      if (b < HIST_BUCKETS - 1 && (1LL << b) <= T) { n_tail_cols += (long long)hc[b]; n_tail_ent += (long long)he[b]; tail_work += hw[b]; }
+      else Dc += (long long)hc[b];
+    }
+    const long long Dc_pad = (Dc + q.bk - 1) / q.bk * q.bk;
+    const unsigned long long max_count = sc->max_count, max_diag = sc->max_diag;
+    int bad = 0;
+    if (max_count > 256ULL || max_diag >= (1ULL << 24)) bad |= 1;
+    if (Dc == 0) bad |= 2;
+    if (Dc_pad > q.stride_cap) bad |= 4;
+    if (n_tail_cols > q.cap_tail_cols || n_tail_ent > q.cap_tail_ent) bad |= 8;
+    if (sc->collision) bad |= 16;
+    if (sc->ft_overflow) bad |= 32;
+    dyn->T = T;
+    dyn->Dc = (int)Dc; dyn->Dc_pad = (int)Dc_pad;
+    dyn->num_k_blocks = bad ? 1 : (int)(Dc_pad / q.bk);
+    dyn->n_tail_cols = bad ? 0 : (int)n_tail_cols;
+    dyn->n_tail_ent = (int)n_tail_ent;
+    dyn->bad = bad;
+    dyn->tail_work = tail_work;
+    dyn->max_count = max_count; dyn->max_diag = max_diag; dyn->n_entries = sc->n_entries;
+    dyn->n_columns = sc->level_base[q.L];
+    dyn->hist.T = T;
+    dyn->ticket = 0u;  // ready for the next pass
+    // the tail counters of col_classify live in the first words of the histogram block
+    unsigned* counters = reinterpret_cast<unsigned*>(q.cs);
+    counters[0] = counters[1] = counters[2] = counters[3] = 0u;
+  }
+}
+
+// zero the panel: `w16` 16-byte units of every row (row pitch `ld` elements); one warp per row, grid-stride
+__global__ void __launch_bounds__(256)
+panel_zero_rows(__nv_bfloat16* __restrict__ panel, long long n_rows, long long ld, int w16) {
+  const int lane = threadIdx.x & 31;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += n_warps) {
+    uint4* row = reinterpret_cast<uint4*>(panel + r * ld);
+    for (int c = lane; c < w16; c += 32) row[c] = z;
+  }
+}
+
 // Classification + slot allocation in ONE pass over the columns (replaces a three-kernel
 // flag / scan / assign pipeline: only ~1.5 % of the columns contribute, so warp-aggregated
 // atomics on three counters are cheaper than scanning 1.6 M columns three times).
@@ -143,12 +306,14 @@ col_hist(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt
 __global__ void __launch_bounds__(256)
 col_classify(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt, const int* __restrict__ colmin,
              const int* __restrict__ colmax, int T, int* __restrict__ colslot, int2* __restrict__ tail_desc,
-             unsigned* __restrict__ tail_cur, unsigned* counters) {
+             unsigned* __restrict__ tail_cur, unsigned* counters, const GramDyn* __restrict__ dyn = nullptr) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int kind = 0;
   unsigned m = 0;
-  if (c < D) {
+  bool off = false;
+  if (dyn) { T = dyn->T; off = dyn->bad != 0; }  // asynchronous pass: the threshold was chosen on the device
+  if (c < D && !off) {
     m = colcnt[c];
     unsigned long long work;
     if (m && col_contributes(m, square ? 0 : colmin[c], square ? 0 : colmax[c], n_fit, square, &work))
@@ -235,26 +400,29 @@ feat_fill_panel_u32(size_t cap, const unsigned long long* __restrict__ keys, con
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 tail_pairs(long long n_tail_cols, const int2* __restrict__ tail_desc, const int2* __restrict__ tail_ent,
-           int n_fit, int square, int row0, int row1, OutT* __restrict__ out, long long ld) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+           int n_fit, int square, int row0, int row1, OutT* __restrict__ out, long long ld,
+           const GramDyn* __restrict__ dyn = nullptr) {
   const int lane = threadIdx.x & 31;
-  if (w >= n_tail_cols) return;
-  const int2 d = tail_desc[w];
-  const int2* ent = tail_ent + d.x;
-  const int m = d.y;
-  const int mm = m * m;
-  for (int p = lane; p < mm; p += 32) {
-    const int a = p / m, b = p - a * m;
-    if (a == b) continue;
-    const int2 ea = ent[a], eb = ent[b];
-    int r, c;
-    if (square) { r = ea.x; c = eb.x; }
-    else {
-      if (ea.x < n_fit || eb.x >= n_fit) continue;
-      r = ea.x - n_fit; c = eb.x;
+  if (dyn) n_tail_cols = dyn->n_tail_cols;  // asynchronous pass: fixed grid, the column count lives on the device
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_tail_cols; w += n_warps) {
+    const int2 d = tail_desc[w];
+    const int2* ent = tail_ent + d.x;
+    const int m = d.y;
+    const int mm = m * m;
+    for (int p = lane; p < mm; p += 32) {
+      const int a = p / m, b = p - a * m;
+      if (a == b) continue;
+      const int2 ea = ent[a], eb = ent[b];
+      int r, c;
+      if (square) { r = ea.x; c = eb.x; }
+      else {
+        if (ea.x < n_fit || eb.x >= n_fit) continue;
+        r = ea.x - n_fit; c = eb.x;
+      }
+      if (r < row0 || r >= row1) continue;
+      atomicAdd(&out[(long long)(r - row0) * ld + c], (OutT)((float)ea.y * (float)eb.y));
     }
-    if (r < row0 || r >= row1) continue;
-    atomicAdd(&out[(long long)(r - row0) * ld + c], (OutT)((float)ea.y * (float)eb.y));
   }
 }
 

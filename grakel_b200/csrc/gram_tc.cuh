@@ -61,6 +61,8 @@ struct GramParams {
   int k_block0;
   int k_chunk;         // k-blocks per accumulator (0 = all): the kernel folds every chunk of a tile into `out` itself
   int k_split;         // chunking applies to k-blocks [0, k_split); the rest is ONE chunk (0 = chunk everything)
+  const int* nkb_dev;  // gram_tc2_kernel: number of k-blocks chosen ON THE DEVICE (asynchronous pass, features.cuh
+                       // GramDyn), NULL = num_k_blocks
 };
 
 // ------------------------------------------------------------------ PTX wrappers

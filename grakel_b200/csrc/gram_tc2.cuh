@@ -89,6 +89,7 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int nkb = p.nkb_dev ? __ldg(p.nkb_dev) : p.num_k_blocks;  // >= 1 by construction (gram_choose)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmA) : "memory");
@@ -121,7 +122,7 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int t = cid; t < p.n_tiles; t += ncl) {
         const int2 tile = p.tiles[t];
         const int arow = tile.x + (int)rank * BM, brow = tile.y + (int)rank * (BN / 2);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t lfull = mapa_u32(full_bar(stage), 0);
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
@@ -144,7 +145,7 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;

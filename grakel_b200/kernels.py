@@ -125,6 +125,65 @@ class Kernel(BaseEstimator, TransformerMixin):
     def pairwise_operation(self, x, y):
         raise NotImplementedError("Pairwise operation is not implemented!")
 
+    # ---- generic pairwise driver (kernel.py:236-296, 298-336) ---------------------
+    # For kernels whose value needs a per-pair Python callback (ShortestPathAttr with a user metric): `self.X` is then
+    # a plain list of per-graph items produced on the device and the matrix is filled pair by pair on the host, in the
+    # reference's order and with its symmetrisation.  The Gram kernels never take this route.
+    def _calculate_kernel_matrix(self, Y=None):
+        if Y is None:
+            n = len(self.X)
+            K = np.zeros(shape=(n, n))
+            cache = []
+            for i, x in enumerate(self.X):
+                K[i, i] = self.pairwise_operation(x, x)
+                for j, y in enumerate(cache):
+                    K[j, i] = self.pairwise_operation(y, x)
+                cache.append(x)
+            return np.triu(K) + np.triu(K, 1).T
+        K = np.zeros(shape=(len(Y), len(self.X)))
+        for j, y in enumerate(Y):
+            for i, x in enumerate(self.X):
+                K[j, i] = self.pairwise_operation(y, x)
+        return K
+
+    def _pairwise_fit_transform(self, X):
+        self._method_calling = 2
+        self.fit(X)
+        km = self._calculate_kernel_matrix()
+        self._X_diag = np.diagonal(km).copy()
+        if self.normalize:  # kernel.py:196-203
+            self._warn_unnormalizable(self._X_diag)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                km = km / np.sqrt(np.outer(self._X_diag, self._X_diag))
+        return km
+
+    def _pairwise_transform(self, X):
+        self._method_calling = 3
+        check_is_fitted(self, ["X"])
+        if X is None:
+            raise ValueError("`transform` input cannot be None")
+        Y = self.parse_input(X)
+        km = self._calculate_kernel_matrix(Y)
+        self._Y = Y
+        self._is_transformed = True
+        if self.normalize:  # kernel.py:155-164
+            X_diag, Y_diag = self._pairwise_diagonal()
+            self._warn_unnormalizable(X_diag, Y_diag)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                km /= np.sqrt(np.outer(Y_diag, X_diag))
+        return km
+
+    def _pairwise_diagonal(self):
+        check_is_fitted(self, ["X"])
+        try:
+            check_is_fitted(self, ["_X_diag"])
+        except NotFittedError:
+            self._X_diag = np.array([self.pairwise_operation(x, x) for x in self.X], dtype=float)
+        if getattr(self, "_is_transformed", False) and hasattr(self, "_Y"):
+            self._Y_diag = np.array([self.pairwise_operation(y, y) for y in self._Y], dtype=float)
+            return self._X_diag, self._Y_diag
+        return self._X_diag
+
     def set_params(self, **params):
         """kernel.py:417-433: a changed parameter is re-validated at the next fit."""
         if len(self._initialized):
@@ -698,10 +757,13 @@ class ShortestPathAttr(Kernel):
                 raise TypeError('"metric" must be callable')
             self._initialized["metric"] = True
 
+    def _bilinear(self):
+        """The explicit feature map (and with it the tensor-core Gram) is valid for the default metric only."""
+        return self.metric is np.dot
+
     def parse_input(self, X):
-        if self.metric is not np.dot:
-            raise NotImplementedError("grakel_b200 evaluates ShortestPathAttr through its bilinear feature map, which "
-                                      "is only valid for the default metric=np.dot")
+        if not self._bilinear():
+            return self._parse_pairs(X)
         if isinstance(X, Block):  # packed input (datasets.read_tu(prefer_attr_nodes=True))
             if X.require("sp", labels=False).attrs is None:
                 raise ValueError("Graph does not have any labels for vertices.")
@@ -713,7 +775,64 @@ class ShortestPathAttr(Kernel):
         self._dijkstra_order = _path_sum_order(block, self.algorithm_type) or getattr(self, "_dijkstra_order", False)
         return Fitted(block, None, {})
 
+    # ---- a user metric: shortest-path matrices on the device, the reference's per-pair contraction on the host
+    def _parse_pairs(self, X):
+        """shortest_path.py:77-129 for a callable metric: one (S, phi) tuple per graph.  S comes from the device APSP
+        kernels (gk_spattr_features -> gk_sp_distances; the path-sum order the reference would use), phi are the
+        attribute rows.  The metric is a Python callback per attribute pair by definition, so the contraction of
+        shortest_path.py:130-164 runs on the host (`pairwise_operation`), through the generic driver of the base
+        class (kernel.py:236-296)."""
+        if isinstance(X, Block):
+            block = X.require("sp", labels=False)
+            if block.attrs is None:
+                raise ValueError("Graph does not have any labels for vertices.")
+        else:
+            block = pack(X, "sp", need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=True,
+                         fw_zero_is_absent=self.algorithm_type == "floyd_warshall", attributes=True,
+                         type_error_msg="each element of X must be either a graph or an iterable with at least 2 and at "
+                                        "most 3 elements\n")
+        dj = _path_sum_order(block, self.algorithm_type)
+        items = []
+        with _lib.engine(getattr(self, "device_", None)) as eng:
+            eng.pack(block.graph_ptr, block.row_ptr, block.col_idx, None, block.weights, block.attrs)
+            self.stats_ = eng.spattr_features(dijkstra_order=bool(dj))
+            gp = block.graph_ptr
+            for g in range(block.n_graphs):
+                n = int(gp[g + 1] - gp[g])
+                S = eng.sp_distances(g, n) if n else np.zeros((0, 0))
+                items.append((S, np.array(block.attrs[gp[g]:gp[g + 1]], dtype=float)))
+        return items
+
+    def pairwise_operation(self, x, y):
+        """shortest_path.py:130-164, vectorised over the path lengths: sum over ordered vertex pairs (i, j) of x and
+        (k, m) of y with equal finite shortest-path length of metric(phi_x[i], phi_y[k]) * metric(phi_x[j], phi_y[m])."""
+        Sx, phi_x = x
+        Sy, phi_y = y
+        nx, ny = Sx.shape[0], Sy.shape[0]
+        if nx < 2 or ny < 2:
+            return 0
+        M = np.empty((nx, ny), dtype=float)
+        for i in range(nx):
+            for k in range(ny):
+                M[i, k] = self.metric(phi_x[i], phi_y[k])
+        offx, offy = ~np.eye(nx, dtype=bool), ~np.eye(ny, dtype=bool)
+        fx, fy = offx & np.isfinite(Sx), offy & np.isfinite(Sy)
+        kernel = 0.0
+        for d in np.intersect1d(np.unique(Sx[fx]), np.unique(Sy[fy])):
+            Ax = (fx & (Sx == d)).astype(float)
+            Ay = fy & (Sy == d)
+            kernel += float(np.sum((M.T @ Ax @ M)[Ay]))
+        return kernel
+
+    def diagonal(self):
+        if not self._bilinear():
+            return self._pairwise_diagonal()
+        return super().diagonal()
+
     def fit_transform(self, X, y=None):
+        self.initialize()
+        if not self._bilinear():
+            return self._pairwise_fit_transform(X)
         self._method_calling = 2
         self.fit(X)
         K, xdiag, _ = self._run(self.X.block, None, n_fit=self.X.block.n_graphs)
@@ -723,6 +842,8 @@ class ShortestPathAttr(Kernel):
         return K
 
     def transform(self, X):
+        if not self._bilinear():
+            return self._pairwise_transform(X)
         self._method_calling = 3
         check_is_fitted(self, ["X"])
         if X is None:

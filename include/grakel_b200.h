@@ -193,8 +193,19 @@ int gk_fetch(gk_handle* h, void* K_out, int32_t out_dtype, int64_t ld);
  * (dense ids, first-occurrence order) */
 int gk_wl_labels(gk_handle* h, int32_t level, int32_t* out);
 
-/* SP inspection: APSP matrix of graph g (n x n fp64, inf = unreachable) */
+/* APSP matrix of graph g (n x n fp64, inf = unreachable): after gk_sp_features(GK_SP_KEEP_DIST), or after
+ * gk_spattr_features -- the (S, phi) tuples of shortest_path.py:77-129 that ShortestPathAttr with a user `metric`
+ * contracts pair by pair on the host (grakel/kernels/shortest_path.py:130-164, kernel.py:236-296) */
 int gk_sp_distances(gk_handle* h, int64_t g, double* out);
+
+/* WL features + square Gram of the packed block in ONE call: gk_wl_features followed by gk_gram(n_fit = N)
+ * (weisfeiler_lehman.py:199-328 for fit_transform).  When the request is the plain square case with an fp32 device
+ * result (flags 0 / GK_OUT_DEVICE / GK_DENSE_ALL; K_out NULL = library-owned, a device pointer, or a float64 host
+ * matrix) the whole pass is enqueued without a host synchronisation in the middle: the head/tail threshold is chosen
+ * on the device and the host sizes buffers by the capacities earlier passes left; anything that does not fit (first
+ * call, hash collision, counts beyond the exact range) repeats through the two synchronous calls. */
+int gk_wl_gram(gk_handle* h, int32_t n_iter, int32_t flags, void* K_out, int32_t out_dtype, int64_t ld,
+               double* xdiag, gk_stats* stats);
 
 /* One-call forms with host buffers (the e2e path that bench.py times). */
 int gk_wl_fit_transform(gk_handle* h, int64_t n_graphs, const int32_t* graph_ptr,

@@ -356,6 +356,66 @@ def test_fp32_transport_with_host_widening_is_exact(monkeypatch):
         monkeypatch.delenv("GRAKEL_B200_NO_TRI", raising=False)
 
 
+def test_asynchronous_pass_equals_the_synchronous_route(monkeypatch):
+    """gk_wl_gram: the one-synchronisation pass (head/tail threshold chosen on the device, buffers sized by the
+    capacities earlier passes left) must give the matrix, self similarities and statistics of gk_wl_features +
+    gk_gram bit for bit -- for the float64 host delivery, the library-owned device result and the dense-all mode --
+    and must fall back by itself when a capacity does not fit (a larger block packed on the same handle)."""
+    from grakel_b200 import _lib
+    from grakel_b200.packing import pack, label_ids
+    eng = _lib.Engine(0)
+
+    def load(X):
+        b = pack(X, "wl")
+        ids, _ = label_ids(b.labels, None, sort_new=False)
+        eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, ids)
+        return b.n_graphs
+
+    def sync_route(n, h, **kw):
+        s = eng.wl_features(h)
+        K, xd, _ = eng.gram(n, stats=s, **kw)
+        return K, xd, s
+
+    for n_graphs, nbar, h in ((700, 14, 3), (1800, 9, 4)):  # the second block is larger: capacities of the first do not fit
+        n = load(gen(n_graphs, nbar, 31))
+        K0, xd0, s0 = sync_route(n, h)
+        assert s0.gemm_launches > 0
+        for rep in range(3):
+            K1, xd1, s1 = eng.wl_gram(h, want_diag=True)
+            _same(K1, K0)
+            assert np.array_equal(xd1, xd0)
+            assert [s1.level_dims[i] for i in range(h + 1)] == [s0.level_dims[i] for i in range(h + 1)]
+            assert (s1.threshold, s1.n_dense_columns, s1.n_tail_columns, s1.tail_updates) == \
+                   (s0.threshold, s0.n_dense_columns, s0.n_tail_columns, s0.tail_updates)
+        assert s1.gemm_launches == 0, "the asynchronous pass was expected to run (gemm_launches marks the synchronous gk_gram)"
+        # library-owned fp32 device result
+        _, _, s2 = eng.wl_gram(h, out=False, dtype=np.float32)
+        assert s2.gemm_launches == 0
+        full = np.empty((n, n), dtype=np.float32)
+        eng.fetch(full)
+        _same(full, K0)
+        # every shared column dense
+        Kd, _, s3 = eng.wl_gram(h, dense_all=True)
+        _same(Kd, K0)
+        assert s3.n_tail_columns == 0
+        # the switch
+        monkeypatch.setenv("GRAKEL_B200_NO_ASYNC", "1")
+        K4, _, s4 = eng.wl_gram(h)
+        assert s4.gemm_launches > 0
+        _same(K4, K0)
+        monkeypatch.delenv("GRAKEL_B200_NO_ASYNC")
+    # the oracle, through the one-call host form (pack + gk_wl_gram), twice: synchronous first, asynchronous second
+    X = gen(300, 12, 5)
+    b = pack(X, "wl")
+    ids, _ = label_ids(b.labels, None, sort_new=False)
+    Ko = WLOracle(n_iter=3).fit_transform(X)
+    e2 = _lib.Engine(0)
+    for rep in range(3):
+        out = np.empty((b.n_graphs, b.n_graphs), dtype=np.float64)
+        e2.wl_fit_transform_raw(b.graph_ptr, b.row_ptr, b.col_idx, ids, 3, out)
+        _same(out, Ko)
+
+
 # --------------------------------------------------------------- SP
 def test_apsp_known_answers(eng):
     """grakel/tests/test_graph.py:40,62-65 and doc/documentation/introduction.rst:313-343."""
@@ -438,8 +498,38 @@ def test_shortest_path_attr_matches_reference_loop(mode, monkeypatch):
         K64 = k.ShortestPathAttr().fit_transform(Xm)
         assert np.array_equal(K32, K32.T)
         np.testing.assert_allclose(K32, K64, rtol=3e-6)
-    with pytest.raises(NotImplementedError):
-        k.ShortestPathAttr(metric=lambda a, b: float(np.dot(a, b))).fit_transform(Xc[:2])
+    # a metric that is np.dot in disguise takes the generic pairwise route (device APSP + host contraction): same matrix
+    Kp = k.ShortestPathAttr(metric=lambda a, b: float(np.dot(a, b))).fit_transform(Xc[:3])
+    np.testing.assert_allclose(Kp, Ko[:3, :3], rtol=1e-9)
+
+
+def test_spattr_user_metric_against_reference_goldens():
+    """ShortestPathAttr(metric=<callable>): shortest-path matrices from the device (gk_spattr_features ->
+    gk_sp_distances; unit weights and real-valued weights in Dijkstra order), the reference's per-pair contraction on
+    the host through the generic driver (kernel.py:236-296, shortest_path.py:130-164).  Goldens: the real reference
+    (tests/golden/make_golden_spattr_metric.py).  Tolerance 1e-9: only the summation order differs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk_spattr_metric", os.path.join(G, "make_golden_spattr_metric.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    k = _k()
+    ref = np.load(os.path.join(G, "spattr_metric.npz"))
+    X = mk.gen_attr(9, 7, 11)
+    fit, new = X[:6], X[6:]
+    e = k.ShortestPathAttr(metric=mk.rbf)
+    K = e.fit_transform(fit)
+    np.testing.assert_allclose(K, ref["unit_K"], rtol=1e-9)
+    np.testing.assert_allclose(e.transform(new), ref["unit_Kt"], rtol=1e-9)
+    e = k.ShortestPathAttr(metric=mk.rbf, normalize=True)
+    np.testing.assert_allclose(e.fit_transform(fit), ref["unit_Kn"], rtol=1e-9)
+    np.testing.assert_allclose(e.transform(new), ref["unit_Ktn"], rtol=1e-9)
+    W = mk.gen_attr(6, 6, 12, real_weights=True)
+    e = k.ShortestPathAttr(metric=mk.rbf)
+    np.testing.assert_allclose(e.fit_transform(W[:4]), ref["real_K"], rtol=1e-9)
+    np.testing.assert_allclose(e.transform(W[4:]), ref["real_Kt"], rtol=1e-9)
+    # through GraphKernel, as the reference spells it
+    gk_ = k.GraphKernel(kernel={"name": "shortest_path", "as_attributes": True, "metric": mk.rbf})
+    np.testing.assert_allclose(gk_.fit_transform(fit), ref["unit_K"], rtol=1e-9)
 
 
 # --------------------------------------------------------------- BASELINE sizes
