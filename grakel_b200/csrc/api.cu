@@ -2303,11 +2303,12 @@ static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_ou
   GK_CUDA(cudaMemcpyAsync(h->h_dyn.p, dyn, sizeof(GramDyn), cudaMemcpyDeviceToHost, h->stream2));
   GK_CUDA(cudaEventRecord(h->ev_join, h->stream2));  // the host waits for THIS, not for the GEMM behind it
   unsigned* col_counters = reinterpret_cast<unsigned*>(cs);  // cleared by the deciding block
-  col_classify<<<nbc, 256, 0, h->stream>>>(Dn, 1, (int)N, h->colcnt.as<unsigned>(), nullptr, nullptr, 1, h->colslot.as<int>(),
-                                           h->tail_desc.as<int2>(), h->tail_cur.as<unsigned>(), col_counters, dyn);
+  col_classify<<<std::min(nbc, h->sm_count * 8), 256, 0, h->stream>>>(Dn, 1, (int)N, h->colcnt.as<unsigned>(), nullptr, nullptr, 1,
+                                                                     h->colslot.as<int>(), h->tail_desc.as<int2>(),
+                                                                     h->tail_cur.as<unsigned>(), col_counters, dyn);
   LAUNCH_CHECK(h);
   GK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_stage[0], 0));  // the zeroed panel
-  feat_scatter<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
+  feat_scatter<<<std::min(cdiv((long long)h->ft_cap, 256), h->sm_count * 16), 256, 0, h->stream>>>(
       h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(), nullptr,
       h->panel.as<__nv_bfloat16>(), S, h->tail_cur.as<unsigned>(), h->tail_desc.as<int2>(), h->tail_ent.as<int2>());
   LAUNCH_CHECK(h);

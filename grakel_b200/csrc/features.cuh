@@ -307,12 +307,14 @@ __global__ void __launch_bounds__(256)
 col_classify(long long D, int square, int n_fit, const unsigned* __restrict__ colcnt, const int* __restrict__ colmin,
              const int* __restrict__ colmax, int T, int* __restrict__ colslot, int2* __restrict__ tail_desc,
              unsigned* __restrict__ tail_cur, unsigned* counters, const GramDyn* __restrict__ dyn = nullptr) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  int kind = 0;
-  unsigned m = 0;
   bool off = false;
   if (dyn) { T = dyn->T; off = dyn->bad != 0; }  // asynchronous pass: the threshold was chosen on the device
+  // grid-stride over whole warps (a launch may have one thread per column or a few hundred fat blocks)
+  const long long D32 = (D + 31) / 32 * 32;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < D32; c += (long long)gridDim.x * blockDim.x) {
+  int kind = 0;
+  unsigned m = 0;
   if (c < D && !off) {
     m = colcnt[c];
     unsigned long long work;
@@ -352,6 +354,7 @@ col_classify(long long D, int square, int n_fit, const unsigned* __restrict__ co
     }
   }
   if (c < D) colslot[c] = slot;
+  }
 }
 
 // pass 2 over the table: head entries -> zeroed bf16 panel, tail entries -> per-column lists
@@ -360,20 +363,20 @@ feat_scatter(size_t cap, const unsigned long long* __restrict__ keys, const unsi
              const int* __restrict__ colslot, const int* __restrict__ row_map, __nv_bfloat16* __restrict__ panel,
              long long ld, unsigned* __restrict__ tail_cur, const int2* __restrict__ tail_desc,
              int2* __restrict__ tail_ent) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cap) return;
-  unsigned long long k = keys[i];
-  if (k == EMPTY64) return;
-  const unsigned c = (unsigned)k;
-  const int slot = colslot[c];
-  if (slot == -1) return;
-  const int g = row_map ? row_map[(int)(k >> 32)] : (int)(k >> 32);
-  if (slot >= 0) {
-    panel[(long long)g * ld + slot] = __float2bfloat16_rn((float)cnt[i]);
-  } else {
-    const int t = -(slot + 2);
-    const unsigned pos = atomicAdd(&tail_cur[t], 1u);
-    tail_ent[tail_desc[t].x + pos] = make_int2(g, (int)cnt[i]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long k = keys[i];
+    if (k == EMPTY64) continue;
+    const unsigned c = (unsigned)k;
+    const int slot = colslot[c];
+    if (slot == -1) continue;
+    const int g = row_map ? row_map[(int)(k >> 32)] : (int)(k >> 32);
+    if (slot >= 0) {
+      panel[(long long)g * ld + slot] = __float2bfloat16_rn((float)cnt[i]);
+    } else {
+      const int t = -(slot + 2);
+      const unsigned pos = atomicAdd(&tail_cur[t], 1u);
+      tail_ent[tail_desc[t].x + pos] = make_int2(g, (int)cnt[i]);
+    }
   }
 }
 

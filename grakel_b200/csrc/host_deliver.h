@@ -39,7 +39,11 @@ class HostPool {
       if (!cpus.empty()) {
         cpu_set_t set;
         CPU_ZERO(&set);
-        if ((int)cpus.size() >= n) CPU_SET(cpus[(first + i) % (int)cpus.size()], &set);
+        // GRAKEL_B200_HOST_FLOAT=1: workers may run on ANY of the picked CPUs (one per physical core) instead of one
+        // fixed CPU each -- a worker whose core is taken by somebody else (the caller's own spinning thread after a
+        // migration, a proxy thread) is moved by the scheduler instead of waiting for a time slice
+        static const bool floating = getenv("GRAKEL_B200_HOST_FLOAT") && atoi(getenv("GRAKEL_B200_HOST_FLOAT")) != 0;
+        if ((int)cpus.size() >= n && !floating) CPU_SET(cpus[(first + i) % (int)cpus.size()], &set);
         else for (int c : cpus) CPU_SET(c, &set);
         pthread_setaffinity_np(th_.back().native_handle(), sizeof(set), &set);
       }

@@ -235,6 +235,49 @@ constexpr int WLF2_SMEM = WLF_SMEM + WLF_TILE_V /*frz_s*/ + WLF_TILE_V * 4 /*gid
                           WLF2_LTAB * 4 /*ltab*/ + WLF2_LTAB / 8 /*lmulti*/ + WLF_TILE_V * 2 /*lslot*/;
 static_assert(WLF2_SMEM <= 232448, "shared memory budget of one CTA");
 
+// Global -> shared staging of a tile with several loads in flight per thread.  A plain strided loop keeps ONE load
+// per thread outstanding: 1024 threads x 4 bytes per ~1 us of L2 latency is ~4 GB/s per SM, and a CTA that owns more
+// than one tile (V > 148 x 4096) re-staged ~100 KB per tile, level and phase that way -- 23 us per tile, most of the
+// kernel at the multi-GPU sizes (profiles/r03f_wl_prof_28284.txt).
+#define WLF2_STAGE4(N_, LOAD_, STORE_)                                                     \
+  for (int i0_ = tid; i0_ < (N_); i0_ += 4 * WLF_THREADS) {                                 \
+    const int i1_ = i0_ + WLF_THREADS, i2_ = i0_ + 2 * WLF_THREADS, i3_ = i0_ + 3 * WLF_THREADS; \
+    const int x0_ = LOAD_(i0_);                                                              \
+    const int x1_ = i1_ < (N_) ? LOAD_(i1_) : 0;                                             \
+    const int x2_ = i2_ < (N_) ? LOAD_(i2_) : 0;                                             \
+    const int x3_ = i3_ < (N_) ? LOAD_(i3_) : 0;                                             \
+    STORE_(i0_, x0_);                                                                        \
+    if (i1_ < (N_)) STORE_(i1_, x1_);                                                        \
+    if (i2_ < (N_)) STORE_(i2_, x2_);                                                        \
+    if (i3_ < (N_)) STORE_(i3_, x3_);                                                        \
+  }
+__device__ __forceinline__ void wlf2_stage_csr(const WlFused2Params& p, int v0, int nv, int e0, int ne, int* rp_s,
+                                               unsigned short* col_s, int tid) {
+#define LD_(i) p.row_ptr[v0 + (i)]
+#define ST_(i, x) rp_s[(i)] = (x) - e0
+  WLF2_STAGE4(nv + 1, LD_, ST_)
+#undef LD_
+#undef ST_
+#define LD_(k) p.col_idx[e0 + (k)]
+#define ST_(k, x) col_s[(k)] = (unsigned short)((x) - v0)
+  WLF2_STAGE4(ne, LD_, ST_)
+#undef LD_
+#undef ST_
+}
+__device__ __forceinline__ void wlf2_stage_labels(const WlFused2Params& p, const int* lab_in, int v0, int nv, int* lab_s,
+                                                  unsigned char* frz_s, int tid) {
+#define LD_(i) lab_in[v0 + (i)]
+#define ST_(i, x) lab_s[(i)] = (x)
+  WLF2_STAGE4(nv, LD_, ST_)
+#undef LD_
+#undef ST_
+#define LD_(i) (int)p.frozen[v0 + (i)]
+#define ST_(i, x) frz_s[(i)] = (unsigned char)(x)
+  WLF2_STAGE4(nv, LD_, ST_)
+#undef LD_
+#undef ST_
+}
+
 // PAY: slot payloads (see [A3]) instead of the representative's CSR row as the verification reference.  A template
 // parameter, not a runtime switch: with both schemes live in one instance the kernel spilled 368 bytes per thread
 // at its 64-register budget and every phase slowed down (profiles/r02w_*).
@@ -296,29 +339,37 @@ wl_fused2_kernel(WlFused2Params p) {
   };
 
   auto stage_graphs = [&](int v0, int nv) {
-    for (int i = tid; i < nv; i += WLF_THREADS) {
-      const int g = p.vgraph[v0 + i];
-      gid_s[i] = g;
-      gbeg_s[i] = (unsigned short)(p.graph_ptr[g] - v0);
-      gend_s[i] = (unsigned short)(p.graph_ptr[g + 1] - v0);
-    }
+#define LD_(i) p.vgraph[v0 + (i)]
+#define ST_(i, x) gid_s[(i)] = (x)
+    WLF2_STAGE4(nv, LD_, ST_)
+#undef LD_
+#undef ST_
+    // (each thread re-reads what it wrote itself: same index mapping, no barrier needed)
+#define LD_(i) p.graph_ptr[gid_s[(i)]]
+#define ST_(i, x) gbeg_s[(i)] = (unsigned short)((x) - v0)
+    WLF2_STAGE4(nv, LD_, ST_)
+#undef LD_
+#undef ST_
+#define LD_(i) p.graph_ptr[gid_s[(i)] + 1]
+#define ST_(i, x) gend_s[(i)] = (unsigned short)((x) - v0)
+    WLF2_STAGE4(nv, LD_, ST_)
+#undef LD_
+#undef ST_
   };
 
   // ---- level 0: labels as given (dense ids); nothing is frozen yet
   for (int t = t_beg; t < t_end; ++t) {
     const int v0 = p.tile_vbeg[t], nv = p.tile_vbeg[t + 1] - v0;
     __syncthreads();
-    for (int i = tid; i < nv; i += WLF_THREADS) {
-      const int x = p.labels0[v0 + i];
-      lab_s[i] = x;
-      p.labels_all[v0 + i] = x;
-      frz_s[i] = 0;
-    }
+#define LD_(i) p.labels0[v0 + (i)]
+#define ST_(i, x) { lab_s[(i)] = (x); p.labels_all[v0 + (i)] = (x); frz_s[(i)] = 0; }
+    WLF2_STAGE4(nv, LD_, ST_)
+#undef LD_
+#undef ST_
     stage_graphs(v0, nv);
     if (resident) {  // stage the CSR slice once
       const int e0 = p.row_ptr[v0], ne = p.row_ptr[v0 + nv] - e0;
-      for (int i = tid; i <= nv; i += WLF_THREADS) rp_s[i] = p.row_ptr[v0 + i] - e0;
-      for (int k = tid; k < ne; k += WLF_THREADS) col_s[k] = (unsigned short)(p.col_idx[e0 + k] - v0);
+      wlf2_stage_csr(p, v0, nv, e0, ne, rp_s, col_s, tid);
     }
     __syncthreads();
     WLF_STAMP(0, 1);
@@ -351,9 +402,8 @@ wl_fused2_kernel(WlFused2Params p) {
       const int e0 = p.row_ptr[v0], ne = p.row_ptr[v0 + nv] - e0;
       if (!resident) {
         __syncthreads();  // previous tile's shared memory is no longer read
-        for (int i = tid; i <= nv; i += WLF_THREADS) rp_s[i] = p.row_ptr[v0 + i] - e0;
-        for (int k = tid; k < ne; k += WLF_THREADS) col_s[k] = (unsigned short)(p.col_idx[e0 + k] - v0);
-        for (int i = tid; i < nv; i += WLF_THREADS) { lab_s[i] = lab_in[v0 + i]; frz_s[i] = p.frozen[v0 + i]; }
+        wlf2_stage_csr(p, v0, nv, e0, ne, rp_s, col_s, tid);
+        wlf2_stage_labels(p, lab_in, v0, nv, lab_s, frz_s, tid);
         __syncthreads();
       }
       WLF_STAMP(lv, 8);
@@ -599,7 +649,7 @@ wl_fused2_kernel(WlFused2Params p) {
       const int v0 = p.tile_vbeg[t], nv = p.tile_vbeg[t + 1] - v0;
       if (!resident) {
         __syncthreads();
-        for (int i = tid; i < nv; i += WLF_THREADS) { lab_s[i] = lab_in[v0 + i]; frz_s[i] = p.frozen[v0 + i]; }
+        wlf2_stage_labels(p, lab_in, v0, nv, lab_s, frz_s, tid);
         stage_graphs(v0, nv);
         __syncthreads();
       }

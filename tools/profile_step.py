@@ -35,11 +35,12 @@ def main():
 
         def wl():
             eng.pack(gp, rp, ci, lab)
-            st = eng.wl_features(H)
-            if "wl" in what:
-                eng.gram(n, out=False, dtype=np.float32, stats=st, want_diag=False)
+            if "wl" in what:  # the pass as bench.py times it: gk_wl_gram (asynchronous from the second call on)
+                eng.wl_gram(H, out=False, dtype=np.float32)
+            else:
+                eng.wl_features(H)
             if "dense" in what:
-                eng.gram(n, out=False, dtype=np.float32, stats=st, want_diag=False, dense_all=True)
+                eng.gram(n, out=False, dtype=np.float32, want_diag=False, dense_all=True)
         jobs.append(wl)
     if "sp" in what:
         from grakel_b200.packing import label_ids, pack

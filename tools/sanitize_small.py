@@ -34,4 +34,19 @@ print("SP real", float(Kr.sum()), float(Kf.sum()))
 At = gen_list(60, 12, 5, attr=4, as_adj=True)
 Ka = ShortestPathAttr().fit_transform(At)
 print("SP-attr", Ka.shape, float(Ka.sum()))
+# the asynchronous pass (gk_wl_gram): first call synchronous (capacities), the next ones asynchronous
+from grakel_b200 import _lib  # noqa: E402
+from grakel_b200.packing import label_ids, pack  # noqa: E402
+b = pack(X, "wl")
+ids, _ = label_ids(b.labels, None, sort_new=False)
+eng = _lib.Engine(0)
+eng.pack(b.graph_ptr, b.row_ptr, b.col_idx, ids)
+for rep in range(3):
+    Kg, _, st = eng.wl_gram(3)
+    assert np.array_equal(Kg, K), rep
+assert st.gemm_launches == 0
+print("async", Kg.shape, float(Kg.sum()))
+# a user metric: device APSP + host contraction
+Km = ShortestPathAttr(metric=lambda a, c: float(np.exp(-np.sum((np.asarray(a) - np.asarray(c)) ** 2)))).fit_transform(At[:8])
+print("SP-attr metric", Km.shape, float(Km.sum()))
 print("sanitize_small ok")
