@@ -131,6 +131,7 @@ struct HandleExtra {
   // GEMM tile list on the device (h->tiles): rebuilt and uploaded only when its key changes
   long long tiles_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
   long long tiles_n = 0;
+  long long head_dc_pad = 0;  // panel width of the last pass whose threshold came from the cost model (not GK_DENSE_ALL / FORCE_T)
 };
 static std::vector<std::pair<gk_handle*, HandleExtra*>> g_extra;
 static HandleExtra* extra_of(gk_handle* h) {
@@ -1787,6 +1788,7 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   if (path == 1 && Dc == 0) path = 3;
   h->Dc = Dc;
   h->Dc_pad = (Dc + BK - 1) / BK * BK;
+  if (force_T < 0 && path == 1 && square) hx->head_dc_pad = h->Dc_pad;
 
   // ---- transport type.  Tensor-core results are integers < 2^24 (checked above), i.e. exact in fp32: a float64
   // HOST result is produced and moved as fp32 (half the HBM writes; a quarter of the PCIe bytes for the
@@ -1873,9 +1875,8 @@ int gk_gram(gk_handle* h, int64_t n_fit, int32_t flags, int64_t row_begin, int64
   GK_CUDA(cudaEventRecord(h->tev[5], h->stream));
   int64_t n_tiles = 0;
   if (k_rows > 0) {
-    if (has_tail) {
-      GK_TRY(h->tail_ent.ensure((size_t)n_tail_ent * sizeof(int2)));
-    }
+    // (always at least a stub: gk_wl_gram's asynchronous pass sizes its tail by the capacity left here)
+    GK_TRY(h->tail_ent.ensure((size_t)std::max<int64_t>(has_tail ? n_tail_ent : 0, 64) * sizeof(int2)));
     if (path == 1 || path == 3) {
       const size_t panel_bytes = (size_t)N * std::max<int64_t>(h->Dc_pad, BK) * 2;
       GK_TRY(h->panel.ensure(panel_bytes));
@@ -2200,7 +2201,13 @@ static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_ou
   if (ld > 0 && ld < N) return GK_OK;  // (the synchronous route reports the error)
   if (dev_out && (((uintptr_t)K_out) % 16 != 0 || ((ld > 0 ? ld : N) * 4) % 16 != 0)) return GK_OK;
   // capacities left by earlier passes
-  const int64_t S = (int64_t)(h->panel.cap / ((size_t)N * 2)) / BK * BK;
+  int64_t S = (int64_t)(h->panel.cap / ((size_t)N * 2)) / BK * BK;
+  {  // no wider than the last cost-model pass needed, plus a quarter (a dense-all pass may have left a much larger buffer,
+     // and the whole pitch is zeroed: 466 MB in profiles/r03_full_summary.md before this cap)
+    const long long want = extra_of(h)->head_dc_pad;
+    if (!(flags & GK_DENSE_ALL) && !getenv("GRAKEL_B200_FORCE_T") && want > 0)
+      S = std::min<int64_t>(S, (want + want / 4 + BK - 1) / BK * BK + BK);
+  }
   if (S < BK || !h->tail_desc.p || !h->tail_cur.p || !h->tail_ent.p) return GK_OK;
   const long long cap_tail_cols = (long long)std::min(h->tail_desc.cap / sizeof(int2), h->tail_cur.cap / 4);
   const long long cap_tail_ent = (long long)(h->tail_ent.cap / sizeof(int2));
@@ -2303,12 +2310,11 @@ static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_ou
   GK_CUDA(cudaMemcpyAsync(h->h_dyn.p, dyn, sizeof(GramDyn), cudaMemcpyDeviceToHost, h->stream2));
   GK_CUDA(cudaEventRecord(h->ev_join, h->stream2));  // the host waits for THIS, not for the GEMM behind it
   unsigned* col_counters = reinterpret_cast<unsigned*>(cs);  // cleared by the deciding block
-  col_classify<<<std::min(nbc, h->sm_count * 8), 256, 0, h->stream>>>(Dn, 1, (int)N, h->colcnt.as<unsigned>(), nullptr, nullptr, 1,
-                                                                     h->colslot.as<int>(), h->tail_desc.as<int2>(),
-                                                                     h->tail_cur.as<unsigned>(), col_counters, dyn);
+  col_classify<<<nbc, 256, 0, h->stream>>>(Dn, 1, (int)N, h->colcnt.as<unsigned>(), nullptr, nullptr, 1, h->colslot.as<int>(),
+                                           h->tail_desc.as<int2>(), h->tail_cur.as<unsigned>(), col_counters, dyn);
   LAUNCH_CHECK(h);
   GK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_stage[0], 0));  // the zeroed panel
-  feat_scatter<<<std::min(cdiv((long long)h->ft_cap, 256), h->sm_count * 16), 256, 0, h->stream>>>(
+  feat_scatter<<<cdiv((long long)h->ft_cap, 256), 256, 0, h->stream>>>(
       h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(), nullptr,
       h->panel.as<__nv_bfloat16>(), S, h->tail_cur.as<unsigned>(), h->tail_desc.as<int2>(), h->tail_ent.as<int2>());
   LAUNCH_CHECK(h);
@@ -2355,6 +2361,7 @@ static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_ou
   h->features_ready = true; h->feat_serial++;
   h->feature_kind = 1;
   h->Dc = hd.Dc; h->Dc_pad = hd.Dc_pad;
+  if (force_T < 0) hx->head_dc_pad = hd.Dc_pad;
   hx->pro_hist = hd.hist;
   hx->pro_max_count = (long long)hd.max_count; hx->pro_max_diag = (long long)hd.max_diag; hx->pro_n_entries = (long long)hd.n_entries;
   h->pro_serial = h->feat_serial;

@@ -38,8 +38,10 @@ def main(path, tag):
     if len(g) >= 2:
         out["gram_tc2_kernel dense (all shared columns)"] = g[1]
     for k in ("tail_pairs<float>", "wl_fused2_kernel"):
-        if k in seen:
-            out[k] = seen[k][0]
+        for name in seen:  # template instances print as wl_fused2_kernel<1> / <true>
+            if name == k or name.startswith(k + "<"):
+                out[k] = seen[name][0]
+                break
     json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 
