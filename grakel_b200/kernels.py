@@ -542,6 +542,19 @@ class WeisfeilerLehman(Kernel):
             return eng.wl_sp_features(self._n_iter - 1, dijkstra_order=True)  # the base kernel gets edge dictionaries
         return eng.wl_features(self._n_iter - 1)
 
+    def _run(self, block, ids, n_fit, want_matrix=True):
+        """The plain subtree fit_transform (square, un-normalised) is ONE C call, gk_wl_gram: relabel, column statistics,
+        head/tail decision on the device, GEMM, tail and delivery with a single host synchronisation."""
+        if (want_matrix and not self.normalize and n_fit == block.n_graphs and self._base_graph_kernel is VertexHistogram
+                and type(self) is WeisfeilerLehman):
+            with _lib.engine(getattr(self, "device_", None)) as eng:
+                eng.pack(block.graph_ptr, block.row_ptr, block.col_idx, ids, block.weights, block.attrs)
+                K, xd, self.stats_ = eng.wl_gram(self._n_iter - 1, want_diag=True)
+            if self.verbose:
+                print(type(self).__name__, self.stats_.as_dict())
+            return K, xd, None
+        return super()._run(block, ids, n_fit, want_matrix)
+
     def _export_level_dictionaries(self):
         """`_inv_labels[i]` for i >= 1 (weisfeiler_lehman.py:257): the fitted graphs are relabelled on the device, the
         per-level classes come back through `gk_wl_labels`, and the host names every class the way the reference
