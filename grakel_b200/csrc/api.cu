@@ -286,7 +286,7 @@ int gk_destroy(gk_handle* h) {
                         &h->tail_ent, &h->tail_cur, &h->part_max, &h->part_new, &h->diag_u64, &h->diag_f64, &h->panel,
                         &h->sp_dist, &h->sp_dict_keys, &h->sp_dict_ids, &h->sp_dkeys, &h->sp_graph_off, &h->fattr, &h->tiles,
                         &h->K, &h->K_stage, &h->wlf_buf, &h->row_map, &h->diag_rows, &h->oa_keys, &h->oa_cnt, &h->oa_colcnt, &h->wl_single,
-                        &h->diag_frozen, &h->sp_lists, &h->wl_payload, &h->gram_dyn};
+                        &h->diag_frozen, &h->sp_lists, &h->wl_payload, &h->gram_dyn, &h->tb_cnt, &h->tb_ent, &h->tb_ovf};
   for (auto* b : bufs) b->release();
   h->h_scalars.release();
   h->h_colstats.release();
@@ -2247,7 +2247,7 @@ static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_ou
   GK_CUDA(cudaEventRecord(h->ev_stage[0], h->stream2));
 
   GK_TRY(h->colslot.ensure(std::max<int64_t>(D, 1) * 4));
-  GK_TRY(h->h_dyn.ensure(sizeof(GramDyn)));
+  GK_TRY(h->h_dyn.ensure(sizeof(GramDyn) + 64));
   GK_TRY(h->diag_f64.ensure(N * 8));
   // output
   void* d_out;
@@ -2318,6 +2318,32 @@ static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_ou
       h->ft_cap, h->ft_keys.as<unsigned long long>(), h->ft_cnt.as<unsigned>(), h->colslot.as<int>(), nullptr,
       h->panel.as<__nv_bfloat16>(), S, h->tail_cur.as<unsigned>(), h->tail_desc.as<int2>(), h->tail_ent.as<int2>());
   LAUNCH_CHECK(h);
+  // ---- tail: bucketed by 32 x 32 block of K for the GEMM epilogue (GRAKEL_B200_TAIL_FUSED=0: the separate tail_pairs kernel)
+  const char* e_tf = getenv("GRAKEL_B200_TAIL_FUSED");
+  const bool tail_fused = !(e_tf && atoi(e_tf) == 0);
+  const int nb32 = (int)((N + 31) / 32);
+  const unsigned ovf_cap = 1u << 20;
+  const char* e_sym = getenv("GRAKEL_B200_TB_SYM");
+  const int tb_sym = (e_sym && atoi(e_sym) != 0) ? 1 : 0;  // symmetric lists (pairs with row < column only): half the atomics
+  int tb_cap = TB_CAP;  // tests shrink it (GRAKEL_B200_TB_CAP) to drive updates through the overflow list
+  if (const char* e = getenv("GRAKEL_B200_TB_CAP")) tb_cap = std::max(0, std::min(TB_CAP, atoi(e)));
+  unsigned* d_ovf_n = nullptr;
+  unsigned* d_tb_cnt_all = nullptr;
+  if (tail_fused) {
+    const size_t n_blk = (size_t)nb32 * nb32;
+    // one buffer, one memset: [entry lines (n_blk x 128 B) | block counters | overflow counter]
+    const size_t tb_words = n_blk * TB_CAP + n_blk + 16;
+    GK_TRY(h->tb_ent.ensure(tb_words * 4));
+    GK_TRY(h->tb_ovf.ensure((size_t)ovf_cap * sizeof(int4)));
+    unsigned* d_tb_cnt = h->tb_ent.as<unsigned>() + n_blk * TB_CAP;
+    d_tb_cnt_all = d_tb_cnt;
+    d_ovf_n = d_tb_cnt + n_blk;
+    GK_CUDA(cudaMemsetAsync(h->tb_ent.p, 0, tb_words * 4, h->stream));
+    tail_bucket<<<h->sm_count * 16, 256, 0, h->stream>>>(h->tail_desc.as<int2>(), h->tail_ent.as<int2>(), dyn, nb32, tb_cap, TB_CAP, tb_sym,
+                                                         d_tb_cnt, h->tb_ent.as<unsigned>(), h->tb_ovf.as<int4>(), ovf_cap, d_ovf_n);
+    LAUNCH_CHECK(h);
+    GK_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h->h_dyn.p) + sizeof(GramDyn), d_ovf_n, 4, cudaMemcpyDeviceToHost, h->stream));
+  }
   // ---- GEMM (k extent read from the device) + tail
   GramParams p;
   memset(&p, 0, sizeof(p));
@@ -2332,13 +2358,17 @@ static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_ou
   p.n_tiles = (int)n_tiles;
   p.num_k_blocks = 1;
   p.nkb_dev = &dyn->num_k_blocks;
+  if (tail_fused) { p.tb_cnt = d_tb_cnt_all; p.tb_ent = h->tb_ent.as<unsigned>(); p.tb_nb32 = nb32; p.tb_cap = tb_cap; p.tb_sym = tb_sym; }
   const int grid = 2 * (int)std::min<int64_t>(n_tiles, h->sm_count / 2);
   GK_CUDA(cudaEventRecord(h->tev[6], h->stream));
   gram_tc2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM, h->stream>>>(tmA, tmC, p, peer_maps);
   LAUNCH_CHECK(h);
   GK_CUDA(cudaEventRecord(h->tev[7], h->stream));
-  tail_pairs<float><<<h->sm_count * 16, 256, 0, h->stream>>>(0, h->tail_desc.as<int2>(), h->tail_ent.as<int2>(), (int)N, 1, 0, (int)N,
-                                                            (float*)d_out, d_ld, dyn);
+  if (tail_fused)
+    tail_overflow_apply<<<64, 256, 0, h->stream>>>(h->tb_ovf.as<int4>(), d_ovf_n, ovf_cap, (float*)d_out, d_ld, tb_sym);
+  else
+    tail_pairs<float><<<h->sm_count * 16, 256, 0, h->stream>>>(0, h->tail_desc.as<int2>(), h->tail_ent.as<int2>(), (int)N, 1, 0, (int)N,
+                                                              (float*)d_out, d_ld, dyn);
   LAUNCH_CHECK(h);
   GK_CUDA(cudaEventRecord(h->ev[13], h->stream));
   const int64_t launches_all = h->launches - launches0;
@@ -2356,6 +2386,8 @@ static int wl_gram_async(gk_handle* h, int32_t n_iter, int32_t flags, void* K_ou
   if (xdiag) GK_CUDA(cudaMemcpyAsync(xdiag, h->diag_f64.p, N * 8, cudaMemcpyDeviceToHost, h->stream));
   GK_CUDA(cudaEventRecord(h->ev[15], h->stream));
   GK_CUDA(cudaStreamSynchronize(h->stream));
+  if (tail_fused && *reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(h->h_dyn.p) + sizeof(GramDyn)) > ovf_cap)
+    return GK_OK;  // more block overflows than the list holds (never seen): the synchronous route recomputes everything
   // ---- state as gk_wl_features + gk_gram leave it
   h->n_columns = hd.n_columns;
   h->features_ready = true; h->feat_serial++;

@@ -169,6 +169,7 @@ struct gk_handle {
   int64_t n_part = 0;
   gk::DevBuf tail_desc, tail_ent, tail_cur;
   gk::PinBuf h_colstats;
+  gk::DevBuf tb_cnt, tb_ent, tb_ovf;  // tail fused into the GEMM epilogue: per-block update lists + overflow (features.cuh tail_bucket)
   gk::DevBuf gram_dyn;   // gk::GramDyn: device-side decisions of the asynchronous pass (gk_wl_gram)
   gk::PinBuf h_dyn;
   gk::DevBuf diag_u64, diag_f64;

@@ -429,6 +429,64 @@ tail_pairs(long long n_tail_cols, const int2* __restrict__ tail_desc, const int2
   }
 }
 
+// Tail fused into the GEMM epilogue (gram_tc.cuh, GramParams::tb_cnt): the ordered pairs of every tail column, bucketed by
+// 32 x 32 block of K.  Entry = row | col << 5 | value << 10 in ONE word (counts are at most 256 on this path, so a product
+// has 17 bits); a block's TB_CAP entries are one 128-byte line, the rest go to the overflow list {row, col, value} that
+// tail_overflow_apply adds with global atomics after the GEMM.  Several columns may update the same element: the
+// epilogue adds entries one by one (exact integer sums in fp32).  The host clears counters AND entry lines first: a
+// fully written line is allocated in L2 without a fetch, so the 1.5 M scattered 4-byte stores below hit there instead of
+// costing a DRAM sector read each (which is what made the separate tail kernel slow in the first place).
+__global__ void __launch_bounds__(256)
+tail_bucket(const int2* __restrict__ tail_desc, const int2* __restrict__ tail_ent, const GramDyn* __restrict__ dyn, int nb32, int cap, int stride, int sym,
+            unsigned* __restrict__ tb_cnt, unsigned* __restrict__ tb_ent, int4* __restrict__ ovf, unsigned ovf_cap, unsigned* __restrict__ ovf_n) {
+  const int lane = threadIdx.x & 31;
+  const long long n_cols = dyn->n_tail_cols;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_cols; w += n_warps) {
+    const int2 d = tail_desc[w];
+    const int2* ent = tail_ent + d.x;
+    const int m = d.y;
+    const int mm = m * m;
+    // a column of at most 32 graphs (the usual threshold): one entry per lane, pairs through shuffles -- no loads in the loop
+    const bool in_regs = m <= 32;
+    int2 mine = make_int2(0, 0);
+    if (in_regs && lane < m) mine = ent[lane];
+    for (int p0 = 0; p0 < mm; p0 += 32) {  // (whole warp iterates: the shuffles need every lane)
+      const int p = p0 + lane;
+      const int a = p < mm ? p / m : 0, b = p < mm ? p - a * m : 0;
+      int2 ea, eb;
+      if (in_regs) {
+        ea.x = __shfl_sync(0xffffffffu, mine.x, a); ea.y = __shfl_sync(0xffffffffu, mine.y, a);
+        eb.x = __shfl_sync(0xffffffffu, mine.x, b); eb.y = __shfl_sync(0xffffffffu, mine.y, b);
+      } else {
+        ea = ent[a]; eb = ent[b];
+      }
+      if (p >= mm || a == b) continue;
+      const int r = ea.x, c = eb.x;
+      if (sym && r > c) continue;  // symmetric lists: the pair (c, r) of this column files the update (half the atomics)
+      const unsigned val = (unsigned)ea.y * (unsigned)eb.y;
+      const long long blk = (long long)(r >> 5) * nb32 + (c >> 5);
+      const unsigned pos = atomicAdd(&tb_cnt[blk], 1u);
+      if (pos < (unsigned)cap && val < (1u << 22)) {
+        tb_ent[blk * stride + pos] = (unsigned)(r & 31) | ((unsigned)(c & 31) << 5) | (val << 10);
+      } else {
+        const unsigned o = atomicAdd(ovf_n, 1u);
+        if (o < ovf_cap) ovf[o] = make_int4(r, c, (int)__float_as_uint((float)val), 0);
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+tail_overflow_apply(const int4* __restrict__ ovf, const unsigned* __restrict__ ovf_n, unsigned ovf_cap, float* __restrict__ out, long long ld,
+                    int sym) {
+  const unsigned n = min(*ovf_n, ovf_cap);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 e = ovf[i];
+    atomicAdd(&out[(long long)e.x * ld + e.y], __uint_as_float((unsigned)e.z));
+    if (sym) atomicAdd(&out[(long long)e.y * ld + e.x], __uint_as_float((unsigned)e.z));
+  }
+}
+
 __global__ void __launch_bounds__(256) add_u64(int n, const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];

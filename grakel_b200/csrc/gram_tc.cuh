@@ -63,7 +63,18 @@ struct GramParams {
   int k_split;         // chunking applies to k-blocks [0, k_split); the rest is ONE chunk (0 = chunk everything)
   const int* nkb_dev;  // gram_tc2_kernel: number of k-blocks chosen ON THE DEVICE (asynchronous pass, features.cuh
                        // GramDyn), NULL = num_k_blocks
+  // Tail fused into the epilogue (TMA-store path with the TMA mirror): the pair updates of the sparse tail, bucketed by
+  // 32 x 32 block of K (tail_bucket, features.cuh: tb_cnt[block] entries {row | col << 5 | integer value << 10} at
+  // tb_ent[block * TB_CAP ...]), are added to the staged block in shared memory before its bulk store -- instead of a
+  // DRAM read-modify-write per update after the GEMM.  NULL = off.
+  const unsigned* tb_cnt;
+  const unsigned* tb_ent;
+  int tb_nb32;         // blocks per row of K
+  int tb_cap;          // entries per block the epilogue applies (<= TB_CAP, the storage stride; smaller only in tests)
+  int tb_sym;          // 1: only pairs with row < column are bucketed (blocks on or above the block diagonal); a block below
+                       // it reads its transpose's list with rows and columns swapped, a diagonal block applies both orders
 };
+constexpr int TB_CAP = 32;  // entries per block applied in the epilogue (one per lane); the rest go through tb overflow
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -211,6 +222,28 @@ __device__ __forceinline__ void epi_tma_store_tile(const GramParams& p, const CU
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     uint32_t v[32];
+    // fused tail: this block's and the mirrored block's update lists are fetched before the accumulator is (no
+    // dependent chain: every lane loads "its" entry slot speculatively, the count says which lanes hold one)
+    unsigned tn_d = 0, tn_m = 0;
+    unsigned te_d = 0u, te_m = 0u;
+    int swap_d = 0, swap_m = 0;  // 0: entry as stored, 1: rows and columns swapped, 2: both (diagonal block, symmetric lists)
+    if (p.tb_cnt && rows_in && tile.y + c0 < p.b_row_end) {
+      const int bx = arow0 >> 5, by = (tile.y + c0) >> 5;
+      if (p.tb_sym) {  // one list serves the block and its mirror image
+        const long long bl = (long long)min(bx, by) * p.tb_nb32 + max(bx, by);
+        tn_d = tn_m = min(__ldg(&p.tb_cnt[bl]), (unsigned)p.tb_cap);
+        te_d = te_m = __ldg(&p.tb_ent[bl * TB_CAP + lane]);
+        swap_d = bx < by ? 0 : (bx > by ? 1 : 2);
+        swap_m = bx < by ? 1 : (bx > by ? 0 : 2);
+      } else {
+        const long long bd = (long long)bx * p.tb_nb32 + by;
+        const long long bm = (long long)by * p.tb_nb32 + bx;
+        tn_d = min(__ldg(&p.tb_cnt[bd]), (unsigned)p.tb_cap);
+        tn_m = min(__ldg(&p.tb_cnt[bm]), (unsigned)p.tb_cap);
+        te_d = __ldg(&p.tb_ent[bd * TB_CAP + lane]);
+        te_m = __ldg(&p.tb_ent[bm * TB_CAP + lane]);
+      }
+    }
     tc_ld32(acc + (uint32_t)c0, v);
     const int bcol0 = tile.y + c0;
     if (bcol0 >= p.b_row_end || !rows_in) { mptr += 32 * ld; continue; }  // warp-uniform
@@ -233,6 +266,23 @@ __device__ __forceinline__ void epi_tma_store_tile(const GramParams& p, const CU
                    "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
                    : "memory");
     }
+    if (tn_d) {  // warp-uniform
+      __syncwarp();
+      if ((unsigned)lane < tn_d) {
+        const uint32_t e0 = te_d & 31u, e1 = (te_d >> 5) & 31u;
+        const float val = (float)(te_d >> 10);
+        if (swap_d != 1) {
+          const uint32_t r = e0, c = e1;
+          const uint32_t a = buf + r * 128u + ((((c >> 2) ^ (r & 7u))) << 4) + ((c & 3u) << 2);
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(val) : "memory");
+        }
+        if (swap_d != 0) {
+          const uint32_t r = e1, c = e0;
+          const uint32_t a = buf + r * 128u + ((((c >> 2) ^ (r & 7u))) << 4) + ((c & 3u) << 2);
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(val) : "memory");
+        }
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
@@ -252,6 +302,23 @@ __device__ __forceinline__ void epi_tma_store_tile(const GramParams& p, const CU
       for (int j = 0; j < 32; ++j) {
         const uint32_t a = cbase + (uint32_t)j * 128u + ((cq ^ (uint32_t)(j & 7)) << 4);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v[j]) : "memory");
+      }
+      if (tn_m) {  // the mirrored block K[bcol0 + r][arow0 + c] has its own list (the updates are symmetric, both halves are bucketed)
+        __syncwarp();
+        if ((unsigned)lane < tn_m) {
+          const uint32_t e0 = te_m & 31u, e1 = (te_m >> 5) & 31u;
+          const float val = (float)(te_m >> 10);
+          if (swap_m != 1) {
+            const uint32_t r = e0, c = e1;
+            const uint32_t a = mbuf + r * 128u + ((((c >> 2) ^ (r & 7u))) << 4) + ((c & 3u) << 2);
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(val) : "memory");
+          }
+          if (swap_m != 0) {
+            const uint32_t r = e1, c = e0;
+            const uint32_t a = mbuf + r * 128u + ((((c >> 2) ^ (r & 7u))) << 4) + ((c & 3u) << 2);
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(val) : "memory");
+          }
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();

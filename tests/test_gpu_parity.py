@@ -398,6 +398,14 @@ def test_asynchronous_pass_equals_the_synchronous_route(monkeypatch):
         Kd, _, s3 = eng.wl_gram(h, dense_all=True)
         _same(Kd, K0)
         assert s3.n_tail_columns == 0
+        # the tail inside the GEMM epilogue: one entry per block applied there, the rest through the overflow list; and
+        # the separate tail kernel
+        for name, val in (("GRAKEL_B200_TB_CAP", "1"), ("GRAKEL_B200_TB_CAP", "0"), ("GRAKEL_B200_TAIL_FUSED", "0")):
+            monkeypatch.setenv(name, val)
+            K5, _, s5 = eng.wl_gram(h)
+            assert s5.gemm_launches == 0
+            _same(K5, K0)
+            monkeypatch.delenv(name)
         # the switch
         monkeypatch.setenv("GRAKEL_B200_NO_ASYNC", "1")
         K4, _, s4 = eng.wl_gram(h)
