@@ -267,6 +267,16 @@ def _fast_edge_dict(g, L, mode, need_labels):
     return n, src[order], dst[order], ww[order], lab_list
 
 
+def _lengths_ok(X, len_ok):
+    """Element lengths acceptable to the whole-input fast path?  One C-level pass (`map(len, ...)`) instead of a Python
+    generator over every element (2-3 ms for 10 000 graphs); the element TYPES are checked by the C packer itself, which
+    declines anything that is not an exact list / tuple."""
+    try:
+        return all(n >= 2 and len_ok(n) for n in set(map(len, X)))
+    except TypeError:  # an element without a length: the general loop raises the reference's error
+        return False
+
+
 def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=False,
          fw_zero_is_absent=False, attributes=False, type_error_msg=None):
     """Pack an iterable of reference-style elements.
@@ -282,7 +292,7 @@ def pack(X, mode, need_labels=True, len_ok=lambda n: n in (2, 3), want_weights=F
                   (weisfeiler_lehman_optimal_assignment.py:179, 203-209).
     """
     if (_fastpack is not None and type(X) is list and X and not attributes and not fw_zero_is_absent
-            and all(type(x) in (list, tuple) and len(x) >= 2 and len_ok(len(x)) for x in X)):
+            and _lengths_ok(X, len_ok)):
         # whole-input fast path: {(u, v): w} graphs with integer symbols, walked with the CPython API on several
         # threads; it declines (None) on anything unusual and the general loop below decides -- and raises -- as before
         res = _fastpack.pack_edge_dicts(X, 0 if mode == "wl" else 1, 1 if need_labels else 0, 1 if want_weights else 0,
